@@ -1,0 +1,262 @@
+"""Build-container script: validate the oracle restatement against the REAL reference code and write
+tests/golden/*.npz (TEST INFRASTRUCTURE; needs /root/reference, so it never runs on the GPU box).
+
+    python -m oracle.make_golden [--full]
+
+The reference modules are imported unmodified from /root/reference on top of oracle/vggt_shim (the
+un-vendored upstream).  Every golden array is an output of the reference's own code.
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle", "vggt_shim"))
+sys.path.insert(1, "/root/reference")
+
+from oracle import aligned as OA          # noqa: E402
+from oracle import functional as OF       # noqa: E402
+from oracle import weights as OW          # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def rnd(seed, *shape, scale=1.0):
+    g = np.random.Generator(np.random.PCG64(seed))
+    return torch.from_numpy((g.standard_normal(shape, dtype=np.float32) * np.float32(scale)))
+
+
+def maxdiff(a, b):
+    return float((a - b).abs().max())
+
+
+def check(name, a, b, tol):
+    d = maxdiff(a, b)
+    ref = float(b.abs().max())
+    print(f"  {name:38s} max|diff|={d:.3e}  (max|ref|={ref:.3e})")
+    assert d <= tol * max(1.0, ref), f"{name}: restatement deviates from the reference ({d} > {tol})"
+
+
+def save(fname, **arrs):
+    np.savez_compressed(os.path.join(GOLD, fname), **{k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v))
+                                                      for k, v in arrs.items()})
+    print(f"  wrote tests/golden/{fname}")
+
+
+# --------------------------------------------------------------------------------------------
+def case_layers():
+    """rope.py, gated_update.py, cross_attention.py."""
+    print("[layers]")
+    from aligned_vggt.layers.rope import RotaryPositionEmbedding
+    from aligned_vggt.layers.gated_update import GatedUpdate
+    from aligned_vggt.layers.cross_attention import CrossAttentionBlock
+    x = rnd(1, 3, 8, 5, 64)
+    pos = torch.tensor([[0, 3, 4, 9, 70]]).expand(3, -1)
+    ref = RotaryPositionEmbedding(100.0)(x, pos)
+    check("rope1d", OF.rope_apply_1d(x, pos, 100.0), ref, 1e-6)
+
+    gu = GatedUpdate(512, 8)
+    sd = OW.fill_state_dict(OW.spec_of(gu), seed=3)
+    gu.load_state_dict(sd, strict=True)
+    mem = torch.nn.functional.normalize(rnd(2, 2, 8, 512), dim=-1)
+    upd = rnd(4, 2, 1, 512)
+    ref_g = gu(mem, upd)
+    check("gated_update", OA.gated_update(sd, "", mem, upd), ref_g, 1e-5)
+
+    cb = CrossAttentionBlock(dim=512, num_heads=8, init_values=0.01, qk_norm=True, rope=RotaryPositionEmbedding(100.0))
+    sdc = OW.fill_state_dict(OW.spec_of(cb), seed=5, ls_gamma=0.3)
+    cb.load_state_dict(sdc, strict=True)
+    xq, yk = rnd(6, 2, 5, 512), rnd(7, 2, 7, 512)
+    pq = torch.tensor([[0, 1, 2, 3, 4]]).expand(2, -1)
+    pk = torch.tensor([[0, 1, 2, 3, 4, 10, 11]]).expand(2, -1)
+    ref_c = cb(xq, yk, pos=(pq, pk))
+    check("cross_block", OA.cross_block(sdc, "", xq, yk, (pq, pk), 8), ref_c, 1e-5)
+    save("layers.npz", rope_x=x, rope_pos=pos, rope_out=ref, gu_mem=mem, gu_upd=upd, gu_out=ref_g,
+         cb_x=xq, cb_y=yk, cb_pq=pq, cb_pk=pk, cb_out=ref_c)
+
+
+def case_geometry():
+    """alignment.py Sim(3) apply, geometry.py pose average, data.py pose enc / chunks, IRLS Umeyama."""
+    print("[geometry]")
+    from aligned_vggt.utils import alignment as RA
+    from aligned_vggt.utils import data as RD
+    from aligned_vggt.utils import geometry as RG
+    from aligned_vggt.models.pointAligned_wrapped_vggt import irls_sim3_umeyama, weighted_umeyama_sim3
+    B, S, H, W = 2, 3, 5, 7
+    pts = rnd(10, B, S, H, W, 3, scale=10.0)
+    q = rnd(11, B, 4)
+    R = OF.quat_to_mat(q / q.norm(dim=-1, keepdim=True))
+    T = torch.eye(4).repeat(B, 1, 1)
+    T[:, :3, :3] = R
+    T[:, :3, 3] = rnd(12, B, 3, scale=3.0)
+    s = torch.tensor([0.7, 1.9])
+    ref_p = RA.apply_sim3_alignment_on_point_maps(pts, T, s)
+    check("sim3_points", OA.apply_sim3_points(pts, T, s), ref_p, 1e-6)
+    qe = rnd(13, B, S, 4)
+    extr = torch.cat([OF.quat_to_mat(qe), rnd(14, B, S, 3, 1, scale=2.0)], dim=-1)  # (B,S,3,4)
+    ref_w = RA.apply_sim3_alignment_on_w2c(extr.clone(), T, s)
+    check("sim3_w2c", OA.apply_sim3_w2c(extr, T, s), ref_w, 1e-5)
+    c2w = OA.inv_se3(extr)
+    ref_c = RA.apply_sim3_alignment_on_c2w(c2w.clone(), T, s)
+    check("sim3_c2w", OA.apply_sim3_c2w(c2w, T, s), ref_c, 1e-6)
+
+    enc = torch.cat([rnd(15, B, 4, 3), torch.nn.functional.normalize(rnd(16, 1, 1, 4) + 0.05 * rnd(17, B, 4, 4), dim=-1)], -1)
+    ref_avg = RG.averagePoseEncodings(enc)
+    mine = OA.average_pose_encodings(enc)
+    sgn = torch.sign((mine[..., 3:] * ref_avg[..., 3:]).sum(-1, keepdim=True))
+    check("average_pose(t)", mine[..., :3], ref_avg[..., :3], 1e-6)
+    check("average_pose(q up to sign)", mine[..., 3:] * sgn, ref_avg[..., 3:], 1e-5)
+    e44 = RD.pose_encoding_to_extri(enc)
+    check("pose_encoding_to_extri", OA.pose_encoding_to_extri(enc), e44, 1e-6)
+    back = RD.extri_to_pose_encoding(e44)
+    check("extri_to_pose_encoding", OA.extri_to_pose_encoding(e44), back, 1e-6)
+
+    # IRLS Umeyama: dst = s R src + t + noise, a few gross outliers
+    n, h, w = 2, 12, 16
+    src = rnd(20, n, h, w, 3, scale=4.0)
+    Rg, tg, sg = R[0], T[0, :3, 3], 1.3
+    dst = sg * (src @ Rg.T) + tg + rnd(21, n, h, w, 3, scale=0.01)
+    dst[0, 0, :5] += 3.0
+    cs, cd = 1 + torch.exp(rnd(22, n, h, w)), 1 + torch.exp(rnd(23, n, h, w))
+    Rr, tr, sr = irls_sim3_umeyama(src, dst, cs, cd)
+    Ro, to, so = OA.irls_umeyama(src, dst, cs, cd)
+    check("irls R", Ro, Rr, 1e-5); check("irls t", to, tr, 1e-4); check("irls s", so, sr, 1e-5)
+    wts = torch.sqrt(cs * cd).reshape(-1)
+    Ru, tu, su = weighted_umeyama_sim3(src.reshape(-1, 3), dst.reshape(-1, 3), wts)
+    Rm, tm, sm = OA.weighted_umeyama(src.reshape(-1, 3), dst.reshape(-1, 3), wts)
+    check("umeyama R", Rm, Ru, 1e-5); check("umeyama t", tm, tu, 1e-4); check("umeyama s", sm, su, 1e-5)
+
+    chunks = {}
+    for (nf, mode, wd, ov) in [(1000, "chunk_overlap", 32, 8), (14, "chunk_overlap", 5, 1), (3, "chunk_overlap", 5, 1),
+                               (20, "chunk_overlap", 8, 2), (17, "chunk_gt", 5, 0), (9, "all", 4, 1), (32, "chunk_overlap", 32, 8),
+                               (33, "chunk_overlap", 32, 8)]:
+        ref = RD.generate_chunks(nf, mode, wd, ov)
+        assert OA.generate_chunks(nf, mode, wd, ov) == ref, (nf, mode, wd, ov)
+        chunks[f"chunks_{nf}_{mode}_{wd}_{ov}"] = np.array([[c[0], c[-1], len(c)] for c in ref])
+    print(f"  generate_chunks: {len(chunks)} cases identical (1000/32/8 -> {len(RD.generate_chunks(1000,'chunk_overlap',32,8))} chunks)")
+    save("geometry.npz", pts=pts, T=T, s=s, sim3_points=ref_p, extr=extr, sim3_w2c=ref_w, c2w=c2w, sim3_c2w=ref_c,
+         enc=enc, avg=ref_avg, enc_extr=e44, enc_back=back, u_src=src, u_dst=dst, u_cs=cs, u_cd=cd,
+         irls_R=Rr, irls_t=tr, irls_s=sr, um_R=Ru, um_t=tu, um_s=su, **chunks)
+
+
+def case_head():
+    """AlignmentHead (real reference class) over two chained chunks; both temporal and global variants."""
+    print("[alignment head]")
+    from aligned_vggt.heads.alignment_head import AlignmentHead
+    S, gh, gw, ov = 4, 4, 6, 2
+    P = 5 + gh * gw
+    # temporal_attention=False is unusable in the reference itself (aa_order bug, alignment_head.py:80,146)
+    try:
+        AlignmentHead(in_dim=2048, temporal_attention=False).eval()(rnd(1, 1, 2, 5 + 4, 2048), (28, 28), 1)
+        raise SystemExit("reference temporal_attention=False unexpectedly works; restate it")
+    except AttributeError as e:
+        print(f"  reference temporal_attention=False fails as expected: {e}")
+    for variant, temporal in (("temporal", True),):
+        head = AlignmentHead(in_dim=2048, patch_size=14, num_memory_tokens=8, temporal_attention=temporal).eval()
+        sd = OW.fill_state_dict(OW.spec_of(head), seed=7, ls_gamma=0.2)
+        head.load_state_dict(sd, strict=True)
+        tok1, tok2 = rnd(30, 1, S, P, 2048), rnd(31, 1, S, P, 2048)
+        with torch.no_grad():
+            r1 = head(tok1, (gh * 14, gw * 14), ov)
+            r2 = head(tok2, (gh * 14, gw * 14), ov, overlap_tokens=r1[3], memory_tokens=r1[2])
+            o1 = OA.alignment_head_forward(sd, "", tok1, (gh * 14, gw * 14), ov, temporal_attention=temporal)
+            o2 = OA.alignment_head_forward(sd, "", tok2, (gh * 14, gw * 14), ov, o1[3], o1[2], temporal_attention=temporal)
+        for nm, a, b in zip(("sim3", "se3", "memory", "overlap"), o1, r1):
+            check(f"{variant} chunk1 {nm}", a, b, 2e-5)
+        for nm, a, b in zip(("sim3", "se3", "memory", "overlap"), o2, r2):
+            check(f"{variant} chunk2 {nm}", a, b, 2e-5)
+        save(f"head_{variant}.npz", S=S, gh=gh, gw=gw, ov=ov, wsum=OW.checksum(sd),
+             c1_sim3=r1[0], c1_se3=r1[1], c1_mem=r1[2], c1_overlap=r1[3],
+             c2_sim3=r2[0], c2_se3=r2[1], c2_mem=r2[2], c2_overlap=r2[3])
+
+
+def build_reference_model(depths=None):
+    from aligned_vggt.models.featureAligned_vggt import FeatureAlignedVGGT
+    if depths:
+        os.environ["VGGT_SHIM_DEPTH"] = f"{depths[0]},{depths[1]}"
+    else:
+        os.environ.pop("VGGT_SHIM_DEPTH", None)
+    t0 = time.time()
+    with torch.device("meta"):
+        model = FeatureAlignedVGGT(enable_point=False, enable_depth=False, enable_track=False)
+    spec = OW.spec_of(model)
+    sd = OW.fill_state_dict(spec, seed=0)
+    model = model.to_empty(device="cpu")
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    print(f"  reference model built: {sum(v.numel() for v in sd.values())/1e6:.0f} M params in {time.time()-t0:.1f}s")
+    return model, sd
+
+
+def run_two_chunks(model, sd, S, H, W, ov, taps, depth, dino_depth, tag, sample=None):
+    imgs = [torch.from_numpy(np.random.Generator(np.random.PCG64(100 + i)).random((1, S, 3, H, W), dtype=np.float32))
+            for i in range(2)]
+    model.intermediate_layer_indices = list(taps)
+    captured = []
+    hook = model.alignment_head.register_forward_pre_hook(lambda m, a: captured.append(a[0].detach().clone()))
+    with torch.no_grad():
+        t0 = time.time()
+        ref1 = model(imgs[0], ov)
+        t1 = time.time()
+        snap1 = {k: (v[-1] if isinstance(v, list) else v).clone() for k, v in ref1.items() if k != "images"}
+        ref2 = model(imgs[1], ov, ref1)
+        t2 = time.time()
+    hook.remove()
+    print(f"  reference forward: chunk1 {t1-t0:.1f}s, chunk2 {t2-t1:.1f}s  ({torch.get_num_threads()} threads)")
+    snap2 = {k: (v[-1] if isinstance(v, list) else v).clone() for k, v in ref2.items() if k != "images"}
+    snap2["chunk_sim3_alignment_enc"] = ref2["chunk_sim3_alignment_enc"][:, -1:]
+    snap2["frame_se3_alignment_enc"] = ref2["frame_se3_alignment_enc"][:, -(S - 1):]
+    with torch.no_grad():
+        o1 = OA.feature_aligned_forward(sd, imgs[0], ov, None, depth=depth, dino_depth=dino_depth, taps=taps)
+        ctx = {"overlap_tokens": o1["overlap_tokens"], "memory_tokens": o1["memory_tokens"], "pose_enc": o1["pose_enc"]}
+        o2 = OA.feature_aligned_forward(sd, imgs[1], ov, ctx, depth=depth, dino_depth=dino_depth, taps=taps)
+    tol = 5e-4
+    for ci, (o, r, cap) in enumerate(((o1, snap1, captured[0]), (o2, snap2, captured[1])), 1):
+        check(f"{tag} c{ci} last tap", o["taps"][-1], cap, tol)
+        for k in ("chunk_sim3_alignment_enc", "frame_se3_alignment_enc", "memory_tokens", "overlap_tokens", "pose_enc"):
+            check(f"{tag} c{ci} {k}", o[k], r[k], tol)
+    arrs = {"S": S, "H": H, "W": W, "ov": ov, "taps": np.array(taps), "wsum": OW.checksum(sd),
+            "secs_chunk1": t1 - t0, "secs_chunk2": t2 - t1, "threads": torch.get_num_threads()}
+    st = sample or 1
+    for ci, (r, cap) in enumerate(((snap1, captured[0]), (snap2, captured[1])), 1):
+        arrs[f"c{ci}_tap_last"] = cap[..., ::st].contiguous() if st > 1 else cap
+        for k in ("chunk_sim3_alignment_enc", "frame_se3_alignment_enc", "memory_tokens", "pose_enc"):
+            arrs[f"c{ci}_{k}"] = r[k]
+        arrs[f"c{ci}_overlap_tokens"] = r["overlap_tokens"][..., ::st].contiguous() if st > 1 else r["overlap_tokens"]
+    arrs["sample_stride"] = st
+    save(f"model_{tag}.npz", **arrs)
+
+
+def case_model_small():
+    print("[FeatureAlignedVGGT, depth 2/2, S=4, 56x84, overlap 2]")
+    model, sd = build_reference_model((2, 2))
+    run_two_chunks(model, sd, 4, 56, 84, 2, (0, 0, 1, 1), 2, 2, "small")
+
+
+def case_model_full():
+    print("[FeatureAlignedVGGT, full depth, config 1: S=4, 154x518, overlap 1]")
+    model, sd = build_reference_model(None)
+    run_two_chunks(model, sd, 4, 154, 518, 1, (4, 11, 17, 23), 24, 24, "full", sample=8)
+
+
+if __name__ == "__main__":
+    torch.set_grad_enabled(False)
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="also run the full-depth config-1 case (minutes, ~10 GB RAM)")
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    torch.manual_seed(0)
+    os.makedirs(GOLD, exist_ok=True)
+    cases = {"layers": case_layers, "geometry": case_geometry, "head": case_head, "model_small": case_model_small}
+    if args.full:
+        cases["model_full"] = case_model_full
+    for name, fn in cases.items():
+        if args.only and name != args.only:
+            continue
+        fn()
+    print("oracle restatement matches the reference on all cases")
