@@ -1,0 +1,81 @@
+"""Drop-in for the hot-path part of the reference's aligned_vggt/utils/alignment.py (:491-594).
+
+Same function names, argument meaning and error behaviour; the arithmetic runs in liblsvs_b200.so
+(csrc/sim3.cu) on the tensors' CUDA device.  No CPU fallback: CPU tensors raise.
+"""
+import ctypes
+
+import torch
+
+from lsvs_b200 import native as _n
+
+
+def _prep(x: torch.Tensor, name: str) -> torch.Tensor:
+    if not x.is_cuda:
+        raise _n.NativeError(f"{name} must be a CUDA tensor (no CPU fallback on this path)")
+    return x.detach().to(torch.float32).contiguous()
+
+
+def apply_sim3_alignment_on_point_maps(point_maps: torch.Tensor, alignment_transforms: torch.Tensor,
+                                       alignment_scales: torch.Tensor) -> torch.Tensor:
+    """reference alignment.py:491-526.  (B,S,H,W,3)|(S,H,W,3), (B,4,4)|(4,4), (B,)|() -> (B,S,H,W,3)."""
+    if point_maps.dim() == 4:
+        point_maps = point_maps.unsqueeze(0)
+        alignment_transforms = alignment_transforms.unsqueeze(0)
+        alignment_scales = alignment_scales.unsqueeze(0)
+    assert point_maps.shape[0] == alignment_transforms.shape[0] == alignment_scales.shape[0], \
+        "Inputs must have matching batch dimension"
+    B, S, H, W, _ = point_maps.shape
+    pts = _prep(point_maps, "point_maps")
+    T = _prep(alignment_transforms, "alignment_transforms")
+    s = _prep(alignment_scales, "alignment_scales").reshape(B)
+    out = torch.empty_like(pts)
+    _n.check(_n.lib().lsvs_sim3_apply_points(_n.ptr(pts), _n.ptr(T), _n.ptr(s), _n.ptr(out), ctypes.c_int(B),
+                                             ctypes.c_longlong(S * H * W), _n.stream_ptr()), "sim3_apply_points")
+    return out
+
+
+def apply_sim3_alignment_on_c2w(poses: torch.Tensor, alignment_transform: torch.Tensor,
+                                alignment_scales: torch.Tensor) -> torch.Tensor:
+    """reference alignment.py:558-594.  (B,S,4,4) -> (B,S,4,4)."""
+    if poses.dim() == 3:
+        poses = poses.unsqueeze(0)
+        alignment_transform = alignment_transform.unsqueeze(0)
+        alignment_scales = alignment_scales.unsqueeze(0)
+    assert poses.shape[0] == alignment_transform.shape[0] == alignment_scales.shape[0], \
+        "Inputs must have matching batch dimension"
+    B, S = poses.shape[:2]
+    p = _prep(poses, "poses")
+    out = torch.empty((B, S, 4, 4), dtype=torch.float32, device=p.device)
+    _n.check(_n.lib().lsvs_sim3_apply_c2w(_n.ptr(p), _n.ptr(_prep(alignment_transform, "alignment_transform")),
+                                          _n.ptr(_prep(alignment_scales, "alignment_scales").reshape(B)), _n.ptr(out),
+                                          ctypes.c_int(B), ctypes.c_int(S), _n.stream_ptr()), "sim3_apply_c2w")
+    return out
+
+
+def apply_sim3_alignment_on_w2c(extr: torch.Tensor, alignment_transform: torch.Tensor,
+                                alignment_scales: torch.Tensor) -> torch.Tensor:
+    """reference alignment.py:528-556.  (B,S,3,4)|(B,S,4,4) -> (B,S,4,4)."""
+    if extr.dim() == 3:
+        extr = extr.unsqueeze(0)
+        alignment_transform = alignment_transform.unsqueeze(0)
+        alignment_scales = alignment_scales.unsqueeze(0)
+    assert extr.shape[0] == alignment_transform.shape[0] == alignment_scales.shape[0], \
+        "Inputs must have matching batch dimension"
+    B, S, rows = extr.shape[:3]
+    e = _prep(extr, "extr")
+    out = torch.empty((B, S, 4, 4), dtype=torch.float32, device=e.device)
+    _n.check(_n.lib().lsvs_sim3_apply_w2c(_n.ptr(e), ctypes.c_int(rows), _n.ptr(_prep(alignment_transform, "alignment_transform")),
+                                          _n.ptr(_prep(alignment_scales, "alignment_scales").reshape(B)), _n.ptr(out),
+                                          ctypes.c_int(B), ctypes.c_int(S), _n.stream_ptr()), "sim3_apply_w2c")
+    return out
+
+
+def scale_depth(depth: torch.Tensor, scales: torch.Tensor) -> torch.Tensor:
+    """`depth *= chunk_scale.view(B,1,1,1,1)` (featureAligned_vggt.py:171), out of place."""
+    B = depth.shape[0]
+    d = _prep(depth, "depth")
+    out = torch.empty_like(d)
+    _n.check(_n.lib().lsvs_scale_rows(_n.ptr(d), _n.ptr(_prep(scales, "scales").reshape(B)), _n.ptr(out), ctypes.c_int(B),
+                                      ctypes.c_longlong(d.numel() // B), _n.stream_ptr()), "scale_rows")
+    return out

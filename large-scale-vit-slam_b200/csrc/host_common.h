@@ -1,0 +1,53 @@
+// Host-side helpers shared by all translation units of liblsvs_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <atomic>
+#include "../../include/lsvs_b200.h"
+
+namespace lsvs {
+
+extern thread_local char g_err[512];
+extern std::atomic<unsigned long long> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+#define LSVS_CHECK_ARG(cond, ...) \
+  do { if (!(cond)) return ::lsvs::fail(LSVS_EINVAL, __VA_ARGS__); } while (0)
+
+#define LSVS_CUDA(expr)                                                                       \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return ::lsvs::fail(LSVS_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define LSVS_LAUNCH_CHECK()                                                                   \
+  do {                                                                                        \
+    ::lsvs::count_launch();                                                                   \
+    cudaError_t e_ = cudaGetLastError();                                                      \
+    if (e_ != cudaSuccess)                                                                    \
+      return ::lsvs::fail(LSVS_ECUDA, "%s:%d launch: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+  } while (0)
+
+}  // namespace lsvs
