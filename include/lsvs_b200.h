@@ -54,6 +54,36 @@ int lsvs_sim3_apply_c2w(const float* poses, const float* T, const float* s, floa
 /* replaces apply_sim3_alignment_on_w2c alignment.py:528-556 : extr (B,S,rows,4), rows in {3,4} -> (B,S,4,4) */
 int lsvs_sim3_apply_w2c(const float* extr, int rows, const float* T, const float* s, float* out, int batch, int frames, void* stream);
 
+/* ---- bf16 tensor-core GEMM (tcgen05 / TMEM / TMA) ----------------------------------------------
+ * C[M,N] = A[M,K] . W[N,K]^T with fp32 accumulation; A, W bf16 K-major (nn.Linear weight layout).
+ * replaces the cuBLASLt calls behind UPSTREAM Attention.qkv/proj and Mlp.fc1/fc2,
+ * alignment_head.py:242 (project_in) and cross_attention.py:55-57,76 (q/k/v/proj), fused with the
+ * elementwise work that follows them in the reference (bias, GELU, LayerScale + residual add,
+ * q_norm/k_norm LayerNorm, RoPE).  K % 64 == 0, N % 128 == 0. */
+enum { LSVS_EPI_BIAS_BF16 = 0,      /* out bf16 [M,ldo]  = acc + bias                                      */
+       LSVS_EPI_BIAS_GELU_BF16 = 1, /* out bf16          = gelu_erf(acc + bias)                            */
+       LSVS_EPI_BIAS_F32 = 2,       /* out fp32          = acc + bias                                      */
+       LSVS_EPI_RESID_F32 = 3,      /* resid fp32 [M,ldr] += gamma * (acc + bias); out2 (optional) = resid */
+       LSVS_EPI_HEADNORM64_BF16 = 4,  /* out bf16: per 64-wide head LayerNorm (+RoPE) on q/k columns, bias only on the rest */
+       LSVS_EPI_HEADNORM128_BF16 = 5 };
+enum { LSVS_ROPE_NONE = 0, LSVS_ROPE_2D = 1, LSVS_ROPE_1D = 2 };
+
+typedef struct lsvs_gemm_epilogue {
+  const float* bias;  void* out;  int ldo;
+  const float* gamma; float* resid; int ldr; float* out2; int ld2;
+  const float* qn_w; const float* qn_b; const float* kn_w; const float* kn_b;
+  int n_q_cols; int n_k_cols; float ln_eps;
+  int rope_mode; const float* rope_tab;   /* [pos][n_freq][2] = (cos, sin) */
+  int tokens_per_frame; int n_special; int grid_w;   /* LSVS_ROPE_2D: row -> (y,x) */
+  const int* pos_ids; int pos_period;                /* LSVS_ROPE_1D: pos_ids[row % pos_period] */
+} lsvs_gemm_epilogue;
+
+int lsvs_gemm_bf16(const lsvs_bf16* A, int lda, const lsvs_bf16* W, int ldw, int M, int N, int K, int epilogue_kind,
+                   const lsvs_gemm_epilogue* epilogue, void* stream);
+/* cos/sin table used by the RoPE epilogues: tab[p][j] = (cos, sin)(p * base^(-2j/(2*n_freq))), p < n_pos.
+ * (rope.py:46-58; fp32 angles)  `tab` holds n_pos*n_freq*2 floats. */
+int lsvs_rope_table(float* tab, int n_pos, int n_freq, float base, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,38 @@
+// C-ABI entry points for the GEMM and its helper tables.
+#include "gemm.h"
+#include "host_common.h"
+
+namespace {
+__global__ void rope_table_kernel(float2* tab, int n_pos, int n_freq, float base) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pos * n_freq) return;
+  const int p = i / n_freq, j = i % n_freq;
+  // inv_freq_j = 1 / base^(2j / dim), dim = 2 * n_freq  (rope.py:46-48), angle in fp32 (rope.py:51-55)
+  const float expo = (float)(2 * j) / (float)(2 * n_freq);
+  const float inv_freq = 1.0f / powf(base, expo);
+  const float ang = (float)p * inv_freq;
+  tab[i] = make_float2(cosf(ang), sinf(ang));
+}
+}  // namespace
+
+extern "C" int lsvs_rope_table(float* tab, int n_pos, int n_freq, float base, void* stream) {
+  LSVS_CHECK_ARG(tab && n_pos > 0 && n_freq > 0 && base > 0, "rope_table: bad arguments");
+  const int n = n_pos * n_freq;
+  rope_table_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(tab), n_pos, n_freq, base);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+
+extern "C" int lsvs_gemm_bf16(const lsvs_bf16* A, int lda, const lsvs_bf16* W, int ldw, int M, int N, int K, int kind,
+                              const lsvs_gemm_epilogue* ep, void* stream) {
+  LSVS_CHECK_ARG(ep, "gemm: epilogue descriptor is null");
+  lsvs::GemmEpilogue e;
+  e.bias = ep->bias; e.out = ep->out; e.ldo = ep->ldo; e.gamma = ep->gamma; e.resid = ep->resid; e.ldr = ep->ldr;
+  e.out2 = ep->out2; e.ld2 = ep->ld2; e.qn_w = ep->qn_w; e.qn_b = ep->qn_b; e.kn_w = ep->kn_w; e.kn_b = ep->kn_b;
+  e.n_q_cols = ep->n_q_cols; e.n_k_cols = ep->n_k_cols; e.ln_eps = ep->ln_eps; e.rope_mode = ep->rope_mode;
+  e.rope_tab = reinterpret_cast<const float2*>(ep->rope_tab); e.tokens_per_frame = ep->tokens_per_frame;
+  e.n_special = ep->n_special; e.grid_w = ep->grid_w; e.pos_ids = ep->pos_ids; e.pos_period = ep->pos_period;
+  if (kind == LSVS_EPI_RESID_F32) LSVS_CHECK_ARG(e.resid && e.ldr >= N, "gemm: residual epilogue needs resid with ldr >= N");
+  else LSVS_CHECK_ARG(e.out && e.ldo >= N, "gemm: epilogue needs out with ldo >= N");
+  return lsvs::gemm_bf16(A, lda, W, ldw, M, N, K, kind, e, (cudaStream_t)stream);
+}

@@ -1,0 +1,335 @@
+// bf16 GEMM  C[M,N] = A[M,K] . W[N,K]^T  (both operands K-major, i.e. nn.Linear layout) on the 5th-gen
+// tensor cores: TMA (128B swizzle) -> 4-stage shared-memory ring -> tcgen05.mma (cta_group::1, 128xBNx16)
+// accumulating fp32 in TMEM (double-buffered, 2 x BN columns) -> tcgen05.ld epilogue fused with
+//   bias | bias+GELU(erf) | bias+LayerScale+fp32 residual | bias + per-head LayerNorm + RoPE (q,k) .
+// Persistent: one CTA per SM walks tiles n-fastest so that an A row-panel stays in L2 across its N tiles.
+//
+// Replaces the library calls at: UPSTREAM Attention.qkv/proj, Mlp.fc1/fc2,
+// alignment_head.py:242 (project_in), cross_attention.py:55-57,76 (q/k/v/proj), plus the elementwise
+// q_norm/k_norm/RoPE/LayerScale/residual passes that the reference runs as separate ATen kernels.
+#include "gemm.h"
+#include "host_common.h"
+#include "ptx.cuh"
+#include "tensormap.h"
+
+namespace lsvs {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int NUM_THREADS = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + slack for 1024-byte alignment
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// ---- epilogue helpers: `v` holds NC consecutive fp32 accumulator columns of one output row ----------
+template <int NC>
+__device__ __forceinline__ void store_bf16_row(__nv_bfloat16* dst, const float* v) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < NC / 8; ++i) {
+    uint4 u;
+    u.x = ptx::pack_bf16(v[8 * i + 0], v[8 * i + 1]);
+    u.y = ptx::pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+    u.z = ptx::pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+    u.w = ptx::pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+    d4[i] = u;
+  }
+}
+
+template <int NC>
+__device__ __forceinline__ void load_acc(uint32_t taddr, float* v) {
+#pragma unroll
+  for (int c = 0; c < NC; c += 32) ptx::tmem_ld_32x32b_x32(taddr + c, reinterpret_cast<uint32_t*>(v + c));
+  ptx::tmem_ld_wait();
+}
+
+// Token position of global row m for the 2-D RoPE: frames of `tpf` tokens, the first `nsp` of each are
+// special (position 0,0), patches are row-major on a grid `gw` wide and get (y+1, x+1).
+__device__ __forceinline__ void pos2d(const GemmEpilogue& e, int m, int& py, int& px) {
+  const int t = m % e.tokens_per_frame;
+  if (t < e.n_special) { py = 0; px = 0; return; }
+  const int pp = t - e.n_special;
+  py = pp / e.grid_w + 1;
+  px = pp % e.grid_w + 1;
+}
+
+// Rotate pairs (j, j+R/2) of the R-wide region v[0..R) by angle table row `tab` (cos,sin per frequency).
+template <int R>
+__device__ __forceinline__ void rope_region(float* v, const float2* __restrict__ tab) {
+#pragma unroll
+  for (int j = 0; j < R / 2; ++j) {
+    const float2 cs = __ldg(tab + j);
+    const float a = v[j], b = v[j + R / 2];
+    v[j] = a * cs.x - b * cs.y;
+    v[j + R / 2] = b * cs.x + a * cs.y;
+  }
+}
+
+// bias + LayerNorm over one head (HD columns, all in this thread) + RoPE, in place.
+template <int HD>
+__device__ __forceinline__ void head_norm_rope(float* v, const float* __restrict__ bias, const float* __restrict__ w,
+                                               const float* __restrict__ b, const GemmEpilogue& e, int m) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < HD; ++i) { v[i] += __ldg(bias + i); s += v[i]; }
+  const float mean = s * (1.0f / HD);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < HD; ++i) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(q * (1.0f / HD) + e.ln_eps);
+#pragma unroll
+  for (int i = 0; i < HD; ++i) v[i] = (v[i] - mean) * rstd * __ldg(w + i) + __ldg(b + i);
+  if (e.rope_mode == ROPE_2D) {
+    int py, px;
+    pos2d(e, m, py, px);
+    rope_region<HD / 2>(v, e.rope_tab + (size_t)py * (HD / 4));
+    rope_region<HD / 2>(v + HD / 2, e.rope_tab + (size_t)px * (HD / 4));
+  } else if (e.rope_mode == ROPE_1D) {
+    const int p = __ldg(e.pos_ids + (m % e.pos_period));
+    rope_region<HD>(v, e.rope_tab + (size_t)p * (HD / 2));
+  }
+}
+
+template <int BN, int EPI>
+__device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, uint32_t taddr, int m, int n0, bool row_ok) {
+  if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_F32) {
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      __syncwarp();
+      load_acc<32>(taddr + c, v);
+      if (row_ok) {
+        const int n = n0 + c;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = v[i] + (e.bias ? __ldg(e.bias + n + i) : 0.f);
+          if constexpr (EPI == EPI_BIAS_GELU_BF16) x = gelu_erf(x);
+          v[i] = x;
+        }
+        if constexpr (EPI == EPI_BIAS_F32) {
+          float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)m * e.ldo + n);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+          store_bf16_row<32>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ldo + n, v);
+        }
+      }
+    }
+  } else if constexpr (EPI == EPI_RESID_F32) {
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      __syncwarp();
+      load_acc<32>(taddr + c, v);
+      if (!row_ok) continue;  // reconverges at the __syncwarp above / after the loop
+      const int n = n0 + c;
+      float4* r4 = reinterpret_cast<float4*>(e.resid + (size_t)m * e.ldr + n);
+      float4* o2 = e.out2 ? reinterpret_cast<float4*>(e.out2 + (size_t)m * e.ld2 + n) : nullptr;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 r = r4[i];
+        const float4 g = e.gamma ? __ldg(reinterpret_cast<const float4*>(e.gamma + n) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 bb = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        r.x += g.x * (v[4 * i + 0] + bb.x);
+        r.y += g.y * (v[4 * i + 1] + bb.y);
+        r.z += g.z * (v[4 * i + 2] + bb.z);
+        r.w += g.w * (v[4 * i + 3] + bb.w);
+        r4[i] = r;
+        if (o2) o2[i] = r;
+      }
+    }
+  } else {  // EPI_QKV_NORM_ROPE_64 / _128 : columns [0,n_q) q heads, [n_q, n_q+n_k) k heads, remainder plain (+bias)
+    constexpr int HD = (EPI == EPI_HEADNORM64_BF16) ? 64 : 128;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += HD) {
+      float v[HD];
+      __syncwarp();
+      load_acc<HD>(taddr + c, v);
+      if (!row_ok) continue;  // reconverges at the __syncwarp above / after the loop
+      const int n = n0 + c;
+      if (n < e.n_q_cols) {
+        head_norm_rope<HD>(v, e.bias + n, e.qn_w, e.qn_b, e, m);
+      } else if (n < e.n_q_cols + e.n_k_cols) {
+        head_norm_rope<HD>(v, e.bias + n, e.kn_w, e.kn_b, e, m);
+      } else {
+#pragma unroll
+        for (int i = 0; i < HD; ++i) v[i] += __ldg(e.bias + n + i);
+      }
+      store_bf16_row<HD>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ldo + n, v);
+    }
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                  GemmEpilogue epi) {
+  using L = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles_n = N / BN;
+  const int n_tiles_m = (M + BM - 1) / BM;
+  const int n_tiles = n_tiles_m * n_tiles_n;
+  const int n_kb = K / BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(full_bar + i, 1); ptx::mbar_init(empty_bar + i, 1); }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tmem_full + i, 1); ptx::mbar_init(tmem_empty + i, 4); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 2 * BN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+        if (lane == 0) {
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          ptx::mbar_expect_tx(full_bar + stage, L::STAGE_BYTES);
+          ptx::tma_load_2d(sa, &tmA, full_bar + stage, kb * BK, m0);
+          ptx::tma_load_2d(sa + L::A_BYTES, &tmB, full_bar + stage, kb * BK, n0);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        ptx::mbar_wait(full_bar + stage, phase);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = ptx::smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint64_t adesc = ptx::umma_desc_sw128(sa, 16, 1024);
+          const uint64_t bdesc = ptx::umma_desc_sw128(sa + L::A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)  // advance 32 bytes (encoded >> 4) inside the swizzle row per K step
+            ptx::umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          ptx::umma_commit(empty_bar + stage);  // frees the smem slot when these MMAs retire
+          if (kb == n_kb - 1) ptx::umma_commit(tmem_full + acc);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5 -> TMEM lane quarter warp%4)
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles_n) * BM, n0 = (tile % n_tiles_n) * BN;
+      ptx::mbar_wait(tmem_full + acc, acc_phase);
+      ptx::tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+      epilogue_row<BN, EPI>(epi, taddr, m, n0, m < M);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tmem_empty + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 2 * BN);
+}
+
+template <int BN, int EPI>
+int launch(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const GemmEpilogue& e, cudaStream_t st) {
+  using L = SmemLayout<BN>;
+  auto kern = gemm_bf16_tcgen05<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    LSVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * (N / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(*tmA, *tmB, M, N, K, e);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+
+}  // namespace
+
+int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epi_kind, const GemmEpilogue& e,
+              cudaStream_t st) {
+  LSVS_CHECK_ARG(A && W && M > 0 && N > 0 && K > 0, "gemm: null operand or empty shape (M=%d N=%d K=%d)", M, N, K);
+  LSVS_CHECK_ARG(K % BK == 0, "gemm: K=%d must be a multiple of %d", K, BK);
+  LSVS_CHECK_ARG(lda >= K && ldw >= K && lda % 8 == 0 && ldw % 8 == 0, "gemm: leading dimensions must be >= K and 16-byte aligned");
+  const bool bn256 = (N % 256 == 0);
+  LSVS_CHECK_ARG(bn256 || N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
+  const int BN = bn256 ? 256 : 128;
+  const CUtensorMap* tmA = tmap_2d_bf16(A, K, M, (uint64_t)lda * 2, BK, BM);
+  const CUtensorMap* tmB = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, BN);
+  if (!tmA || !tmB) return LSVS_ECUDA;
+  if (epi_kind == EPI_HEADNORM64_BF16 || epi_kind == EPI_HEADNORM128_BF16) {
+    LSVS_CHECK_ARG(e.bias && e.out, "gemm: head-norm epilogue needs bias and out");
+    LSVS_CHECK_ARG((e.n_q_cols == 0 || (e.qn_w && e.qn_b)) && (e.n_k_cols == 0 || (e.kn_w && e.kn_b)), "gemm: missing q/k norm weights");
+    LSVS_CHECK_ARG(e.rope_mode == ROPE_NONE || e.rope_tab, "gemm: rope table missing");
+    LSVS_CHECK_ARG(e.rope_mode != ROPE_2D || (e.tokens_per_frame > 0 && e.grid_w > 0), "gemm: 2-D rope needs the token grid");
+    LSVS_CHECK_ARG(e.rope_mode != ROPE_1D || (e.pos_ids && e.pos_period > 0), "gemm: 1-D rope needs position ids");
+  }
+#define LSVS_GEMM_CASE(KIND)                                                            \
+  case KIND:                                                                            \
+    return bn256 ? launch<256, KIND>(tmA, tmB, M, N, K, e, st) : launch<128, KIND>(tmA, tmB, M, N, K, e, st);
+  switch (epi_kind) {
+    LSVS_GEMM_CASE(EPI_BIAS_BF16)
+    LSVS_GEMM_CASE(EPI_BIAS_GELU_BF16)
+    LSVS_GEMM_CASE(EPI_BIAS_F32)
+    LSVS_GEMM_CASE(EPI_RESID_F32)
+    LSVS_GEMM_CASE(EPI_HEADNORM64_BF16)
+    LSVS_GEMM_CASE(EPI_HEADNORM128_BF16)
+    default:
+      return fail(LSVS_EINVAL, "gemm: unknown epilogue %d", epi_kind);
+  }
+#undef LSVS_GEMM_CASE
+  (void)BN;
+}
+
+}  // namespace lsvs

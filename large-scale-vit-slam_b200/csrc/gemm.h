@@ -1,0 +1,36 @@
+// Internal interface of the tcgen05 GEMM (csrc/gemm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/lsvs_b200.h"
+
+namespace lsvs {
+
+enum { EPI_BIAS_BF16 = LSVS_EPI_BIAS_BF16, EPI_BIAS_GELU_BF16 = LSVS_EPI_BIAS_GELU_BF16, EPI_BIAS_F32 = LSVS_EPI_BIAS_F32,
+       EPI_RESID_F32 = LSVS_EPI_RESID_F32, EPI_HEADNORM64_BF16 = LSVS_EPI_HEADNORM64_BF16,
+       EPI_HEADNORM128_BF16 = LSVS_EPI_HEADNORM128_BF16 };
+enum { ROPE_NONE = LSVS_ROPE_NONE, ROPE_2D = LSVS_ROPE_2D, ROPE_1D = LSVS_ROPE_1D };
+
+// same POD as the public struct, with typed pointers
+struct GemmEpilogue {
+  const float* bias = nullptr;   // [N]
+  void* out = nullptr;           // bf16 or fp32 [M, ldo]
+  int ldo = 0;
+  const float* gamma = nullptr;  // [N] LayerScale (RESID)
+  float* resid = nullptr;        // fp32 [M, ldr], updated in place: resid += gamma * (acc + bias)
+  int ldr = 0;
+  float* out2 = nullptr;         // optional second copy of the updated residual (tapped layer output)
+  int ld2 = 0;
+  const float* qn_w = nullptr; const float* qn_b = nullptr;   // per-head LayerNorm of q columns
+  const float* kn_w = nullptr; const float* kn_b = nullptr;   // per-head LayerNorm of k columns
+  int n_q_cols = 0, n_k_cols = 0;  // [0,n_q) q heads | [n_q, n_q+n_k) k heads | rest: bias only
+  float ln_eps = 1e-5f;
+  int rope_mode = ROPE_NONE;
+  const float2* rope_tab = nullptr;  // [pos][n_freq] (cos, sin)
+  int tokens_per_frame = 0, n_special = 0, grid_w = 0;  // ROPE_2D: position from the row index
+  const int* pos_ids = nullptr; int pos_period = 0;     // ROPE_1D: position = pos_ids[row % pos_period]
+};
+
+int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epi_kind, const GemmEpilogue& e,
+              cudaStream_t st);
+
+}  // namespace lsvs

@@ -1,0 +1,69 @@
+#include "tensormap.h"
+#include "host_common.h"
+#include <cudaTypedefs.h>
+#include <mutex>
+#include <unordered_map>
+#include <memory>
+#include <string>
+#include <cstring>
+
+namespace lsvs {
+namespace {
+struct Key {
+  const void* base; uint64_t inner, outer, pitch; uint32_t bi, bo;
+  bool operator==(const Key& o) const { return std::memcmp(this, &o, sizeof(Key)) == 0; }
+};
+struct KeyHash {
+  size_t operator()(const Key& k) const {
+    const uint64_t* p = reinterpret_cast<const uint64_t*>(&k);
+    size_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(Key) / 8; ++i) h = (h ^ p[i]) * 1099511628211ull;
+    return h;
+  }
+};
+std::mutex g_mu;
+std::unordered_map<Key, std::unique_ptr<CUtensorMap>, KeyHash> g_cache;
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+}  // namespace
+
+const CUtensorMap* tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                                uint32_t box_inner, uint32_t box_outer) {
+  Key key;
+  std::memset(&key, 0, sizeof(key));
+  key.base = base; key.inner = inner; key.outer = outer; key.pitch = pitch_bytes; key.bi = box_inner; key.bo = box_outer;
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_cache.find(key);
+  if (it != g_cache.end()) return it->second.get();
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      fail(LSVS_ECUDA, "cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+      return nullptr;
+    }
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  if (((uintptr_t)base & 15) || (pitch_bytes & 15) || box_inner * 2 != 128 || box_outer > 256 || box_outer == 0) {
+    fail(LSVS_EINVAL, "tensor map: base %p pitch %llu box %ux%u not TMA compatible", base, (unsigned long long)pitch_bytes,
+         box_inner, box_outer);
+    return nullptr;
+  }
+  auto tm = std::make_unique<CUtensorMap>();
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(tm.get(), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fail(LSVS_ECUDA, "cuTensorMapEncodeTiled failed (%d) dims %llux%llu pitch %llu box %ux%u", (int)r,
+         (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_bytes, box_inner, box_outer);
+    return nullptr;
+  }
+  const CUtensorMap* out = tm.get();
+  g_cache.emplace(key, std::move(tm));
+  return out;
+}
+}  // namespace lsvs
