@@ -84,6 +84,16 @@ int lsvs_gemm_bf16(const lsvs_bf16* A, int lda, const lsvs_bf16* W, int ldw, int
  * (rope.py:46-58; fp32 angles)  `tab` holds n_pos*n_freq*2 floats. */
 int lsvs_rope_table(float* tab, int n_pos, int n_freq, float base, void* stream);
 
+/* ---- fused attention (tcgen05 / TMEM / TMA, online softmax) --------------------------------------
+ * O = softmax(Q K^T * scale) V per (batch, head); no mask (the reference never masks: SDPA without mask in
+ * UPSTREAM Attention; the all-true mask of cross_attention.py:66-67 is a no-op).
+ * q/k/v/o: bf16, row = token, head h occupies columns [h*head_dim, (h+1)*head_dim); batch b owns rows
+ * [b*Lq,(b+1)*Lq) of q/o and [b*Lk,(b+1)*Lk) of k/v.  head_dim in {64,128}.  q,k,v may be column slices of
+ * one fused qkv buffer (pass the slice pointers and the common row stride). */
+int lsvs_attention_bf16(const lsvs_bf16* q, int ldq, const lsvs_bf16* k, int ldk, const lsvs_bf16* v, int ldv,
+                        lsvs_bf16* o, int ldo, int batches, int heads, int head_dim, int Lq, int Lk, float scale,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,328 @@
+// Fused flash-style attention  O = softmax(Q K^T * scale) V  on tcgen05 / TMEM / TMA (no mask; ragged tails).
+//
+// One CTA owns up to two 128-row query tiles (A, B) of one (batch, head) and streams the K/V blocks once for
+// both.  Warp roles (10 warps):
+//   warp 0      TMA producer: Q tiles once, then K and V blocks through two independent 3-stage rings
+//   warp 1      tcgen05.mma issuer: S_t = Q_t K^T (SS, fp32 in TMEM), O_t += P_t V (SS, P from shared memory)
+//   warps 2-5   softmax for tile A, warps 6-9 softmax for tile B: one thread per query row (TMEM lane), so the
+//               row max / row sum need no shuffles.  exp2 with the softmax scale folded in; running max and sum
+//               in registers; O stays in TMEM and is rescaled in place (tcgen05.ld/st) only when a row max moved.
+// The two tiles ping-pong on the tensor core: while the softmax warps of one tile work, the MMAs of the other
+// run.  S_t(i+1) is issued as soon as the softmax warps have pulled S_t(i) into registers (s_free barrier).
+//
+// Replaces F.scaled_dot_product_attention behind UPSTREAM Attention (Aggregator frame/global/DINO blocks,
+// alignment-head frame blocks alignment_head.py:363, camera-head trunk); q_norm/k_norm/RoPE are already applied
+// by the QKV GEMM epilogue (csrc/gemm.cu).
+#include "attention.h"
+#include "host_common.h"
+#include "ptx.cuh"
+#include "tensormap.h"
+
+namespace lsvs {
+namespace {
+
+constexpr int QT = 128;            // query rows per tile (UMMA M)
+constexpr int NTHREADS = 320;
+constexpr int KV_STAGES = 3;
+
+template <int HD>
+struct Cfg {
+  static constexpr int BKV = (HD == 64) ? 128 : 64;        // keys per block (UMMA N of S, K of PV)
+  static constexpr int KB = HD / 64;                        // 64-element (128 B) column blocks of the head dim
+  static constexpr int Q_TILE_BYTES = QT * HD * 2;
+  static constexpr int K_TILE_BYTES = BKV * HD * 2;
+  static constexpr int V_TILE_BYTES = BKV * HD * 2;
+  static constexpr int P_TILE_BYTES = QT * BKV * 2;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + 2 * Q_TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_STAGES * K_TILE_BYTES;
+  static constexpr int OFF_P = OFF_V + KV_STAGES * V_TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 2 * P_TILE_BYTES;
+  static constexpr int SMEM = OFF_BAR + 512 + 1024;
+  static constexpr int S_COL = 0;                            // TMEM columns: S_A, S_B, O_A, O_B
+  static constexpr int O_COL = 2 * BKV;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(O_COL + 2 * HD <= 512, "TMEM budget");
+};
+
+struct Bars {
+  uint64_t q_full;
+  uint64_t k_full[KV_STAGES], k_empty[KV_STAGES], v_full[KV_STAGES], v_empty[KV_STAGES];
+  uint64_t s_full[2], s_free[2], p_ready[2], pv_done[2];
+  uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(NTHREADS, 1)
+attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int Lq, int Lk,
+                      float scale_log2e) {
+  using C = Cfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Bars* bars = reinterpret_cast<Bars*>(smem + C::OFF_BAR);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * QT);       // first query row (within the sequence) of this CTA
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int n_tiles = (Lq - q0 > QT) ? 2 : 1;  // tile B only if it has at least one valid row
+  const int n_kv = (Lk + C::BKV - 1) / C::BKV;
+  const int q_row0 = batch * Lq + q0;          // global row of tile A's first query
+  const int kv_row0 = batch * Lk;
+  const int col0 = head * HD;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
+    ptx::mbar_init(&bars->q_full, 1);
+    for (int i = 0; i < KV_STAGES; ++i) {
+      ptx::mbar_init(&bars->k_full[i], 1); ptx::mbar_init(&bars->k_empty[i], 1);
+      ptx::mbar_init(&bars->v_full[i], 1); ptx::mbar_init(&bars->v_empty[i], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      ptx::mbar_init(&bars->s_full[t], 1); ptx::mbar_init(&bars->s_free[t], 4);
+      ptx::mbar_init(&bars->p_ready[t], 4); ptx::mbar_init(&bars->pv_done[t], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc(&bars->tmem_slot, C::TMEM_COLS); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = bars->tmem_slot;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      ptx::mbar_expect_tx(&bars->q_full, n_tiles * C::Q_TILE_BYTES);
+      for (int t = 0; t < n_tiles; ++t)
+        for (int kb = 0; kb < C::KB; ++kb)
+          ptx::tma_load_2d(smem + C::OFF_Q + t * C::Q_TILE_BYTES + kb * (QT * 128), &tmQ, &bars->q_full, col0 + kb * 64,
+                           q_row0 + t * QT);
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < n_kv; ++i) {
+      // K(i) first (needed early for S), then V(i)
+      ptx::mbar_wait(&bars->k_empty[stage], phase ^ 1);
+      if (lane == 0) {
+        ptx::mbar_expect_tx(&bars->k_full[stage], C::K_TILE_BYTES);
+        for (int kb = 0; kb < C::KB; ++kb)
+          ptx::tma_load_2d(smem + C::OFF_K + stage * C::K_TILE_BYTES + kb * (C::BKV * 128), &tmK, &bars->k_full[stage],
+                           col0 + kb * 64, kv_row0 + i * C::BKV);
+      }
+      ptx::mbar_wait(&bars->v_empty[stage], phase ^ 1);
+      if (lane == 0) {
+        ptx::mbar_expect_tx(&bars->v_full[stage], C::V_TILE_BYTES);
+        for (int kb = 0; kb < C::KB; ++kb)
+          ptx::tma_load_2d(smem + C::OFF_V + stage * C::V_TILE_BYTES + kb * (C::BKV * 128), &tmV, &bars->v_full[stage],
+                           col0 + kb * 64, kv_row0 + i * C::BKV);
+      }
+      __syncwarp();
+      if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(QT, C::BKV, 0, 0);  // S = Q K^T : both K-major
+    constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(QT, HD, 0, 1);      // O = P V   : A K-major, B (V) MN-major
+    const uint32_t sQ = ptx::smem_u32(smem + C::OFF_Q), sK = ptx::smem_u32(smem + C::OFF_K);
+    const uint32_t sV = ptx::smem_u32(smem + C::OFF_V), sP = ptx::smem_u32(smem + C::OFF_P);
+
+    auto issue_S = [&](int t, int stage) {
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) {
+        const uint64_t a = ptx::umma_desc_sw128(sQ + t * C::Q_TILE_BYTES + (k / 4) * (QT * 128) + (k % 4) * 32, 16, 1024);
+        const uint64_t b = ptx::umma_desc_sw128(sK + stage * C::K_TILE_BYTES + (k / 4) * (C::BKV * 128) + (k % 4) * 32, 16, 1024);
+        ptx::umma_bf16_ss(tmem + C::S_COL + t * C::BKV, a, b, idesc_s, k != 0);
+      }
+    };
+    auto issue_PV = [&](int t, int stage, bool accumulate) {
+#pragma unroll
+      for (int k = 0; k < C::BKV / 16; ++k) {
+        const uint64_t a = ptx::umma_desc_sw128(sP + t * C::P_TILE_BYTES + (k / 4) * (QT * 128) + (k % 4) * 32, 16, 1024);
+        // V block: rows = keys (K dim), 64-wide column blocks (N dim) C::BKV*128 bytes apart; 16 keys per step
+        const uint64_t b = ptx::umma_desc_sw128(sV + stage * C::V_TILE_BYTES + k * (16 * 128), C::BKV * 128, 1024);
+        ptx::umma_bf16_ss(tmem + C::O_COL + t * HD, a, b, idesc_o, (accumulate || k != 0) ? 1u : 0u);
+      }
+    };
+
+    ptx::mbar_wait(&bars->q_full, 0);
+    ptx::mbar_wait(&bars->k_full[0], 0);
+    ptx::tc_fence_after();
+    if (lane == 0) {
+      for (int t = 0; t < n_tiles; ++t) { issue_S(t, 0); ptx::umma_commit(&bars->s_full[t]); }
+      ptx::umma_commit(&bars->k_empty[0]);  // K(0) free once S_A(0), S_B(0) retire
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < n_kv; ++i) {
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1; }
+      if (i + 1 < n_kv) {
+        // S_t(i+1) as soon as the softmax warps hold S_t(i) in registers
+        ptx::mbar_wait(&bars->k_full[nstage], nphase);
+        for (int t = 0; t < n_tiles; ++t) {
+          ptx::mbar_wait(&bars->s_free[t], i & 1);
+          ptx::tc_fence_after();
+          if (lane == 0) { issue_S(t, nstage); ptx::umma_commit(&bars->s_full[t]); }
+          __syncwarp();
+        }
+        if (lane == 0) ptx::umma_commit(&bars->k_empty[nstage]);  // K(i+1) free once both S MMAs retire
+        __syncwarp();
+      }
+      ptx::mbar_wait(&bars->v_full[stage], phase);
+      for (int t = 0; t < n_tiles; ++t) {
+        ptx::mbar_wait(&bars->p_ready[t], i & 1);
+        ptx::tc_fence_after();
+        if (lane == 0) { issue_PV(t, stage, i > 0); ptx::umma_commit(&bars->pv_done[t]); }
+        __syncwarp();
+      }
+      if (lane == 0) ptx::umma_commit(&bars->v_empty[stage]);
+      __syncwarp();
+      stage = nstage;
+      phase = nphase;
+    }
+  } else {
+    // ============================================================ softmax / correction / epilogue
+    const int t = (warp - 2) >> 2;             // 0: tile A (warps 2-5), 1: tile B (warps 6-9)
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;         // query row within the tile == TMEM lane
+    if (t < n_tiles) {
+      const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+      const uint32_t tS = tmem + lane_addr + C::S_COL + t * C::BKV;
+      const uint32_t tO = tmem + lane_addr + C::O_COL + t * HD;
+      uint8_t* sP = smem + C::OFF_P + t * C::P_TILE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int i = 0; i < n_kv; ++i) {
+        ptx::mbar_wait(&bars->s_full[t], i & 1);
+        ptx::tc_fence_after();
+        float s[C::BKV];
+#pragma unroll
+        for (int c = 0; c < C::BKV; c += 32) ptx::tmem_ld_32x32b_x32(tS + c, reinterpret_cast<uint32_t*>(s + c));
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars->s_free[t]);
+        const int kv_valid = Lk - i * C::BKV;  // keys of this block inside the sequence
+        if (kv_valid < C::BKV) {
+#pragma unroll
+          for (int c = 0; c < C::BKV; ++c) if (c >= kv_valid) s[c] = -INFINITY;
+        }
+        float m_new = m_run;
+#pragma unroll
+        for (int c = 0; c < C::BKV; ++c) m_new = fmaxf(m_new, s[c]);
+        const float alpha = ex2((m_run - m_new) * scale_log2e);
+        const float mb = m_new * scale_log2e;
+        float sum = 0.f;
+        uint32_t pk[C::BKV / 2];
+#pragma unroll
+        for (int c = 0; c < C::BKV; c += 2) {
+          const float p0 = ex2(fmaf(s[c], scale_log2e, -mb));
+          const float p1 = ex2(fmaf(s[c + 1], scale_log2e, -mb));
+          sum += p0 + p1;
+          pk[c / 2] = ptx::pack_bf16(p0, p1);
+        }
+        l_run = l_run * alpha + sum;
+        if (i > 0) {
+          // PV(i-1) must have retired before P is overwritten and before O is rescaled
+          ptx::mbar_wait(&bars->pv_done[t], (i - 1) & 1);
+          ptx::tc_fence_after();
+          if (__any_sync(0xffffffffu, m_new != m_run)) {
+#pragma unroll
+            for (int c = 0; c < HD; c += 16) {
+              uint32_t o[16];
+              ptx::tmem_ld_32x32b_x16(tO + c, o);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+              ptx::tmem_st_32x32b_x16(tO + c, o);
+            }
+            ptx::tmem_st_wait();
+          }
+        }
+        m_run = m_new;
+        // P (bf16) into shared memory in the K-major 128B-swizzled layout the UMMA A descriptor expects
+#pragma unroll
+        for (int j = 0; j < C::BKV / 8; ++j) {
+          const int kb = j >> 3, chunk = j & 7;
+          uint4 v = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          *reinterpret_cast<uint4*>(sP + kb * (QT * 128) + ((chunk ^ (r & 7)) << 4)) = v;
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars->p_ready[t]);
+      }
+      // ---- epilogue: O / l -> bf16 -> global
+      ptx::mbar_wait(&bars->pv_done[t], (n_kv - 1) & 1);
+      ptx::tc_fence_after();
+      const float inv_l = 1.0f / l_run;
+      const int q_local = q0 + t * QT + r;
+      __nv_bfloat16* dst = O + (size_t)(batch * (size_t)Lq + q_local) * ldo + col0;
+#pragma unroll
+      for (int c = 0; c < HD; c += 32) {
+        uint32_t o[32];
+        ptx::tmem_ld_32x32b_x32(tO + c, o);
+        ptx::tmem_ld_wait();
+        if (q_local < Lq) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = ptx::pack_bf16(__uint_as_float(o[8 * j + 0]) * inv_l, __uint_as_float(o[8 * j + 1]) * inv_l);
+            u.y = ptx::pack_bf16(__uint_as_float(o[8 * j + 2]) * inv_l, __uint_as_float(o[8 * j + 3]) * inv_l);
+            u.z = ptx::pack_bf16(__uint_as_float(o[8 * j + 4]) * inv_l, __uint_as_float(o[8 * j + 5]) * inv_l);
+            u.w = ptx::pack_bf16(__uint_as_float(o[8 * j + 6]) * inv_l, __uint_as_float(o[8 * j + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(dst + c + 8 * j) = u;
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
+}
+
+template <int HD>
+int launch(const AttentionArgs& a, cudaStream_t st) {
+  using C = Cfg<HD>;
+  const size_t rows_q = (size_t)a.batches * a.Lq, rows_k = (size_t)a.batches * a.Lk;
+  const CUtensorMap* tq = tmap_2d_bf16(a.q, (uint64_t)a.heads * HD, rows_q, (uint64_t)a.ldq * 2, 64, QT);
+  const CUtensorMap* tk = tmap_2d_bf16(a.k, (uint64_t)a.heads * HD, rows_k, (uint64_t)a.ldk * 2, 64, C::BKV);
+  const CUtensorMap* tv = tmap_2d_bf16(a.v, (uint64_t)a.heads * HD, rows_k, (uint64_t)a.ldv * 2, 64, C::BKV);
+  if (!tq || !tk || !tv) return LSVS_ECUDA;
+  auto kern = attention_fwd_tcgen05<HD>;
+  static bool configured = false;
+  if (!configured) {
+    LSVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    configured = true;
+  }
+  dim3 grid((a.Lq + 2 * QT - 1) / (2 * QT), a.heads, a.batches);
+  const float scale_log2e = a.scale * 1.4426950408889634f;
+  kern<<<grid, NTHREADS, C::SMEM, st>>>(*tq, *tk, *tv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, a.Lk, scale_log2e);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+
+}  // namespace
+
+int attention_fwd(const AttentionArgs& a, cudaStream_t st) {
+  LSVS_CHECK_ARG(a.q && a.k && a.v && a.o, "attention: null pointer");
+  LSVS_CHECK_ARG(a.batches > 0 && a.heads > 0 && a.Lq > 0 && a.Lk > 0, "attention: empty shape");
+  LSVS_CHECK_ARG(a.batches <= 65535 && a.heads <= 65535, "attention: batch/head count exceeds the grid limit");
+  LSVS_CHECK_ARG(a.head_dim == 64 || a.head_dim == 128, "attention: head_dim %d unsupported (64 or 128)", a.head_dim);
+  const int D = a.heads * a.head_dim;
+  LSVS_CHECK_ARG(a.ldq >= D && a.ldk >= D && a.ldv >= D && a.ldo >= D, "attention: leading dimension smaller than heads*head_dim");
+  LSVS_CHECK_ARG(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: leading dimensions must be multiples of 8");
+  return a.head_dim == 64 ? launch<64>(a, st) : launch<128>(a, st);
+}
+
+}  // namespace lsvs

@@ -36,3 +36,11 @@ extern "C" int lsvs_gemm_bf16(const lsvs_bf16* A, int lda, const lsvs_bf16* W, i
   else LSVS_CHECK_ARG(e.out && e.ldo >= N, "gemm: epilogue needs out with ldo >= N");
   return lsvs::gemm_bf16(A, lda, W, ldw, M, N, K, kind, e, (cudaStream_t)stream);
 }
+
+#include "attention.h"
+extern "C" int lsvs_attention_bf16(const lsvs_bf16* q, int ldq, const lsvs_bf16* k, int ldk, const lsvs_bf16* v, int ldv,
+                                   lsvs_bf16* o, int ldo, int batches, int heads, int head_dim, int Lq, int Lk, float scale,
+                                   void* stream) {
+  lsvs::AttentionArgs a{q, k, v, o, ldq, ldk, ldv, ldo, batches, heads, head_dim, Lq, Lk, scale};
+  return lsvs::attention_fwd(a, (cudaStream_t)stream);
+}

@@ -73,3 +73,19 @@ def gemm(a: torch.Tensor, w: torch.Tensor, kind: int, *, bias=None, out=None, ga
     _n.check(_n.lib().lsvs_gemm_bf16(_n.ptr(a), _i(a.stride(0)), _n.ptr(w), _i(w.stride(0)), _i(M), _i(N), _i(K), _i(kind),
                                      ctypes.byref(e), _n.stream_ptr()), "gemm_bf16")
     return resid if kind == EPI_RESID_F32 else out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batches: int, heads: int, head_dim: int, Lq: int,
+              Lk: int, scale: float = None, out: torch.Tensor = None) -> torch.Tensor:
+    """softmax(q k^T scale) v.  q (batches*Lq, >=heads*head_dim) bf16 with row stride; k, v (batches*Lk, ...)."""
+    for t in (q, k, v):
+        assert t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1
+    D = heads * head_dim
+    if out is None:
+        out = torch.empty(batches * Lq, D, dtype=torch.bfloat16, device=q.device)
+    if scale is None:
+        scale = head_dim ** -0.5
+    _n.check(_n.lib().lsvs_attention_bf16(_n.ptr(q), _i(q.stride(0)), _n.ptr(k), _i(k.stride(0)), _n.ptr(v), _i(v.stride(0)),
+                                          _n.ptr(out), _i(out.stride(0)), _i(batches), _i(heads), _i(head_dim), _i(Lq), _i(Lk),
+                                          _f(scale), _n.stream_ptr()), "attention_bf16")
+    return out
