@@ -94,6 +94,53 @@ int lsvs_attention_bf16(const lsvs_bf16* q, int ldq, const lsvs_bf16* k, int ldk
                         lsvs_bf16* o, int ldo, int batches, int heads, int head_dim, int Lq, int Lk, float scale,
                         void* stream);
 
+/* ---- engine: packed weights + kernel sequencing for the module forwards ---------------------------
+ * One engine per process / GPU.  Parameters are pushed by state_dict name (the names are the reference's
+ * checkpoint contract) from DEVICE fp32 pointers; the engine keeps its own copies (bf16 for the
+ * tensor-core GEMM weights, fp32 otherwise), so the caller's tensors may be freed or moved afterwards. */
+typedef struct lsvs_engine lsvs_engine;
+typedef struct lsvs_engine_config {
+  int embed_dim, num_heads, patch_size, num_register_tokens; /* VGGT-1B geometry: 1024, 16, 14, 4          */
+  int depth, dino_depth;                                     /* alternating-attention pairs, DINOv2 blocks */
+  int head_depth_aa, num_memory_tokens;                      /* alignment head: 4, 8                       */
+  int with_alignment_head, with_camera_head;
+  float rope_base;                                           /* 100                                        */
+} lsvs_engine_config;
+
+int lsvs_engine_create(const lsvs_engine_config* cfg, lsvs_engine** out);
+int lsvs_engine_destroy(lsvs_engine* e);
+/* rows/cols: 2-D view of weight matrices (rows = out features, cols = in features, conv kernels flattened);
+ * 0,0 for everything else. */
+int lsvs_engine_set_param(lsvs_engine* e, const char* name, const float* data, long long numel, int rows, int cols, void* stream);
+/* resolve all names into per-block weight tables; fails with the first missing / mis-shaped key */
+int lsvs_engine_finalize(lsvs_engine* e, void* stream);
+/* DINOv2 position embedding already interpolated to the (gh, gw) patch grid: (1 + gh*gw, 1024) fp32
+ * (row 0 = class token).  Weight preprocessing, done once per image size by the host side. */
+int lsvs_engine_set_pos_embed(lsvs_engine* e, const float* pos, int gh, int gw, void* stream);
+
+/* replaces UPSTREAM vggt Aggregator.forward (call site featureAligned_vggt.py:78; poseAligned_wrapped_vggt.py:62;
+ * pointAligned_wrapped_vggt.py:60).  images (B,S,3,H,W) fp32 in [0,1].  For each requested layer id the
+ * concatenated [frame | global] block outputs are written to taps[i]: (B,S,P,2048) fp32, P = 5 + (H/14)(W/14). */
+int lsvs_aggregator_forward(lsvs_engine* e, const float* images, int B, int S, int H, int W, float* const* taps,
+                            const int* tap_layers, int n_taps, void* stream);
+/* replaces AlignmentHead.forward  aligned_vggt/heads/alignment_head.py:224-345 (eval path).
+ * tokens (B,S,P,2048) fp32; overlap_in (B,T,P+1,1024) fp32 or NULL (first chunk); memory_in (B,8,512) or NULL.
+ * out: chunk_sim3 (B,1,8), frame_se3 (B,S-1,7), memory_out (B,8,512), overlap_out (B,1+next_overlap,P+1,1024). */
+int lsvs_alignment_head_forward(lsvs_engine* e, const float* tokens, int B, int S, int P, int H, int W, int next_overlap,
+                                const float* overlap_in, int T, const float* memory_in, float* chunk_sim3,
+                                float* frame_se3, float* memory_out, float* overlap_out, void* stream);
+/* replaces UPSTREAM vggt CameraHead.forward (call site featureAligned_vggt.py:106): tokens_last (B,S,P,2048)
+ * -> pose_enc (B,S,9) of the last refinement iteration. */
+int lsvs_camera_head_forward(lsvs_engine* e, const float* tokens_last, int B, int S, int P, int num_iterations,
+                             float* pose_enc, void* stream);
+/* replaces the pose / Sim(3) composition featureAligned_vggt.py:97-143 and :190-196 (and data.py:12-52,
+ * geometry.py:4-37 underneath).  chunk_sim3 (B,1,8), frame_se3 (B,S-1,7), cam_enc (B,S,9) camera-head output,
+ * prev_pose_enc (B,S_prev,9) aligned poses of the previous chunk or NULL.
+ * out: pose_enc_out (B,S,9), point_T (B,4,4) transform for the (scaled) point maps, scale_out (B). */
+int lsvs_pose_chain(const float* chunk_sim3, const float* frame_se3, const float* cam_enc, const float* prev_pose_enc,
+                    int S_prev, int overlap, int B, int S, int H, int W, float* pose_enc_out, float* point_T,
+                    float* scale_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

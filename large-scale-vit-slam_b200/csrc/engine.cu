@@ -1,0 +1,653 @@
+// Native runtime of the hot path: owns the packed weights (bf16 for the tensor-core GEMMs, fp32 for norms /
+// biases / the fp32 decode), the activation workspace, and sequences the kernels of
+//   * Aggregator.forward        (UPSTREAM vggt; call site featureAligned_vggt.py:78)
+//   * AlignmentHead.forward     (aligned_vggt/heads/alignment_head.py:224-345, decode :427-540)
+//   * CameraHead.forward        (UPSTREAM vggt; call site featureAligned_vggt.py:106)
+// on one CUDA stream with no host synchronisation.  The Python modules in large-scale-vit-slam_b200/aligned_vggt
+// hold the nn.Parameters (state_dict contract) and push them here once (lsvs_engine_set_param).
+#include <cuda_bf16.h>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "attention.h"
+#include "elementwise.h"
+#include "gemm.h"
+#include "host_common.h"
+#include "small_f32.h"
+
+namespace lsvs {
+namespace {
+
+#define TRY(expr) do { int rc_ = (expr); if (rc_ != LSVS_OK) return rc_; } while (0)
+
+struct Param {
+  float* f32 = nullptr;          // engine-owned fp32 copy (always kept for small tensors / fp32 path)
+  __nv_bfloat16* bf16 = nullptr; // engine-owned bf16 copy of GEMM weights (K padded to a multiple of 64)
+  long long numel = 0;
+  int rows = 0, cols = 0, cols_padded = 0;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return LSVS_OK;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    LSVS_CUDA(cudaMalloc(&p, need));
+    bytes = need;
+    return LSVS_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct BlockW {  // UPSTREAM Block / reference CrossAttentionBlock parameters
+  const float *n1w, *n1b, *n2w, *n2b, *n3w = nullptr, *n3b = nullptr;
+  const __nv_bfloat16 *qkv_w = nullptr, *q_w = nullptr, *kv_w = nullptr, *proj_w, *fc1_w, *fc2_w;
+  const float *qkv_b = nullptr, *q_b = nullptr, *kv_b = nullptr, *proj_b, *fc1_b, *fc2_b;
+  const float *qn_w = nullptr, *qn_b = nullptr, *kn_w = nullptr, *kn_b = nullptr;
+  const float *ls1 = nullptr, *ls2 = nullptr;
+};
+
+struct BlockWF {  // fp32 block (camera trunk, decode cross blocks)
+  const float *n1w, *n1b, *n2w, *n2b, *n3w = nullptr, *n3b = nullptr;
+  const float *qkv_w = nullptr, *qkv_b = nullptr, *q_w = nullptr, *q_b = nullptr, *k_w = nullptr, *k_b = nullptr, *v_w = nullptr, *v_b = nullptr;
+  const float *proj_w, *proj_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+  const float *qn_w = nullptr, *qn_b = nullptr, *kn_w = nullptr, *kn_b = nullptr, *ls1 = nullptr, *ls2 = nullptr;
+};
+
+struct RopeCfg { int mode = ROPE_NONE; const float2* tab = nullptr; int tpf = 0, nsp = 0, gw = 0; const int* ids = nullptr; int period = 0; };
+
+}  // namespace
+
+struct Engine {
+  lsvs_engine_config cfg;
+  std::map<std::string, Param> params;
+  bool finalized = false;
+  // derived weights
+  std::vector<BlockW> dino, frame, global, h_frame, h_temporal;
+  std::vector<BlockWF> cam_trunk, chunk_cross, frame_cross;
+  std::vector<DevBuf> fused;  // concatenated k|v weights etc.
+  // position embedding of the DINO ViT interpolated to the current patch grid (set by the host side)
+  DevBuf pos_embed; int pos_gh = 0, pos_gw = 0;
+  // tables
+  DevBuf rope2d_64, rope2d_128, rope1d_128, ids_q, ids_k;
+  int rope_npos2d = 0, rope_npos1d = 0;
+  // workspace
+  DevBuf x, xn, qkv, att, h, tmp, im2col, yn, kvb, scratch;
+  size_t scratch_off = 0;
+
+  ~Engine() {
+    for (auto& kv : params) { if (kv.second.f32) cudaFree(kv.second.f32); if (kv.second.bf16) cudaFree(kv.second.bf16); }
+    for (auto& b : fused) b.release();
+    for (DevBuf* b : {&pos_embed, &rope2d_64, &rope2d_128, &rope1d_128, &ids_q, &ids_k, &x, &xn, &qkv, &att, &h, &tmp, &im2col, &yn, &kvb, &scratch}) b->release();
+  }
+
+  const Param* find(const std::string& n) const { auto it = params.find(n); return it == params.end() ? nullptr : &it->second; }
+  bool scratch_overflow = false;
+  float* scratch_f32(size_t n) {  // bump allocation inside `scratch` (caller sized it; overflow is reported, not faulted)
+    const size_t need = (n + 63) & ~size_t(63);
+    if ((scratch_off + need) * sizeof(float) > scratch.bytes) { scratch_overflow = true; return scratch.as<float>(); }
+    float* p = scratch.as<float>() + scratch_off;
+    scratch_off += need;
+    return p;
+  }
+};
+
+namespace {
+
+bool ends_with(const std::string& s, const char* suf) {
+  const size_t n = std::strlen(suf);
+  return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+bool contains(const std::string& s, const char* sub) { return s.find(sub) != std::string::npos; }
+
+// GEMM weights that run on the tensor cores in bf16 (everything the reference runs under bf16 autocast at scale).
+bool wants_bf16(const std::string& n) {
+  if (!ends_with(n, ".weight")) return false;
+  if (contains(n, "camera_head.")) return false;
+  const bool big_block = contains(n, "aggregator.") || contains(n, "alignment_head.frame_blocks.") || contains(n, "alignment_head.temporal_blocks.");
+  if (big_block && (contains(n, "attn.qkv.") || contains(n, "attn.proj.") || contains(n, "attn.q.") || contains(n, "attn.k.") ||
+                    contains(n, "attn.v.") || contains(n, "mlp.fc1.") || contains(n, "mlp.fc2.") || contains(n, "patch_embed.proj.")))
+    return true;
+  return n == "alignment_head.project_in.weight";
+}
+
+int need(const Engine& e, const std::string& name, const Param** out) {
+  const Param* p = e.find(name);
+  if (!p) return fail(LSVS_EINVAL, "engine: parameter '%s' was never set (state_dict key missing)", name.c_str());
+  *out = p;
+  return LSVS_OK;
+}
+int need_f32(const Engine& e, const std::string& name, const float** out, long long numel = -1) {
+  const Param* p;
+  TRY(need(e, name, &p));
+  if (!p->f32) return fail(LSVS_EINVAL, "engine: parameter '%s' has no fp32 copy", name.c_str());
+  if (numel >= 0 && p->numel != numel) return fail(LSVS_EINVAL, "engine: parameter '%s' has %lld elements, expected %lld", name.c_str(), p->numel, numel);
+  *out = p->f32;
+  return LSVS_OK;
+}
+int need_bf16(const Engine& e, const std::string& name, const __nv_bfloat16** out, int rows, int cols) {
+  const Param* p;
+  TRY(need(e, name, &p));
+  if (!p->bf16) return fail(LSVS_EINVAL, "engine: parameter '%s' has no bf16 copy", name.c_str());
+  if (p->rows != rows || p->cols != cols) return fail(LSVS_EINVAL, "engine: parameter '%s' is %dx%d, expected %dx%d", name.c_str(), p->rows, p->cols, rows, cols);
+  *out = p->bf16;
+  return LSVS_OK;
+}
+
+int load_block(const Engine& e, const std::string& pre, int D, bool qk_norm, bool layer_scale, BlockW* w) {
+  const int hd_unused = 0; (void)hd_unused;
+  TRY(need_f32(e, pre + "norm1.weight", &w->n1w, D)); TRY(need_f32(e, pre + "norm1.bias", &w->n1b, D));
+  TRY(need_f32(e, pre + "norm2.weight", &w->n2w, D)); TRY(need_f32(e, pre + "norm2.bias", &w->n2b, D));
+  TRY(need_bf16(e, pre + "attn.qkv.weight", &w->qkv_w, 3 * D, D)); TRY(need_f32(e, pre + "attn.qkv.bias", &w->qkv_b, 3 * D));
+  TRY(need_bf16(e, pre + "attn.proj.weight", &w->proj_w, D, D)); TRY(need_f32(e, pre + "attn.proj.bias", &w->proj_b, D));
+  TRY(need_bf16(e, pre + "mlp.fc1.weight", &w->fc1_w, 4 * D, D)); TRY(need_f32(e, pre + "mlp.fc1.bias", &w->fc1_b, 4 * D));
+  TRY(need_bf16(e, pre + "mlp.fc2.weight", &w->fc2_w, D, 4 * D)); TRY(need_f32(e, pre + "mlp.fc2.bias", &w->fc2_b, D));
+  if (qk_norm) {
+    TRY(need_f32(e, pre + "attn.q_norm.weight", &w->qn_w)); TRY(need_f32(e, pre + "attn.q_norm.bias", &w->qn_b));
+    TRY(need_f32(e, pre + "attn.k_norm.weight", &w->kn_w)); TRY(need_f32(e, pre + "attn.k_norm.bias", &w->kn_b));
+  }
+  if (layer_scale) { TRY(need_f32(e, pre + "ls1.gamma", &w->ls1, D)); TRY(need_f32(e, pre + "ls2.gamma", &w->ls2, D)); }
+  return LSVS_OK;
+}
+
+int load_block_f32(const Engine& e, const std::string& pre, int D, bool cross, bool qk_norm, BlockWF* w) {
+  TRY(need_f32(e, pre + "norm1.weight", &w->n1w, D)); TRY(need_f32(e, pre + "norm1.bias", &w->n1b, D));
+  TRY(need_f32(e, pre + "norm2.weight", &w->n2w, D)); TRY(need_f32(e, pre + "norm2.bias", &w->n2b, D));
+  if (cross) {
+    TRY(need_f32(e, pre + "norm3.weight", &w->n3w, D)); TRY(need_f32(e, pre + "norm3.bias", &w->n3b, D));
+    TRY(need_f32(e, pre + "attn.q.weight", &w->q_w, (long long)D * D)); TRY(need_f32(e, pre + "attn.q.bias", &w->q_b, D));
+    TRY(need_f32(e, pre + "attn.k.weight", &w->k_w, (long long)D * D)); TRY(need_f32(e, pre + "attn.k.bias", &w->k_b, D));
+    TRY(need_f32(e, pre + "attn.v.weight", &w->v_w, (long long)D * D)); TRY(need_f32(e, pre + "attn.v.bias", &w->v_b, D));
+  } else {
+    TRY(need_f32(e, pre + "attn.qkv.weight", &w->qkv_w, 3LL * D * D)); TRY(need_f32(e, pre + "attn.qkv.bias", &w->qkv_b, 3 * D));
+  }
+  TRY(need_f32(e, pre + "attn.proj.weight", &w->proj_w, (long long)D * D)); TRY(need_f32(e, pre + "attn.proj.bias", &w->proj_b, D));
+  TRY(need_f32(e, pre + "mlp.fc1.weight", &w->fc1_w, 4LL * D * D)); TRY(need_f32(e, pre + "mlp.fc1.bias", &w->fc1_b, 4 * D));
+  TRY(need_f32(e, pre + "mlp.fc2.weight", &w->fc2_w, 4LL * D * D)); TRY(need_f32(e, pre + "mlp.fc2.bias", &w->fc2_b, D));
+  if (qk_norm) {
+    TRY(need_f32(e, pre + "attn.q_norm.weight", &w->qn_w)); TRY(need_f32(e, pre + "attn.q_norm.bias", &w->qn_b));
+    TRY(need_f32(e, pre + "attn.k_norm.weight", &w->kn_w)); TRY(need_f32(e, pre + "attn.k_norm.bias", &w->kn_b));
+  }
+  TRY(need_f32(e, pre + "ls1.gamma", &w->ls1, D)); TRY(need_f32(e, pre + "ls2.gamma", &w->ls2, D));
+  return LSVS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bf16 transformer block on the fp32 residual stream x (M rows of D=1024).
+int run_block(Engine& e, float* x, long long M, const BlockW& w, float eps, int heads, int hd, int attn_batches, int L,
+              const RopeCfg& rope, float* tap, int tap_ld, cudaStream_t st) {
+  const int D = heads * hd;
+  __nv_bfloat16 *xn = e.xn.as<__nv_bfloat16>(), *qkv = e.qkv.as<__nv_bfloat16>(), *att = e.att.as<__nv_bfloat16>(), *h = e.h.as<__nv_bfloat16>();
+  TRY(layernorm(x, D, RowMap{}, w.n1w, w.n1b, eps, xn, D, RowMap{}, true, M, D, st));
+  GemmEpilogue ep;
+  ep.bias = w.qkv_b; ep.out = qkv; ep.ldo = 3 * D;
+  int kind = EPI_BIAS_BF16;
+  if (w.qn_w) {
+    kind = hd == 64 ? EPI_HEADNORM64_BF16 : EPI_HEADNORM128_BF16;
+    ep.qn_w = w.qn_w; ep.qn_b = w.qn_b; ep.kn_w = w.kn_w; ep.kn_b = w.kn_b; ep.n_q_cols = D; ep.n_k_cols = D; ep.ln_eps = 1e-5f;
+    ep.rope_mode = rope.mode; ep.rope_tab = rope.tab; ep.tokens_per_frame = rope.tpf; ep.n_special = rope.nsp; ep.grid_w = rope.gw;
+  }
+  TRY(gemm_bf16(xn, D, w.qkv_w, D, (int)M, 3 * D, D, kind, ep, st));
+  AttentionArgs aa{qkv, qkv + D, qkv + 2 * D, att, 3 * D, 3 * D, 3 * D, D, attn_batches, heads, hd, L, L, 1.0f / sqrtf((float)hd)};
+  TRY(attention_fwd(aa, st));
+  GemmEpilogue er;
+  er.bias = w.proj_b; er.gamma = w.ls1; er.resid = x; er.ldr = D;
+  TRY(gemm_bf16(att, D, w.proj_w, D, (int)M, D, D, EPI_RESID_F32, er, st));
+  TRY(layernorm(x, D, RowMap{}, w.n2w, w.n2b, eps, xn, D, RowMap{}, true, M, D, st));
+  GemmEpilogue e1;
+  e1.bias = w.fc1_b; e1.out = h; e1.ldo = 4 * D;
+  TRY(gemm_bf16(xn, D, w.fc1_w, D, (int)M, 4 * D, D, EPI_BIAS_GELU_BF16, e1, st));
+  GemmEpilogue e2;
+  e2.bias = w.fc2_b; e2.gamma = w.ls2; e2.resid = x; e2.ldr = D; e2.out2 = tap; e2.ld2 = tap_ld;
+  TRY(gemm_bf16(h, 4 * D, w.fc2_w, 4 * D, (int)M, D, 4 * D, EPI_RESID_F32, e2, st));
+  return LSVS_OK;
+}
+
+int ensure_tables(Engine& e, int gh, int gw, int n1d, cudaStream_t st) {
+  const int n2d = (gh > gw ? gh : gw) + 2;
+  if (n2d > e.rope_npos2d) {
+    TRY(e.rope2d_64.ensure((size_t)n2d * 16 * 8)); TRY(e.rope2d_128.ensure((size_t)n2d * 32 * 8));
+    TRY(lsvs_rope_table(e.rope2d_64.as<float>(), n2d, 16, e.cfg.rope_base, st));
+    TRY(lsvs_rope_table(e.rope2d_128.as<float>(), n2d, 32, e.cfg.rope_base, st));
+    e.rope_npos2d = n2d;
+  }
+  if (n1d > e.rope_npos1d) {
+    TRY(e.rope1d_128.ensure((size_t)n1d * 64 * 8));
+    TRY(lsvs_rope_table(e.rope1d_128.as<float>(), n1d, 64, e.cfg.rope_base, st));
+    e.rope_npos1d = n1d;
+  }
+  return LSVS_OK;
+}
+
+int ensure_workspace(Engine& e, long long rows, long long patch_rows) {
+  TRY(e.x.ensure((size_t)rows * 1024 * 4)); TRY(e.xn.ensure((size_t)rows * 1024 * 2)); TRY(e.qkv.ensure((size_t)rows * 3072 * 2));
+  TRY(e.att.ensure((size_t)rows * 1024 * 2)); TRY(e.h.ensure((size_t)rows * 4096 * 2)); TRY(e.tmp.ensure((size_t)rows * 1024 * 4));
+  if (patch_rows) TRY(e.im2col.ensure((size_t)patch_rows * 640 * 2));
+  return LSVS_OK;
+}
+
+}  // namespace
+}  // namespace lsvs
+
+using lsvs::Engine;
+using namespace lsvs;
+
+extern "C" int lsvs_engine_create(const lsvs_engine_config* cfg, lsvs_engine** out) {
+  LSVS_CHECK_ARG(cfg && out, "engine_create: null argument");
+  LSVS_CHECK_ARG(cfg->embed_dim == 1024 && cfg->num_heads == 16 && cfg->patch_size == 14 && cfg->num_register_tokens == 4,
+                 "engine_create: only the VGGT-1B geometry (dim 1024, 16 heads, patch 14, 4 registers) is built");
+  LSVS_CHECK_ARG(cfg->depth >= 0 && cfg->dino_depth >= 0 && cfg->head_depth_aa >= 0, "engine_create: bad depth");
+  Engine* e = new Engine();
+  e->cfg = *cfg;
+  *out = reinterpret_cast<lsvs_engine*>(e);
+  return LSVS_OK;
+}
+
+extern "C" int lsvs_engine_destroy(lsvs_engine* h) {
+  delete reinterpret_cast<Engine*>(h);
+  return LSVS_OK;
+}
+
+extern "C" int lsvs_engine_set_param(lsvs_engine* h, const char* name, const float* data, long long numel, int rows, int cols, void* stream) {
+  Engine& e = *reinterpret_cast<Engine*>(h);
+  LSVS_CHECK_ARG(name && data && numel > 0, "engine_set_param: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const std::string n(name);
+  Param& p = e.params[n];
+  const bool as_bf16 = wants_bf16(n);
+  if (as_bf16) {
+    LSVS_CHECK_ARG(rows > 0 && cols > 0 && (long long)rows * cols == numel, "engine_set_param: '%s' needs a 2-D (rows, cols) view", name);
+    const int kp = (cols + 63) / 64 * 64;
+    if (p.bf16 && ((long long)p.rows * p.cols_padded != (long long)rows * kp)) { cudaFree(p.bf16); p.bf16 = nullptr; }
+    if (!p.bf16) LSVS_CUDA(cudaMalloc(&p.bf16, (size_t)rows * kp * 2));
+    TRY(pack_weight_bf16(data, p.bf16, rows, cols, kp, st));
+    p.rows = rows; p.cols = cols; p.cols_padded = kp;
+    if (p.f32) { cudaFree(p.f32); p.f32 = nullptr; }
+  } else {
+    if (p.f32 && p.numel != numel) { cudaFree(p.f32); p.f32 = nullptr; }
+    if (!p.f32) LSVS_CUDA(cudaMalloc(&p.f32, (size_t)numel * 4));
+    LSVS_CUDA(cudaMemcpyAsync(p.f32, data, (size_t)numel * 4, cudaMemcpyDeviceToDevice, st));
+    p.rows = rows; p.cols = cols; p.cols_padded = cols;
+  }
+  p.numel = numel;
+  e.finalized = false;
+  return LSVS_OK;
+}
+
+extern "C" int lsvs_engine_finalize(lsvs_engine* h, void* stream) {
+  Engine& e = *reinterpret_cast<Engine*>(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = 1024;
+  e.dino.assign(e.cfg.dino_depth, BlockW{}); e.frame.assign(e.cfg.depth, BlockW{}); e.global.assign(e.cfg.depth, BlockW{});
+  for (int i = 0; i < e.cfg.dino_depth; ++i) TRY(load_block(e, "aggregator.patch_embed.blocks." + std::to_string(i) + ".", D, false, true, &e.dino[i]));
+  for (int i = 0; i < e.cfg.depth; ++i) {
+    TRY(load_block(e, "aggregator.frame_blocks." + std::to_string(i) + ".", D, true, true, &e.frame[i]));
+    TRY(load_block(e, "aggregator.global_blocks." + std::to_string(i) + ".", D, true, true, &e.global[i]));
+  }
+  for (auto& b : e.fused) b.release();
+  e.fused.clear();
+  e.h_frame.clear(); e.h_temporal.clear(); e.chunk_cross.clear(); e.frame_cross.clear(); e.cam_trunk.clear();
+  if (e.cfg.with_alignment_head) {
+    e.h_frame.assign(e.cfg.head_depth_aa, BlockW{}); e.h_temporal.assign(e.cfg.head_depth_aa, BlockW{});
+    e.fused.reserve(2 * e.cfg.head_depth_aa);
+    for (int i = 0; i < e.cfg.head_depth_aa; ++i) {
+      TRY(load_block(e, "alignment_head.frame_blocks." + std::to_string(i) + ".", D, true, true, &e.h_frame[i]));
+      const std::string pre = "alignment_head.temporal_blocks." + std::to_string(i) + ".";
+      BlockW& w = e.h_temporal[i];
+      TRY(need_f32(e, pre + "norm1.weight", &w.n1w, D)); TRY(need_f32(e, pre + "norm1.bias", &w.n1b, D));
+      TRY(need_f32(e, pre + "norm2.weight", &w.n2w, D)); TRY(need_f32(e, pre + "norm2.bias", &w.n2b, D));
+      TRY(need_f32(e, pre + "norm3.weight", &w.n3w, D)); TRY(need_f32(e, pre + "norm3.bias", &w.n3b, D));
+      TRY(need_bf16(e, pre + "attn.q.weight", &w.q_w, D, D)); TRY(need_f32(e, pre + "attn.q.bias", &w.q_b, D));
+      // k and v read the same input: fuse into one (2D, D) weight so one GEMM produces [k | v]
+      const __nv_bfloat16 *kw, *vw; const float *kb, *vb;
+      TRY(need_bf16(e, pre + "attn.k.weight", &kw, D, D)); TRY(need_bf16(e, pre + "attn.v.weight", &vw, D, D));
+      TRY(need_f32(e, pre + "attn.k.bias", &kb, D)); TRY(need_f32(e, pre + "attn.v.bias", &vb, D));
+      e.fused.emplace_back(); DevBuf& fw = e.fused.back(); TRY(fw.ensure((size_t)2 * D * D * 2));
+      e.fused.emplace_back(); DevBuf& fb = e.fused.back(); TRY(fb.ensure((size_t)2 * D * 4));
+      LSVS_CUDA(cudaMemcpyAsync(fw.p, kw, (size_t)D * D * 2, cudaMemcpyDeviceToDevice, st));
+      LSVS_CUDA(cudaMemcpyAsync(fw.as<__nv_bfloat16>() + (size_t)D * D, vw, (size_t)D * D * 2, cudaMemcpyDeviceToDevice, st));
+      LSVS_CUDA(cudaMemcpyAsync(fb.p, kb, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
+      LSVS_CUDA(cudaMemcpyAsync(fb.as<float>() + D, vb, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
+      w.kv_w = fw.as<__nv_bfloat16>(); w.kv_b = fb.as<float>();
+      TRY(need_bf16(e, pre + "attn.proj.weight", &w.proj_w, D, D)); TRY(need_f32(e, pre + "attn.proj.bias", &w.proj_b, D));
+      TRY(need_bf16(e, pre + "mlp.fc1.weight", &w.fc1_w, 4 * D, D)); TRY(need_f32(e, pre + "mlp.fc1.bias", &w.fc1_b, 4 * D));
+      TRY(need_bf16(e, pre + "mlp.fc2.weight", &w.fc2_w, D, 4 * D)); TRY(need_f32(e, pre + "mlp.fc2.bias", &w.fc2_b, D));
+      TRY(need_f32(e, pre + "attn.q_norm.weight", &w.qn_w, 128)); TRY(need_f32(e, pre + "attn.q_norm.bias", &w.qn_b, 128));
+      TRY(need_f32(e, pre + "attn.k_norm.weight", &w.kn_w, 128)); TRY(need_f32(e, pre + "attn.k_norm.bias", &w.kn_b, 128));
+      TRY(need_f32(e, pre + "ls1.gamma", &w.ls1, D)); TRY(need_f32(e, pre + "ls2.gamma", &w.ls2, D));
+    }
+    e.chunk_cross.assign(2, BlockWF{}); e.frame_cross.assign(2, BlockWF{});
+    for (int i = 0; i < 2; ++i) {
+      TRY(load_block_f32(e, "alignment_head.chunk_cross_blocks." + std::to_string(i) + ".", 512, true, true, &e.chunk_cross[i]));
+      TRY(load_block_f32(e, "alignment_head.frame_cross_blocks." + std::to_string(i) + ".", 512, true, true, &e.frame_cross[i]));
+    }
+  }
+  if (e.cfg.with_camera_head) {
+    e.cam_trunk.assign(4, BlockWF{});
+    for (int i = 0; i < 4; ++i) TRY(load_block_f32(e, "camera_head.trunk." + std::to_string(i) + ".", 2048, false, false, &e.cam_trunk[i]));
+  }
+  e.finalized = true;
+  return LSVS_OK;
+}
+
+extern "C" int lsvs_engine_set_pos_embed(lsvs_engine* h, const float* pos, int gh, int gw, void* stream) {
+  Engine& e = *reinterpret_cast<Engine*>(h);
+  LSVS_CHECK_ARG(pos && gh > 0 && gw > 0, "engine_set_pos_embed: bad arguments");
+  const size_t bytes = (size_t)(1 + gh * gw) * 1024 * 4;
+  TRY(e.pos_embed.ensure(bytes));
+  LSVS_CUDA(cudaMemcpyAsync(e.pos_embed.p, pos, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  e.pos_gh = gh; e.pos_gw = gw;
+  return LSVS_OK;
+}
+
+// ================================================================================================ Aggregator
+extern "C" int lsvs_aggregator_forward(lsvs_engine* h, const float* images, int B, int S, int H, int W, float* const* taps,
+                                       const int* tap_layers, int n_taps, void* stream) {
+  Engine& e = *reinterpret_cast<Engine*>(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  LSVS_CHECK_ARG(e.finalized && e.cfg.depth > 0 && e.cfg.dino_depth > 0, "aggregator_forward: engine has no aggregator / not finalized (call lsvs_engine_finalize after setting parameters)");
+  LSVS_CHECK_ARG(images && B > 0 && S > 0 && H > 0 && W > 0 && H % 14 == 0 && W % 14 == 0, "aggregator_forward: images must be (B,S,3,H,W) with H,W multiples of 14");
+  LSVS_CHECK_ARG(n_taps >= 0 && (n_taps == 0 || (taps && tap_layers)), "aggregator_forward: tap list missing");
+  const int gh = H / 14, gw = W / 14, Pp = gh * gw, P = Pp + 5, frames = B * S, D = 1024;
+  LSVS_CHECK_ARG(e.pos_gh == gh && e.pos_gw == gw, "aggregator_forward: position embedding not set for a %dx%d patch grid", gh, gw);
+  const long long M = (long long)frames * P;
+  TRY(ensure_workspace(e, M, (long long)frames * Pp));
+  TRY(ensure_tables(e, gh, gw, 0, st));
+  float* x = e.x.as<float>();
+  // --- DINOv2 ViT-L/14 patch embedding (A.2)
+  TRY(patch_unfold(images, e.im2col.p, frames, H, W, st));
+  const Param* pw; const float *pb, *cls, *reg, *nw, *nb, *cam, *regtok;
+  TRY(need(e, "aggregator.patch_embed.patch_embed.proj.weight", &pw));
+  LSVS_CHECK_ARG(pw->bf16 && pw->rows == 1024 && pw->cols == 588, "aggregator: patch_embed.proj.weight must be (1024, 3*14*14)");
+  TRY(need_f32(e, "aggregator.patch_embed.patch_embed.proj.bias", &pb, D));
+  TRY(need_f32(e, "aggregator.patch_embed.cls_token", &cls, D)); TRY(need_f32(e, "aggregator.patch_embed.register_tokens", &reg, 4 * D));
+  TRY(need_f32(e, "aggregator.patch_embed.norm.weight", &nw, D)); TRY(need_f32(e, "aggregator.patch_embed.norm.bias", &nb, D));
+  TRY(need_f32(e, "aggregator.camera_token", &cam, 2 * D)); TRY(need_f32(e, "aggregator.register_token", &regtok, 8 * D));
+  GemmEpilogue ep;
+  ep.bias = pb; ep.out = e.tmp.p; ep.ldo = D;
+  TRY(gemm_bf16(e.im2col.p, 640, pw->bf16, 640, frames * Pp, D, 640, EPI_BIAS_F32, ep, st));
+  TRY(dino_assemble(e.tmp.as<float>(), cls, reg, e.pos_embed.as<float>(), x, frames, Pp, 4, D, st));
+  RopeCfg none;
+  for (int i = 0; i < e.cfg.dino_depth; ++i) TRY(run_block(e, x, M, e.dino[i], 1e-6f, 16, 64, frames, P, none, nullptr, 0, st));
+  // final norm on the patch rows (x_norm_patchtokens), then camera / register tokens replace cls / DINO registers (A.1)
+  RowMap pm{Pp, P, 5};
+  TRY(layernorm(x, D, pm, nw, nb, 1e-6f, x, D, pm, false, (long long)frames * Pp, D, st));
+  TRY(fill_special(cam, x, frames, S, P, 0, 1, D, st));
+  TRY(fill_special(regtok, x, frames, S, P, 1, 4, D, st));
+  // --- alternating frame / global attention
+  RopeCfg rope; rope.mode = ROPE_2D; rope.tab = e.rope2d_64.as<float2>(); rope.tpf = P; rope.nsp = 5; rope.gw = gw;
+  for (int i = 0; i < e.cfg.depth; ++i) {
+    float* tap = nullptr;
+    for (int t = 0; t < n_taps; ++t) if (tap_layers[t] == i) tap = taps[t];
+    TRY(run_block(e, x, M, e.frame[i], 1e-5f, 16, 64, frames, P, rope, tap, 2 * D, st));
+    TRY(run_block(e, x, M, e.global[i], 1e-5f, 16, 64, B, S * P, rope, tap ? tap + D : nullptr, 2 * D, st));
+    // a layer requested several times (reduced-depth test configs) shares one computation
+    for (int t = 0, first = -1; t < n_taps; ++t) {
+      if (tap_layers[t] != i) continue;
+      if (first < 0) { first = t; continue; }
+      if (taps[t] != taps[first]) LSVS_CUDA(cudaMemcpyAsync(taps[t], taps[first], (size_t)M * 2 * D * 4, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return LSVS_OK;
+}
+
+// ================================================================================================ fp32 helpers
+namespace lsvs {
+namespace {
+
+// fp32 cross-attention block on few rows (decode): x (B*Nq, D) updated in place, y (B*Nk, D).
+int run_cross_block_f32(Engine& e, float* x, int B, int Nq, const float* y, int Nk, const BlockWF& w, int D, int heads,
+                        const int* pos_q, const int* pos_k, cudaStream_t st) {
+  const int Mq = B * Nq, Mk = B * Nk;
+  float* xn = e.scratch_f32((size_t)Mq * D); float* yn = e.scratch_f32((size_t)Mk * D);
+  float* q = e.scratch_f32((size_t)Mq * D); float* k = e.scratch_f32((size_t)Mk * D); float* v = e.scratch_f32((size_t)Mk * D);
+  float* att = e.scratch_f32((size_t)Mq * D); float* hb = e.scratch_f32((size_t)Mq * 4 * D);
+  TRY(layernorm(x, D, RowMap{}, w.n1w, w.n1b, 1e-5f, xn, D, RowMap{}, false, Mq, D, st));
+  TRY(layernorm(y, D, RowMap{}, w.n3w, w.n3b, 1e-5f, yn, D, RowMap{}, false, Mk, D, st));
+  TRY(linear_f32(xn, D, w.q_w, w.q_b, q, D, Mq, D, D, ACT_NONE, ACT_NONE, nullptr, false, st));
+  TRY(linear_f32(yn, D, w.k_w, w.k_b, k, D, Mk, D, D, ACT_NONE, ACT_NONE, nullptr, false, st));
+  TRY(linear_f32(yn, D, w.v_w, w.v_b, v, D, Mk, D, D, ACT_NONE, ACT_NONE, nullptr, false, st));
+  SmallAttnArgs a{q, D, k, D, v, D, att, D, B, heads, D / heads, Nq, Nk, w.qn_w, w.qn_b, w.kn_w, w.kn_b, pos_q, pos_k, e.cfg.rope_base,
+                  1.0f / sqrtf((float)(D / heads))};
+  TRY(attn_small_f32(a, st));
+  TRY(linear_f32(att, D, w.proj_w, w.proj_b, x, D, Mq, D, D, ACT_NONE, ACT_NONE, w.ls1, true, st));
+  TRY(layernorm(x, D, RowMap{}, w.n2w, w.n2b, 1e-5f, xn, D, RowMap{}, false, Mq, D, st));
+  TRY(linear_f32(xn, D, w.fc1_w, w.fc1_b, hb, 4 * D, Mq, 4 * D, D, ACT_NONE, ACT_GELU, nullptr, false, st));
+  TRY(linear_f32(hb, 4 * D, w.fc2_w, w.fc2_b, x, D, Mq, D, 4 * D, ACT_NONE, ACT_NONE, w.ls2, true, st));
+  return LSVS_OK;
+}
+
+int upload_ids(DevBuf& buf, const std::vector<int>& ids, cudaStream_t st) {
+  TRY(buf.ensure(ids.size() * sizeof(int) + 256));
+  LSVS_CUDA(cudaMemcpyAsync(buf.p, ids.data(), ids.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  return LSVS_OK;
+}
+
+}  // namespace
+}  // namespace lsvs
+
+// ================================================================================================ AlignmentHead
+extern "C" int lsvs_alignment_head_forward(lsvs_engine* h, const float* tokens, int B, int S, int P, int H, int W, int next_overlap,
+                                           const float* overlap_in, int T, const float* memory_in, float* chunk_sim3,
+                                           float* frame_se3, float* memory_out, float* overlap_out, void* stream) {
+  Engine& e = *reinterpret_cast<Engine*>(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  LSVS_CHECK_ARG(e.finalized && e.cfg.with_alignment_head, "alignment_head_forward: engine has no alignment head / not finalized");
+  LSVS_CHECK_ARG(tokens && chunk_sim3 && memory_out && overlap_out && B > 0 && S > 0 && P > 5, "alignment_head_forward: bad arguments");
+  LSVS_CHECK_ARG(S == 1 || frame_se3, "alignment_head_forward: frame_se3 output missing");
+  const int gh = H / 14, gw = W / 14, D = 1024, DD = 512, NM = e.cfg.num_memory_tokens, P1 = P + 1, frames = B * S;
+  LSVS_CHECK_ARG(gh * gw + 5 == P, "Size of tokens and image do not match (P=%d, grid %dx%d)", P, gh, gw);
+  LSVS_CHECK_ARG(NM == 8, "alignment_head_forward: num_memory_tokens must be 8");
+  LSVS_CHECK_ARG(!overlap_in || T >= 2, "Size of tokens and overlap tokens must match");
+  LSVS_CHECK_ARG(next_overlap >= 0 && next_overlap <= S, "alignment_head_forward: next_num_overlap out of range");
+  const bool first = overlap_in == nullptr;
+  if (first) T = S;
+  LSVS_CHECK_ARG(T - 1 <= S, "alignment_head_forward: more overlap tokens than frames");
+  const long long M = (long long)frames * P, Mh = (long long)frames * P1, My = (long long)B * T * P1;
+  TRY(ensure_workspace(e, Mh > My ? Mh : My, 0));
+  TRY(e.yn.ensure((size_t)My * D * 2)); TRY(e.kvb.ensure((size_t)My * 2 * D * 2));
+  TRY(ensure_tables(e, gh, gw, 2 * S + NM + 2, st));
+  // temporal position ids (alignment_head.py:279-285)
+  std::vector<int> qi(S), ki(T);
+  for (int j = 0; j < S; ++j) qi[j] = first ? j : j + (S - (T - 1));
+  if (first) for (int j = 0; j < T; ++j) ki[j] = j;
+  else { ki[0] = 0; for (int j = 1; j < T; ++j) ki[j] = S - (T - 1) + (j - 1); }
+  // decode ids (:446-455): frame queries 1..S-1 vs key 0; chunk query 0 vs keys 0..S-1, then S+i+S
+  std::vector<int> dec(S + (S + NM) + 1);
+  for (int j = 0; j < S; ++j) dec[j] = j;                        // [0,S): 0..S-1  (dec+1 = frame query ids; dec = chunk key ids)
+  for (int j = 0; j < NM; ++j) dec[S + j] = 2 * S + j;           // memory keys
+  std::vector<int> all(qi); all.insert(all.end(), ki.begin(), ki.end()); all.insert(all.end(), dec.begin(), dec.end());
+  TRY(upload_ids(e.ids_q, all, st));
+  const int* d_qi = e.ids_q.as<int>(); const int* d_ki = d_qi + S; const int* d_dec = d_ki + T;
+
+  float* x = e.x.as<float>();
+  __nv_bfloat16* xn = e.xn.as<__nv_bfloat16>();
+  const Param* pin; const float *pin_b, *tnw, *tnb, *atok;
+  TRY(need(e, "alignment_head.project_in.weight", &pin));
+  LSVS_CHECK_ARG(pin->bf16 && pin->rows == D && pin->cols == 2 * D, "alignment_head.project_in.weight must be (1024, 2048)");
+  TRY(need_f32(e, "alignment_head.project_in.bias", &pin_b, D));
+  TRY(need_f32(e, "alignment_head.token_norm.weight", &tnw, D)); TRY(need_f32(e, "alignment_head.token_norm.bias", &tnb, D));
+  TRY(need_f32(e, "alignment_head.per_frame_alignment_token", &atok, 2 * D));
+  // project_in + token_norm, written behind the per-frame alignment token (:242-270)
+  TRY(cast_rows_bf16(tokens, 2 * D, e.h.p, 2 * D, M, 2 * D, st));
+  GemmEpilogue ep; ep.bias = pin_b; ep.out = e.tmp.p; ep.ldo = D;
+  TRY(gemm_bf16(e.h.p, 2 * D, pin->bf16, 2 * D, (int)M, D, 2 * D, EPI_BIAS_F32, ep, st));
+  TRY(layernorm(e.tmp.as<float>(), D, RowMap{}, tnw, tnb, 1e-5f, x, D, RowMap{P, P1, 1}, false, M, D, st));
+  TRY(fill_special(atok, x, frames, S, P1, 0, 1, D, st));
+
+  RopeCfg r2; r2.mode = ROPE_2D; r2.tab = e.rope2d_128.as<float2>(); r2.tpf = P1; r2.nsp = 6; r2.gw = gw;
+  for (int i = 0; i < e.cfg.head_depth_aa; ++i) {
+    TRY(run_block(e, x, Mh, e.h_frame[i], 1e-5f, 8, 128, frames, P1, r2, nullptr, 0, st));
+    // temporal cross block on the RAW (B*P1, S, C) view: groups of S consecutive flat rows (:372-377)
+    const BlockW& w = e.h_temporal[i];
+    __nv_bfloat16 *yn = e.yn.as<__nv_bfloat16>(), *q = e.qkv.as<__nv_bfloat16>(), *kv = e.kvb.as<__nv_bfloat16>(), *att = e.att.as<__nv_bfloat16>(), *hb = e.h.as<__nv_bfloat16>();
+    TRY(layernorm(x, D, RowMap{}, w.n1w, w.n1b, 1e-5f, xn, D, RowMap{}, true, Mh, D, st));
+    TRY(layernorm(first ? x : overlap_in, D, RowMap{}, w.n3w, w.n3b, 1e-5f, yn, D, RowMap{}, true, My, D, st));
+    GemmEpilogue eq; eq.bias = w.q_b; eq.out = q; eq.ldo = D; eq.qn_w = w.qn_w; eq.qn_b = w.qn_b; eq.n_q_cols = D; eq.n_k_cols = 0;
+    eq.rope_mode = ROPE_1D; eq.rope_tab = e.rope1d_128.as<float2>(); eq.pos_ids = d_qi; eq.pos_period = S;
+    TRY(gemm_bf16(xn, D, w.q_w, D, (int)Mh, D, D, EPI_HEADNORM128_BF16, eq, st));
+    GemmEpilogue ek; ek.bias = w.kv_b; ek.out = kv; ek.ldo = 2 * D; ek.kn_w = w.kn_w; ek.kn_b = w.kn_b; ek.n_q_cols = 0; ek.n_k_cols = D;
+    ek.rope_mode = ROPE_1D; ek.rope_tab = e.rope1d_128.as<float2>(); ek.pos_ids = d_ki; ek.pos_period = T;
+    TRY(gemm_bf16(yn, D, w.kv_w, D, (int)My, 2 * D, D, EPI_HEADNORM128_BF16, ek, st));
+    AttentionArgs aa{q, kv, kv + D, att, D, 2 * D, 2 * D, D, B * P1, 8, 128, S, T, 1.0f / sqrtf(128.f)};
+    TRY(attention_fwd(aa, st));
+    GemmEpilogue er; er.bias = w.proj_b; er.gamma = w.ls1; er.resid = x; er.ldr = D;
+    TRY(gemm_bf16(att, D, w.proj_w, D, (int)Mh, D, D, EPI_RESID_F32, er, st));
+    TRY(layernorm(x, D, RowMap{}, w.n2w, w.n2b, 1e-5f, xn, D, RowMap{}, true, Mh, D, st));
+    GemmEpilogue e1; e1.bias = w.fc1_b; e1.out = hb; e1.ldo = 4 * D;
+    TRY(gemm_bf16(xn, D, w.fc1_w, D, (int)Mh, 4 * D, D, EPI_BIAS_GELU_BF16, e1, st));
+    GemmEpilogue e2; e2.bias = w.fc2_b; e2.gamma = w.ls2; e2.resid = x; e2.ldr = D;
+    TRY(gemm_bf16(hb, 4 * D, w.fc2_w, 4 * D, (int)Mh, D, 4 * D, EPI_RESID_F32, e2, st));
+  }
+  // processed overlap tokens for the next chunk: frame 0 and the last `next_overlap` frames (:343)
+  for (int b = 0; b < B; ++b) {
+    const size_t frame_bytes = (size_t)P1 * D * 4;
+    float* dst = overlap_out + (size_t)b * (1 + next_overlap) * P1 * D;
+    const float* src = x + (size_t)b * S * P1 * D;
+    LSVS_CUDA(cudaMemcpyAsync(dst, src, frame_bytes, cudaMemcpyDeviceToDevice, st));
+    if (next_overlap > 0)
+      LSVS_CUDA(cudaMemcpyAsync(dst + (size_t)P1 * D, src + (size_t)(S - next_overlap) * P1 * D, frame_bytes * next_overlap, cudaMemcpyDeviceToDevice, st));
+  }
+
+  // ------------------------------------------------------------------ fp32 decode (:427-540)
+  const size_t need_scratch = (size_t)B * ((size_t)(S + NM) * DD * 16 + (size_t)S * DD * 24 + (size_t)NM * DD * 16 + 8192) + (1 << 16);
+  TRY(e.scratch.ensure(need_scratch * 4));
+  e.scratch_off = 0;
+  const float *pdw, *pdb, *dnw, *dnb, *memp, *alpha, *fpw, *fpb, *cnw, *cnb, *fnw, *fnb;
+  TRY(need_f32(e, "alignment_head.project_dec.weight", &pdw, (long long)DD * D)); TRY(need_f32(e, "alignment_head.project_dec.bias", &pdb, DD));
+  TRY(need_f32(e, "alignment_head.dec_norm.weight", &dnw, DD)); TRY(need_f32(e, "alignment_head.dec_norm.bias", &dnb, DD));
+  TRY(need_f32(e, "alignment_head.memory_token", &memp, (long long)NM * DD)); TRY(need_f32(e, "alignment_head.alpha", &alpha, 1));
+  TRY(need_f32(e, "alignment_head.frame_proj.weight", &fpw, (long long)NM * DD * DD)); TRY(need_f32(e, "alignment_head.frame_proj.bias", &fpb, NM * DD));
+  TRY(need_f32(e, "alignment_head.chunk_norm.weight", &cnw, DD)); TRY(need_f32(e, "alignment_head.chunk_norm.bias", &cnb, DD));
+  TRY(need_f32(e, "alignment_head.frame_norm.weight", &fnw, DD)); TRY(need_f32(e, "alignment_head.frame_norm.bias", &fnb, DD));
+  float* t0 = e.scratch_f32((size_t)frames * DD); float* tok = e.scratch_f32((size_t)frames * DD);
+  // per-frame alignment token = row 0 of every frame: stride P1*D
+  TRY(linear_f32(x, (long long)P1 * D, pdw, pdb, t0, DD, frames, DD, D, ACT_NONE, ACT_NONE, nullptr, false, st));
+  TRY(layernorm(t0, DD, RowMap{}, dnw, dnb, 1e-5f, tok, DD, RowMap{}, false, frames, DD, st));
+  float* mean_norm = e.scratch_f32(B);
+  TRY(mean_row_norm(tok, B, S, DD, mean_norm, st));
+  float* frame_init = nullptr;
+  if (!memory_in) {
+    frame_init = e.scratch_f32((size_t)B * NM * DD);
+    TRY(linear_f32(tok, (long long)S * DD, fpw, fpb, frame_init, (long long)NM * DD, B, NM * DD, DD, ACT_NONE, ACT_NONE, nullptr, false, st));
+  }
+  float* kvt = e.scratch_f32((size_t)B * (S + NM) * DD); float* directional = e.scratch_f32((size_t)B * NM * DD);
+  TRY(memory_prepare(tok, memp, memory_in, frame_init, alpha, mean_norm, kvt, directional, B, S, NM, DD, st));
+  // chunk token: frame-0 token attends over [all frame tokens ; scaled memory]
+  float* chunk_tok = e.scratch_f32((size_t)B * DD);
+  LSVS_CUDA(cudaMemcpy2DAsync(chunk_tok, DD * 4, tok, (size_t)S * DD * 4, DD * 4, B, cudaMemcpyDeviceToDevice, st));
+  for (int i = 0; i < 2; ++i) TRY(run_cross_block_f32(e, chunk_tok, B, 1, kvt, S + NM, e.chunk_cross[i], DD, 8, d_dec /*[0]*/, d_dec, st));
+  // gated memory update (gated_update.py:43-78)
+  {
+    float* inp = e.scratch_f32((size_t)B * NM * 3 * DD); float* mem_scaled = e.scratch_f32((size_t)B * NM * DD);
+    float* hid = e.scratch_f32((size_t)B * NM * DD); float* deltas = e.scratch_f32((size_t)B * NM * DD);
+    float* gate_in = e.scratch_f32((size_t)B * NM * 2 * DD); float* ghid = e.scratch_f32((size_t)B * NM * DD); float* gate = e.scratch_f32((size_t)B * NM);
+    TRY(gu_prepare(directional, chunk_tok, inp, mem_scaled, B, NM, DD, st));
+    for (int i = 0; i < NM; ++i) {
+      const std::string pre = "alignment_head.gated_update.delta_mlps." + std::to_string(i) + ".";
+      const float *w0, *b0, *w2, *b2;
+      TRY(need_f32(e, pre + "0.weight", &w0, 3LL * DD * DD)); TRY(need_f32(e, pre + "0.bias", &b0, DD));
+      TRY(need_f32(e, pre + "2.weight", &w2, (long long)DD * DD)); TRY(need_f32(e, pre + "2.bias", &b2, DD));
+      TRY(linear_f32(inp + (size_t)i * 3 * DD, (long long)NM * 3 * DD, w0, b0, hid + (size_t)i * DD, (long long)NM * DD, B, DD, 3 * DD, ACT_NONE, ACT_GELU, nullptr, false, st));
+      TRY(linear_f32(hid + (size_t)i * DD, (long long)NM * DD, w2, b2, deltas + (size_t)i * DD, (long long)NM * DD, B, DD, DD, ACT_NONE, ACT_NONE, nullptr, false, st));
+    }
+    const float *g0w, *g0b, *g2w, *g2b;
+    TRY(need_f32(e, "alignment_head.gated_update.gate_mlp.0.weight", &g0w, 2LL * DD * DD)); TRY(need_f32(e, "alignment_head.gated_update.gate_mlp.0.bias", &g0b, DD));
+    TRY(need_f32(e, "alignment_head.gated_update.gate_mlp.2.weight", &g2w, DD)); TRY(need_f32(e, "alignment_head.gated_update.gate_mlp.2.bias", &g2b, 1));
+    TRY(gu_gate_input(deltas, directional, mem_scaled, gate_in, B * NM, DD, st));
+    TRY(linear_f32(gate_in, 2 * DD, g0w, g0b, ghid, DD, B * NM, DD, 2 * DD, ACT_NONE, ACT_GELU, nullptr, false, st));
+    TRY(linear_f32(ghid, DD, g2w, g2b, gate, 1, B * NM, 1, DD, ACT_NONE, ACT_SIGMOID, nullptr, false, st));
+    TRY(gu_finish(gate_in, directional, gate, memory_out, B * NM, DD, st));
+  }
+  float* chunk_n = e.scratch_f32((size_t)B * DD);
+  TRY(layernorm(chunk_tok, DD, RowMap{}, cnw, cnb, 1e-5f, chunk_n, DD, RowMap{}, false, B, DD, st));
+  const float *c1w, *c1b, *c2w, *c2b, *f1w, *f1b, *f2w, *f2b;
+  TRY(need_f32(e, "alignment_head.chunk_sim3_decoder.fc1.weight", &c1w, 256LL * DD)); TRY(need_f32(e, "alignment_head.chunk_sim3_decoder.fc1.bias", &c1b, 256));
+  TRY(need_f32(e, "alignment_head.chunk_sim3_decoder.fc2.weight", &c2w, 8LL * 256)); TRY(need_f32(e, "alignment_head.chunk_sim3_decoder.fc2.bias", &c2b, 8));
+  TRY(need_f32(e, "alignment_head.frame_se3_decoder.fc1.weight", &f1w, 256LL * DD)); TRY(need_f32(e, "alignment_head.frame_se3_decoder.fc1.bias", &f1b, 256));
+  TRY(need_f32(e, "alignment_head.frame_se3_decoder.fc2.weight", &f2w, 7LL * 256)); TRY(need_f32(e, "alignment_head.frame_se3_decoder.fc2.bias", &f2b, 7));
+  if (S > 1) {  // per-frame tokens (frames 1..S-1) attend to the normed chunk token (:510-534)
+    float* ft = e.scratch_f32((size_t)B * (S - 1) * DD);
+    LSVS_CUDA(cudaMemcpy2DAsync(ft, (size_t)(S - 1) * DD * 4, tok + DD, (size_t)S * DD * 4, (size_t)(S - 1) * DD * 4, B, cudaMemcpyDeviceToDevice, st));
+    for (int i = 0; i < 2; ++i) TRY(run_cross_block_f32(e, ft, B, S - 1, chunk_n, 1, e.frame_cross[i], DD, 8, d_dec + 1, d_dec, st));
+    float* ftn = e.scratch_f32((size_t)B * (S - 1) * DD); float* fh = e.scratch_f32((size_t)B * (S - 1) * 256);
+    TRY(layernorm(ft, DD, RowMap{}, fnw, fnb, 1e-5f, ftn, DD, RowMap{}, false, (long long)B * (S - 1), DD, st));
+    TRY(linear_f32(ftn, DD, f1w, f1b, fh, 256, B * (S - 1), 256, DD, ACT_NONE, ACT_GELU, nullptr, false, st));
+    TRY(linear_f32(fh, 256, f2w, f2b, frame_se3, 7, B * (S - 1), 7, 256, ACT_NONE, ACT_NONE, nullptr, false, st));
+  }
+  float* ch = e.scratch_f32((size_t)B * 256); float* c8 = e.scratch_f32((size_t)B * 8);
+  TRY(linear_f32(chunk_n, DD, c1w, c1b, ch, 256, B, 256, DD, ACT_NONE, ACT_GELU, nullptr, false, st));
+  TRY(linear_f32(ch, 256, c2w, c2b, c8, 8, B, 8, 256, ACT_NONE, ACT_NONE, nullptr, false, st));
+  TRY(combine_rows(c8, 8, nullptr, 0, chunk_sim3, 8, B, 8, -1, 7, st));  // exp on the scale entry (:538)
+  if (e.scratch_overflow) { e.scratch_overflow = false; return fail(LSVS_ECUDA, "alignment_head_forward: decode scratch under-sized"); }
+  return LSVS_OK;
+}
+
+// ================================================================================================ CameraHead
+extern "C" int lsvs_camera_head_forward(lsvs_engine* h, const float* tokens_last, int B, int S, int P, int num_iterations,
+                                        float* pose_enc, void* stream) {
+  Engine& e = *reinterpret_cast<Engine*>(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  LSVS_CHECK_ARG(e.finalized && e.cfg.with_camera_head, "camera_head_forward: engine has no camera head / not finalized");
+  LSVS_CHECK_ARG(tokens_last && pose_enc && B > 0 && S > 0 && P > 0 && num_iterations > 0, "camera_head_forward: bad arguments");
+  const int C = 2048, frames = B * S;
+  const size_t need_scratch = (size_t)frames * (size_t)(C * 8 + 3 * C + 3 * C + 4 * C + 4096) + (1 << 14);
+  TRY(e.scratch.ensure(need_scratch * 4));
+  e.scratch_off = 0;
+  const float *tnw, *tnb, *trw, *trb, *empty, *epw, *epb, *mw, *mb, *b1w, *b1b, *b2w, *b2b;
+  TRY(need_f32(e, "camera_head.token_norm.weight", &tnw, C)); TRY(need_f32(e, "camera_head.token_norm.bias", &tnb, C));
+  TRY(need_f32(e, "camera_head.trunk_norm.weight", &trw, C)); TRY(need_f32(e, "camera_head.trunk_norm.bias", &trb, C));
+  TRY(need_f32(e, "camera_head.empty_pose_tokens", &empty, 9));
+  TRY(need_f32(e, "camera_head.embed_pose.weight", &epw, 9LL * C)); TRY(need_f32(e, "camera_head.embed_pose.bias", &epb, C));
+  TRY(need_f32(e, "camera_head.poseLN_modulation.1.weight", &mw, 3LL * C * C)); TRY(need_f32(e, "camera_head.poseLN_modulation.1.bias", &mb, 3 * C));
+  TRY(need_f32(e, "camera_head.pose_branch.fc1.weight", &b1w, (long long)(C / 2) * C)); TRY(need_f32(e, "camera_head.pose_branch.fc1.bias", &b1b, C / 2));
+  TRY(need_f32(e, "camera_head.pose_branch.fc2.weight", &b2w, 9LL * (C / 2))); TRY(need_f32(e, "camera_head.pose_branch.fc2.bias", &b2b, 9));
+  float* tok = e.scratch_f32((size_t)frames * C); float* normed = e.scratch_f32((size_t)frames * C);
+  float* emb = e.scratch_f32((size_t)frames * C); float* mod = e.scratch_f32((size_t)frames * 3 * C);
+  float* xx = e.scratch_f32((size_t)frames * C); float* xn = e.scratch_f32((size_t)frames * C);
+  float* qkv = e.scratch_f32((size_t)frames * 3 * C); float* att = e.scratch_f32((size_t)frames * C);
+  float* hb = e.scratch_f32((size_t)frames * 4 * C); float* bh = e.scratch_f32((size_t)frames * (C / 2));
+  float* pred = e.scratch_f32((size_t)frames * 9); float* delta = e.scratch_f32((size_t)frames * 9); float* pin = e.scratch_f32((size_t)frames * 9);
+  // camera token of the last tapped layer = row 0 of every frame
+  TRY(layernorm(tokens_last, (long long)P * C, RowMap{}, tnw, tnb, 1e-5f, tok, C, RowMap{}, false, frames, C, st));
+  TRY(layernorm(tok, C, RowMap{}, nullptr, nullptr, 1e-6f, normed, C, RowMap{}, false, frames, C, st));  // adaln_norm (no affine)
+  for (int it = 0; it < num_iterations; ++it) {
+    if (it == 0) TRY(combine_rows(empty, 0, nullptr, 0, pin, 9, frames, 9, -1, -1, st));  // broadcast the empty pose token
+    else TRY(combine_rows(pred, 9, nullptr, 0, pin, 9, frames, 9, -1, -1, st));
+    TRY(linear_f32(pin, 9, epw, epb, emb, C, frames, C, 9, ACT_NONE, ACT_NONE, nullptr, false, st));
+    TRY(linear_f32(emb, C, mw, mb, mod, 3 * C, frames, 3 * C, C, ACT_SILU, ACT_NONE, nullptr, false, st));
+    TRY(modulate(normed, tok, mod, xx, frames, C, st));
+    for (int i = 0; i < 4; ++i) {
+      const BlockWF& w = e.cam_trunk[i];
+      TRY(layernorm(xx, C, RowMap{}, w.n1w, w.n1b, 1e-5f, xn, C, RowMap{}, false, frames, C, st));
+      TRY(linear_f32(xn, C, w.qkv_w, w.qkv_b, qkv, 3 * C, frames, 3 * C, C, ACT_NONE, ACT_NONE, nullptr, false, st));
+      SmallAttnArgs a{qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, att, C, B, 16, 128, S, S, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                      e.cfg.rope_base, 1.0f / sqrtf(128.f)};
+      TRY(attn_small_f32(a, st));
+      TRY(linear_f32(att, C, w.proj_w, w.proj_b, xx, C, frames, C, C, ACT_NONE, ACT_NONE, w.ls1, true, st));
+      TRY(layernorm(xx, C, RowMap{}, w.n2w, w.n2b, 1e-5f, xn, C, RowMap{}, false, frames, C, st));
+      TRY(linear_f32(xn, C, w.fc1_w, w.fc1_b, hb, 4 * C, frames, 4 * C, C, ACT_NONE, ACT_GELU, nullptr, false, st));
+      TRY(linear_f32(hb, 4 * C, w.fc2_w, w.fc2_b, xx, C, frames, C, 4 * C, ACT_NONE, ACT_NONE, w.ls2, true, st));
+    }
+    TRY(layernorm(xx, C, RowMap{}, trw, trb, 1e-5f, xn, C, RowMap{}, false, frames, C, st));
+    TRY(linear_f32(xn, C, b1w, b1b, bh, C / 2, frames, C / 2, C, ACT_NONE, ACT_GELU, nullptr, false, st));
+    TRY(linear_f32(bh, C / 2, b2w, b2b, delta, 9, frames, 9, C / 2, ACT_NONE, ACT_NONE, nullptr, false, st));
+    if (it == 0) TRY(combine_rows(delta, 9, nullptr, 0, pred, 9, frames, 9, -1, -1, st));
+    else TRY(combine_rows(pred, 9, delta, 9, pred, 9, frames, 9, -1, -1, st));
+  }
+  TRY(combine_rows(pred, 9, nullptr, 0, pose_enc, 9, frames, 9, 7, -1, st));  // activate_pose: T, quat linear; FoV relu
+  if (e.scratch_overflow) { e.scratch_overflow = false; return fail(LSVS_ECUDA, "camera_head_forward: scratch under-sized"); }
+  return LSVS_OK;
+}
+
+extern "C" int lsvs_pose_chain(const float* chunk_sim3, const float* frame_se3, const float* cam_enc, const float* prev_pose_enc,
+                               int S_prev, int overlap, int B, int S, int H, int W, float* pose_enc_out, float* point_T,
+                               float* scale_out, void* stream) {
+  return lsvs::pose_chain(chunk_sim3, frame_se3, cam_enc, prev_pose_enc, S_prev, overlap, B, S, H, W, pose_enc_out, point_T, scale_out,
+                          (cudaStream_t)stream);
+}

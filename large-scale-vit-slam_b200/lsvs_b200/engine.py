@@ -1,0 +1,168 @@
+"""ctypes wrapper of the native engine (csrc/engine.cu): parameter push + module forwards.
+Everything here is plumbing: device memory comes from torch, the work runs in liblsvs_b200.so."""
+import ctypes
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import native as _n
+
+_i, _f, _ll, _vp = ctypes.c_int, ctypes.c_float, ctypes.c_longlong, ctypes.c_void_p
+
+
+class EngineConfig(ctypes.Structure):
+    """mirror of `lsvs_engine_config` in include/lsvs_b200.h"""
+    _fields_ = [("embed_dim", _i), ("num_heads", _i), ("patch_size", _i), ("num_register_tokens", _i), ("depth", _i),
+                ("dino_depth", _i), ("head_depth_aa", _i), ("num_memory_tokens", _i), ("with_alignment_head", _i),
+                ("with_camera_head", _i), ("rope_base", _f)]
+
+
+def interpolate_pos_embed(pos_embed: torch.Tensor, gh: int, gw: int) -> torch.Tensor:
+    """DINOv2 interpolate_pos_encoding (UPSTREAM A.2): bicubic + antialias resize of the learned M x M table to
+    (gh, gw); identity for the native square grid.  Weight preprocessing, runs once per image size."""
+    n = pos_embed.shape[1] - 1
+    m = int(math.sqrt(n))
+    if gh == m and gw == m:
+        return pos_embed[0].float().contiguous()
+    pe = pos_embed.float()
+    c = pe.shape[-1]
+    patch = F.interpolate(pe[:, 1:].reshape(1, m, m, c).permute(0, 3, 1, 2), size=(gh, gw), mode="bicubic", antialias=True)
+    patch = patch.permute(0, 2, 3, 1).reshape(gh * gw, c)
+    return torch.cat([pe[0, :1], patch], dim=0).contiguous()
+
+
+class Engine:
+    """One native engine per (model, device).  `sync(named_params)` pushes changed parameters."""
+
+    def __init__(self, depth=24, dino_depth=24, head_depth_aa=4, num_memory_tokens=8, with_alignment_head=True,
+                 with_camera_head=True, rope_base=100.0):
+        self.cfg = EngineConfig(1024, 16, 14, 4, depth, dino_depth, head_depth_aa, num_memory_tokens,
+                                int(with_alignment_head), int(with_camera_head), rope_base)
+        self._h = _vp()
+        _n.check(_n.lib().lsvs_engine_create(ctypes.byref(self.cfg), ctypes.byref(self._h)), "engine_create")
+        self._seen: Dict[str, Tuple[int, int]] = {}
+        self._pos_key = None
+        self.device = None
+
+    def __del__(self):
+        try:
+            if self._h:
+                _n.lib().lsvs_engine_destroy(self._h)
+                self._h = _vp()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ parameters
+    def sync(self, named_params) -> int:
+        """Push parameters whose storage or version changed since the last call; returns how many were pushed."""
+        pushed = 0
+        pos = None
+        for name, p in named_params:
+            if not p.is_cuda:
+                raise _n.NativeError(f"parameter {name} lives on {p.device}: move the model to a CUDA device "
+                                     "(there is no CPU fallback on this path)")
+            if self.device is None:
+                self.device = p.device
+            if name.endswith("patch_embed.pos_embed"):
+                pos = p
+            key = (p.data_ptr(), p._version)
+            if self._seen.get(name) == key:
+                continue
+            t = p.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            rows, cols = (t.shape[0], t[0].numel()) if t.dim() >= 2 and name.endswith(".weight") else (0, 0)
+            _n.check(_n.lib().lsvs_engine_set_param(self._h, name.encode(), _n.ptr(t), _ll(t.numel()), _i(rows), _i(cols),
+                                                    _n.stream_ptr()), f"engine_set_param({name})")
+            self._seen[name] = key
+            pushed += 1
+            if name.endswith("patch_embed.pos_embed"):
+                self._pos_key = None
+        if pushed:
+            _n.check(_n.lib().lsvs_engine_finalize(self._h, _n.stream_ptr()), "engine_finalize")
+        self._pos_param = pos if pos is not None else getattr(self, "_pos_param", None)
+        return pushed
+
+    def _ensure_pos(self, gh: int, gw: int):
+        if self._pos_key == (gh, gw):
+            return
+        pe = interpolate_pos_embed(self._pos_param.detach(), gh, gw)
+        _n.check(_n.lib().lsvs_engine_set_pos_embed(self._h, _n.ptr(pe), _i(gh), _i(gw), _n.stream_ptr()), "engine_set_pos_embed")
+        torch.cuda.current_stream().synchronize()  # `pe` is a temporary; once per image size
+        self._pos_key = (gh, gw)
+
+    # ------------------------------------------------------------------ forwards
+    def aggregator_forward(self, images: torch.Tensor, tap_layers: Sequence[int]) -> List[torch.Tensor]:
+        B, S, C, H, W = images.shape
+        assert C == 3
+        img = images.detach()
+        if img.dtype != torch.float32 or not img.is_contiguous():
+            img = img.float().contiguous()
+        gh, gw = H // 14, W // 14
+        self._ensure_pos(gh, gw)
+        P = 5 + gh * gw
+        uniq = sorted(set(int(t) for t in tap_layers))
+        bufs = {t: torch.empty(B, S, P, 2048, dtype=torch.float32, device=img.device) for t in uniq}
+        ptrs = (_vp * len(uniq))(*[bufs[t].data_ptr() for t in uniq])
+        ids = (_i * len(uniq))(*uniq)
+        _n.check(_n.lib().lsvs_aggregator_forward(self._h, _n.ptr(img), _i(B), _i(S), _i(H), _i(W), ptrs, ids, _i(len(uniq)),
+                                                  _n.stream_ptr()), "aggregator_forward")
+        return [bufs[int(t)] for t in tap_layers]
+
+    def alignment_head_forward(self, tokens: torch.Tensor, image_size, next_overlap: int,
+                               overlap_tokens: Optional[torch.Tensor], memory_tokens: Optional[torch.Tensor]):
+        B, S, P, C = tokens.shape
+        H, W = image_size
+        dev = tokens.device
+        tok = tokens.detach().float().contiguous()
+        T = 0
+        ov = mem = None
+        if overlap_tokens is not None:
+            assert overlap_tokens.shape[0] == B and overlap_tokens.shape[2] == 1 + P and overlap_tokens.shape[3] == 1024, \
+                "Size of tokens and overlap tokens must match"
+            T = overlap_tokens.shape[1]
+            ov = overlap_tokens.detach().to(dev, torch.float32).contiguous()
+        if memory_tokens is not None:
+            assert memory_tokens.shape[0] == B, "Memory tokens must have same batch dimension as frame tokens"
+            mem = memory_tokens.detach().to(dev, torch.float32).contiguous()
+        sim3 = torch.empty(B, 1, 8, device=dev)
+        se3 = torch.empty(B, max(S - 1, 0), 7, device=dev)
+        mem_out = torch.empty(B, 8, 512, device=dev)
+        ov_out = torch.empty(B, 1 + next_overlap, P + 1, 1024, device=dev)
+        _n.check(_n.lib().lsvs_alignment_head_forward(self._h, _n.ptr(tok), _i(B), _i(S), _i(P), _i(H), _i(W), _i(next_overlap),
+                                                      _n.ptr(ov), _i(T), _n.ptr(mem), _n.ptr(sim3), _n.ptr(se3), _n.ptr(mem_out),
+                                                      _n.ptr(ov_out), _n.stream_ptr()), "alignment_head_forward")
+        return sim3, se3, mem_out, ov_out
+
+    def camera_head_forward(self, tokens_last: torch.Tensor, num_iterations: int = 4) -> torch.Tensor:
+        B, S, P, C = tokens_last.shape
+        tok = tokens_last.detach().float().contiguous()
+        out = torch.empty(B, S, 9, device=tok.device)
+        _n.check(_n.lib().lsvs_camera_head_forward(self._h, _n.ptr(tok), _i(B), _i(S), _i(P), _i(num_iterations), _n.ptr(out),
+                                                   _n.stream_ptr()), "camera_head_forward")
+        return out
+
+
+def pose_chain(chunk_sim3: torch.Tensor, frame_se3: torch.Tensor, cam_enc: torch.Tensor, prev_pose_enc: Optional[torch.Tensor],
+               overlap: int, image_hw):
+    """Pose / Sim(3) composition of one chunk (featureAligned_vggt.py:97-143, :190-196) in one kernel.
+    Returns (aligned pose_enc (B,S,9), point transform (B,4,4), chunk scale (B,))."""
+    B, S, _ = cam_enc.shape
+    dev = cam_enc.device
+    H, W = image_hw
+    cs = chunk_sim3.detach().float().contiguous()
+    fs = frame_se3.detach().float().contiguous()
+    ce = cam_enc.detach().float().contiguous()
+    prev = None
+    S_prev = 0
+    if prev_pose_enc is not None:
+        prev = prev_pose_enc.detach().to(dev, torch.float32).contiguous()
+        S_prev = prev.shape[1]
+    pose = torch.empty(B, S, 9, device=dev)
+    pt = torch.empty(B, 4, 4, device=dev)
+    sc = torch.empty(B, device=dev)
+    _n.check(_n.lib().lsvs_pose_chain(_n.ptr(cs), _n.ptr(fs), _n.ptr(ce), _n.ptr(prev), _i(S_prev), _i(overlap), _i(B), _i(S),
+                                      _i(H), _i(W), _n.ptr(pose), _n.ptr(pt), _n.ptr(sc), _n.stream_ptr()), "pose_chain")
+    return pose, pt, sc

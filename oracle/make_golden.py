@@ -232,6 +232,20 @@ def run_two_chunks(model, sd, S, H, W, ov, taps, depth, dino_depth, tag, sample=
     save(f"model_{tag}.npz", **arrs)
 
 
+def case_spec():
+    """state_dict key/shape contract of the reference model classes (full depth), for the drop-in's spec test."""
+    print("[state_dict spec]")
+    import json
+    from aligned_vggt.models.featureAligned_vggt import FeatureAlignedVGGT
+    os.environ.pop("VGGT_SHIM_DEPTH", None)
+    with torch.device("meta"):
+        model = FeatureAlignedVGGT(enable_point=False, enable_depth=False, enable_track=False)
+    spec = {k: list(v.shape) for k, v in model.state_dict().items()}
+    with open(os.path.join(GOLD, "state_dict_spec.json"), "w") as f:
+        json.dump(spec, f)
+    print(f"  {len(spec)} keys, {sum(int(np.prod(v)) if v else 1 for v in spec.values())/1e6:.0f} M parameters -> tests/golden/state_dict_spec.json")
+
+
 def case_model_small():
     print("[FeatureAlignedVGGT, depth 2/2, S=4, 56x84, overlap 2]")
     model, sd = build_reference_model((2, 2))
@@ -252,7 +266,7 @@ if __name__ == "__main__":
     args = ap.parse_args()
     torch.manual_seed(0)
     os.makedirs(GOLD, exist_ok=True)
-    cases = {"layers": case_layers, "geometry": case_geometry, "head": case_head, "model_small": case_model_small}
+    cases = {"spec": case_spec, "layers": case_layers, "geometry": case_geometry, "head": case_head, "model_small": case_model_small}
     if args.full:
         cases["model_full"] = case_model_full
     for name, fn in cases.items():
