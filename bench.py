@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the chunk pipeline (BASELINE.json metric: frames/sec per chunk pipeline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One step = one 32-frame chunk (8-frame overlap, 518x154 synthetic driving-aspect frames, random-init VGGT-1B
+shaped weights) through the whole hot path: Aggregator -> alignment head (with the previous chunk's overlap tokens
+and memory) -> camera head -> pose/Sim(3) composition -> Sim(3) applied to a synthetic point map and depth map
+(stand-ins for the DPT head outputs, which are outside this path).  `value` counts OUTPUT frames (S - overlap new
+frames per chunk); frame-forwards/sec is reported next to it.
+
+N > 1: chunks of one sequence are dealt round-robin to the ranks for the Aggregator; the last-layer tokens travel
+over NCCL to the rank that runs the sequential alignment chain (lsvs_b200/scheduler.py).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "large-scale-vit-slam_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+S_CHUNK, OVERLAP, H, W = 32, 8, 154, 518
+METRIC = "frames/sec per chunk pipeline"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.f, self.p = index, None, None
+
+    def __enter__(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+        return self
+
+    def __exit__(self, *a):
+        if self.p:
+            time.sleep(0.25)
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.f:
+            return out
+        try:
+            self.f.flush()
+            rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+            sm = sorted(float(r[0]) for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = sorted({n for r in rows for n, v in zip(names, r[3:7]) if v.strip().lower().startswith("active")})
+            out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(rows[0][1]) if rows else None,
+                   "power_w_max": max(float(r[2]) for r in rows) if rows else None, "reasons": reasons, "samples": len(rows)}
+            os.unlink(self.f.name)
+        except Exception as e:  # pragma: no cover
+            out["error"] = str(e)
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def oracle_state_dict(depth=24, dino_depth=24):
+    """Random-init VGGT-1B shaped weights for the CPU oracle (same synthetic generator as the parity fixtures)."""
+    from lsvs_b200 import specs
+    from oracle import weights as OW
+    spec = [("aggregator." + n, s) for n, s in specs.aggregator_spec(depth, dino_depth)]
+    spec += [("camera_head." + n, s) for n, s in specs.camera_head_spec()]
+    spec += [("alignment_head." + n, s) for n, s in specs.alignment_head_spec()]
+    return OW.fill_state_dict(spec, seed=0)
+
+
+def cpu_reference_run(steps, warmup, frames):
+    """The reference's CPU path (oracle port: reference-own code restated + restated upstream vggt), fp32, all host
+    cores, on a bounded sample: chunks of `frames` frames at 518x154, full depth, with context carry."""
+    from oracle import aligned as OA
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_grad_enabled(False)
+    sd = oracle_state_dict()
+    ov = 1
+    g = np.random.Generator(np.random.PCG64(0))
+    mk = lambda: torch.from_numpy(g.random((1, frames, 3, H, W), dtype=np.float32))
+    pts, dep = torch.randn(1, frames, H, W, 3), torch.rand(1, frames, H, W, 1)
+    ctx = None
+    times = []
+    for i in range(warmup + steps):
+        img = mk()
+        t0 = time.perf_counter()
+        o = OA.feature_aligned_forward(sd, img, ov, ctx, raw_points=pts, raw_depth=dep)
+        dt = time.perf_counter() - t0
+        ctx = {"overlap_tokens": o["overlap_tokens"], "memory_tokens": o["memory_tokens"], "pose_enc": o["pose_enc"]}
+        if i >= warmup:
+            times.append(dt)
+    new_frames = frames - ov
+    total = sum(times)
+    return {"value": new_frames * len(times) / total, "ms_per_step": 1e3 * total / len(times), "frames": frames, "overlap": ov,
+            "cores": torch.get_num_threads()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames = 4 if (args.steps + args.warmup) <= 8 else 2
+    r = cpu_reference_run(args.steps, args.warmup, frames)
+    sample = f"{frames}-frame chunks ({r['overlap']} overlap) of 518x154, full depth, fp32 oracle port on {r['cores']} host threads"
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "feature-aligned VGGT chunk pipeline, 518x154 frames, random-init VGGT-1B weights (CPU sample: "
+                                   f"{frames}-frame chunks instead of {S_CHUNK})", "frames_per_chunk": frames, "overlap": r["overlap"]},
+            "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm
+def trim_context(pred):
+    """Keep only what the next chunk needs (the reference moves older chunks to the CPU, training_metrics.py:650)."""
+    ctx = {}
+    for k, v in pred.items():
+        if k == "images":
+            continue
+        ctx[k] = v[-1:] if isinstance(v, list) else v
+    for k in ("chunk_sim3_alignment_enc", "frame_se3_alignment_enc"):
+        ctx[k] = ctx[k][:, -1:].contiguous() if k.startswith("chunk") else ctx[k][:, -(S_CHUNK - 1):].contiguous()
+    return ctx
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from aligned_vggt.models.featureAligned_vggt import FeatureAlignedVGGT
+    from lsvs_b200 import native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.set_grad_enabled(False)
+
+    torch.manual_seed(0)  # identical replicated weights on every rank
+    with torch.device(dev):
+        model = FeatureAlignedVGGT(enable_point=False, enable_depth=False, enable_track=False).eval()
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    n_bufs = 4
+    imgs = [torch.rand(1, S_CHUNK, 3, H, W, device=dev, generator=gen) for _ in range(n_bufs)]
+    raw_pts = torch.randn(1, S_CHUNK, H, W, 3, device=dev, generator=gen) * 10
+    raw_dep = torch.rand(1, S_CHUNK, H, W, 1, device=dev, generator=gen) + 0.5
+
+    if world > 1:
+        from lsvs_b200.scheduler import ChunkPipeline
+        pipe = ChunkPipeline(model, OVERLAP, rank, world)
+        step_fn = lambda i: pipe.step(imgs[i % n_bufs], raw_pts, raw_dep)
+        frames_per_step = pipe.frames_per_step(S_CHUNK)
+    else:
+        state = {"ctx": trim_context(model(imgs[0], OVERLAP, None, raw_depth=raw_dep, raw_points=raw_pts))}
+
+        def step_fn(i):
+            pred = model(imgs[i % n_bufs], OVERLAP, state["ctx"], raw_depth=raw_dep, raw_points=raw_pts)
+            state["ctx"] = trim_context(pred)
+            return pred
+        frames_per_step = S_CHUNK - OVERLAP
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_fn(i)
+    barrier()
+    l0 = native.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for i in range(args.steps):
+            step_fn(i)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = native.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    ms_per_step = ms / args.steps
+    total_frames = frames_per_step * args.steps
+    if world > 1:
+        total_frames = pipe.total_output_frames(args.steps, S_CHUNK)
+    value = total_frames / (ms / 1e3)
+
+    # ---- end to end through the public module API with HOST buffers (pinned), H2D + D2H inside the timed region
+    e2e = None
+    if world == 1:
+        host_imgs = [torch.rand(1, S_CHUNK, 3, H, W).pin_memory() for _ in range(2)]
+        keep = ("pose_enc", "world_points", "depth")
+        host_out = {}
+        state["ctx"] = trim_context(model(imgs[0], OVERLAP, None, raw_depth=raw_dep, raw_points=raw_pts))
+
+        def e2e_step(i):
+            x = host_imgs[i % 2].to(dev, non_blocking=True)
+            pred = model(x, OVERLAP, state["ctx"], raw_depth=raw_dep, raw_points=raw_pts)
+            d2h = 0
+            for k in keep:
+                t = pred[k][-1]
+                if k not in host_out:
+                    host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                host_out[k].copy_(t, non_blocking=True)
+                d2h += t.numel() * t.element_size()
+            for k in ("chunk_sim3_alignment_enc", "frame_se3_alignment_enc"):
+                t = pred[k]
+                host_out.setdefault(k, torch.empty(t.shape, dtype=t.dtype).pin_memory())
+                if host_out[k].shape != t.shape:
+                    host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                host_out[k].copy_(t, non_blocking=True)
+                d2h += t.numel() * t.element_size()
+            state["ctx"] = trim_context(pred)
+            return d2h
+        for i in range(max(1, min(args.warmup, 2))):
+            d2h_bytes = e2e_step(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(args.steps):
+            d2h_bytes = e2e_step(i)
+        b.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        e2e_ms = max(a.elapsed_time(b), wall * 1e3)
+        e2e = {"value": frames_per_step * args.steps / (e2e_ms / 1e3), "unit": "frames/s",
+               "h2d_bytes_per_step": host_imgs[0].numel() * 4, "d2h_bytes_per_step": int(d2h_bytes)}
+
+    # ---- roofline of the dominant kernel class: CUDA events around every launch of a profiled pass of real steps
+    roofline = None
+    prof_detail = None
+    if rank == 0 and world == 1:
+        import ctypes
+        lib = native.lib()
+        lib.lsvs_profile_enable(1)
+        n_prof = 2
+        for i in range(n_prof):
+            step_fn(i)
+        ncat = 5
+        arr = lambda t: (t * ncat)()
+        pms, pfl, pby, pln = arr(ctypes.c_double), arr(ctypes.c_double), arr(ctypes.c_double), arr(ctypes.c_longlong)
+        lib.lsvs_profile_read(pms, pfl, pby, pln)
+        lib.lsvs_profile_enable(0)
+        names = ["gemm_tcgen05", "attention_tcgen05", "layernorm_cast", "fp32_tail", "sim3_apply"]
+        prof_detail = {n: {"ms_per_step": pms[i] / n_prof, "launches_per_step": pln[i] / n_prof,
+                           "tflops": (pfl[i] / (pms[i] * 1e9) if pms[i] > 0 and pfl[i] > 0 else None),
+                           "gbps": (pby[i] / (pms[i] * 1e6) if pms[i] > 0 and pby[i] > 0 else None)} for i, n in enumerate(names)}
+        dom = max(range(2), key=lambda i: pms[i])  # the tensor-bound classes dominate the step
+        pk = peaks()
+        ach = pfl[dom] / (pms[dom] * 1e9)
+        roofline = {"kernel": names[dom], "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["src"] + " (sustained, kernel timed inside a long step)",
+                    "avg_launch_ms": pms[dom] / max(1, pln[dom]), "share_of_step": (pms[dom] / n_prof) / ms_per_step}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(1, 0, 4)
+        cpu_baseline = {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
+                        "sample": "one 4-frame chunk (BASELINE config 1: 518x154, full depth, first chunk) through the fp32 oracle port"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "feature-aligned VGGT chunk pipeline: 32-frame chunks, 8-frame overlap, 518x154 frames (BASELINE configs[1]/[2] shape), "
+                                       "random-init VGGT-1B Aggregator + alignment head + camera head + Sim(3) apply on synthetic point/depth maps",
+                           "frames_per_chunk": S_CHUNK, "overlap": OVERLAP, "image_hw": [H, W], "output_frames_per_step": frames_per_step,
+                           "frame_forwards_per_s": (S_CHUNK * args.steps / (ms / 1e3)) if world == 1 else None,
+                           "l2_policy": "per-step working set (~0.4 GB activations + 2.5 GB weights) exceeds the 126 MB L2; 4 rotating input buffers",
+                           "parallelism": f"chunks round-robin over {world} GPU(s)"},
+                "clocks": clocks.summary(), "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
+                "kernel_classes": prof_detail}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -38,6 +38,13 @@ int lsvs_version(void);
 /* number of kernels this library has launched since load (monotonic; for bench.py's gpu_launches) */
 unsigned long long lsvs_launch_count(void);
 
+/* per-kernel-class CUDA-event profiler (used by bench.py for the roofline object; adds two event records per
+ * launch while enabled).  Classes: 0 tcgen05 GEMM, 1 tcgen05 attention, 2 LayerNorm/cast, 3 fp32 tail
+ * (decode, camera head), 4 Sim(3) apply. */
+#define LSVS_PROF_NCAT 5
+int lsvs_profile_enable(int on);
+int lsvs_profile_read(double* ms, double* flops, double* bytes, long long* launches);
+
 /* ---- Sim(3) apply (memory-bound) -------------------------------------------------------------
  * replaces apply_sim3_alignment_on_point_maps  aligned_vggt/utils/alignment.py:491-526
  *          and the inlined copies              aligned_vggt/models/featureAligned_vggt.py:198-207,
@@ -129,6 +136,10 @@ int lsvs_aggregator_forward(lsvs_engine* e, const float* images, int B, int S, i
 int lsvs_alignment_head_forward(lsvs_engine* e, const float* tokens, int B, int S, int P, int H, int W, int next_overlap,
                                 const float* overlap_in, int T, const float* memory_in, float* chunk_sim3,
                                 float* frame_se3, float* memory_out, float* overlap_out, void* stream);
+/* the fp32 decode stage alone: AlignmentHead._decode_alignments alignment_head.py:427-540 (+ GatedUpdate,
+ * gated_update.py:43-78).  align_tokens (B,S,1024) fp32 = the processed per-frame alignment tokens. */
+int lsvs_alignment_decode_forward(lsvs_engine* e, const float* align_tokens, int B, int S, const float* memory_in,
+                                  float* chunk_sim3, float* frame_se3, float* memory_out, void* stream);
 /* replaces UPSTREAM vggt CameraHead.forward (call site featureAligned_vggt.py:106): tokens_last (B,S,P,2048)
  * -> pose_enc (B,S,9) of the last refinement iteration. */
 int lsvs_camera_head_forward(lsvs_engine* e, const float* tokens_last, int B, int S, int P, int num_iterations,

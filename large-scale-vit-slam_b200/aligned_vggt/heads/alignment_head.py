@@ -42,3 +42,9 @@ class AlignmentHead(_EngineBound):
         """tokens (B,S,P,2048) -> chunk_sim3 (B,1,8), frame_se3 (B,S-1,7), memory (B,8,512),
         overlap tokens (B,1+next_num_overlap,P+1,1024) contiguous."""
         return self._engine().alignment_head_forward(tokens, image_size, next_num_overlap, overlap_tokens, memory_tokens)
+
+    def _decode_alignments(self, frame_alignment_tokens: torch.Tensor, num_overlap: int, is_first_chunk: bool,
+                           memory_tokens: torch.Tensor = None):
+        """reference :427-540 (eval path): (B,S,1024) -> chunk_sim3 (B,1,8), frame_se3 (B,S-1,7), memory (B,8,512).
+        As in the reference, a first chunk is recognised by memory_tokens being None."""
+        return self._engine().alignment_decode_forward(frame_alignment_tokens, memory_tokens)

@@ -177,6 +177,7 @@ int layernorm(const float* x, long long ld_in, RowMap in_map, const float* w, co
   LSVS_CHECK_ARG(x && out && rows >= 0, "layernorm: null pointer");
   LSVS_CHECK_ARG(D == 512 || D == 1024 || D == 2048, "layernorm: D=%d unsupported (512/1024/2048)", D);
   if (rows == 0) return LSVS_OK;
+  ProfScope prof(PROF_ELEMENTWISE, st, 0, (double)rows * D * (4 + (out_bf16 ? 2 : 4)));
   const int warps = 8;
   const unsigned grid = (unsigned)((rows + warps - 1) / warps);
 #define LSVS_LN(NV)                                                                                                      \
@@ -191,6 +192,7 @@ int layernorm(const float* x, long long ld_in, RowMap in_map, const float* w, co
 int cast_rows_bf16(const float* x, long long ld_in, void* out, long long ld_out, long long rows, int cols, cudaStream_t st) {
   LSVS_CHECK_ARG(x && out && cols % 4 == 0 && ld_in % 4 == 0 && ld_out % 4 == 0, "cast_rows: bad arguments");
   if (rows == 0) return LSVS_OK;
+  ProfScope prof(PROF_ELEMENTWISE, st, 0, (double)rows * cols * 6);
   cast_rows_kernel<<<blocks_for(rows * (cols / 4)), 256, 0, st>>>(x, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out, rows, cols / 4);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;

@@ -68,8 +68,8 @@ struct Engine {
   std::map<std::string, Param> params;
   bool finalized = false;
   // derived weights
-  std::vector<BlockW> dino, frame, global, h_frame, h_temporal;
-  std::vector<BlockWF> cam_trunk, chunk_cross, frame_cross;
+  std::vector<BlockW> dino, frame, global, h_frame, h_temporal, cam_trunk;
+  std::vector<BlockWF> chunk_cross, frame_cross;
   std::vector<DevBuf> fused;  // concatenated k|v weights etc.
   // position embedding of the DINO ViT interpolated to the current patch grid (set by the host side)
   DevBuf pos_embed; int pos_gh = 0, pos_gw = 0;
@@ -108,8 +108,8 @@ bool contains(const std::string& s, const char* sub) { return s.find(sub) != std
 // GEMM weights that run on the tensor cores in bf16 (everything the reference runs under bf16 autocast at scale).
 bool wants_bf16(const std::string& n) {
   if (!ends_with(n, ".weight")) return false;
-  if (contains(n, "camera_head.")) return false;
-  const bool big_block = contains(n, "aggregator.") || contains(n, "alignment_head.frame_blocks.") || contains(n, "alignment_head.temporal_blocks.");
+  if (contains(n, "camera_head.") && !contains(n, "camera_head.trunk.")) return false;
+  const bool big_block = contains(n, "camera_head.trunk.") || contains(n, "aggregator.") || contains(n, "alignment_head.frame_blocks.") || contains(n, "alignment_head.temporal_blocks.");
   if (big_block && (contains(n, "attn.qkv.") || contains(n, "attn.proj.") || contains(n, "attn.q.") || contains(n, "attn.k.") ||
                     contains(n, "attn.v.") || contains(n, "mlp.fc1.") || contains(n, "mlp.fc2.") || contains(n, "patch_embed.proj.")))
     return true;
@@ -328,8 +328,8 @@ extern "C" int lsvs_engine_finalize(lsvs_engine* h, void* stream) {
     }
   }
   if (e.cfg.with_camera_head) {
-    e.cam_trunk.assign(4, BlockWF{});
-    for (int i = 0; i < 4; ++i) TRY(load_block_f32(e, "camera_head.trunk." + std::to_string(i) + ".", 2048, false, false, &e.cam_trunk[i]));
+    e.cam_trunk.assign(4, BlockW{});
+    for (int i = 0; i < 4; ++i) TRY(load_block(e, "camera_head.trunk." + std::to_string(i) + ".", 2048, false, true, &e.cam_trunk[i]));
   }
   e.finalized = true;
   return LSVS_OK;
@@ -431,6 +431,90 @@ int upload_ids(DevBuf& buf, const std::vector<int>& ids, cudaStream_t st) {
 }  // namespace
 }  // namespace lsvs
 
+
+// fp32 decode of the per-frame alignment tokens (alignment_head.py:427-540): `align_tok` row f (stride `ld_tok`)
+// is the alignment token of frame f.  d_dec: device ids [0..S-1, 2S..2S+NM-1] (decode RoPE positions, :446-455).
+namespace lsvs {
+namespace {
+int decode_forward(Engine& e, const float* x, long long ld_tok, int B, int S, const int* d_dec, const float* memory_in,
+                   float* chunk_sim3, float* frame_se3, float* memory_out, cudaStream_t st) {
+  const int D = 1024, DD = 512, NM = e.cfg.num_memory_tokens, frames = B * S;
+  // ------------------------------------------------------------------ fp32 decode (:427-540)
+  const size_t need_scratch = (size_t)B * ((size_t)(S + NM) * DD * 16 + (size_t)S * DD * 24 + (size_t)NM * DD * 16 + 8192) + (1 << 16);
+  TRY(e.scratch.ensure(need_scratch * 4));
+  e.scratch_off = 0;
+  const float *pdw, *pdb, *dnw, *dnb, *memp, *alpha, *fpw, *fpb, *cnw, *cnb, *fnw, *fnb;
+  TRY(need_f32(e, "alignment_head.project_dec.weight", &pdw, (long long)DD * D)); TRY(need_f32(e, "alignment_head.project_dec.bias", &pdb, DD));
+  TRY(need_f32(e, "alignment_head.dec_norm.weight", &dnw, DD)); TRY(need_f32(e, "alignment_head.dec_norm.bias", &dnb, DD));
+  TRY(need_f32(e, "alignment_head.memory_token", &memp, (long long)NM * DD)); TRY(need_f32(e, "alignment_head.alpha", &alpha, 1));
+  TRY(need_f32(e, "alignment_head.frame_proj.weight", &fpw, (long long)NM * DD * DD)); TRY(need_f32(e, "alignment_head.frame_proj.bias", &fpb, NM * DD));
+  TRY(need_f32(e, "alignment_head.chunk_norm.weight", &cnw, DD)); TRY(need_f32(e, "alignment_head.chunk_norm.bias", &cnb, DD));
+  TRY(need_f32(e, "alignment_head.frame_norm.weight", &fnw, DD)); TRY(need_f32(e, "alignment_head.frame_norm.bias", &fnb, DD));
+  float* t0 = e.scratch_f32((size_t)frames * DD); float* tok = e.scratch_f32((size_t)frames * DD);
+  // per-frame alignment token = row 0 of every frame: stride P1*D
+  TRY(linear_f32(x, ld_tok, pdw, pdb, t0, DD, frames, DD, D, ACT_NONE, ACT_NONE, nullptr, false, st));
+  TRY(layernorm(t0, DD, RowMap{}, dnw, dnb, 1e-5f, tok, DD, RowMap{}, false, frames, DD, st));
+  float* mean_norm = e.scratch_f32(B);
+  TRY(mean_row_norm(tok, B, S, DD, mean_norm, st));
+  float* frame_init = nullptr;
+  if (!memory_in) {
+    frame_init = e.scratch_f32((size_t)B * NM * DD);
+    TRY(linear_f32(tok, (long long)S * DD, fpw, fpb, frame_init, (long long)NM * DD, B, NM * DD, DD, ACT_NONE, ACT_NONE, nullptr, false, st));
+  }
+  float* kvt = e.scratch_f32((size_t)B * (S + NM) * DD); float* directional = e.scratch_f32((size_t)B * NM * DD);
+  TRY(memory_prepare(tok, memp, memory_in, frame_init, alpha, mean_norm, kvt, directional, B, S, NM, DD, st));
+  // chunk token: frame-0 token attends over [all frame tokens ; scaled memory]
+  float* chunk_tok = e.scratch_f32((size_t)B * DD);
+  LSVS_CUDA(cudaMemcpy2DAsync(chunk_tok, DD * 4, tok, (size_t)S * DD * 4, DD * 4, B, cudaMemcpyDeviceToDevice, st));
+  for (int i = 0; i < 2; ++i) TRY(run_cross_block_f32(e, chunk_tok, B, 1, kvt, S + NM, e.chunk_cross[i], DD, 8, d_dec /*[0]*/, d_dec, st));
+  // gated memory update (gated_update.py:43-78)
+  {
+    float* inp = e.scratch_f32((size_t)B * NM * 3 * DD); float* mem_scaled = e.scratch_f32((size_t)B * NM * DD);
+    float* hid = e.scratch_f32((size_t)B * NM * DD); float* deltas = e.scratch_f32((size_t)B * NM * DD);
+    float* gate_in = e.scratch_f32((size_t)B * NM * 2 * DD); float* ghid = e.scratch_f32((size_t)B * NM * DD); float* gate = e.scratch_f32((size_t)B * NM);
+    TRY(gu_prepare(directional, chunk_tok, inp, mem_scaled, B, NM, DD, st));
+    for (int i = 0; i < NM; ++i) {
+      const std::string pre = "alignment_head.gated_update.delta_mlps." + std::to_string(i) + ".";
+      const float *w0, *b0, *w2, *b2;
+      TRY(need_f32(e, pre + "0.weight", &w0, 3LL * DD * DD)); TRY(need_f32(e, pre + "0.bias", &b0, DD));
+      TRY(need_f32(e, pre + "2.weight", &w2, (long long)DD * DD)); TRY(need_f32(e, pre + "2.bias", &b2, DD));
+      TRY(linear_f32(inp + (size_t)i * 3 * DD, (long long)NM * 3 * DD, w0, b0, hid + (size_t)i * DD, (long long)NM * DD, B, DD, 3 * DD, ACT_NONE, ACT_GELU, nullptr, false, st));
+      TRY(linear_f32(hid + (size_t)i * DD, (long long)NM * DD, w2, b2, deltas + (size_t)i * DD, (long long)NM * DD, B, DD, DD, ACT_NONE, ACT_NONE, nullptr, false, st));
+    }
+    const float *g0w, *g0b, *g2w, *g2b;
+    TRY(need_f32(e, "alignment_head.gated_update.gate_mlp.0.weight", &g0w, 2LL * DD * DD)); TRY(need_f32(e, "alignment_head.gated_update.gate_mlp.0.bias", &g0b, DD));
+    TRY(need_f32(e, "alignment_head.gated_update.gate_mlp.2.weight", &g2w, DD)); TRY(need_f32(e, "alignment_head.gated_update.gate_mlp.2.bias", &g2b, 1));
+    TRY(gu_gate_input(deltas, directional, mem_scaled, gate_in, B * NM, DD, st));
+    TRY(linear_f32(gate_in, 2 * DD, g0w, g0b, ghid, DD, B * NM, DD, 2 * DD, ACT_NONE, ACT_GELU, nullptr, false, st));
+    TRY(linear_f32(ghid, DD, g2w, g2b, gate, 1, B * NM, 1, DD, ACT_NONE, ACT_SIGMOID, nullptr, false, st));
+    TRY(gu_finish(gate_in, directional, gate, memory_out, B * NM, DD, st));
+  }
+  float* chunk_n = e.scratch_f32((size_t)B * DD);
+  TRY(layernorm(chunk_tok, DD, RowMap{}, cnw, cnb, 1e-5f, chunk_n, DD, RowMap{}, false, B, DD, st));
+  const float *c1w, *c1b, *c2w, *c2b, *f1w, *f1b, *f2w, *f2b;
+  TRY(need_f32(e, "alignment_head.chunk_sim3_decoder.fc1.weight", &c1w, 256LL * DD)); TRY(need_f32(e, "alignment_head.chunk_sim3_decoder.fc1.bias", &c1b, 256));
+  TRY(need_f32(e, "alignment_head.chunk_sim3_decoder.fc2.weight", &c2w, 8LL * 256)); TRY(need_f32(e, "alignment_head.chunk_sim3_decoder.fc2.bias", &c2b, 8));
+  TRY(need_f32(e, "alignment_head.frame_se3_decoder.fc1.weight", &f1w, 256LL * DD)); TRY(need_f32(e, "alignment_head.frame_se3_decoder.fc1.bias", &f1b, 256));
+  TRY(need_f32(e, "alignment_head.frame_se3_decoder.fc2.weight", &f2w, 7LL * 256)); TRY(need_f32(e, "alignment_head.frame_se3_decoder.fc2.bias", &f2b, 7));
+  if (S > 1) {  // per-frame tokens (frames 1..S-1) attend to the normed chunk token (:510-534)
+    float* ft = e.scratch_f32((size_t)B * (S - 1) * DD);
+    LSVS_CUDA(cudaMemcpy2DAsync(ft, (size_t)(S - 1) * DD * 4, tok + DD, (size_t)S * DD * 4, (size_t)(S - 1) * DD * 4, B, cudaMemcpyDeviceToDevice, st));
+    for (int i = 0; i < 2; ++i) TRY(run_cross_block_f32(e, ft, B, S - 1, chunk_n, 1, e.frame_cross[i], DD, 8, d_dec + 1, d_dec, st));
+    float* ftn = e.scratch_f32((size_t)B * (S - 1) * DD); float* fh = e.scratch_f32((size_t)B * (S - 1) * 256);
+    TRY(layernorm(ft, DD, RowMap{}, fnw, fnb, 1e-5f, ftn, DD, RowMap{}, false, (long long)B * (S - 1), DD, st));
+    TRY(linear_f32(ftn, DD, f1w, f1b, fh, 256, B * (S - 1), 256, DD, ACT_NONE, ACT_GELU, nullptr, false, st));
+    TRY(linear_f32(fh, 256, f2w, f2b, frame_se3, 7, B * (S - 1), 7, 256, ACT_NONE, ACT_NONE, nullptr, false, st));
+  }
+  float* ch = e.scratch_f32((size_t)B * 256); float* c8 = e.scratch_f32((size_t)B * 8);
+  TRY(linear_f32(chunk_n, DD, c1w, c1b, ch, 256, B, 256, DD, ACT_NONE, ACT_GELU, nullptr, false, st));
+  TRY(linear_f32(ch, 256, c2w, c2b, c8, 8, B, 8, 256, ACT_NONE, ACT_NONE, nullptr, false, st));
+  TRY(combine_rows(c8, 8, nullptr, 0, chunk_sim3, 8, B, 8, -1, 7, st));  // exp on the scale entry (:538)
+  if (e.scratch_overflow) { e.scratch_overflow = false; return fail(LSVS_ECUDA, "alignment decode: scratch under-sized"); }
+  return LSVS_OK;
+}
+}  // namespace
+}  // namespace lsvs
+
 // ================================================================================================ AlignmentHead
 extern "C" int lsvs_alignment_head_forward(lsvs_engine* h, const float* tokens, int B, int S, int P, int H, int W, int next_overlap,
                                            const float* overlap_in, int T, const float* memory_in, float* chunk_sim3,
@@ -514,78 +598,7 @@ extern "C" int lsvs_alignment_head_forward(lsvs_engine* h, const float* tokens, 
       LSVS_CUDA(cudaMemcpyAsync(dst + (size_t)P1 * D, src + (size_t)(S - next_overlap) * P1 * D, frame_bytes * next_overlap, cudaMemcpyDeviceToDevice, st));
   }
 
-  // ------------------------------------------------------------------ fp32 decode (:427-540)
-  const size_t need_scratch = (size_t)B * ((size_t)(S + NM) * DD * 16 + (size_t)S * DD * 24 + (size_t)NM * DD * 16 + 8192) + (1 << 16);
-  TRY(e.scratch.ensure(need_scratch * 4));
-  e.scratch_off = 0;
-  const float *pdw, *pdb, *dnw, *dnb, *memp, *alpha, *fpw, *fpb, *cnw, *cnb, *fnw, *fnb;
-  TRY(need_f32(e, "alignment_head.project_dec.weight", &pdw, (long long)DD * D)); TRY(need_f32(e, "alignment_head.project_dec.bias", &pdb, DD));
-  TRY(need_f32(e, "alignment_head.dec_norm.weight", &dnw, DD)); TRY(need_f32(e, "alignment_head.dec_norm.bias", &dnb, DD));
-  TRY(need_f32(e, "alignment_head.memory_token", &memp, (long long)NM * DD)); TRY(need_f32(e, "alignment_head.alpha", &alpha, 1));
-  TRY(need_f32(e, "alignment_head.frame_proj.weight", &fpw, (long long)NM * DD * DD)); TRY(need_f32(e, "alignment_head.frame_proj.bias", &fpb, NM * DD));
-  TRY(need_f32(e, "alignment_head.chunk_norm.weight", &cnw, DD)); TRY(need_f32(e, "alignment_head.chunk_norm.bias", &cnb, DD));
-  TRY(need_f32(e, "alignment_head.frame_norm.weight", &fnw, DD)); TRY(need_f32(e, "alignment_head.frame_norm.bias", &fnb, DD));
-  float* t0 = e.scratch_f32((size_t)frames * DD); float* tok = e.scratch_f32((size_t)frames * DD);
-  // per-frame alignment token = row 0 of every frame: stride P1*D
-  TRY(linear_f32(x, (long long)P1 * D, pdw, pdb, t0, DD, frames, DD, D, ACT_NONE, ACT_NONE, nullptr, false, st));
-  TRY(layernorm(t0, DD, RowMap{}, dnw, dnb, 1e-5f, tok, DD, RowMap{}, false, frames, DD, st));
-  float* mean_norm = e.scratch_f32(B);
-  TRY(mean_row_norm(tok, B, S, DD, mean_norm, st));
-  float* frame_init = nullptr;
-  if (!memory_in) {
-    frame_init = e.scratch_f32((size_t)B * NM * DD);
-    TRY(linear_f32(tok, (long long)S * DD, fpw, fpb, frame_init, (long long)NM * DD, B, NM * DD, DD, ACT_NONE, ACT_NONE, nullptr, false, st));
-  }
-  float* kvt = e.scratch_f32((size_t)B * (S + NM) * DD); float* directional = e.scratch_f32((size_t)B * NM * DD);
-  TRY(memory_prepare(tok, memp, memory_in, frame_init, alpha, mean_norm, kvt, directional, B, S, NM, DD, st));
-  // chunk token: frame-0 token attends over [all frame tokens ; scaled memory]
-  float* chunk_tok = e.scratch_f32((size_t)B * DD);
-  LSVS_CUDA(cudaMemcpy2DAsync(chunk_tok, DD * 4, tok, (size_t)S * DD * 4, DD * 4, B, cudaMemcpyDeviceToDevice, st));
-  for (int i = 0; i < 2; ++i) TRY(run_cross_block_f32(e, chunk_tok, B, 1, kvt, S + NM, e.chunk_cross[i], DD, 8, d_dec /*[0]*/, d_dec, st));
-  // gated memory update (gated_update.py:43-78)
-  {
-    float* inp = e.scratch_f32((size_t)B * NM * 3 * DD); float* mem_scaled = e.scratch_f32((size_t)B * NM * DD);
-    float* hid = e.scratch_f32((size_t)B * NM * DD); float* deltas = e.scratch_f32((size_t)B * NM * DD);
-    float* gate_in = e.scratch_f32((size_t)B * NM * 2 * DD); float* ghid = e.scratch_f32((size_t)B * NM * DD); float* gate = e.scratch_f32((size_t)B * NM);
-    TRY(gu_prepare(directional, chunk_tok, inp, mem_scaled, B, NM, DD, st));
-    for (int i = 0; i < NM; ++i) {
-      const std::string pre = "alignment_head.gated_update.delta_mlps." + std::to_string(i) + ".";
-      const float *w0, *b0, *w2, *b2;
-      TRY(need_f32(e, pre + "0.weight", &w0, 3LL * DD * DD)); TRY(need_f32(e, pre + "0.bias", &b0, DD));
-      TRY(need_f32(e, pre + "2.weight", &w2, (long long)DD * DD)); TRY(need_f32(e, pre + "2.bias", &b2, DD));
-      TRY(linear_f32(inp + (size_t)i * 3 * DD, (long long)NM * 3 * DD, w0, b0, hid + (size_t)i * DD, (long long)NM * DD, B, DD, 3 * DD, ACT_NONE, ACT_GELU, nullptr, false, st));
-      TRY(linear_f32(hid + (size_t)i * DD, (long long)NM * DD, w2, b2, deltas + (size_t)i * DD, (long long)NM * DD, B, DD, DD, ACT_NONE, ACT_NONE, nullptr, false, st));
-    }
-    const float *g0w, *g0b, *g2w, *g2b;
-    TRY(need_f32(e, "alignment_head.gated_update.gate_mlp.0.weight", &g0w, 2LL * DD * DD)); TRY(need_f32(e, "alignment_head.gated_update.gate_mlp.0.bias", &g0b, DD));
-    TRY(need_f32(e, "alignment_head.gated_update.gate_mlp.2.weight", &g2w, DD)); TRY(need_f32(e, "alignment_head.gated_update.gate_mlp.2.bias", &g2b, 1));
-    TRY(gu_gate_input(deltas, directional, mem_scaled, gate_in, B * NM, DD, st));
-    TRY(linear_f32(gate_in, 2 * DD, g0w, g0b, ghid, DD, B * NM, DD, 2 * DD, ACT_NONE, ACT_GELU, nullptr, false, st));
-    TRY(linear_f32(ghid, DD, g2w, g2b, gate, 1, B * NM, 1, DD, ACT_NONE, ACT_SIGMOID, nullptr, false, st));
-    TRY(gu_finish(gate_in, directional, gate, memory_out, B * NM, DD, st));
-  }
-  float* chunk_n = e.scratch_f32((size_t)B * DD);
-  TRY(layernorm(chunk_tok, DD, RowMap{}, cnw, cnb, 1e-5f, chunk_n, DD, RowMap{}, false, B, DD, st));
-  const float *c1w, *c1b, *c2w, *c2b, *f1w, *f1b, *f2w, *f2b;
-  TRY(need_f32(e, "alignment_head.chunk_sim3_decoder.fc1.weight", &c1w, 256LL * DD)); TRY(need_f32(e, "alignment_head.chunk_sim3_decoder.fc1.bias", &c1b, 256));
-  TRY(need_f32(e, "alignment_head.chunk_sim3_decoder.fc2.weight", &c2w, 8LL * 256)); TRY(need_f32(e, "alignment_head.chunk_sim3_decoder.fc2.bias", &c2b, 8));
-  TRY(need_f32(e, "alignment_head.frame_se3_decoder.fc1.weight", &f1w, 256LL * DD)); TRY(need_f32(e, "alignment_head.frame_se3_decoder.fc1.bias", &f1b, 256));
-  TRY(need_f32(e, "alignment_head.frame_se3_decoder.fc2.weight", &f2w, 7LL * 256)); TRY(need_f32(e, "alignment_head.frame_se3_decoder.fc2.bias", &f2b, 7));
-  if (S > 1) {  // per-frame tokens (frames 1..S-1) attend to the normed chunk token (:510-534)
-    float* ft = e.scratch_f32((size_t)B * (S - 1) * DD);
-    LSVS_CUDA(cudaMemcpy2DAsync(ft, (size_t)(S - 1) * DD * 4, tok + DD, (size_t)S * DD * 4, (size_t)(S - 1) * DD * 4, B, cudaMemcpyDeviceToDevice, st));
-    for (int i = 0; i < 2; ++i) TRY(run_cross_block_f32(e, ft, B, S - 1, chunk_n, 1, e.frame_cross[i], DD, 8, d_dec + 1, d_dec, st));
-    float* ftn = e.scratch_f32((size_t)B * (S - 1) * DD); float* fh = e.scratch_f32((size_t)B * (S - 1) * 256);
-    TRY(layernorm(ft, DD, RowMap{}, fnw, fnb, 1e-5f, ftn, DD, RowMap{}, false, (long long)B * (S - 1), DD, st));
-    TRY(linear_f32(ftn, DD, f1w, f1b, fh, 256, B * (S - 1), 256, DD, ACT_NONE, ACT_GELU, nullptr, false, st));
-    TRY(linear_f32(fh, 256, f2w, f2b, frame_se3, 7, B * (S - 1), 7, 256, ACT_NONE, ACT_NONE, nullptr, false, st));
-  }
-  float* ch = e.scratch_f32((size_t)B * 256); float* c8 = e.scratch_f32((size_t)B * 8);
-  TRY(linear_f32(chunk_n, DD, c1w, c1b, ch, 256, B, 256, DD, ACT_NONE, ACT_GELU, nullptr, false, st));
-  TRY(linear_f32(ch, 256, c2w, c2b, c8, 8, B, 8, 256, ACT_NONE, ACT_NONE, nullptr, false, st));
-  TRY(combine_rows(c8, 8, nullptr, 0, chunk_sim3, 8, B, 8, -1, 7, st));  // exp on the scale entry (:538)
-  if (e.scratch_overflow) { e.scratch_overflow = false; return fail(LSVS_ECUDA, "alignment_head_forward: decode scratch under-sized"); }
-  return LSVS_OK;
+  return decode_forward(e, x, (long long)P1 * D, B, S, d_dec, memory_in, chunk_sim3, frame_se3, memory_out, st);
 }
 
 // ================================================================================================ CameraHead
@@ -596,6 +609,7 @@ extern "C" int lsvs_camera_head_forward(lsvs_engine* h, const float* tokens_last
   LSVS_CHECK_ARG(e.finalized && e.cfg.with_camera_head, "camera_head_forward: engine has no camera head / not finalized");
   LSVS_CHECK_ARG(tokens_last && pose_enc && B > 0 && S > 0 && P > 0 && num_iterations > 0, "camera_head_forward: bad arguments");
   const int C = 2048, frames = B * S;
+  TRY(ensure_workspace(e, 2 * (long long)frames + 256, 0));
   const size_t need_scratch = (size_t)frames * (size_t)(C * 8 + 3 * C + 3 * C + 4 * C + 4096) + (1 << 14);
   TRY(e.scratch.ensure(need_scratch * 4));
   e.scratch_off = 0;
@@ -622,18 +636,8 @@ extern "C" int lsvs_camera_head_forward(lsvs_engine* h, const float* tokens_last
     TRY(linear_f32(pin, 9, epw, epb, emb, C, frames, C, 9, ACT_NONE, ACT_NONE, nullptr, false, st));
     TRY(linear_f32(emb, C, mw, mb, mod, 3 * C, frames, 3 * C, C, ACT_SILU, ACT_NONE, nullptr, false, st));
     TRY(modulate(normed, tok, mod, xx, frames, C, st));
-    for (int i = 0; i < 4; ++i) {
-      const BlockWF& w = e.cam_trunk[i];
-      TRY(layernorm(xx, C, RowMap{}, w.n1w, w.n1b, 1e-5f, xn, C, RowMap{}, false, frames, C, st));
-      TRY(linear_f32(xn, C, w.qkv_w, w.qkv_b, qkv, 3 * C, frames, 3 * C, C, ACT_NONE, ACT_NONE, nullptr, false, st));
-      SmallAttnArgs a{qkv, 3 * C, qkv + C, 3 * C, qkv + 2 * C, 3 * C, att, C, B, 16, 128, S, S, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                      e.cfg.rope_base, 1.0f / sqrtf(128.f)};
-      TRY(attn_small_f32(a, st));
-      TRY(linear_f32(att, C, w.proj_w, w.proj_b, xx, C, frames, C, C, ACT_NONE, ACT_NONE, w.ls1, true, st));
-      TRY(layernorm(xx, C, RowMap{}, w.n2w, w.n2b, 1e-5f, xn, C, RowMap{}, false, frames, C, st));
-      TRY(linear_f32(xn, C, w.fc1_w, w.fc1_b, hb, 4 * C, frames, 4 * C, C, ACT_NONE, ACT_GELU, nullptr, false, st));
-      TRY(linear_f32(hb, 4 * C, w.fc2_w, w.fc2_b, xx, C, frames, C, 4 * C, ACT_NONE, ACT_NONE, w.ls2, true, st));
-    }
+    // trunk: bf16 tensor-core blocks on the fp32 residual stream (16 heads x 128, sequence = the S frames of a chunk)
+    for (int i = 0; i < 4; ++i) TRY(run_block(e, xx, frames, e.cam_trunk[i], 1e-5f, 16, 128, B, S, RopeCfg{}, nullptr, 0, st));
     TRY(layernorm(xx, C, RowMap{}, trw, trb, 1e-5f, xn, C, RowMap{}, false, frames, C, st));
     TRY(linear_f32(xn, C, b1w, b1b, bh, C / 2, frames, C / 2, C, ACT_NONE, ACT_GELU, nullptr, false, st));
     TRY(linear_f32(bh, C / 2, b2w, b2b, delta, 9, frames, 9, C / 2, ACT_NONE, ACT_NONE, nullptr, false, st));
@@ -650,4 +654,19 @@ extern "C" int lsvs_pose_chain(const float* chunk_sim3, const float* frame_se3, 
                                float* scale_out, void* stream) {
   return lsvs::pose_chain(chunk_sim3, frame_se3, cam_enc, prev_pose_enc, S_prev, overlap, B, S, H, W, pose_enc_out, point_T, scale_out,
                           (cudaStream_t)stream);
+}
+
+extern "C" int lsvs_alignment_decode_forward(lsvs_engine* h, const float* align_tokens, int B, int S, const float* memory_in,
+                                             float* chunk_sim3, float* frame_se3, float* memory_out, void* stream) {
+  Engine& e = *reinterpret_cast<Engine*>(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  LSVS_CHECK_ARG(e.finalized && e.cfg.with_alignment_head, "alignment_decode_forward: engine has no alignment head / not finalized");
+  LSVS_CHECK_ARG(align_tokens && chunk_sim3 && memory_out && B > 0 && S > 0 && (S == 1 || frame_se3), "alignment_decode_forward: bad arguments");
+  LSVS_CHECK_ARG(e.cfg.num_memory_tokens == 8, "alignment_decode_forward: num_memory_tokens must be 8");
+  const int NM = 8;
+  std::vector<int> dec(S + NM);
+  for (int j = 0; j < S; ++j) dec[j] = j;
+  for (int j = 0; j < NM; ++j) dec[S + j] = 2 * S + j;
+  TRY(upload_ids(e.ids_k, dec, st));
+  return decode_forward(e, align_tokens, 1024, B, S, e.ids_k.as<int>(), memory_in, chunk_sim3, frame_se3, memory_out, st);
 }

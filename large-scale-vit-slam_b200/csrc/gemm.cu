@@ -308,6 +308,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   const CUtensorMap* tmA = tmap_2d_bf16(A, K, M, (uint64_t)lda * 2, BK, BM);
   const CUtensorMap* tmB = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, BN);
   if (!tmA || !tmB) return LSVS_ECUDA;
+  ProfScope prof(PROF_GEMM, st, 2.0 * M * (double)N * K, 0);
   if (epi_kind == EPI_HEADNORM64_BF16 || epi_kind == EPI_HEADNORM128_BF16) {
     LSVS_CHECK_ARG(e.bias && e.out, "gemm: head-norm epilogue needs bias and out");
     LSVS_CHECK_ARG((e.n_q_cols == 0 || (e.qn_w && e.qn_b)) && (e.n_k_cols == 0 || (e.kn_w && e.kn_b)), "gemm: missing q/k norm weights");

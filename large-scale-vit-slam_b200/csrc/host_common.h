@@ -32,6 +32,17 @@ inline int num_sms() {
   return n;
 }
 
+// ---- optional per-kernel-class CUDA-event profiler (bench.py's roofline numbers; off by default) ----------
+enum ProfCat { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_ELEMENTWISE = 2, PROF_SMALL_F32 = 3, PROF_SIM3 = 4, PROF_NCAT = 5 };
+extern bool g_prof_on;
+void prof_begin(int cat, cudaStream_t st, double flops, double bytes);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st; bool on;
+  ProfScope(int cat, cudaStream_t s, double flops = 0, double bytes = 0) : st(s), on(g_prof_on) { if (on) prof_begin(cat, s, flops, bytes); }
+  ~ProfScope() { if (on) prof_end(st); }
+};
+
 #define LSVS_CHECK_ARG(cond, ...) \
   do { if (!(cond)) return ::lsvs::fail(LSVS_EINVAL, __VA_ARGS__); } while (0)
 

@@ -174,6 +174,7 @@ extern "C" int lsvs_sim3_apply_points(const float* pts, const float* T, const fl
   LSVS_CHECK_ARG(batch > 0 && batch <= 65535 && n_points >= 0, "sim3_apply_points: Inputs must have matching batch dimension (batch=%d n=%lld)", batch, n_points);
   if (n_points == 0) return LSVS_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  lsvs::ProfScope prof(lsvs::PROF_SIM3, st, 0, 24.0 * batch * (double)n_points);
   const bool aligned = ((n_points & 3) == 0 || batch == 1) && ((uintptr_t)pts % 16 == 0) && ((uintptr_t)out % 16 == 0);
   long long tail_first = 0;
   if (aligned && (n_points >> 2) > 0) {

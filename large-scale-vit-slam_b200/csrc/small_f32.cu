@@ -18,61 +18,82 @@ __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 __device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 constexpr int LIN_MT = 32;  // rows per launch slice (grid.y walks slices)
+constexpr int LIN_NW = 4;   // output columns per warp: each x load feeds 4 weight rows
 
-// y[m,n] = epi( sum_k in_act(x[m,k]) * W[n,k] + b[n] ),  m in [m0, m0+32)
+// y[m,n] = epi( sum_k in_act(x[m,k]) * W[n,k] + b[n] ),  m in [m0, m0+32), n in 4 consecutive columns per warp.
 template <bool VEC>
 __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ W,
                                                          const float* __restrict__ b, float* __restrict__ y, long long ldy, int M,
                                                          int N, int K, int in_act, int out_act, const float* __restrict__ gamma,
                                                          int residual) {
   const int lane = threadIdx.x & 31;
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * LIN_NW;
   const int m0 = blockIdx.y * LIN_MT;
   const int mt = min(LIN_MT, M - m0);
-  if (n >= N) return;
-  float acc[LIN_MT];
+  if (n0 >= N) return;
+  float acc[LIN_MT][LIN_NW];
 #pragma unroll
-  for (int m = 0; m < LIN_MT; ++m) acc[m] = 0.f;
-  const float* wrow = W + (size_t)n * K;
+  for (int m = 0; m < LIN_MT; ++m)
+#pragma unroll
+    for (int j = 0; j < LIN_NW; ++j) acc[m][j] = 0.f;
+  const float* wrow[LIN_NW];
+#pragma unroll
+  for (int j = 0; j < LIN_NW; ++j) wrow[j] = W + (size_t)min(n0 + j, N - 1) * K;
   if constexpr (VEC) {
     for (int k0 = lane * 4; k0 < K; k0 += 128) {
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + k0));
+      float4 w4[LIN_NW];
+#pragma unroll
+      for (int j = 0; j < LIN_NW; ++j) w4[j] = __ldg(reinterpret_cast<const float4*>(wrow[j] + k0));
 #pragma unroll
       for (int m = 0; m < LIN_MT; ++m) {
         if (m < mt) {
           float4 x4 = *reinterpret_cast<const float4*>(x + (size_t)(m0 + m) * ldx + k0);
           if (in_act == ACT_SILU) { x4.x = silu(x4.x); x4.y = silu(x4.y); x4.z = silu(x4.z); x4.w = silu(x4.w); }
-          acc[m] = fmaf(w4.x, x4.x, fmaf(w4.y, x4.y, fmaf(w4.z, x4.z, fmaf(w4.w, x4.w, acc[m]))));
+#pragma unroll
+          for (int j = 0; j < LIN_NW; ++j)
+            acc[m][j] = fmaf(w4[j].x, x4.x, fmaf(w4[j].y, x4.y, fmaf(w4[j].z, x4.z, fmaf(w4[j].w, x4.w, acc[m][j]))));
         }
       }
     }
   } else {
     for (int k = lane; k < K; k += 32) {
-      const float w = __ldg(wrow + k);
+      float w[LIN_NW];
+#pragma unroll
+      for (int j = 0; j < LIN_NW; ++j) w[j] = __ldg(wrow[j] + k);
 #pragma unroll
       for (int m = 0; m < LIN_MT; ++m) {
         if (m < mt) {
           float xv = x[(size_t)(m0 + m) * ldx + k];
           if (in_act == ACT_SILU) xv = silu(xv);
-          acc[m] = fmaf(w, xv, acc[m]);
+#pragma unroll
+          for (int j = 0; j < LIN_NW; ++j) acc[m][j] = fmaf(w[j], xv, acc[m][j]);
         }
       }
     }
   }
-  float mine = 0.f;
+  float mine[LIN_NW];
 #pragma unroll
-  for (int m = 0; m < LIN_MT; ++m) {
-    const float s = warp_sum(acc[m]);
-    if (lane == m) mine = s;
-  }
+  for (int j = 0; j < LIN_NW; ++j) mine[j] = 0.f;
+#pragma unroll
+  for (int m = 0; m < LIN_MT; ++m)
+#pragma unroll
+    for (int j = 0; j < LIN_NW; ++j) {
+      const float s = warp_sum(acc[m][j]);
+      if (lane == m) mine[j] = s;
+    }
   if (lane < mt) {
-    float v = mine + (b ? __ldg(b + n) : 0.f);
-    if (out_act == ACT_GELU) v = gelu_erf(v);
-    else if (out_act == ACT_SIGMOID) v = sigmoidf(v);
-    float* dst = y + (size_t)(m0 + lane) * ldy + n;
-    if (gamma) v *= __ldg(gamma + n);
-    if (residual) v += *dst;
-    *dst = v;
+#pragma unroll
+    for (int j = 0; j < LIN_NW; ++j) {
+      const int n = n0 + j;
+      if (n >= N) break;
+      float v = mine[j] + (b ? __ldg(b + n) : 0.f);
+      if (out_act == ACT_GELU) v = gelu_erf(v);
+      else if (out_act == ACT_SIGMOID) v = sigmoidf(v);
+      float* dst = y + (size_t)(m0 + lane) * ldy + n;
+      if (gamma) v *= __ldg(gamma + n);
+      if (residual) v += *dst;
+      *dst = v;
+    }
   }
 }
 
@@ -305,7 +326,8 @@ int nblk(long long items) {
 int linear_f32(const float* x, long long ldx, const float* W, const float* b, float* y, long long ldy, int M, int N, int K,
                int in_act, int out_act, const float* gamma, bool residual, cudaStream_t st) {
   LSVS_CHECK_ARG(x && W && y && M > 0 && N > 0 && K > 0, "linear_f32: bad arguments");
-  dim3 grid((N + 7) / 8, (M + LIN_MT - 1) / LIN_MT);
+  ProfScope prof(PROF_SMALL_F32, st, 2.0 * M * (double)N * K, (double)N * K * 4);
+  dim3 grid((N + 8 * LIN_NW - 1) / (8 * LIN_NW), (M + LIN_MT - 1) / LIN_MT);
   const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)W % 16 == 0);
   if (vec) linear_f32_kernel<true><<<grid, 256, 0, st>>>(x, ldx, W, b, y, ldy, M, N, K, in_act, out_act, gamma, residual ? 1 : 0);
   else linear_f32_kernel<false><<<grid, 256, 0, st>>>(x, ldx, W, b, y, ldy, M, N, K, in_act, out_act, gamma, residual ? 1 : 0);
@@ -316,6 +338,7 @@ int linear_f32(const float* x, long long ldx, const float* W, const float* b, fl
 int attn_small_f32(const SmallAttnArgs& a, cudaStream_t st) {
   LSVS_CHECK_ARG(a.q && a.k && a.v && a.out && a.B > 0 && a.H > 0 && a.Nq > 0 && a.Nk > 0, "attn_small: bad arguments");
   LSVS_CHECK_ARG(a.hd == 64 || a.hd == 128, "attn_small: head_dim %d unsupported", a.hd);
+  ProfScope prof(PROF_SMALL_F32, st, 0, 0);
   const int total = a.B * a.H * a.Nq;
   if (a.hd == 64) attn_small_kernel<64><<<(total + 3) / 4, 128, 0, st>>>(a);
   else attn_small_kernel<128><<<(total + 3) / 4, 128, 0, st>>>(a);

@@ -136,6 +136,18 @@ class Engine:
                                                       _n.ptr(ov_out), _n.stream_ptr()), "alignment_head_forward")
         return sim3, se3, mem_out, ov_out
 
+    def alignment_decode_forward(self, align_tokens: torch.Tensor, memory_tokens: Optional[torch.Tensor]):
+        """fp32 decode stage alone (alignment_head.py:427-540): (B,S,1024) -> sim3 (B,1,8), se3 (B,S-1,7), memory (B,8,512)."""
+        B, S, C = align_tokens.shape
+        assert C == 1024
+        dev = align_tokens.device
+        tok = align_tokens.detach().float().contiguous()
+        mem = None if memory_tokens is None else memory_tokens.detach().to(dev, torch.float32).contiguous()
+        sim3, se3, mem_out = torch.empty(B, 1, 8, device=dev), torch.empty(B, max(S - 1, 0), 7, device=dev), torch.empty(B, 8, 512, device=dev)
+        _n.check(_n.lib().lsvs_alignment_decode_forward(self._h, _n.ptr(tok), _i(B), _i(S), _n.ptr(mem), _n.ptr(sim3), _n.ptr(se3),
+                                                        _n.ptr(mem_out), _n.stream_ptr()), "alignment_decode_forward")
+        return sim3, se3, mem_out
+
     def camera_head_forward(self, tokens_last: torch.Tensor, num_iterations: int = 4) -> torch.Tensor:
         B, S, P, C = tokens_last.shape
         tok = tokens_last.detach().float().contiguous()

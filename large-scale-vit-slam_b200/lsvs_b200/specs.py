@@ -115,7 +115,8 @@ def init_default_(root: nn.Module, seed: int = None) -> None:
     orthonormal memory tokens, alpha 0.1, gate bias 0 / weight std 0.1 (alignment_head.py:208-218,
     gated_update.py:38-40)."""
     gen = torch.Generator().manual_seed(seed) if seed is not None else None
-    for name, p in root.named_parameters():
+    all_params = dict(root.named_parameters())
+    for name, p in all_params.items():
         leaf = name.rsplit(".", 1)[-1]
         dino = "patch_embed." in name
         if leaf == "gamma":
@@ -149,7 +150,7 @@ def init_default_(root: nn.Module, seed: int = None) -> None:
             else:
                 fan_in = None
                 wname = name[:-4] + "weight"
-                w = dict(root.named_parameters()).get(wname)
+                w = all_params.get(wname)
                 fan_in = w[0].numel() if w is not None and w.dim() > 1 else p.numel()
                 bound = 1.0 / math.sqrt(fan_in)
                 p.uniform_(-bound, bound, generator=gen)

@@ -138,9 +138,28 @@ def alignment_head_forward(p: Params, pre: str, tokens: torch.Tensor, image_size
                            next_num_overlap: int, overlap_tokens: Optional[torch.Tensor] = None,
                            memory_tokens: Optional[torch.Tensor] = None, *, patch_size: int = 14, depth_aa: int = 4,
                            heads: int = 8, num_register_tokens: int = 4, num_memory_tokens: int = 8,
-                           temporal_attention: bool = True, rope_base: float = 100.0, return_tokens: bool = False):
+                           temporal_attention: bool = True, rope_base: float = 100.0, return_tokens: bool = False,
+                           amp: bool = False):
     """AlignmentHead.forward (eval) — alignment_head.py:224-345.
-    tokens (B,S,P,2048) -> chunk_sim3 (B,1,8), frame_se3 (B,S-1,7), memory (B,8,512), overlap (B,1+o,P+1,1024)."""
+    tokens (B,S,P,2048) -> chunk_sim3 (B,1,8), frame_se3 (B,S-1,7), memory (B,8,512), overlap (B,1+o,P+1,1024).
+    amp=True emulates the reference's shipping precision (Lightning bf16-mixed, run_model.py:472): the token blocks
+    run under bf16 autocast, the decode with autocast disabled (alignment_head.py:340)."""
+    with torch.autocast("cpu", dtype=torch.bfloat16, enabled=amp):
+        x, T, first_chunk, S, P1, C, B = _head_blocks(p, pre, tokens, image_size, overlap_tokens, patch_size, depth_aa, heads,
+                                                      num_register_tokens, temporal_attention, rope_base)
+    x = x.float()
+    with torch.autocast("cpu", enabled=False):
+        chunk_sim3, frame_se3, memory = decode_alignments(p, pre, x[:, :, 0], first_chunk, memory_tokens, heads,
+                                                          num_memory_tokens=num_memory_tokens, rope_base=rope_base)
+    new_overlap = torch.cat([x[:, :1], x[:, S - next_num_overlap:]], dim=1).contiguous()  # :343
+    if return_tokens:
+        return chunk_sim3, frame_se3, memory, new_overlap, x
+    return chunk_sim3, frame_se3, memory, new_overlap
+
+
+def _head_blocks(p, pre, tokens, image_size, overlap_tokens, patch_size, depth_aa, heads, num_register_tokens,
+                 temporal_attention, rope_base):
+    """project_in .. the 4 x (frame block, temporal cross block) loop of AlignmentHead.forward (:242-337)."""
     H, W = image_size
     x = OF.layer_norm(p, pre + "token_norm", OF.linear(p, pre + "project_in", tokens))  # :242-247
     B, S, P, C = x.shape
@@ -179,13 +198,7 @@ def alignment_head_forward(p: Params, pre: str, tokens: torch.Tensor, image_size
         yt = xt if first_chunk else overlap_tokens.reshape(B, T * P1 * C).view(B * P1, T, C)
         x = cross_block(p, f"{pre}temporal_blocks.{i}.", xt, yt, pos_t, heads, rope_base)
 
-    x = x.reshape(B, S, P1, C)
-    chunk_sim3, frame_se3, memory = decode_alignments(p, pre, x[:, :, 0], first_chunk, memory_tokens, heads,
-                                                      num_memory_tokens=num_memory_tokens, rope_base=rope_base)
-    new_overlap = torch.cat([x[:, :1], x[:, S - next_num_overlap:]], dim=1).contiguous()  # :343
-    if return_tokens:
-        return chunk_sim3, frame_se3, memory, new_overlap, x
-    return chunk_sim3, frame_se3, memory, new_overlap
+    return x.reshape(B, S, P1, C), T, first_chunk, S, P1, C, B
 
 
 # =============================================================================================
@@ -382,14 +395,15 @@ def point_transform(per_frame_se3: torch.Tensor, point_identity: torch.Tensor, h
 def feature_aligned_forward(p: Params, images: torch.Tensor, num_overlap: int, context: Optional[dict] = None, *,
                             raw_points: Optional[torch.Tensor] = None, raw_depth: Optional[torch.Tensor] = None,
                             depth: int = 24, dino_depth: int = 24, taps=(4, 11, 17, 23), depth_aa: int = 4,
-                            num_memory_tokens: int = 8) -> dict:
+                            num_memory_tokens: int = 8, amp: bool = False) -> dict:
     """FeatureAlignedVGGT.forward (eval, gt_poses=None, enable_camera=True) — featureAligned_vggt.py:48-225.
     The DPT heads are out of scope: ``raw_points`` (B,S,H,W,3) / ``raw_depth`` (B,S,H,W,1)
     stand in for their outputs so the Sim(3) application can be checked.  Returns this chunk's tensors
     (not the accumulated lists) plus the context entries needed by the next chunk."""
     B, S, _, H, W = images.shape
-    toks, _ = OF.aggregator_forward(p, "aggregator.", images, depth=depth, dino_depth=dino_depth, keep=taps)
-    taps_t = [toks[i] for i in taps]
+    with torch.autocast("cpu", dtype=torch.bfloat16, enabled=amp):  # amp: the reference's bf16-mixed inference precision
+        toks, _ = OF.aggregator_forward(p, "aggregator.", images, depth=depth, dino_depth=dino_depth, keep=taps)
+    taps_t = [toks[i].float() for i in taps]
     ctx_overlap = ctx_mem = prev_pose = None
     if context is not None:
         ctx_overlap = context["overlap_tokens"]
@@ -398,7 +412,7 @@ def feature_aligned_forward(p: Params, images: torch.Tensor, num_overlap: int, c
     overlap = num_overlap if S > num_overlap else S - 1  # :93
     chunk_sim3, frame_se3, memory, overlap_tokens = alignment_head_forward(
         p, "alignment_head.", taps_t[-1], (H, W), overlap, ctx_overlap, ctx_mem, depth_aa=depth_aa,
-        num_memory_tokens=num_memory_tokens)
+        num_memory_tokens=num_memory_tokens, amp=amp)
     per_frame, scale = compose_alignment(chunk_sim3, frame_se3)
     cam_enc = OF.camera_head_forward(p, "camera_head.", taps_t[-1])[-1]
     pose_enc, per_frame, pt_ident = pose_chain(cam_enc, (H, W), per_frame, scale, prev_pose, overlap)
