@@ -1,0 +1,115 @@
+"""CPU: chunk index generation and the multi-rank chunk pipeline (gloo, world_size 2 and 3) with stand-in stage
+functions: the pipelined / sharded execution must reproduce the sequential chunk loop exactly."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from lsvs_b200 import scheduler as sch
+from oracle import aligned as OA
+
+
+def test_generate_chunks_matches_oracle():
+    for args in [(1000, "chunk_overlap", 32, 8), (14, "chunk_overlap", 5, 1), (3, "chunk_overlap", 5, 1), (33, "chunk_overlap", 32, 8),
+                 (17, "chunk_gt", 5, 0), (9, "all", 4, 1), (75, "chunk_overlap", 75, 30), (1, "chunk_overlap", 5, 1)]:
+        assert sch.generate_chunks(*args) == OA.generate_chunks(*args)
+    ch = sch.generate_chunks(1000, "chunk_overlap", 32, 8)
+    assert len(ch) == 42 and ch[-1] == list(range(984, 1000))
+    with pytest.raises(ValueError):
+        sch.generate_chunks(10, "two_chunks_typo", 4, 1)
+
+
+def test_round_owners():
+    assert sch.round_owners(0, 1, 0.1) == [0]
+    # world 8, head 12 % of an aggregator pass: rank 0 only aligns
+    assert all(sch.round_owners(j, 8, 0.125) == list(range(1, 8)) for j in range(10))
+    # world 2, head cost 0.1: rank 0 encodes in 80 % of the rounds
+    took = sum(0 in sch.round_owners(j, 2, 0.1) for j in range(100))
+    assert took == 80
+    assert all(set(sch.round_owners(j, 4, 0.1)) >= {1, 2, 3} for j in range(20))
+
+
+# ---- stand-in stages: cheap deterministic arithmetic with a genuinely sequential context ------------
+def _encode(inputs):
+    x = inputs[0]
+    return (x * 2.0 + 1.0), x.sum().reshape(1, 1)
+
+
+def _align(tokens, cam, ctx):
+    prev = torch.zeros(1) if ctx is None else ctx["state"]
+    state = 0.5 * prev + tokens.mean().reshape(1) + cam.reshape(1)   # depends on every earlier chunk, in order
+    packet = torch.cat([state, tokens.flatten()[:3]])
+    return packet, {"state": state}
+
+
+def _apply(packet, inputs):
+    return packet[0] * inputs[1] + packet[1:4].sum()
+
+
+def _sequential(n_rounds, world, head_cost):
+    ctx, outs, k = None, [], 0
+    for j in range(n_rounds):
+        for o in sch.round_owners(j, world, head_cost):
+            inp = _inputs(k)
+            t, c = _encode(inp)
+            packet, ctx = _align(t, c, ctx)
+            outs.append((o, _apply(packet, inp)))
+            k += 1
+    return outs
+
+
+def _inputs(k):
+    g = torch.Generator().manual_seed(k)
+    return (torch.randn(4, 5, generator=g), torch.randn(3, generator=g))
+
+
+def _worker(rank, world, port, head_cost, n_rounds, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fwd, bwd = dist.new_group(), dist.new_group()
+    pipe = sch.ChunkPipeline(_encode, _align, _apply, rank, world, head_cost=head_cost, packet_numel=4,
+                             tokens_like=lambda: torch.empty(4, 5), cam_like=lambda: torch.empty(1, 1), fwd_group=fwd, bwd_group=bwd)
+    k = 0
+    for j in range(n_rounds):
+        owners = pipe.owners()
+        mine = None
+        for o in owners:
+            if o == rank:
+                mine = _inputs(k)
+            k += 1
+        pipe.step(mine)
+    res = pipe.flush()
+    q.put((rank, [r.clone() for r in res]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world,head_cost", [(2, 0.1), (3, 0.4), (2, 0.6)])
+def test_pipeline_equals_sequential_gloo(world, head_cost):
+    n_rounds = 7
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, head_cost, n_rounds, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = _sequential(n_rounds, world, head_cost)
+    for r in range(world):
+        mine = [v for o, v in ref if o == r]
+        assert len(mine) == len(got[r])
+        for a, b in zip(mine, got[r]):
+            assert torch.allclose(a, b, atol=0, rtol=0)
+    assert sum(len(v) for v in got.values()) == len(ref) == sum(len(sch.round_owners(j, world, head_cost)) for j in range(n_rounds))
