@@ -44,3 +44,9 @@ extern "C" int lsvs_attention_bf16(const lsvs_bf16* q, int ldq, const lsvs_bf16*
   lsvs::AttentionArgs a{q, k, v, o, ldq, ldk, ldv, ldo, batches, heads, head_dim, Lq, Lk, scale};
   return lsvs::attention_fwd(a, (cudaStream_t)stream);
 }
+
+namespace lsvs { extern int g_gemm_mode; }
+extern "C" int lsvs_debug_gemm_mode(int mode) {
+  lsvs::g_gemm_mode = mode;
+  return LSVS_OK;
+}

@@ -13,6 +13,7 @@
 #include "tensormap.h"
 
 namespace lsvs {
+int g_gemm_mode = 0;  // 0 auto, 1 force the single-CTA kernel (lsvs_debug_gemm_mode; A/B testing)
 namespace {
 
 constexpr int BM = 128;
@@ -102,10 +103,10 @@ __device__ __forceinline__ void head_norm_rope(float* v, const float* __restrict
 }
 
 template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, uint32_t taddr, int m, int n0, bool row_ok) {
+__device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, uint32_t taddr, int m, int n0, bool row_ok, int c_begin = 0, int c_end = BN) {
   if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_F32) {
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = c_begin; c < c_end; c += 32) {
       float v[32];
       __syncwarp();
       load_acc<32>(taddr + c, v);
@@ -127,32 +128,50 @@ __device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, uint32_t tad
       }
     }
   } else if constexpr (EPI == EPI_RESID_F32) {
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
-      __syncwarp();
-      load_acc<32>(taddr + c, v);
-      if (!row_ok) continue;  // reconverges at the __syncwarp above / after the loop
-      const int n = n0 + c;
-      float4* r4 = reinterpret_cast<float4*>(e.resid + (size_t)m * e.ldr + n);
-      float4* o2 = e.out2 ? reinterpret_cast<float4*>(e.out2 + (size_t)m * e.ld2 + n) : nullptr;
+    // residual rows are prefetched one 32-column chunk ahead: the fp32 read-modify-write is latency-bound
+    float4 rnext[8];
+    float4* r4 = row_ok ? reinterpret_cast<float4*>(e.resid + (size_t)m * e.ldr + n0 + c_begin) : nullptr;
+    if (row_ok) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 r = r4[i];
-        const float4 g = e.gamma ? __ldg(reinterpret_cast<const float4*>(e.gamma + n) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
-        const float4 bb = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        r.x += g.x * (v[4 * i + 0] + bb.x);
-        r.y += g.y * (v[4 * i + 1] + bb.y);
-        r.z += g.z * (v[4 * i + 2] + bb.z);
-        r.w += g.w * (v[4 * i + 3] + bb.w);
-        r4[i] = r;
-        if (o2) o2[i] = r;
+      for (int i = 0; i < 8; ++i) rnext[i] = r4[i];
+    }
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+      float v[32];
+      float4 rcur[8];
+      __syncwarp();
+      ptx::tmem_ld_32x32b_x32(taddr + c, reinterpret_cast<uint32_t*>(v));
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rcur[i] = rnext[i];
+        if (c + 32 < c_end) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rnext[i] = r4[8 + i];
+        }
+      }
+      ptx::tmem_ld_wait();
+      if (row_ok) {
+        const int n = n0 + c;
+        float4* o2 = e.out2 ? reinterpret_cast<float4*>(e.out2 + (size_t)m * e.ld2 + n) : nullptr;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 r = rcur[i];
+          const float4 g = e.gamma ? __ldg(reinterpret_cast<const float4*>(e.gamma + n) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+          const float4 bb = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          r.x += g.x * (v[4 * i + 0] + bb.x);
+          r.y += g.y * (v[4 * i + 1] + bb.y);
+          r.z += g.z * (v[4 * i + 2] + bb.z);
+          r.w += g.w * (v[4 * i + 3] + bb.w);
+          r4[i] = r;
+          if (o2) o2[i] = r;
+        }
+        r4 += 8;
       }
     }
   } else {  // EPI_QKV_NORM_ROPE_64 / _128 : columns [0,n_q) q heads, [n_q, n_q+n_k) k heads, remainder plain (+bias)
     constexpr int HD = (EPI == EPI_HEADNORM64_BF16) ? 64 : 128;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += HD) {
+    for (int c = c_begin; c < c_end; c += HD) {
       float v[HD];
       __syncwarp();
       load_acc<HD>(taddr + c, v);
@@ -279,6 +298,162 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 2 * BN);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs computes one 256 x 256 tile.  Each CTA stages its own 128 rows
+// of A and HALF of the B tile (128 of the 256 weight rows); the leader's single MMA thread issues tcgen05.mma
+// .cta_group::2 (M = 256), which reads both halves of B from the two CTAs' shared memory and writes each CTA's 128
+// accumulator rows into that CTA's TMEM.  Per CTA and k-block that is 32 KB of L2 traffic instead of 48 KB for the same
+// 128x256x64 MACs, and the stage shrinks so that 6 stages fit: both attack what bounds the 1-CTA kernel (L2->SM bytes in
+// flight).  Barriers: TMA of both CTAs credits the leader's `full`; `empty` / `tmem_full` are signalled in both CTAs by a
+// multicast commit; the peer's epilogue warps arrive remotely on the leader's `tmem_empty`.
+constexpr int STAGES2 = 6;
+constexpr int BN2 = 256;
+struct Smem2 {
+  static constexpr int A_BYTES = BM * BK * 2;          // 16 KB: this CTA's 128 rows
+  static constexpr int B_BYTES = (BN2 / 2) * BK * 2;   // 16 KB: this CTA's half of the weight tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES2 * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int EPI, int EW>  // EW epilogue warps per CTA (4 or 8)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
+gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                       GemmEpilogue epi) {
+  using L = Smem2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES2;
+  uint64_t* tmem_full = empty_bar + STAGES2;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = ptx::cluster_ctarank();  // 0 = leader
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_tiles_n = N / BN2;
+  const int n_tiles_m = (M + 2 * BM - 1) / (2 * BM);
+  const int n_tiles = n_tiles_m * n_tiles_n;
+  const int n_kb = K / BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+#pragma unroll
+    for (int i = 0; i < STAGES2; ++i) { ptx::mbar_init(full_bar + i, 2); ptx::mbar_init(empty_bar + i, 1); }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(tmem_full + i, 1); ptx::mbar_init(tmem_empty + i, 2 * EW); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_slot, 2 * BN2);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+      const int m0 = (tile / n_tiles_n) * (2 * BM) + (int)cta * BM;
+      const int n0 = (tile % n_tiles_n) * BN2 + (int)cta * (BN2 / 2);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+        if (lane == 0) {
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          if (cta == 0) ptx::mbar_expect_tx(full_bar + stage, 2 * L::STAGE_BYTES);  // bytes of both CTAs land here
+          else ptx::mbar_arrive_remote(full_bar + stage, 0);
+          ptx::tma_load_2d_2sm(sa, &tmA, full_bar + stage, kb * BK, m0);
+          ptx::tma_load_2d_2sm(sa + L::A_BYTES, &tmB, full_bar + stage, kb * BK, n0);
+        }
+        __syncwarp();
+        if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (cta == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, BN2, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+        ptx::mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN2;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          ptx::mbar_wait(full_bar + stage, phase);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = ptx::smem_u32(smem + stage * L::STAGE_BYTES);
+            const uint64_t adesc = ptx::umma_desc_sw128(sa, 16, 1024);
+            const uint64_t bdesc = ptx::umma_desc_sw128(sa + L::A_BYTES, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              ptx::umma_bf16_ss_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            ptx::umma_commit_2sm(empty_bar + stage, 3);
+            if (kb == n_kb - 1) ptx::umma_commit_2sm(tmem_full + acc, 3);
+          }
+          __syncwarp();
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (EW warps: lane quarter = warp % 4, column half = (warp-2)/4)
+    const int quarter = warp & 3;
+    const int part = (warp - 2) >> 2;
+    constexpr int COLS = BN2 / (EW / 4);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+      const int m0 = (tile / n_tiles_n) * (2 * BM) + (int)cta * BM;
+      const int n0 = (tile % n_tiles_n) * BN2;
+      ptx::mbar_wait(tmem_full + acc, acc_phase);
+      ptx::tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2;
+      epilogue_row<BN2, EPI>(epi, taddr, m, n0, m < M, part * COLS, (part + 1) * COLS);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (cta == 0) ptx::mbar_arrive(tmem_empty + acc);
+        else ptx::mbar_arrive_remote(tmem_empty + acc, 0);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 1) ptx::tmem_dealloc_2sm(tmem_base, 2 * BN2);
+}
+
+template <int EPI>
+int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const GemmEpilogue& e, cudaStream_t st) {
+  constexpr int EW = (EPI == EPI_HEADNORM64_BF16 || EPI == EPI_HEADNORM128_BF16) ? 4 : 8;
+  auto kern = gemm_bf16_tcgen05_2cta<EPI, EW>;
+  static bool configured = false;
+  if (!configured) {
+    LSVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::TOTAL));
+    configured = true;
+  }
+  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN2);
+  const int max_pairs = num_sms() / 2;
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  kern<<<2 * pairs, 64 + 32 * EW, Smem2::TOTAL, st>>>(*tmA, *tmB, M, N, K, e);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+
 template <int BN, int EPI>
 int launch(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const GemmEpilogue& e, cudaStream_t st) {
   using L = SmemLayout<BN>;
@@ -305,8 +480,9 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   const bool bn256 = (N % 256 == 0);
   LSVS_CHECK_ARG(bn256 || N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
   const int BN = bn256 ? 256 : 128;
+  const bool pair = bn256 && M > 2 * BM && g_gemm_mode != 1;  // CTA pairs (256x256 tiles) once there are enough rows
   const CUtensorMap* tmA = tmap_2d_bf16(A, K, M, (uint64_t)lda * 2, BK, BM);
-  const CUtensorMap* tmB = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, BN);
+  const CUtensorMap* tmB = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, pair ? BN2 / 2 : BN);
   if (!tmA || !tmB) return LSVS_ECUDA;
   ProfScope prof(PROF_GEMM, st, 2.0 * M * (double)N * K, 0);
   if (epi_kind == EPI_HEADNORM64_BF16 || epi_kind == EPI_HEADNORM128_BF16) {
@@ -318,7 +494,20 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   }
 #define LSVS_GEMM_CASE(KIND)                                                            \
   case KIND:                                                                            \
+    if (pair) return launch2<KIND>(tmA, tmB, M, N, K, e, st);                           \
     return bn256 ? launch<256, KIND>(tmA, tmB, M, N, K, e, st) : launch<128, KIND>(tmA, tmB, M, N, K, e, st);
+  // few rows (camera-head trunk, M = frames of one chunk): the job is weight streaming, so spread N over many CTAs
+  if (M <= BM && N % 64 == 0 && N / 64 >= 32) {
+    const CUtensorMap* tmB64 = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, 64);
+    if (!tmB64) return LSVS_ECUDA;
+    switch (epi_kind) {
+      case EPI_BIAS_BF16: return launch<64, EPI_BIAS_BF16>(tmA, tmB64, M, N, K, e, st);
+      case EPI_BIAS_GELU_BF16: return launch<64, EPI_BIAS_GELU_BF16>(tmA, tmB64, M, N, K, e, st);
+      case EPI_BIAS_F32: return launch<64, EPI_BIAS_F32>(tmA, tmB64, M, N, K, e, st);
+      case EPI_RESID_F32: return launch<64, EPI_RESID_F32>(tmA, tmB64, M, N, K, e, st);
+      default: break;
+    }
+  }
   switch (epi_kind) {
     LSVS_GEMM_CASE(EPI_BIAS_BF16)
     LSVS_GEMM_CASE(EPI_BIAS_GELU_BF16)

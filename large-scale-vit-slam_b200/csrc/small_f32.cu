@@ -97,6 +97,72 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
   }
 }
 
+// Skinny fp32 GEMM for K % 4 == 0: a 256-thread block owns 8 output columns x (8*MS) rows.  The 8 warps are arranged as
+// MS row groups (8 rows each) x KS slices of K; each lane streams float4s of the weight rows (coalesced) and of the x
+// rows (L1/L2 resident), partial sums are reduced by shuffles, then across the K slices through shared memory.
+// Many small blocks (N/8 per row tile) keep all SMs busy even for N = 512; weights are read once per row tile.
+template <int MS, int KS>
+__global__ void __launch_bounds__(256) linear_f32_tiled_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ W,
+                                                               const float* __restrict__ b, float* __restrict__ y, long long ldy,
+                                                               int M, int N, int K, int in_act, int out_act,
+                                                               const float* __restrict__ gamma, int residual) {
+  static_assert(MS * KS == 8, "8 warps");
+  constexpr int NC = 8, RW = 8;  // columns per block, rows per warp
+  __shared__ float red[KS][MS * RW][NC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ms = warp % MS, ks = warp / MS;
+  const int n0 = blockIdx.x * NC;
+  const int m0 = blockIdx.y * (MS * RW) + ms * RW;
+  float acc[RW][NC];
+#pragma unroll
+  for (int r = 0; r < RW; ++r)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[r][c] = 0.f;
+  const int kchunk = ((K / 4 + KS - 1) / KS) * 4;  // K slice of this warp (multiple of 4)
+  const int kbeg = ks * kchunk, kend = min(K, kbeg + kchunk);
+  for (int k = kbeg + lane * 4; k < kend; k += 128) {
+    float4 w4[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) w4[c] = __ldg(reinterpret_cast<const float4*>(W + (size_t)min(n0 + c, N - 1) * K + k));
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      if (m0 + r < M) {
+        float4 x4 = *reinterpret_cast<const float4*>(x + (size_t)(m0 + r) * ldx + k);
+        if (in_act == ACT_SILU) { x4.x = silu(x4.x); x4.y = silu(x4.y); x4.z = silu(x4.z); x4.w = silu(x4.w); }
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          acc[r][c] = fmaf(w4[c].x, x4.x, fmaf(w4[c].y, x4.y, fmaf(w4[c].z, x4.z, fmaf(w4[c].w, x4.w, acc[r][c]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RW; ++r)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const float sres = warp_sum(acc[r][c]);
+      if (lane == 0) red[ks][ms * RW + r][c] = sres;
+    }
+  __syncthreads();
+  // 64..256 outputs per block: thread t -> (row t / 8, col t % 8)
+  const int t = threadIdx.x;
+  if (t < MS * RW * NC) {
+    const int r = t / NC, c = t % NC;
+    const int m = blockIdx.y * (MS * RW) + r, n = n0 + c;
+    if (m < M && n < N) {
+      float v = 0.f;
+#pragma unroll
+      for (int q = 0; q < KS; ++q) v += red[q][r][c];
+      v += b ? __ldg(b + n) : 0.f;
+      if (out_act == ACT_GELU) v = gelu_erf(v);
+      else if (out_act == ACT_SIGMOID) v = sigmoidf(v);
+      float* dst = y + (size_t)m * ldy + n;
+      if (gamma) v *= __ldg(gamma + n);
+      if (residual) v += *dst;
+      *dst = v;
+    }
+  }
+}
+
 // One warp per (batch, head, query): optional per-head LayerNorm on q/k, optional 1-D RoPE, softmax over Nk keys.
 // Lane holds elements e = lane + 32*j, so rotate-half partners (e, e + hd/2) sit in the same lane.
 template <int HD>
@@ -329,8 +395,15 @@ int linear_f32(const float* x, long long ldx, const float* W, const float* b, fl
   ProfScope prof(PROF_SMALL_F32, st, 2.0 * M * (double)N * K, (double)N * K * 4);
   dim3 grid((N + 8 * LIN_NW - 1) / (8 * LIN_NW), (M + LIN_MT - 1) / LIN_MT);
   const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)W % 16 == 0);
-  if (vec) linear_f32_kernel<true><<<grid, 256, 0, st>>>(x, ldx, W, b, y, ldy, M, N, K, in_act, out_act, gamma, residual ? 1 : 0);
-  else linear_f32_kernel<false><<<grid, 256, 0, st>>>(x, ldx, W, b, y, ldy, M, N, K, in_act, out_act, gamma, residual ? 1 : 0);
+  if (vec && M > 8) {
+    dim3 g2((N + 7) / 8, (M + 31) / 32);
+    linear_f32_tiled_kernel<4, 2><<<g2, 256, 0, st>>>(x, ldx, W, b, y, ldy, M, N, K, in_act, out_act, gamma, residual ? 1 : 0);
+  } else if (vec) {
+    dim3 g2((N + 7) / 8, 1);
+    linear_f32_tiled_kernel<1, 8><<<g2, 256, 0, st>>>(x, ldx, W, b, y, ldy, M, N, K, in_act, out_act, gamma, residual ? 1 : 0);
+  } else {
+    linear_f32_kernel<false><<<grid, 256, 0, st>>>(x, ldx, W, b, y, ldy, M, N, K, in_act, out_act, gamma, residual ? 1 : 0);
+  }
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
