@@ -2,9 +2,9 @@
 //
 // One CTA owns up to two 128-row query tiles (A, B) of one (batch, head) and streams the K/V blocks once for
 // both.  Warp roles (10 warps):
-//   warp 0      TMA producer: Q tiles once, then K and V blocks through two independent 3-stage rings
-//   warp 1      tcgen05.mma issuer: S_t = Q_t K^T (SS, fp32 in TMEM), O_t += P_t V (SS, P from shared memory)
-//   warps 2-5   softmax for tile A, warps 6-9 softmax for tile B: one thread per query row (TMEM lane), so the
+//   warp 8      TMA producer: Q tiles once, then K and V blocks through two independent 3-stage rings
+//   warp 9      tcgen05.mma issuer: S_t = Q_t K^T (SS, fp32 in TMEM), O_t += P_t V (SS, P from shared memory)
+//   warps 0-3   softmax for tile A, warps 4-7 softmax for tile B (registers moved to them with setmaxnreg): one thread per query row (TMEM lane), so the
 //               row max / row sum need no shuffles.  exp2 with the softmax scale folded in; running max and sum
 //               in registers; O stays in TMEM and is rescaled in place (tcgen05.ld/st) only when a row max moved.
 // The two tiles ping-pong on the tensor core: while the softmax warps of one tile work, the MMAs of the other
@@ -22,8 +22,8 @@ namespace lsvs {
 namespace {
 
 constexpr int QT = 128;            // query rows per tile (UMMA M)
-constexpr int NTHREADS = 320;
-constexpr int KV_STAGES = 3;
+constexpr int NTHREADS = 384;  // warpgroup 0: softmax tile A, warpgroup 1: softmax tile B, warpgroup 2: TMA warp, MMA warp, 2 idle
+constexpr int KV_STAGES = 2;
 
 template <int HD>
 struct Cfg {
@@ -37,7 +37,7 @@ struct Cfg {
   static constexpr int OFF_K = OFF_Q + 2 * Q_TILE_BYTES;
   static constexpr int OFF_V = OFF_K + KV_STAGES * K_TILE_BYTES;
   static constexpr int OFF_P = OFF_V + KV_STAGES * V_TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_P + 2 * P_TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 4 * P_TILE_BYTES;   // P double-buffered per query tile
   static constexpr int SMEM = OFF_BAR + 512 + 1024;
   static constexpr int S_COL = 0;                            // TMEM columns: S_A, S_B, O_A, O_B
   static constexpr int O_COL = 2 * BKV;
@@ -48,18 +48,37 @@ struct Cfg {
 struct Bars {
   uint64_t q_full;
   uint64_t k_full[KV_STAGES], k_empty[KV_STAGES], v_full[KV_STAGES], v_empty[KV_STAGES];
-  uint64_t s_full[2], s_free[2], p_ready[2], pv_done[2];
+  uint64_t s_full[2], s_free[2], p_ready[2], pv_done[2][2];  // pv_done[tile][P buffer]
   uint32_t tmem_slot;
 };
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
+// packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): halves the issue slots of the scale-and-shift and of the row sums
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float f2_lo(unsigned long long v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ float f2_hi(unsigned long long v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 template <int HD>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __maxnreg__(168)
 attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int Lq, int Lk,
                       float scale_log2e) {
@@ -77,7 +96,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int kv_row0 = batch * Lk;
   const int col0 = head * HD;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
     ptx::mbar_init(&bars->q_full, 1);
     for (int i = 0; i < KV_STAGES; ++i) {
@@ -86,18 +105,19 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
     for (int t = 0; t < 2; ++t) {
       ptx::mbar_init(&bars->s_full[t], 1); ptx::mbar_init(&bars->s_free[t], 4);
-      ptx::mbar_init(&bars->p_ready[t], 4); ptx::mbar_init(&bars->pv_done[t], 1);
+      ptx::mbar_init(&bars->p_ready[t], 4); ptx::mbar_init(&bars->pv_done[t][0], 1); ptx::mbar_init(&bars->pv_done[t][1], 1);
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 1) { ptx::tmem_alloc(&bars->tmem_slot, C::TMEM_COLS); ptx::tmem_relinquish(); }
+  if (warp == 9) { ptx::tmem_alloc(&bars->tmem_slot, C::TMEM_COLS); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 8) {
     // ============================================================ TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     if (lane == 0) {
       ptx::mbar_expect_tx(&bars->q_full, n_tiles * C::Q_TILE_BYTES);
       for (int t = 0; t < n_tiles; ++t)
@@ -126,8 +146,9 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       __syncwarp();
       if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == 1) {
+  } else if (warp == 9) {
     // ============================================================ MMA issuer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(QT, C::BKV, 0, 0);  // S = Q K^T : both K-major
     constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(QT, HD, 0, 1);      // O = P V   : A K-major, B (V) MN-major
     const uint32_t sQ = ptx::smem_u32(smem + C::OFF_Q), sK = ptx::smem_u32(smem + C::OFF_K);
@@ -141,10 +162,10 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         ptx::umma_bf16_ss(tmem + C::S_COL + t * C::BKV, a, b, idesc_s, k != 0);
       }
     };
-    auto issue_PV = [&](int t, int stage, bool accumulate) {
+    auto issue_PV = [&](int t, int stage, int pbuf, bool accumulate) {
 #pragma unroll
       for (int k = 0; k < C::BKV / 16; ++k) {
-        const uint64_t a = ptx::umma_desc_sw128(sP + t * C::P_TILE_BYTES + (k / 4) * (QT * 128) + (k % 4) * 32, 16, 1024);
+        const uint64_t a = ptx::umma_desc_sw128(sP + (t * 2 + pbuf) * C::P_TILE_BYTES + (k / 4) * (QT * 128) + (k % 4) * 32, 16, 1024);
         // V block: rows = keys (K dim), 64-wide column blocks (N dim) C::BKV*128 bytes apart; 16 keys per step
         const uint64_t b = ptx::umma_desc_sw128(sV + stage * C::V_TILE_BYTES + k * (16 * 128), C::BKV * 128, 1024);
         ptx::umma_bf16_ss(tmem + C::O_COL + t * HD, a, b, idesc_o, (accumulate || k != 0) ? 1u : 0u);
@@ -181,7 +202,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int t = 0; t < n_tiles; ++t) {
         ptx::mbar_wait(&bars->p_ready[t], i & 1);
         ptx::tc_fence_after();
-        if (lane == 0) { issue_PV(t, stage, i > 0); ptx::umma_commit(&bars->pv_done[t]); }
+        if (lane == 0) { issue_PV(t, stage, i & 1, i > 0); ptx::umma_commit(&bars->pv_done[t][i & 1]); }
         __syncwarp();
       }
       if (lane == 0) ptx::umma_commit(&bars->v_empty[stage]);
@@ -189,17 +210,23 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       stage = nstage;
       phase = nphase;
     }
+  } else if (warp >= 10) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");  // idle warps of warpgroup 2 (the instruction is warpgroup-wide)
   } else {
     // ============================================================ softmax / correction / epilogue
-    const int t = (warp - 2) >> 2;             // 0: tile A (warps 2-5), 1: tile B (warps 6-9)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const int t = warp >> 2;                   // 0: tile A (warps 0-3), 1: tile B (warps 4-7)
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;         // query row within the tile == TMEM lane
     if (t < n_tiles) {
       const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
       const uint32_t tS = tmem + lane_addr + C::S_COL + t * C::BKV;
       const uint32_t tO = tmem + lane_addr + C::O_COL + t * HD;
-      uint8_t* sP = smem + C::OFF_P + t * C::P_TILE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
-      float m_run = -INFINITY, l_run = 0.f;
+      uint8_t* sP0 = smem + C::OFF_P + (t * 2) * C::P_TILE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+      // m_ref is the reference maximum used inside exp2; it trails the true running maximum by at most 8 (log2
+      // units), so P <= 2^8 and O / l stay exact after the final division, while the TMEM rescale of O (and the wait
+      // for the previous PV product it needs) only happens on the rare block where a row's maximum jumps by more.
+      float m_ref = -INFINITY, l_run = 0.f;
       for (int i = 0; i < n_kv; ++i) {
         ptx::mbar_wait(&bars->s_full[t], i & 1);
         ptx::tc_fence_after();
@@ -215,26 +242,55 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
           for (int c = 0; c < C::BKV; ++c) if (c >= kv_valid) s[c] = -INFINITY;
         }
-        float m_new = m_run;
+        // the P buffer of this parity was last read by PV(i-2)
+        if (i >= 2) ptx::mbar_wait(&bars->pv_done[t][i & 1], ((i - 2) >> 1) & 1);
+        uint8_t* sP = sP0 + (i & 1) * C::P_TILE_BYTES;
+        // exp2 (packed fp32x2 scale-and-shift), row sum, and P (bf16) straight into shared memory in the K-major
+        // 128B-swizzled layout of the UMMA A operand; returns the row sum of this block
+        auto emit_P = [&](float m_use) -> float {
+          const float nmb = -m_use * scale_log2e;
+          const unsigned long long sc2 = f2_pack(scale_log2e, scale_log2e), nmb2 = f2_pack(nmb, nmb);
+          unsigned long long sum2[2] = {0ull, 0ull};
 #pragma unroll
-        for (int c = 0; c < C::BKV; ++c) m_new = fmaxf(m_new, s[c]);
-        const float alpha = ex2((m_run - m_new) * scale_log2e);
-        const float mb = m_new * scale_log2e;
-        float sum = 0.f;
-        uint32_t pk[C::BKV / 2];
+          for (int j = 0; j < C::BKV / 8; ++j) {
+            float p[8];
 #pragma unroll
-        for (int c = 0; c < C::BKV; c += 2) {
-          const float p0 = ex2(fmaf(s[c], scale_log2e, -mb));
-          const float p1 = ex2(fmaf(s[c + 1], scale_log2e, -mb));
-          sum += p0 + p1;
-          pk[c / 2] = ptx::pack_bf16(p0, p1);
+            for (int e = 0; e < 8; e += 2) {
+              const unsigned long long x = f2_fma(f2_pack(s[8 * j + e], s[8 * j + e + 1]), sc2, nmb2);
+              p[e] = ex2(f2_lo(x));
+              p[e + 1] = ex2(f2_hi(x));
+            }
+            sum2[0] = f2_add(sum2[0], f2_add(f2_pack(p[0], p[1]), f2_pack(p[4], p[5])));
+            sum2[1] = f2_add(sum2[1], f2_add(f2_pack(p[2], p[3]), f2_pack(p[6], p[7])));
+            const int kb = j >> 3, chunk = j & 7;
+            const uint4 v = make_uint4(ptx::pack_bf16(p[0], p[1]), ptx::pack_bf16(p[2], p[3]), ptx::pack_bf16(p[4], p[5]), ptx::pack_bf16(p[6], p[7]));
+            *reinterpret_cast<uint4*>(sP + kb * (QT * 128) + ((chunk ^ (r & 7)) << 4)) = v;
+          }
+          const unsigned long long tot = f2_add(sum2[0], sum2[1]);
+          return f2_lo(tot) + f2_hi(tot);
+        };
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < C::BKV; c += 4) {
+          mx[0] = fmaxf(mx[0], s[c]); mx[1] = fmaxf(mx[1], s[c + 1]); mx[2] = fmaxf(mx[2], s[c + 2]); mx[3] = fmaxf(mx[3], s[c + 3]);
         }
-        l_run = l_run * alpha + sum;
-        if (i > 0) {
-          // PV(i-1) must have retired before P is overwritten and before O is rescaled
-          ptx::mbar_wait(&bars->pv_done[t], (i - 1) & 1);
-          ptx::tc_fence_after();
-          if (__any_sync(0xffffffffu, m_new != m_run)) {
+        const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        float blk_sum;
+        if (i == 0) {
+          m_ref = m_blk;
+          blk_sum = emit_P(m_ref);
+        } else {
+          // optimistic: exponentiate against the trailing reference maximum (no dependence on this block's maximum, so
+          // the MUFU work starts as soon as S is in registers); redo only if some row's maximum jumped by > 2^8
+          blk_sum = emit_P(m_ref);
+          const bool jump = (m_blk - m_ref) * scale_log2e > 8.0f;
+          if (__any_sync(0xffffffffu, jump)) {
+            // rescale O in TMEM: every earlier PV product must have retired (they complete in order)
+            ptx::mbar_wait(&bars->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
+            ptx::tc_fence_after();
+            const float alpha = jump ? ex2((m_ref - m_blk) * scale_log2e) : 1.0f;
+            if (jump) m_ref = m_blk;
+            l_run *= alpha;
 #pragma unroll
             for (int c = 0; c < HD; c += 16) {
               uint32_t o[16];
@@ -245,23 +301,17 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
               ptx::tmem_st_32x32b_x16(tO + c, o);
             }
             ptx::tmem_st_wait();
+            blk_sum = emit_P(m_ref);
           }
         }
-        m_run = m_new;
-        // P (bf16) into shared memory in the K-major 128B-swizzled layout the UMMA A descriptor expects
-#pragma unroll
-        for (int j = 0; j < C::BKV / 8; ++j) {
-          const int kb = j >> 3, chunk = j & 7;
-          uint4 v = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          *reinterpret_cast<uint4*>(sP + kb * (QT * 128) + ((chunk ^ (r & 7)) << 4)) = v;
-        }
+        l_run += blk_sum;
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->p_ready[t]);
       }
       // ---- epilogue: O / l -> bf16 -> global
-      ptx::mbar_wait(&bars->pv_done[t], (n_kv - 1) & 1);
+      ptx::mbar_wait(&bars->pv_done[t][(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
       ptx::tc_fence_after();
       const float inv_l = 1.0f / l_run;
       const int q_local = q0 + t * QT + r;
@@ -288,7 +338,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
+  if (warp == 9) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
 template <int HD>
