@@ -153,6 +153,21 @@ int lsvs_camera_head_forward(lsvs_engine* e, const float* tokens_last, int B, in
 int lsvs_pose_chain(const float* chunk_sim3, const float* frame_se3, const float* cam_enc, const float* prev_pose_enc,
                     int S_prev, int overlap, int B, int S, int H, int W, float* pose_enc_out, float* point_T,
                     float* scale_out, void* stream);
+/* replaces pointAligned_wrapped_vggt.py:113-122: pose_enc (B,S,9) -> extrinsics -> apply_sim3_alignment_on_w2c (alignment.py:528)
+ * -> pose_enc (B,S,9), FoV entries passed through the reference's tan/atan round trip. */
+int lsvs_pose_enc_apply_sim3(const float* pose_enc, const float* T, const float* s, float* out, int B, int S, int H, int W, void* stream);
+
+/* ---- IRLS weighted Umeyama Sim(3) (point-aligned baseline) ---------------------------------------
+ * replaces irls_sim3_umeyama / weighted_umeyama_sim3  aligned_vggt/models/pointAligned_wrapped_vggt.py:159-305.
+ * src, dst: (n_points,3) fp32; conf_src, conf_dst: (n_points) fp32.  Finds (R (3,3), t (3), s ()) with
+ * dst ~ s R src + t: w0 = sqrt(conf_src*conf_dst), points with w0 < factor*median(w0) dropped, one weighted Umeyama
+ * solve, then up to max_iters Huber(delta)-reweighted solves (stops early when |dR|,|dt|,|ds| < tol).
+ * No host synchronisation; *status (device int) is set to 1 if the total weight is too small (the reference raises
+ * ValueError).  workspace: lsvs_irls_umeyama_workspace_bytes() bytes of device memory. */
+size_t lsvs_irls_umeyama_workspace_bytes(void);
+int lsvs_irls_umeyama(const float* src, const float* dst, const float* conf_src, const float* conf_dst, long long n_points,
+                      float conf_threshold_factor, float delta, int max_iters, float tol, float* R, float* t, float* s,
+                      int* status, void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -670,3 +670,8 @@ extern "C" int lsvs_alignment_decode_forward(lsvs_engine* h, const float* align_
   TRY(upload_ids(e.ids_k, dec, st));
   return decode_forward(e, align_tokens, 1024, B, S, e.ids_k.as<int>(), memory_in, chunk_sim3, frame_se3, memory_out, st);
 }
+
+extern "C" int lsvs_pose_enc_apply_sim3(const float* pose_enc, const float* T, const float* s, float* out, int B, int S, int H, int W,
+                                        void* stream) {
+  return lsvs::pose_enc_apply_sim3(pose_enc, T, s, out, B, S, H, W, (cudaStream_t)stream);
+}

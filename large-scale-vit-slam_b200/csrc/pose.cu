@@ -173,7 +173,37 @@ __global__ void __launch_bounds__(128) pose_chain_kernel(const float* __restrict
   }
 }
 
+// pose_enc -> w2c extrinsics -> Sim(3) applied in camera-to-world space -> back to a pose encoding
+// (pointAligned_wrapped_vggt.py:113-122 = pose_encoding_to_extri_intri -> apply_sim3_alignment_on_w2c, alignment.py:528-594
+//  -> extri_intri_to_pose_encoding).  One thread per frame.
+__global__ void pose_enc_sim3_kernel(const float* __restrict__ enc, const float* __restrict__ T, const float* __restrict__ s,
+                                     float* __restrict__ out, int B, int S, int H, int W) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * S) return;
+  const int b = idx / S;
+  const float* e = enc + (size_t)idx * 9;
+  M4 c2w = inv_se3(enc_to_mat(e, false));
+  const float sc = s[b];
+  c2w.m[3] *= sc; c2w.m[7] *= sc; c2w.m[11] *= sc;
+  M4 Tb;
+  for (int i = 0; i < 16; ++i) Tb.m[i] = T[(size_t)b * 16 + i];
+  const M4 w2c = inv_se3(mul(Tb, c2w));
+  float* o = out + (size_t)idx * 9;
+  o[0] = w2c.m[3]; o[1] = w2c.m[7]; o[2] = w2c.m[11];
+  mat_to_quat(w2c, o + 3);
+  const float fy = (H / 2.0f) / tanf(e[7] / 2.0f), fx = (W / 2.0f) / tanf(e[8] / 2.0f);
+  o[7] = 2.0f * atanf((H / 2.0f) / fy);
+  o[8] = 2.0f * atanf((W / 2.0f) / fx);
+}
+
 }  // namespace
+
+int pose_enc_apply_sim3(const float* enc, const float* T, const float* s, float* out, int B, int S, int H, int W, cudaStream_t st) {
+  LSVS_CHECK_ARG(enc && T && s && out && B > 0 && S > 0, "pose_enc_apply_sim3: Inputs must have matching batch dimension");
+  pose_enc_sim3_kernel<<<(B * S + 127) / 128, 128, 0, st>>>(enc, T, s, out, B, S, H, W);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
 
 int pose_chain(const float* chunk_sim3, const float* frame_se3, const float* cam_enc, const float* prev_pose_enc, int S_prev,
                int overlap, int B, int S, int H, int W, float* pose_enc_out, float* point_T, float* scale_out, cudaStream_t st) {

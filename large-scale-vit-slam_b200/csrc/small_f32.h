@@ -33,4 +33,10 @@ int combine_rows(const float* a, long long lda, const float* b, long long ldb, f
 int pose_chain(const float* chunk_sim3, const float* frame_se3, const float* cam_enc, const float* prev_pose_enc, int S_prev,
                int overlap, int B, int S, int H, int W, float* pose_enc_out, float* point_T, float* scale_out, cudaStream_t st);
 
+int pose_enc_apply_sim3(const float* enc, const float* T, const float* s, float* out, int B, int S, int H, int W, cudaStream_t st);
+// IRLS weighted Umeyama (csrc/umeyama.cu); status: 0 ok, 1 = total weight too small
+size_t irls_umeyama_workspace_bytes();
+int irls_umeyama(const float* src, const float* dst, const float* conf_src, const float* conf_dst, long long M, float factor, float delta,
+                 int max_iters, float tol, float* R, float* t, float* s, int* status, void* workspace, cudaStream_t stream);
+
 }  // namespace lsvs

@@ -178,3 +178,14 @@ def pose_chain(chunk_sim3: torch.Tensor, frame_se3: torch.Tensor, cam_enc: torch
     _n.check(_n.lib().lsvs_pose_chain(_n.ptr(cs), _n.ptr(fs), _n.ptr(ce), _n.ptr(prev), _i(S_prev), _i(overlap), _i(B), _i(S),
                                       _i(H), _i(W), _n.ptr(pose), _n.ptr(pt), _n.ptr(sc), _n.stream_ptr()), "pose_chain")
     return pose, pt, sc
+
+
+def pose_enc_apply_sim3(pose_enc: torch.Tensor, T: torch.Tensor, s: torch.Tensor, image_hw) -> torch.Tensor:
+    """pose_enc (B,S,9) w2c encodings -> Sim(3)-aligned encodings (pointAligned_wrapped_vggt.py:113-122)."""
+    B, S, _ = pose_enc.shape
+    H, W = image_hw
+    pe, Tm, sc = pose_enc.detach().float().contiguous(), T.detach().float().contiguous(), s.detach().float().reshape(B).contiguous()
+    out = torch.empty_like(pe)
+    _n.check(_n.lib().lsvs_pose_enc_apply_sim3(_n.ptr(pe), _n.ptr(Tm), _n.ptr(sc), _n.ptr(out), _i(B), _i(S), _i(H), _i(W), _n.stream_ptr()),
+             "pose_enc_apply_sim3")
+    return out

@@ -425,3 +425,29 @@ def feature_aligned_forward(p: Params, images: torch.Tensor, num_overlap: int, c
         out["world_points"] = apply_sim3_points(raw_points, Tp, scale.view(B))  # :198-207
         out["point_transform"] = Tp
     return out
+
+
+def pose_aligned_forward(p: Params, images: torch.Tensor, num_overlap: int, context: Optional[dict] = None, *,
+                         raw_points: Optional[torch.Tensor] = None, depth: int = 24, dino_depth: int = 24,
+                         taps=(4, 11, 17, 23)) -> dict:
+    """pose-aligned baseline VGGT.forward (eval, gt_poses=None) — aligned_vggt/models/poseAligned_wrapped_vggt.py:36-204.
+    Same chain as the feature-aligned model with identity learned alignment and unit scale (:107-130, :171-187)."""
+    B, S, _, H, W = images.shape
+    toks, _ = OF.aggregator_forward(p, "aggregator.", images, depth=depth, dino_depth=dino_depth, keep=taps)
+    cam_enc = OF.camera_head_forward(p, "camera_head.", toks[taps[-1]])[-1]
+    eye = torch.eye(4).view(1, 1, 4, 4).expand(B, S, -1, -1)
+    prev = context["pose_enc"] if context is not None else None
+    pose_enc, per_frame, pt_ident = pose_chain(cam_enc, (H, W), eye, torch.ones(B, 1), prev, num_overlap)
+    out = {"pose_enc": pose_enc, "camera_pose_enc": cam_enc}
+    if raw_points is not None:
+        Tp = point_transform(per_frame, pt_ident, context is not None)
+        out["world_points"] = apply_sim3_points(raw_points, Tp, torch.ones(B))
+        out["point_transform"] = Tp
+    return out
+
+
+def pose_enc_apply_sim3(pose_enc: torch.Tensor, image_hw, T: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    """pointAligned_wrapped_vggt.py:113-122: pose_enc -> extrinsics -> apply_sim3_alignment_on_w2c -> pose_enc."""
+    extr, intr = OF.pose_encoding_to_extri_intri(pose_enc, image_size_hw=image_hw)
+    aligned = apply_sim3_w2c(extr, T, s)
+    return OF.extri_intri_to_pose_encoding(aligned, intr, image_size_hw=image_hw)

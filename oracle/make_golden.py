@@ -252,6 +252,44 @@ def case_model_small():
     run_two_chunks(model, sd, 4, 56, 84, 2, (0, 0, 1, 1), 2, 2, "small")
 
 
+def case_pose_aligned_small():
+    """pose-aligned baseline (poseAligned_wrapped_vggt.VGGT, real reference class) over two chained chunks."""
+    print("[pose-aligned VGGT, depth 2/2, S=4, 56x84, overlap 2]")
+    from aligned_vggt.models.poseAligned_wrapped_vggt import VGGT
+    os.environ["VGGT_SHIM_DEPTH"] = "2,2"
+    with torch.device("meta"):
+        model = VGGT(enable_point=False, enable_depth=False, enable_track=False)
+    sd = OW.fill_state_dict(OW.spec_of(model), seed=0)
+    model = model.to_empty(device="cpu")
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    model.intermediate_layer_indices = [0, 0, 1, 1]
+    S, H, W, ov = 4, 56, 84, 2
+    imgs = [torch.from_numpy(np.random.Generator(np.random.PCG64(100 + i)).random((1, S, 3, H, W), dtype=np.float32)) for i in range(2)]
+    r1 = model(imgs[0], ov)
+    e1 = r1["pose_enc"][-1].clone()
+    r2 = model(imgs[1], ov, r1)
+    e2 = r2["pose_enc"][-1].clone()
+    o1 = OA.pose_aligned_forward(sd, imgs[0], ov, None, depth=2, dino_depth=2, taps=(0, 0, 1, 1))
+    o2 = OA.pose_aligned_forward(sd, imgs[1], ov, {"pose_enc": o1["pose_enc"]}, depth=2, dino_depth=2, taps=(0, 0, 1, 1))
+    check("pose-aligned c1 pose_enc", o1["pose_enc"], e1, 5e-4)
+    check("pose-aligned c2 pose_enc", o2["pose_enc"], e2, 5e-4)
+    save("model_pose_aligned_small.npz", S=S, H=H, W=W, ov=ov, wsum=OW.checksum(sd), c1_pose_enc=e1, c2_pose_enc=e2)
+    # function-level fixture for the point-aligned pose update (pointAligned_wrapped_vggt.py:113-122), real reference helpers
+    from aligned_vggt.utils.alignment import apply_sim3_alignment_on_w2c
+    from vggt.vggt.utils.pose_enc import extri_intri_to_pose_encoding, pose_encoding_to_extri_intri
+    q = rnd(11, 2, 4)
+    T = torch.eye(4).repeat(2, 1, 1)
+    T[:, :3, :3] = OF.quat_to_mat(q / q.norm(dim=-1, keepdim=True))
+    T[:, :3, 3] = rnd(12, 2, 3, scale=3.0)
+    s = torch.tensor([0.7, 1.9])
+    enc = torch.cat([rnd(40, 2, 5, 3), torch.nn.functional.normalize(rnd(41, 2, 5, 4), dim=-1), 0.5 + 0.3 * torch.rand(2, 5, 2, generator=torch.Generator().manual_seed(42))], -1)
+    extr, intr = pose_encoding_to_extri_intri(enc, (H, W))
+    ref = extri_intri_to_pose_encoding(apply_sim3_alignment_on_w2c(extr, T, s), intr, (H, W))
+    check("pose_enc_apply_sim3", OA.pose_enc_apply_sim3(enc, (H, W), T, s), ref, 1e-5)
+    save("pose_enc_sim3.npz", enc=enc, T=T, s=s, H=H, W=W, out=ref)
+
+
 def case_model_full():
     print("[FeatureAlignedVGGT, full depth, config 1: S=4, 154x518, overlap 1]")
     model, sd = build_reference_model(None)
@@ -266,7 +304,8 @@ if __name__ == "__main__":
     args = ap.parse_args()
     torch.manual_seed(0)
     os.makedirs(GOLD, exist_ok=True)
-    cases = {"spec": case_spec, "layers": case_layers, "geometry": case_geometry, "head": case_head, "model_small": case_model_small}
+    cases = {"spec": case_spec, "layers": case_layers, "geometry": case_geometry, "head": case_head, "model_small": case_model_small,
+             "pose_aligned": case_pose_aligned_small}
     if args.full:
         cases["model_full"] = case_model_full
     for name, fn in cases.items():
