@@ -1,4 +1,6 @@
-"""Body of __graft_entry__.smoke(): small hot-path invocation on cuda:0 checked against the oracle."""
+"""Body of __graft_entry__.smoke(): one small invocation of the hot path on cuda:0 checked against the CPU oracle:
+a reduced-depth FeatureAlignedVGGT (1 DINO block, 1 frame/global pair, full-width alignment head + camera head) over
+two chained 3-frame chunks, plus the Sim(3) application on a synthetic point map."""
 import numpy as np
 import torch
 
@@ -10,16 +12,31 @@ def rnd(seed, *shape, scale=1.0):
 
 def run():
     from oracle import aligned as OA
-    from oracle import functional as OF
-    from aligned_vggt.utils import alignment as A
+    from oracle import weights as OW
+    from aligned_vggt.models.featureAligned_vggt import FeatureAlignedVGGT
+    torch.set_grad_enabled(False)
     dev = torch.device("cuda:0")
-    pts = rnd(1, 2, 3, 16, 20, 3, scale=10.0)
-    q = torch.nn.functional.normalize(rnd(2, 2, 4), dim=-1)
-    T = torch.eye(4).repeat(2, 1, 1)
-    T[:, :3, :3] = OF.quat_to_mat(q)
-    T[:, :3, 3] = rnd(3, 2, 3)
-    s = torch.tensor([0.5, 2.0])
-    got = A.apply_sim3_alignment_on_point_maps(pts.to(dev), T.to(dev), s.to(dev)).cpu()
-    ref = OA.apply_sim3_points(pts, T, s)
-    err = float((got - ref).abs().max() / ref.abs().max())
-    assert err < 1e-5, f"sim3 apply mismatch {err}"
+    taps = (0, 0, 0, 0)
+    model = FeatureAlignedVGGT(enable_point=False, enable_depth=False, enable_track=False, depth=1, patch_embed_depth=1,
+                               intermediate_layer_indices=taps)
+    sd = OW.fill_state_dict([(k, tuple(v.shape)) for k, v in model.state_dict().items()], seed=0)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).eval()
+    S, H, W, ov = 3, 28, 42, 1
+    g = np.random.Generator(np.random.PCG64(5))
+    imgs = [torch.from_numpy(g.random((1, S, 3, H, W), dtype=np.float32)) for _ in range(2)]
+    pts = rnd(1, 1, S, H, W, 3, scale=5.0)
+    p1 = model(imgs[0].to(dev), ov, None, raw_points=pts.to(dev))
+    p2 = model(imgs[1].to(dev), ov, p1, raw_points=pts.to(dev))
+    o1 = OA.feature_aligned_forward(sd, imgs[0], ov, None, raw_points=pts, depth=1, dino_depth=1, taps=taps)
+    ctx = {"overlap_tokens": o1["overlap_tokens"], "memory_tokens": o1["memory_tokens"], "pose_enc": o1["pose_enc"]}
+    o2 = OA.feature_aligned_forward(sd, imgs[1], ov, ctx, raw_points=pts, depth=1, dino_depth=1, taps=taps)
+
+    def rel(a, b):
+        return float((a.float().cpu() - b).norm() / b.norm())
+    errs = {"overlap_tokens": rel(p2["overlap_tokens"], o2["overlap_tokens"]), "memory": rel(p2["memory_tokens"][-1], o2["memory_tokens"]),
+            "sim3": rel(p2["chunk_sim3_alignment_enc"][:, -1:], o2["chunk_sim3_alignment_enc"]), "pose_enc": rel(p2["pose_enc"][-1], o2["pose_enc"]),
+            "world_points": rel(p2["world_points"][-1], o2["world_points"])}
+    print("smoke rel-L2 vs CPU oracle:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["overlap_tokens"] < 1e-2 and errs["memory"] < 1e-2, errs
+    assert errs["sim3"] < 3e-2 and errs["pose_enc"] < 3e-2 and errs["world_points"] < 3e-2, errs
