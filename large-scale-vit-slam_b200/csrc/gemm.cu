@@ -28,7 +28,8 @@ struct SmemLayout {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + slack for 1024-byte alignment
+  static constexpr int PARAM_OFFSET = BAR_OFFSET + 256;
+  static constexpr int TOTAL = PARAM_OFFSET + 2048 + 1024;  // barriers + epilogue params + slack for 1024-byte alignment
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -66,44 +67,70 @@ __device__ __forceinline__ void pos2d(const GemmEpilogue& e, int m, int& py, int
 }
 
 // Rotate pairs (j, j+R/2) of the R-wide region v[0..R) by angle table row `tab` (cos,sin per frequency).
-template <int R>
-__device__ __forceinline__ void rope_region(float* v, const float2* __restrict__ tab) {
-#pragma unroll
-  for (int j = 0; j < R / 2; ++j) {
-    const float2 cs = __ldg(tab + j);
-    const float a = v[j], b = v[j + R / 2];
-    v[j] = a * cs.x - b * cs.y;
-    v[j + R / 2] = b * cs.x + a * cs.y;
+// q/k LayerNorm parameters staged once per CTA in shared memory (broadcast LDS.128 instead of one LDG per element)
+struct EpiSmem { float qn_w[128], qn_b[128], kn_w[128], kn_b[128]; };
+
+__device__ __forceinline__ void stage_epi_params(EpiSmem* sp, const GemmEpilogue& e, int hd) {
+  const int t = threadIdx.x;
+  if (t < hd) {
+    sp->qn_w[t] = e.qn_w ? __ldg(e.qn_w + t) : 1.f; sp->qn_b[t] = e.qn_b ? __ldg(e.qn_b + t) : 0.f;
+    sp->kn_w[t] = e.kn_w ? __ldg(e.kn_w + t) : 1.f; sp->kn_b[t] = e.kn_b ? __ldg(e.kn_b + t) : 0.f;
   }
 }
 
-// bias + LayerNorm over one head (HD columns, all in this thread) + RoPE, in place.
+// Rotate pairs (j, j+R/2) of the R-wide region v[0..R) by the angle table row `tab4` ((cos,sin) per frequency, two
+// frequencies per 16-byte load).
+template <int R>
+__device__ __forceinline__ void rope_region(float* v, const float4* __restrict__ tab4) {
+#pragma unroll
+  for (int j = 0; j < R / 2; j += 2) {
+    const float4 cs = __ldg(tab4 + j / 2);
+    const float a0 = v[j], b0 = v[j + R / 2], a1 = v[j + 1], b1 = v[j + 1 + R / 2];
+    v[j] = a0 * cs.x - b0 * cs.y;
+    v[j + R / 2] = b0 * cs.x + a0 * cs.y;
+    v[j + 1] = a1 * cs.z - b1 * cs.w;
+    v[j + 1 + R / 2] = b1 * cs.z + a1 * cs.w;
+  }
+}
+
+// bias + LayerNorm over one head (HD columns, all in this thread) + RoPE, in place.  bias: global (16-byte loads),
+// w / b: shared-memory copies of the head LayerNorm parameters.
 template <int HD>
-__device__ __forceinline__ void head_norm_rope(float* v, const float* __restrict__ bias, const float* __restrict__ w,
-                                               const float* __restrict__ b, const GemmEpilogue& e, int m) {
+__device__ __forceinline__ void head_norm_rope(float* v, const float* __restrict__ bias, const float* w, const float* b,
+                                               const GemmEpilogue& e, int m) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < HD; ++i) { v[i] += __ldg(bias + i); s += v[i]; }
+  for (int i = 0; i < HD; i += 4) {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + i));
+    v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+    s += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
+  }
   const float mean = s * (1.0f / HD);
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < HD; ++i) { const float d = v[i] - mean; q += d * d; }
   const float rstd = rsqrtf(q * (1.0f / HD) + e.ln_eps);
 #pragma unroll
-  for (int i = 0; i < HD; ++i) v[i] = (v[i] - mean) * rstd * __ldg(w + i) + __ldg(b + i);
+  for (int i = 0; i < HD; i += 4) {
+    const float4 ww = *reinterpret_cast<const float4*>(w + i), bb = *reinterpret_cast<const float4*>(b + i);
+    v[i] = (v[i] - mean) * rstd * ww.x + bb.x;
+    v[i + 1] = (v[i + 1] - mean) * rstd * ww.y + bb.y;
+    v[i + 2] = (v[i + 2] - mean) * rstd * ww.z + bb.z;
+    v[i + 3] = (v[i + 3] - mean) * rstd * ww.w + bb.w;
+  }
   if (e.rope_mode == ROPE_2D) {
     int py, px;
     pos2d(e, m, py, px);
-    rope_region<HD / 2>(v, e.rope_tab + (size_t)py * (HD / 4));
-    rope_region<HD / 2>(v + HD / 2, e.rope_tab + (size_t)px * (HD / 4));
+    rope_region<HD / 2>(v, reinterpret_cast<const float4*>(e.rope_tab + (size_t)py * (HD / 4)));
+    rope_region<HD / 2>(v + HD / 2, reinterpret_cast<const float4*>(e.rope_tab + (size_t)px * (HD / 4)));
   } else if (e.rope_mode == ROPE_1D) {
     const int p = __ldg(e.pos_ids + (m % e.pos_period));
-    rope_region<HD>(v, e.rope_tab + (size_t)p * (HD / 2));
+    rope_region<HD>(v, reinterpret_cast<const float4*>(e.rope_tab + (size_t)p * (HD / 2)));
   }
 }
 
 template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, uint32_t taddr, int m, int n0, bool row_ok, int c_begin = 0, int c_end = BN) {
+__device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, const EpiSmem* sp, uint32_t taddr, int m, int n0, bool row_ok, int c_begin = 0, int c_end = BN) {
   if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_F32) {
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 32) {
@@ -113,10 +140,11 @@ __device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, uint32_t tad
       if (row_ok) {
         const int n = n0 + c;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = v[i] + (e.bias ? __ldg(e.bias + n + i) : 0.f);
-          if constexpr (EPI == EPI_BIAS_GELU_BF16) x = gelu_erf(x);
-          v[i] = x;
+        for (int i = 0; i < 32; i += 4) {
+          const float4 bb = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float x0 = v[i] + bb.x, x1 = v[i + 1] + bb.y, x2 = v[i + 2] + bb.z, x3 = v[i + 3] + bb.w;
+          if constexpr (EPI == EPI_BIAS_GELU_BF16) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
+          v[i] = x0; v[i + 1] = x1; v[i + 2] = x2; v[i + 3] = x3;
         }
         if constexpr (EPI == EPI_BIAS_F32) {
           float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)m * e.ldo + n);
@@ -178,12 +206,15 @@ __device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, uint32_t tad
       if (!row_ok) continue;  // reconverges at the __syncwarp above / after the loop
       const int n = n0 + c;
       if (n < e.n_q_cols) {
-        head_norm_rope<HD>(v, e.bias + n, e.qn_w, e.qn_b, e, m);
+        head_norm_rope<HD>(v, e.bias + n, sp->qn_w, sp->qn_b, e, m);
       } else if (n < e.n_q_cols + e.n_k_cols) {
-        head_norm_rope<HD>(v, e.bias + n, e.kn_w, e.kn_b, e, m);
+        head_norm_rope<HD>(v, e.bias + n, sp->kn_w, sp->kn_b, e, m);
       } else {
 #pragma unroll
-        for (int i = 0; i < HD; ++i) v[i] += __ldg(e.bias + n + i);
+        for (int i = 0; i < HD; i += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(e.bias + n + i));
+          v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+        }
       }
       store_bf16_row<HD>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ldo + n, v);
     }
@@ -202,6 +233,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  EpiSmem* sp = reinterpret_cast<EpiSmem*>(smem + L::PARAM_OFFSET);
+  if constexpr (EPI == EPI_HEADNORM64_BF16 || EPI == EPI_HEADNORM128_BF16) stage_epi_params(sp, epi, EPI == EPI_HEADNORM64_BF16 ? 64 : 128);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -286,7 +319,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ptx::tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
-      epilogue_row<BN, EPI>(epi, taddr, m, n0, m < M);
+      epilogue_row<BN, EPI>(epi, sp, taddr, m, n0, m < M);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tmem_empty + acc);
@@ -313,7 +346,8 @@ struct Smem2 {
   static constexpr int B_BYTES = (BN2 / 2) * BK * 2;   // 16 KB: this CTA's half of the weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES2 * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+  static constexpr int PARAM_OFFSET = BAR_OFFSET + 256;
+  static constexpr int TOTAL = PARAM_OFFSET + 2048 + 1024;
 };
 
 template <int EPI, int EW>  // EW epilogue warps per CTA (4 or 8)
@@ -328,6 +362,8 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* tmem_full = empty_bar + STAGES2;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  EpiSmem* sp = reinterpret_cast<EpiSmem*>(smem + L::PARAM_OFFSET);
+  if constexpr (EPI == EPI_HEADNORM64_BF16 || EPI == EPI_HEADNORM128_BF16) stage_epi_params(sp, epi, EPI == EPI_HEADNORM64_BF16 ? 64 : 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta = ptx::cluster_ctarank();  // 0 = leader
@@ -421,7 +457,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       ptx::tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2;
-      epilogue_row<BN2, EPI>(epi, taddr, m, n0, m < M, part * COLS, (part + 1) * COLS);
+      epilogue_row<BN2, EPI>(epi, sp, taddr, m, n0, m < M, part * COLS, (part + 1) * COLS);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
