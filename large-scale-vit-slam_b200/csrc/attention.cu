@@ -22,33 +22,40 @@ namespace lsvs {
 namespace {
 
 constexpr int QT = 128;            // query rows per tile (UMMA M)
-constexpr int NTHREADS = 384;  // warpgroup 0: softmax tile A, warpgroup 1: softmax tile B, warpgroup 2: TMA warp, MMA warp, 2 idle
+// threads = (NT + 1) warpgroups: one softmax warpgroup per query tile, the last one holds the TMA warp, the MMA warp and 2 idle warps
 constexpr int KV_STAGES = 2;
 
 template <int HD>
 struct Cfg {
-  static constexpr int BKV = (HD == 64) ? 128 : 64;        // keys per block (UMMA N of S, K of PV)
+  // Two 128-row query tiles per CTA; 128-key blocks at head dim 64, 64-key blocks at head dim 128 (shared memory).
+  // (Measured alternative at head dim 64: four tiles x 64-key blocks, i.e. 16 softmax warps: 455 vs 666 TFLOP/s —
+  //  the per-block barrier / fence overhead doubles per key and outweighs the extra latency hiding.)
+  static constexpr int NT = 2;                              // query tiles per CTA
+  static constexpr int BKV = (HD == 64) ? 128 : 64;         // keys per block (UMMA N of S, K of PV)
+  static constexpr int NTHREADS = (NT + 1) * 128;
+  static constexpr int MAXNREG = 168;                       // launch-time registers / thread (65536 / NTHREADS, multiple of 8)
   static constexpr int KB = HD / 64;                        // 64-element (128 B) column blocks of the head dim
   static constexpr int Q_TILE_BYTES = QT * HD * 2;
   static constexpr int K_TILE_BYTES = BKV * HD * 2;
   static constexpr int V_TILE_BYTES = BKV * HD * 2;
   static constexpr int P_TILE_BYTES = QT * BKV * 2;
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + 2 * Q_TILE_BYTES;
+  static constexpr int OFF_K = OFF_Q + NT * Q_TILE_BYTES;
   static constexpr int OFF_V = OFF_K + KV_STAGES * K_TILE_BYTES;
   static constexpr int OFF_P = OFF_V + KV_STAGES * V_TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_P + 4 * P_TILE_BYTES;   // P double-buffered per query tile
+  static constexpr int OFF_BAR = OFF_P + 2 * NT * P_TILE_BYTES;   // P double-buffered per query tile
   static constexpr int SMEM = OFF_BAR + 512 + 1024;
   static constexpr int S_COL = 0;                            // TMEM columns: S_A, S_B, O_A, O_B
-  static constexpr int O_COL = 2 * BKV;
+  static constexpr int O_COL = NT * BKV;
   static constexpr int TMEM_COLS = 512;
-  static_assert(O_COL + 2 * HD <= 512, "TMEM budget");
+  static_assert(O_COL + NT * HD <= 512, "TMEM budget");
+  static_assert(OFF_BAR + 1024 + 1024 <= 232448, "shared memory budget");
 };
 
 struct Bars {
   uint64_t q_full;
   uint64_t k_full[KV_STAGES], k_empty[KV_STAGES], v_full[KV_STAGES], v_empty[KV_STAGES];
-  uint64_t s_full[2], s_free[2], p_ready[2], pv_done[2][2];  // pv_done[tile][P buffer]
+  uint64_t s_full[4], s_free[4], p_ready[4][2], pv_done[4][2];  // [tile][P buffer = iteration parity]
   uint32_t tmem_slot;
 };
 
@@ -77,8 +84,43 @@ __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsig
   return r;
 }
 
+// exp2 on the FMA/ALU pipes for a share of the elements (the MUFU pipe is the bottleneck at head dim 64):
+// round-to-nearest split x = n + f via the 1.5*2^23 magic add, degree-3 minimax 2^f on [-0.5, 0.5] (max rel. error
+// 7.5e-5, far below the bf16 rounding of P), exponent patched in with an integer add.  Two elements per call.
+__device__ __forceinline__ void ex2_poly2(unsigned long long x2, float& r0, float& r1) {
+  const float MAGIC = 12582912.0f;  // 1.5 * 2^23
+  const unsigned long long xc = f2_pack(fmaxf(f2_lo(x2), -125.0f), fmaxf(f2_hi(x2), -125.0f));
+  const unsigned long long xf = f2_add(xc, f2_pack(MAGIC, MAGIC));
+  const unsigned long long fi = f2_add(xf, f2_pack(-MAGIC, -MAGIC));
+  const unsigned long long fr = f2_fma(fi, f2_pack(-1.0f, -1.0f), xc);
+  unsigned long long p = f2_fma(f2_pack(0.055171654f, 0.055171654f), fr, f2_pack(0.24261113f, 0.24261113f));
+  p = f2_fma(p, fr, f2_pack(0.69326097f, 0.69326097f));
+  p = f2_fma(p, fr, f2_pack(0.99992806f, 0.99992806f));
+  r0 = __int_as_float(__float_as_int(f2_lo(p)) + (__float_as_int(f2_lo(xf)) << 23));
+  r1 = __int_as_float(__float_as_int(f2_hi(p)) + (__float_as_int(f2_hi(xf)) << 23));
+}
+
+// register re-balancing between the service warpgroup and the softmax warpgroups (setmaxnreg, warpgroup-wide)
+template <int HD> __device__ __forceinline__ void reg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+}
+template <int HD> __device__ __forceinline__ void reg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+}
+
+#ifndef LSVS_ATTN_POLY_PAIRS
+#define LSVS_ATTN_POLY_PAIRS 0  // of every 4 element pairs, this many use the polynomial path (0 disables)
+#endif
+
+#ifdef LSVS_DEBUG_HANG
+__device__ int g_dbg_iter[64];
+#define DBG_ITER(i) do { if (lane == 0 && blockIdx.x < 2 && ptx::g_lsvs_hang[0] == 0) g_dbg_iter[blockIdx.x * 32 + warp] = (i); } while (0)
+#else
+#define DBG_ITER(i) do {} while (0)
+#endif
+
 template <int HD>
-__global__ void __maxnreg__(168)
+__global__ void __maxnreg__(Cfg<HD>::MAXNREG)
 attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int Lq, int Lk,
                       float scale_log2e) {
@@ -88,36 +130,39 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   Bars* bars = reinterpret_cast<Bars*>(smem + C::OFF_BAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (2 * QT);       // first query row (within the sequence) of this CTA
+  constexpr int NT = C::NT;
+  constexpr int W_TMA = 4 * NT, W_MMA = 4 * NT + 1;  // warp ids of the two service warps
+  const int q0 = blockIdx.x * (NT * QT);      // first query row (within the sequence) of this CTA
   const int head = blockIdx.y, batch = blockIdx.z;
-  const int n_tiles = (Lq - q0 > QT) ? 2 : 1;  // tile B only if it has at least one valid row
+  const int n_tiles = min(NT, (Lq - q0 + QT - 1) / QT);  // only tiles with at least one valid row
   const int n_kv = (Lk + C::BKV - 1) / C::BKV;
   const int q_row0 = batch * Lq + q0;          // global row of tile A's first query
   const int kv_row0 = batch * Lk;
   const int col0 = head * HD;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
     ptx::mbar_init(&bars->q_full, 1);
     for (int i = 0; i < KV_STAGES; ++i) {
       ptx::mbar_init(&bars->k_full[i], 1); ptx::mbar_init(&bars->k_empty[i], 1);
       ptx::mbar_init(&bars->v_full[i], 1); ptx::mbar_init(&bars->v_empty[i], 1);
     }
-    for (int t = 0; t < 2; ++t) {
+    for (int t = 0; t < NT; ++t) {
       ptx::mbar_init(&bars->s_full[t], 1); ptx::mbar_init(&bars->s_free[t], 4);
-      ptx::mbar_init(&bars->p_ready[t], 4); ptx::mbar_init(&bars->pv_done[t][0], 1); ptx::mbar_init(&bars->pv_done[t][1], 1);
+      ptx::mbar_init(&bars->p_ready[t][0], 4); ptx::mbar_init(&bars->p_ready[t][1], 4);
+      ptx::mbar_init(&bars->pv_done[t][0], 1); ptx::mbar_init(&bars->pv_done[t][1], 1);
     }
     ptx::fence_mbar_init();
   }
-  if (warp == 9) { ptx::tmem_alloc(&bars->tmem_slot, C::TMEM_COLS); ptx::tmem_relinquish(); }
+  if (warp == W_MMA) { ptx::tmem_alloc(&bars->tmem_slot, C::TMEM_COLS); ptx::tmem_relinquish(); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
 
-  if (warp == 8) {
+  if (warp == W_TMA) {
     // ============================================================ TMA producer
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    reg_dec<HD>();
     if (lane == 0) {
       ptx::mbar_expect_tx(&bars->q_full, n_tiles * C::Q_TILE_BYTES);
       for (int t = 0; t < n_tiles; ++t)
@@ -128,6 +173,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < n_kv; ++i) {
+      DBG_ITER(i);
       // K(i) first (needed early for S), then V(i)
       ptx::mbar_wait(&bars->k_empty[stage], phase ^ 1);
       if (lane == 0) {
@@ -146,9 +192,9 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       __syncwarp();
       if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
     }
-  } else if (warp == 9) {
+  } else if (warp == W_MMA) {
     // ============================================================ MMA issuer
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    reg_dec<HD>();
     constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(QT, C::BKV, 0, 0);  // S = Q K^T : both K-major
     constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(QT, HD, 0, 1);      // O = P V   : A K-major, B (V) MN-major
     const uint32_t sQ = ptx::smem_u32(smem + C::OFF_Q), sK = ptx::smem_u32(smem + C::OFF_K);
@@ -183,6 +229,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < n_kv; ++i) {
+      DBG_ITER(i);
       int nstage = stage + 1;
       uint32_t nphase = phase;
       if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1; }
@@ -200,7 +247,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       ptx::mbar_wait(&bars->v_full[stage], phase);
       for (int t = 0; t < n_tiles; ++t) {
-        ptx::mbar_wait(&bars->p_ready[t], i & 1);
+        ptx::mbar_wait(&bars->p_ready[t][i & 1], (i >> 1) & 1);
         ptx::tc_fence_after();
         if (lane == 0) { issue_PV(t, stage, i & 1, i > 0); ptx::umma_commit(&bars->pv_done[t][i & 1]); }
         __syncwarp();
@@ -210,12 +257,12 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       stage = nstage;
       phase = nphase;
     }
-  } else if (warp >= 10) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");  // idle warps of warpgroup 2 (the instruction is warpgroup-wide)
+  } else if (warp > W_MMA) {
+    reg_dec<HD>();  // idle warps of the service warpgroup (setmaxnreg is warpgroup-wide)
   } else {
     // ============================================================ softmax / correction / epilogue
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-    const int t = warp >> 2;                   // 0: tile A (warps 0-3), 1: tile B (warps 4-7)
+    reg_inc<HD>();
+    const int t = warp >> 2;                   // query tile of this softmax warpgroup
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;         // query row within the tile == TMEM lane
     if (t < n_tiles) {
@@ -228,6 +275,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       // for the previous PV product it needs) only happens on the rare block where a row's maximum jumps by more.
       float m_ref = -INFINITY, l_run = 0.f;
       for (int i = 0; i < n_kv; ++i) {
+        DBG_ITER(i);
         ptx::mbar_wait(&bars->s_full[t], i & 1);
         ptx::tc_fence_after();
         float s[C::BKV];
@@ -257,8 +305,12 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
               const unsigned long long x = f2_fma(f2_pack(s[8 * j + e], s[8 * j + e + 1]), sc2, nmb2);
-              p[e] = ex2(f2_lo(x));
-              p[e + 1] = ex2(f2_hi(x));
+              if (HD == 64 && e / 2 < LSVS_ATTN_POLY_PAIRS) {
+                ex2_poly2(x, p[e], p[e + 1]);
+              } else {
+                p[e] = ex2(f2_lo(x));
+                p[e + 1] = ex2(f2_hi(x));
+              }
             }
             sum2[0] = f2_add(sum2[0], f2_add(f2_pack(p[0], p[1]), f2_pack(p[4], p[5])));
             sum2[1] = f2_add(sum2[1], f2_add(f2_pack(p[2], p[3]), f2_pack(p[6], p[7])));
@@ -305,10 +357,12 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           }
         }
         l_run += blk_sum;
+        // p_ready is double-buffered by iteration parity like the P tiles: P(i+2) is only written after PV(i) retired (wait
+        // above), so the softmax warps can never lap the MMA warp on a barrier (parity waits only tell adjacent phases apart).
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bars->p_ready[t]);
+        if (lane == 0) ptx::mbar_arrive(&bars->p_ready[t][i & 1]);
       }
       // ---- epilogue: O / l -> bf16 -> global
       ptx::mbar_wait(&bars->pv_done[t][(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
@@ -338,7 +392,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 9) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
+  if (warp == W_MMA) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
 template <int HD>
@@ -355,9 +409,9 @@ int launch(const AttentionArgs& a, cudaStream_t st) {
     LSVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
-  dim3 grid((a.Lq + 2 * QT - 1) / (2 * QT), a.heads, a.batches);
+  dim3 grid((a.Lq + C::NT * QT - 1) / (C::NT * QT), a.heads, a.batches);
   const float scale_log2e = a.scale * 1.4426950408889634f;
-  kern<<<grid, NTHREADS, C::SMEM, st>>>(*tq, *tk, *tv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, a.Lk, scale_log2e);
+  kern<<<grid, C::NTHREADS, C::SMEM, st>>>(*tq, *tk, *tv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, a.Lk, scale_log2e);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
@@ -377,3 +431,15 @@ int attention_fwd(const AttentionArgs& a, cudaStream_t st) {
 }
 
 }  // namespace lsvs
+
+#ifdef LSVS_DEBUG_HANG
+extern "C" int lsvs_debug_hang_read(int* out257, int* bar_base_offset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out257, ptx::g_lsvs_hang, 257 * sizeof(int));
+  cudaMemcpyFromSymbol(out257 + 257, lsvs::g_dbg_iter, 64 * sizeof(int));
+  *bar_base_offset = lsvs::Cfg<64>::OFF_BAR;
+  static int zero[257] = {0};
+  cudaMemcpyToSymbol(ptx::g_lsvs_hang, zero, sizeof(zero));
+  return 0;
+}
+#endif

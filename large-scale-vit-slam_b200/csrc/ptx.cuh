@@ -37,9 +37,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+#ifdef LSVS_DEBUG_HANG
+// Debug build only: a wait that spins too long records (shared address of the barrier, parity, warp, block) and then
+// gives up, so a dead-locked kernel terminates and the stuck waits can be read back (lsvs_debug_hang_read).
+__device__ int g_lsvs_hang[1 + 64 * 4];
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (long long spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    if (spins > (1ll << 19)) {
+      if ((threadIdx.x & 31) == 0) {
+        const int k = atomicAdd(&g_lsvs_hang[0], 1);
+        if (k < 64) {
+          g_lsvs_hang[1 + 4 * k] = (int)smem_u32(bar); g_lsvs_hang[2 + 4 * k] = (int)parity;
+          g_lsvs_hang[3 + 4 * k] = threadIdx.x >> 5; g_lsvs_hang[4 + 4 * k] = blockIdx.x;
+        }
+      }
+      return;
+    }
+  }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+#endif
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
