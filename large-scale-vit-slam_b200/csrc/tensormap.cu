@@ -10,7 +10,7 @@
 namespace lsvs {
 namespace {
 struct Key {
-  const void* base; uint64_t inner, outer, pitch; uint32_t bi, bo;
+  const void* base; uint64_t inner, outer, pitch; uint32_t bi, bo; uint64_t kind;
   bool operator==(const Key& o) const { return std::memcmp(this, &o, sizeof(Key)) == 0; }
 };
 struct KeyHash {
@@ -26,11 +26,23 @@ std::unordered_map<Key, std::unique_ptr<CUtensorMap>, KeyHash> g_cache;
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 }  // namespace
 
+namespace {
+const CUtensorMap* tmap_2d(const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
+                           CUtensorMapDataType dtype, int elem_bytes);
+}
 const CUtensorMap* tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                                 uint32_t box_inner, uint32_t box_outer) {
+  return tmap_2d(base, inner, outer, pitch_bytes, box_inner, box_outer, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+}
+const CUtensorMap* tmap_2d_f32_box32(const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_outer) {
+  return tmap_2d(base, inner, outer, pitch_bytes, 32, box_outer, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4);
+}
+namespace {
+const CUtensorMap* tmap_2d(const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer,
+                           CUtensorMapDataType dtype, int elem_bytes) {
   Key key;
   std::memset(&key, 0, sizeof(key));
-  key.base = base; key.inner = inner; key.outer = outer; key.pitch = pitch_bytes; key.bi = box_inner; key.bo = box_outer;
+  key.base = base; key.inner = inner; key.outer = outer; key.pitch = pitch_bytes; key.bi = box_inner; key.bo = box_outer; key.kind = (uint64_t)dtype;
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_cache.find(key);
   if (it != g_cache.end()) return it->second.get();
@@ -44,7 +56,7 @@ const CUtensorMap* tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer
     }
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
   }
-  if (((uintptr_t)base & 15) || (pitch_bytes & 15) || box_inner * 2 != 128 || box_outer > 256 || box_outer == 0) {
+  if (((uintptr_t)base & 15) || (pitch_bytes & 15) || box_inner * elem_bytes != 128 || box_outer > 256 || box_outer == 0) {
     fail(LSVS_EINVAL, "tensor map: base %p pitch %llu box %ux%u not TMA compatible", base, (unsigned long long)pitch_bytes,
          box_inner, box_outer);
     return nullptr;
@@ -54,7 +66,7 @@ const CUtensorMap* tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer
   cuuint64_t strides[1] = {pitch_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(tm.get(), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = g_encode(tm.get(), dtype, 2, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -66,4 +78,5 @@ const CUtensorMap* tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer
   g_cache.emplace(key, std::move(tm));
   return out;
 }
+}  // namespace
 }  // namespace lsvs

@@ -13,4 +13,8 @@ namespace lsvs {
 const CUtensorMap* tmap_2d_bf16(const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                                 uint32_t box_inner, uint32_t box_outer);
 
+// 2-D fp32 tensor (row-major, `inner` columns contiguous), box 32 columns x `box_outer` rows, 128-byte swizzle:
+// destination map of the TMA reduce-add residual epilogue (csrc/gemm.cu).
+const CUtensorMap* tmap_2d_f32_box32(const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_outer);
+
 }  // namespace lsvs
