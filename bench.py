@@ -284,21 +284,26 @@ def run_b200(args):
         n_prof = 2
         for i in range(n_prof):
             step_fn(i)
-        ncat = 5
+        ncat = 6
         arr = lambda t: (t * ncat)()
         pms, pfl, pby, pln = arr(ctypes.c_double), arr(ctypes.c_double), arr(ctypes.c_double), arr(ctypes.c_longlong)
         lib.lsvs_profile_read(pms, pfl, pby, pln)
         lib.lsvs_profile_enable(0)
-        names = ["gemm_tcgen05", "attention_tcgen05", "layernorm_cast", "fp32_tail", "sim3_apply"]
+        names = ["gemm_tcgen05", "attention_tcgen05_frame", "layernorm_cast", "fp32_tail", "sim3_apply", "attention_tcgen05_global"]
         prof_detail = {n: {"ms_per_step": pms[i] / n_prof, "launches_per_step": pln[i] / n_prof,
                            "tflops": (pfl[i] / (pms[i] * 1e9) if pms[i] > 0 and pfl[i] > 0 else None),
                            "gbps": (pby[i] / (pms[i] * 1e6) if pms[i] > 0 and pby[i] > 0 else None)} for i, n in enumerate(names)}
-        dom = max(range(2), key=lambda i: pms[i])  # the tensor-bound classes dominate the step
+        dom = max((0, 1, 5), key=lambda i: pms[i])  # the tensor-bound classes dominate the step
         pk = peaks()
         ach = pfl[dom] / (pms[dom] * 1e9)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")  # dram__bytes_read+write per launch from the ncu --set full capture
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(names[dom], {}).get("dram_bytes_per_launch")
         roofline = {"kernel": names[dom], "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk["src"] + " (sustained, kernel timed inside a long step)",
-                    "avg_launch_ms": pms[dom] / max(1, pln[dom]), "share_of_step": (pms[dom] / n_prof) / ms_per_step}
+                    "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic, "peak_source": pk["src"] + " (sustained, kernel timed inside a long step)",
+                    "avg_launch_ms": pms[dom] / max(1, pln[dom]), "share_of_step": (pms[dom] / n_prof) / ms_per_step,
+                    "algorithmic_flops_per_launch": pfl[dom] / max(1, pln[dom])}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -39,9 +39,9 @@ int lsvs_version(void);
 unsigned long long lsvs_launch_count(void);
 
 /* per-kernel-class CUDA-event profiler (used by bench.py for the roofline object; adds two event records per
- * launch while enabled).  Classes: 0 tcgen05 GEMM, 1 tcgen05 attention, 2 LayerNorm/cast, 3 fp32 tail
- * (decode, camera head), 4 Sim(3) apply. */
-#define LSVS_PROF_NCAT 5
+ * launch while enabled).  Classes: 0 tcgen05 GEMM, 1 tcgen05 attention with < 2048 keys (frame / DINO / head passes),
+ * 2 LayerNorm/cast, 3 fp32 tail (decode, camera head), 4 Sim(3) apply, 5 tcgen05 attention with >= 2048 keys (global pass). */
+#define LSVS_PROF_NCAT 6
 int lsvs_profile_enable(int on);
 int lsvs_profile_read(double* ms, double* flops, double* bytes, long long* launches);
 

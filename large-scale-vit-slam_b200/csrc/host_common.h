@@ -33,7 +33,7 @@ inline int num_sms() {
 }
 
 // ---- optional per-kernel-class CUDA-event profiler (bench.py's roofline numbers; off by default) ----------
-enum ProfCat { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_ELEMENTWISE = 2, PROF_SMALL_F32 = 3, PROF_SIM3 = 4, PROF_NCAT = 5 };
+enum ProfCat { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_ELEMENTWISE = 2, PROF_SMALL_F32 = 3, PROF_SIM3 = 4, PROF_ATTENTION_GLOBAL = 5, PROF_NCAT = 6 };
 extern bool g_prof_on;
 void prof_begin(int cat, cudaStream_t st, double flops, double bytes);
 void prof_end(cudaStream_t st);
