@@ -234,6 +234,43 @@ def run_b200(args):
 
     # ---- end to end through the public module API with HOST buffers (pinned), H2D + D2H inside the timed region
     e2e = None
+    if world > 1:
+        host_img = torch.rand(1, S_CHUNK, 3, H, W).pin_memory()
+        host_out = {}
+
+        def e2e_round():
+            mine = pipe.owns()
+            pipe.step((host_img.to(dev, non_blocking=True), raw_pts, raw_dep) if mine else None)
+            nbytes = 0
+            for res in pipe.results:  # chunks whose Sim(3) packet arrived: copy their outputs to the host
+                for k in ("pose_enc", "world_points", "depth"):
+                    t = res[k]
+                    if k not in host_out:
+                        host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                    host_out[k].copy_(t, non_blocking=True)
+                    nbytes += t.numel() * t.element_size()
+            pipe.results.clear()
+            return nbytes
+        start_round = pipe.round
+        for _ in range(2):
+            e2e_round()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        first = pipe.round
+        a.record()
+        d2h_total = 0
+        for _ in range(args.steps):
+            d2h_total += e2e_round()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n_chunks_e2e = pipe.chunks_in_rounds(args.steps, start=first)
+        bt = torch.tensor([d2h_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(bt)
+        pipe.flush()
+        e2e = {"value": n_chunks_e2e * (S_CHUNK - OVERLAP) / (float(t.item()) / 1e3), "unit": "frames/s",
+               "h2d_bytes_per_step": host_img.numel() * 4 * n_chunks_e2e / args.steps, "d2h_bytes_per_step": float(bt.item()) / args.steps}
     if world == 1:
         host_imgs = [torch.rand(1, S_CHUNK, 3, H, W).pin_memory() for _ in range(2)]
         keep = ("pose_enc", "world_points", "depth")
