@@ -13,6 +13,8 @@
 // Replaces F.scaled_dot_product_attention behind UPSTREAM Attention (Aggregator frame/global/DINO blocks,
 // alignment-head frame blocks alignment_head.py:363, camera-head trunk); q_norm/k_norm/RoPE are already applied
 // by the QKV GEMM epilogue (csrc/gemm.cu).
+#include <cstdlib>
+
 #include "attention.h"
 #include "host_common.h"
 #include "ptx.cuh"
@@ -23,7 +25,18 @@ namespace {
 
 constexpr int QT = 128;            // query rows per tile (UMMA M)
 // threads = (NT + 1) warpgroups: one softmax warpgroup per query tile, the last one holds the TMA warp, the MMA warp and 2 idle warps
-constexpr int KV_STAGES = 2;
+#ifndef LSVS_ATTN_P_TMEM
+#define LSVS_ATTN_P_TMEM 1  // P (bf16) goes back into tensor memory and feeds the PV product as a TMEM A operand (no shared-memory round trip)
+#endif
+constexpr bool P_TMEM = LSVS_ATTN_P_TMEM != 0;
+constexpr int KV_STAGES = P_TMEM ? 4 : 2;
+
+#ifndef LSVS_ATTN_SPLIT64
+#define LSVS_ATTN_SPLIT64 0  // head dim 64: two softmax threads per query row (16 softmax warps); measured 623 vs 658 TFLOP/s
+#endif
+#ifndef LSVS_ATTN_POLY_PAIRS
+#define LSVS_ATTN_POLY_PAIRS 0  // of every 4 element pairs, this many use the polynomial exp2 path (0 disables; measured slower)
+#endif
 
 template <int HD>
 struct Cfg {
@@ -32,8 +45,16 @@ struct Cfg {
   //  the per-block barrier / fence overhead doubles per key and outweighs the extra latency hiding.)
   static constexpr int NT = 2;                              // query tiles per CTA
   static constexpr int BKV = (HD == 64) ? 128 : 64;         // keys per block (UMMA N of S, K of PV)
-  static constexpr int NTHREADS = (NT + 1) * 128;
-  static constexpr int MAXNREG = 168;                       // launch-time registers / thread (65536 / NTHREADS, multiple of 8)
+  // SP softmax warpgroups share one query tile, each thread owning BKV / SP columns of its row: at head dim 64 the
+  // softmax is issue / latency bound at 8 warps (2 per SM sub-partition), so the row is split over two threads.
+  static constexpr int SP = LSVS_ATTN_SPLIT64 && (HD == 64) ? 2 : 1;
+  static constexpr int COLS = BKV / SP;                     // S columns per softmax thread
+  static constexpr int OCOLS = HD / SP;                     // O columns per softmax thread (rescale / epilogue)
+  static constexpr int NWG = NT * SP;                       // softmax warpgroups
+  static constexpr int NTHREADS = (NWG + 1) * 128;
+  static constexpr int MAXNREG = (SP == 2) ? 96 : 168;      // launch-time registers / thread (65536 / NTHREADS, multiple of 8)
+  static constexpr int REG_SOFTMAX = (SP == 2) ? 104 : 200; // after setmaxnreg: NWG*128*REG_SOFTMAX + 128*REG_SERVICE <= NTHREADS*MAXNREG
+  static constexpr int REG_SERVICE = (SP == 2) ? 64 : 96;
   static constexpr int KB = HD / 64;                        // 64-element (128 B) column blocks of the head dim
   static constexpr int Q_TILE_BYTES = QT * HD * 2;
   static constexpr int K_TILE_BYTES = BKV * HD * 2;
@@ -43,13 +64,18 @@ struct Cfg {
   static constexpr int OFF_K = OFF_Q + NT * Q_TILE_BYTES;
   static constexpr int OFF_V = OFF_K + KV_STAGES * K_TILE_BYTES;
   static constexpr int OFF_P = OFF_V + KV_STAGES * V_TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_P + 2 * NT * P_TILE_BYTES;   // P double-buffered per query tile
-  static constexpr int SMEM = OFF_BAR + 512 + 1024;
-  static constexpr int S_COL = 0;                            // TMEM columns: S_A, S_B, O_A, O_B
+  static constexpr int OFF_BAR = OFF_P + (P_TMEM ? 0 : 2 * NT * P_TILE_BYTES);   // (shared-memory P: double-buffered per query tile)
+  static constexpr int OFF_X = OFF_BAR + 512;                     // row-max exchange between the SP threads of a row (bf16)
+  static constexpr int X_BYTES = (SP == 2) ? 2 * NT * SP * QT * 2 : 0;  // [parity][tile][half][row]
+  static constexpr int SMEM = OFF_X + X_BYTES;                    // the dynamic shared window is 1024-aligned (no static smem)
+  static constexpr int S_COL = 0;                            // TMEM columns: S_A, S_B, O_A, O_B, P_A, P_B
   static constexpr int O_COL = NT * BKV;
+  static constexpr int P_COL = O_COL + NT * HD;              // P: bf16 pairs, BKV / 2 columns per tile
+  static constexpr int PCOLS = BKV / 2;
   static constexpr int TMEM_COLS = 512;
-  static_assert(O_COL + NT * HD <= 512, "TMEM budget");
-  static_assert(OFF_BAR + 1024 + 1024 <= 232448, "shared memory budget");
+  static_assert(P_COL + (P_TMEM ? NT * PCOLS : 0) <= 512, "TMEM budget");
+  static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(NWG * 128 * REG_SOFTMAX + 128 * REG_SERVICE <= NTHREADS * MAXNREG, "register pool");
 };
 
 struct Bars {
@@ -102,14 +128,21 @@ __device__ __forceinline__ void ex2_poly2(unsigned long long x2, float& r0, floa
 
 // register re-balancing between the service warpgroup and the softmax warpgroups (setmaxnreg, warpgroup-wide)
 template <int HD> __device__ __forceinline__ void reg_dec() {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg<HD>::REG_SERVICE));
 }
 template <int HD> __device__ __forceinline__ void reg_inc() {
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg<HD>::REG_SOFTMAX));
 }
 
-#ifndef LSVS_ATTN_POLY_PAIRS
-#define LSVS_ATTN_POLY_PAIRS 0  // of every 4 element pairs, this many use the polynomial path (0 disables)
+#ifdef LSVS_ATTN_PHASES
+__device__ unsigned long long g_attn_phase[8 * 8];  // [warp][phase] cycle sums for CTA (0,0,0)
+#define PH_DECL unsigned ph_t = clock(); unsigned long long ph_acc[6] = {0, 0, 0, 0, 0, 0}
+#define PH(k) do { const unsigned now_ = clock(); ph_acc[k] += now_ - ph_t; ph_t = now_; } while (0)
+#define PH_FLUSH() do { if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) for (int k_ = 0; k_ < 6; ++k_) g_attn_phase[warp * 8 + k_] = ph_acc[k_]; } while (0)
+#else
+#define PH_DECL do {} while (0)
+#define PH(k) do {} while (0)
+#define PH_FLUSH() do {} while (0)
 #endif
 
 #ifdef LSVS_DEBUG_HANG
@@ -119,19 +152,27 @@ __device__ int g_dbg_iter[64];
 #define DBG_ITER(i) do {} while (0)
 #endif
 
-template <int HD>
+// P (fp32) -> packed bf16 pair.  PK 0: cvt.rn.bf16x2.f32 (F2FP); 1: truncation with one PRMT; 2: round-half-up with two
+// integer adds + PRMT (exp2 outputs are positive and finite, so the carry never reaches the sign / inf patterns).
+template <int PK> __device__ __forceinline__ uint32_t pack_p(float lo, float hi) {
+  if (PK == 0) return ptx::pack_bf16(lo, hi);
+  uint32_t a = __float_as_uint(lo), b = __float_as_uint(hi);
+  if (PK == 2) { a += 0x8000u; b += 0x8000u; }
+  return __byte_perm(a, b, 0x7632);
+}
+
+template <int HD, int PK>
 __global__ void __maxnreg__(Cfg<HD>::MAXNREG)
 attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int Lq, int Lk,
-                      float scale_log2e) {
+                      float scale_log2e, int stagger_cycles) {
   using C = Cfg<HD>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem + C::OFF_BAR);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NT = C::NT;
-  constexpr int W_TMA = 4 * NT, W_MMA = 4 * NT + 1;  // warp ids of the two service warps
+  constexpr int W_TMA = 4 * C::NWG, W_MMA = 4 * C::NWG + 1, W_TMA_V = 4 * C::NWG + 2;  // warp ids of the two service warps
   const int q0 = blockIdx.x * (NT * QT);      // first query row (within the sequence) of this CTA
   const int head = blockIdx.y, batch = blockIdx.z;
   const int n_tiles = min(NT, (Lq - q0 + QT - 1) / QT);  // only tiles with at least one valid row
@@ -148,8 +189,8 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       ptx::mbar_init(&bars->v_full[i], 1); ptx::mbar_init(&bars->v_empty[i], 1);
     }
     for (int t = 0; t < NT; ++t) {
-      ptx::mbar_init(&bars->s_full[t], 1); ptx::mbar_init(&bars->s_free[t], 4);
-      ptx::mbar_init(&bars->p_ready[t][0], 4); ptx::mbar_init(&bars->p_ready[t][1], 4);
+      ptx::mbar_init(&bars->s_full[t], 1); ptx::mbar_init(&bars->s_free[t], 4 * C::SP);
+      ptx::mbar_init(&bars->p_ready[t][0], 4 * C::SP); ptx::mbar_init(&bars->p_ready[t][1], 4 * C::SP);
       ptx::mbar_init(&bars->pv_done[t][0], 1); ptx::mbar_init(&bars->pv_done[t][1], 1);
     }
     ptx::fence_mbar_init();
@@ -170,11 +211,12 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           ptx::tma_load_2d(smem + C::OFF_Q + t * C::Q_TILE_BYTES + kb * (QT * 128), &tmQ, &bars->q_full, col0 + kb * 64,
                            q_row0 + t * QT);
     }
+    // K blocks only: V has its own producer warp so that a V slot that frees late (after PV(i-1)) never holds back the
+    // request for K(i+2) — each ring then runs a full two key blocks ahead of its consumer
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < n_kv; ++i) {
       DBG_ITER(i);
-      // K(i) first (needed early for S), then V(i)
       ptx::mbar_wait(&bars->k_empty[stage], phase ^ 1);
       if (lane == 0) {
         ptx::mbar_expect_tx(&bars->k_full[stage], C::K_TILE_BYTES);
@@ -182,6 +224,15 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           ptx::tma_load_2d(smem + C::OFF_K + stage * C::K_TILE_BYTES + kb * (C::BKV * 128), &tmK, &bars->k_full[stage],
                            col0 + kb * 64, kv_row0 + i * C::BKV);
       }
+      __syncwarp();
+      if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == W_TMA_V) {
+    // ============================================================ TMA producer (V blocks)
+    reg_dec<HD>();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < n_kv; ++i) {
       ptx::mbar_wait(&bars->v_empty[stage], phase ^ 1);
       if (lane == 0) {
         ptx::mbar_expect_tx(&bars->v_full[stage], C::V_TILE_BYTES);
@@ -211,10 +262,15 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     auto issue_PV = [&](int t, int stage, int pbuf, bool accumulate) {
 #pragma unroll
       for (int k = 0; k < C::BKV / 16; ++k) {
-        const uint64_t a = ptx::umma_desc_sw128(sP + (t * 2 + pbuf) * C::P_TILE_BYTES + (k / 4) * (QT * 128) + (k % 4) * 32, 16, 1024);
         // V block: rows = keys (K dim), 64-wide column blocks (N dim) C::BKV*128 bytes apart; 16 keys per step
         const uint64_t b = ptx::umma_desc_sw128(sV + stage * C::V_TILE_BYTES + k * (16 * 128), C::BKV * 128, 1024);
-        ptx::umma_bf16_ss(tmem + C::O_COL + t * HD, a, b, idesc_o, (accumulate || k != 0) ? 1u : 0u);
+        if (P_TMEM) {
+          // A = P from tensor memory: lane = query row, 8 columns (16 packed bf16) per step
+          ptx::umma_bf16_ts(tmem + C::O_COL + t * HD, tmem + C::P_COL + t * C::PCOLS + k * 8, b, idesc_o, (accumulate || k != 0) ? 1u : 0u);
+        } else {
+          const uint64_t a = ptx::umma_desc_sw128(sP + (t * 2 + pbuf) * C::P_TILE_BYTES + (k / 4) * (QT * 128) + (k % 4) * 32, 16, 1024);
+          ptx::umma_bf16_ss(tmem + C::O_COL + t * HD, a, b, idesc_o, (accumulate || k != 0) ? 1u : 0u);
+        }
       }
     };
 
@@ -257,50 +313,79 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       stage = nstage;
       phase = nphase;
     }
-  } else if (warp > W_MMA) {
-    reg_dec<HD>();  // idle warps of the service warpgroup (setmaxnreg is warpgroup-wide)
+  } else if (warp > W_TMA_V) {
+    reg_dec<HD>();  // idle warp of the service warpgroup (setmaxnreg is warpgroup-wide)
   } else {
     // ============================================================ softmax / correction / epilogue
     reg_inc<HD>();
-    const int t = warp >> 2;                   // query tile of this softmax warpgroup
+    constexpr int SP = C::SP, COLS = C::COLS, OCOLS = C::OCOLS;
+    const int wg = warp >> 2;                  // softmax warpgroup
+    const int t = wg / SP;                     // query tile of this warpgroup
+    const int h = wg % SP;                     // which COLS-wide slice of the key block (and OCOLS-wide slice of O) it owns
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;         // query row within the tile == TMEM lane
     if (t < n_tiles) {
       const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-      const uint32_t tS = tmem + lane_addr + C::S_COL + t * C::BKV;
-      const uint32_t tO = tmem + lane_addr + C::O_COL + t * HD;
+      const uint32_t tS = tmem + lane_addr + C::S_COL + t * C::BKV + h * COLS;
+      const uint32_t tO = tmem + lane_addr + C::O_COL + t * HD + h * OCOLS;
+      const uint32_t tP = tmem + lane_addr + C::P_COL + t * C::PCOLS;
       uint8_t* sP0 = smem + C::OFF_P + (t * 2) * C::P_TILE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+      // SP == 2: the two threads of a row trade their slice maxima through shared memory (bf16, rounded identically on
+      // both sides so that they take the same decisions), synchronised by a 64-thread named barrier per (tile, quarter);
+      // the slot is double-buffered by iteration parity (the partner may still be reading the previous one).
+      __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(smem + C::OFF_X);
+      const int x_mine = (t * 2 + h) * QT + r, x_other = (t * 2 + (h ^ 1)) * QT + r;
+      const int pair_bar = 1 + t * 4 + quarter;
+      auto row_max = [&](float m_half, int par) -> float {
+        if (SP == 1) return m_half;
+        const __nv_bfloat16 mine = __float2bfloat16_rn(m_half);
+        xb[par * (C::NT * 2 * QT) + x_mine] = mine;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        return fmaxf(__bfloat162float(mine), __bfloat162float(xb[par * (C::NT * 2 * QT) + x_other]));
+      };
       // m_ref is the reference maximum used inside exp2; it trails the true running maximum by at most 8 (log2
-      // units), so P <= 2^8 and O / l stay exact after the final division, while the TMEM rescale of O (and the wait
-      // for the previous PV product it needs) only happens on the rare block where a row's maximum jumps by more.
+      // units) plus the bf16 rounding of the exchanged maxima, so P <= ~2^8 and O / l stay exact after the final
+      // division, while the TMEM rescale of O (and the wait for the previous PV product it needs) only happens on the
+      // rare block where a row's maximum jumps by more.
       float m_ref = -INFINITY, l_run = 0.f;
+      // The exp2 phase of one warp alone already fills the MUFU pipe of its SM sub-partition (ptxas paces it at one MUFU
+      // per 8 cycles), so two tiles in lock-step serialise their exp2 phases and then idle the pipe together.  Tile B
+      // starts late once; nothing re-synchronises the tiles afterwards, so B's exp2 phase keeps overlapping A's
+      // TMEM-load / max / barrier phase.
+      if (t == 1 && stagger_cycles > 0) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < stagger_cycles) {}
+      }
+      PH_DECL;
       for (int i = 0; i < n_kv; ++i) {
         DBG_ITER(i);
         ptx::mbar_wait(&bars->s_full[t], i & 1);
         ptx::tc_fence_after();
-        float s[C::BKV];
+        PH(0);
+        float s[COLS];
 #pragma unroll
-        for (int c = 0; c < C::BKV; c += 32) ptx::tmem_ld_32x32b_x32(tS + c, reinterpret_cast<uint32_t*>(s + c));
+        for (int c = 0; c < COLS; c += 32) ptx::tmem_ld_32x32b_x32(tS + c, reinterpret_cast<uint32_t*>(s + c));
         ptx::tmem_ld_wait();
+        PH(1);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->s_free[t]);
-        const int kv_valid = Lk - i * C::BKV;  // keys of this block inside the sequence
-        if (kv_valid < C::BKV) {
+        const int kv_valid = Lk - i * C::BKV - h * COLS;  // keys of this slice inside the sequence
+        if (kv_valid < COLS) {
 #pragma unroll
-          for (int c = 0; c < C::BKV; ++c) if (c >= kv_valid) s[c] = -INFINITY;
+          for (int c = 0; c < COLS; ++c) if (c >= kv_valid) s[c] = -INFINITY;
         }
-        // the P buffer of this parity was last read by PV(i-2)
-        if (i >= 2) ptx::mbar_wait(&bars->pv_done[t][i & 1], ((i - 2) >> 1) & 1);
         uint8_t* sP = sP0 + (i & 1) * C::P_TILE_BYTES;
         // exp2 (packed fp32x2 scale-and-shift), row sum, and P (bf16) straight into shared memory in the K-major
-        // 128B-swizzled layout of the UMMA A operand; returns the row sum of this block
+        // 128B-swizzled layout of the UMMA A operand; returns the row sum of this slice
         auto emit_P = [&](float m_use) -> float {
           const float nmb = -m_use * scale_log2e;
           const unsigned long long sc2 = f2_pack(scale_log2e, scale_log2e), nmb2 = f2_pack(nmb, nmb);
           unsigned long long sum2[2] = {0ull, 0ull};
 #pragma unroll
-          for (int j = 0; j < C::BKV / 8; ++j) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < COLS / 8; ++j) {
             float p[8];
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
@@ -314,37 +399,56 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             }
             sum2[0] = f2_add(sum2[0], f2_add(f2_pack(p[0], p[1]), f2_pack(p[4], p[5])));
             sum2[1] = f2_add(sum2[1], f2_add(f2_pack(p[2], p[3]), f2_pack(p[6], p[7])));
-            const int kb = j >> 3, chunk = j & 7;
-            const uint4 v = make_uint4(ptx::pack_bf16(p[0], p[1]), ptx::pack_bf16(p[2], p[3]), ptx::pack_bf16(p[4], p[5]), ptx::pack_bf16(p[6], p[7]));
-            *reinterpret_cast<uint4*>(sP + kb * (QT * 128) + ((chunk ^ (r & 7)) << 4)) = v;
+            const int jg = h * (COLS / 8) + j;       // 16-byte chunk within the row of the P tile
+            if (P_TMEM) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) pk[4 * (j & 3) + e] = pack_p<PK>(p[2 * e], p[2 * e + 1]);
+              if ((j & 3) == 3) ptx::tmem_st_32x32b_x16(tP + (jg - 3) * 4, pk);   // 32 keys = 16 packed columns
+            } else {
+              const int kb = jg >> 3, chunk = jg & 7;
+              const uint4 v = make_uint4(pack_p<PK>(p[0], p[1]), pack_p<PK>(p[2], p[3]), pack_p<PK>(p[4], p[5]), pack_p<PK>(p[6], p[7]));
+              *reinterpret_cast<uint4*>(sP + kb * (QT * 128) + ((chunk ^ (r & 7)) << 4)) = v;
+            }
           }
           const unsigned long long tot = f2_add(sum2[0], sum2[1]);
           return f2_lo(tot) + f2_hi(tot);
         };
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < C::BKV; c += 4) {
+        for (int c = 0; c < COLS; c += 4) {
           mx[0] = fmaxf(mx[0], s[c]); mx[1] = fmaxf(mx[1], s[c + 1]); mx[2] = fmaxf(mx[2], s[c + 2]); mx[3] = fmaxf(mx[3], s[c + 3]);
         }
-        const float m_blk = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        const float m_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        if (P_TMEM) {
+          // P is single-buffered in tensor memory: PV(i-1) must have consumed it (this also orders the O rescale below)
+          if (i >= 1) ptx::mbar_wait(&bars->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
+        } else {
+          // the shared-memory P buffer of this parity was last read by PV(i-2)
+          if (i >= 2) ptx::mbar_wait(&bars->pv_done[t][i & 1], ((i - 2) >> 1) & 1);
+        }
+        ptx::tc_fence_after();
+        PH(2);
         float blk_sum;
         if (i == 0) {
-          m_ref = m_blk;
+          m_ref = row_max(m_half, 0);
           blk_sum = emit_P(m_ref);
         } else {
           // optimistic: exponentiate against the trailing reference maximum (no dependence on this block's maximum, so
           // the MUFU work starts as soon as S is in registers); redo only if some row's maximum jumped by > 2^8
           blk_sum = emit_P(m_ref);
+          const float m_blk = row_max(m_half, i & 1);
           const bool jump = (m_blk - m_ref) * scale_log2e > 8.0f;
           if (__any_sync(0xffffffffu, jump)) {
             // rescale O in TMEM: every earlier PV product must have retired (they complete in order)
-            ptx::mbar_wait(&bars->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
-            ptx::tc_fence_after();
+            if (!P_TMEM) {
+              ptx::mbar_wait(&bars->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
+              ptx::tc_fence_after();
+            }
             const float alpha = jump ? ex2((m_ref - m_blk) * scale_log2e) : 1.0f;
             if (jump) m_ref = m_blk;
             l_run *= alpha;
 #pragma unroll
-            for (int c = 0; c < HD; c += 16) {
+            for (int c = 0; c < OCOLS; c += 16) {
               uint32_t o[16];
               ptx::tmem_ld_32x32b_x16(tO + c, o);
               ptx::tmem_ld_wait();
@@ -357,21 +461,31 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           }
         }
         l_run += blk_sum;
+        PH(3);
         // p_ready is double-buffered by iteration parity like the P tiles: P(i+2) is only written after PV(i) retired (wait
         // above), so the softmax warps can never lap the MMA warp on a barrier (parity waits only tell adjacent phases apart).
-        ptx::fence_proxy_async_smem();
+        if (P_TMEM) ptx::tmem_st_wait(); else ptx::fence_proxy_async_smem();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->p_ready[t][i & 1]);
+        PH(4);
       }
+      PH_FLUSH();
       // ---- epilogue: O / l -> bf16 -> global
       ptx::mbar_wait(&bars->pv_done[t][(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
       ptx::tc_fence_after();
+      if (SP == 2) {
+        // total row sum = sum of the two slice sums; the Q tile of this query tile is dead once its last S product retired
+        float* lx = reinterpret_cast<float*>(smem + C::OFF_Q + t * C::Q_TILE_BYTES);
+        lx[h * QT + r] = l_run;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        l_run += lx[(h ^ 1) * QT + r];
+      }
       const float inv_l = 1.0f / l_run;
       const int q_local = q0 + t * QT + r;
-      __nv_bfloat16* dst = O + (size_t)(batch * (size_t)Lq + q_local) * ldo + col0;
+      __nv_bfloat16* dst = O + (size_t)(batch * (size_t)Lq + q_local) * ldo + col0 + h * OCOLS;
 #pragma unroll
-      for (int c = 0; c < HD; c += 32) {
+      for (int c = 0; c < OCOLS; c += 32) {
         uint32_t o[32];
         ptx::tmem_ld_32x32b_x32(tO + c, o);
         ptx::tmem_ld_wait();
@@ -395,7 +509,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == W_MMA) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
 }
 
-template <int HD>
+template <int HD, int PK>
 int launch(const AttentionArgs& a, cudaStream_t st) {
   using C = Cfg<HD>;
   const size_t rows_q = (size_t)a.batches * a.Lq, rows_k = (size_t)a.batches * a.Lk;
@@ -403,7 +517,7 @@ int launch(const AttentionArgs& a, cudaStream_t st) {
   const CUtensorMap* tk = tmap_2d_bf16(a.k, (uint64_t)a.heads * HD, rows_k, (uint64_t)a.ldk * 2, 64, C::BKV);
   const CUtensorMap* tv = tmap_2d_bf16(a.v, (uint64_t)a.heads * HD, rows_k, (uint64_t)a.ldv * 2, 64, C::BKV);
   if (!tq || !tk || !tv) return LSVS_ECUDA;
-  auto kern = attention_fwd_tcgen05<HD>;
+  auto kern = attention_fwd_tcgen05<HD, PK>;
   static bool configured = false;
   if (!configured) {
     LSVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -411,7 +525,9 @@ int launch(const AttentionArgs& a, cudaStream_t st) {
   }
   dim3 grid((a.Lq + C::NT * QT - 1) / (C::NT * QT), a.heads, a.batches);
   const float scale_log2e = a.scale * 1.4426950408889634f;
-  kern<<<grid, C::NTHREADS, C::SMEM, st>>>(*tq, *tk, *tv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, a.Lk, scale_log2e);
+  static const int stagger = [] { const char* e = getenv("LSVS_ATTN_STAGGER"); return e ? atoi(e) : 0; }();
+  kern<<<grid, C::NTHREADS, C::SMEM, st>>>(*tq, *tk, *tv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, a.Lk, scale_log2e,
+                                           a.Lk >= 4 * C::BKV ? stagger : 0);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
@@ -427,10 +543,19 @@ int attention_fwd(const AttentionArgs& a, cudaStream_t st) {
   LSVS_CHECK_ARG(a.ldq >= D && a.ldk >= D && a.ldv >= D && a.ldo >= D, "attention: leading dimension smaller than heads*head_dim");
   LSVS_CHECK_ARG(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: leading dimensions must be multiples of 8");
   ProfScope prof(a.Lk >= 2048 ? PROF_ATTENTION_GLOBAL : PROF_ATTENTION, st, 4.0 * a.batches * (double)a.heads * a.Lq * (double)a.Lk * a.head_dim, 0);
-  return a.head_dim == 64 ? launch<64>(a, st) : launch<128>(a, st);
+  static const int pk = [] { const char* e = getenv("LSVS_ATTN_PACK"); return e ? atoi(e) : 0; }();
+  if (a.head_dim == 128) return launch<128, 0>(a, st);
+  return pk == 1 ? launch<64, 1>(a, st) : pk == 2 ? launch<64, 2>(a, st) : launch<64, 0>(a, st);
 }
 
 }  // namespace lsvs
+
+#ifdef LSVS_ATTN_PHASES
+extern "C" int lsvs_debug_attn_phases(unsigned long long* out64) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out64, lsvs::g_attn_phase, 64 * sizeof(unsigned long long));
+}
+#endif
 
 #ifdef LSVS_DEBUG_HANG
 extern "C" int lsvs_debug_hang_read(int* out257, int* bar_base_offset) {

@@ -16,7 +16,8 @@ LIB = os.path.join(LIBDIR, "liblsvs_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
-         "-I", os.path.join(HERE, "..", "include")] + (["-DLSVS_DEBUG_HANG"] if os.environ.get("LSVS_DEBUG_HANG") else [])
+         "-I", os.path.join(HERE, "..", "include")] + (["-DLSVS_DEBUG_HANG"] if os.environ.get("LSVS_DEBUG_HANG") else []) \
+    + os.environ.get("LSVS_NVCC_DEFINES", "").split()   # debug / measurement builds, e.g. LSVS_NVCC_DEFINES="-DLSVS_ATTN_PHASES"
 
 
 def sources():
