@@ -7,7 +7,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_HERE, "lib", "liblsvs_b200.so")
+LIB_PATH = os.environ.get("LSVS_B200_LIB") or os.path.join(_HERE, "lib", "liblsvs_b200.so")  # override: A/B measurement builds
 HEADER = os.path.join(_HERE, "..", "include", "lsvs_b200.h")
 
 _lib = None
