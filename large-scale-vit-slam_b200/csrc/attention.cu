@@ -25,11 +25,7 @@ namespace {
 
 constexpr int QT = 128;            // query rows per tile (UMMA M)
 // threads = (NT + 1) warpgroups: one softmax warpgroup per query tile, the last one holds the TMA warp, the MMA warp and 2 idle warps
-#ifndef LSVS_ATTN_P_TMEM
-#define LSVS_ATTN_P_TMEM 1  // P (bf16) goes back into tensor memory and feeds the PV product as a TMEM A operand (no shared-memory round trip)
-#endif
-constexpr bool P_TMEM = LSVS_ATTN_P_TMEM != 0;
-constexpr int KV_STAGES = P_TMEM ? 4 : 2;
+constexpr int KV_STAGES = 4;
 
 #ifndef LSVS_ATTN_SPLIT64
 #define LSVS_ATTN_SPLIT64 0  // head dim 64: two softmax threads per query row (16 softmax warps); measured 623 vs 658 TFLOP/s
@@ -59,12 +55,10 @@ struct Cfg {
   static constexpr int Q_TILE_BYTES = QT * HD * 2;
   static constexpr int K_TILE_BYTES = BKV * HD * 2;
   static constexpr int V_TILE_BYTES = BKV * HD * 2;
-  static constexpr int P_TILE_BYTES = QT * BKV * 2;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + NT * Q_TILE_BYTES;
   static constexpr int OFF_V = OFF_K + KV_STAGES * K_TILE_BYTES;
-  static constexpr int OFF_P = OFF_V + KV_STAGES * V_TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_P + (P_TMEM ? 0 : 2 * NT * P_TILE_BYTES);   // (shared-memory P: double-buffered per query tile)
+  static constexpr int OFF_BAR = OFF_V + KV_STAGES * V_TILE_BYTES;
   static constexpr int OFF_X = OFF_BAR + 512;                     // row-max exchange between the SP threads of a row (bf16)
   static constexpr int X_BYTES = (SP == 2) ? 2 * NT * SP * QT * 2 : 0;  // [parity][tile][half][row]
   static constexpr int SMEM = OFF_X + X_BYTES;                    // the dynamic shared window is 1024-aligned (no static smem)
@@ -73,7 +67,7 @@ struct Cfg {
   static constexpr int P_COL = O_COL + NT * HD;              // P: bf16 pairs, BKV / 2 columns per tile
   static constexpr int PCOLS = BKV / 2;
   static constexpr int TMEM_COLS = 512;
-  static_assert(P_COL + (P_TMEM ? NT * PCOLS : 0) <= 512, "TMEM budget");
+  static_assert(P_COL + NT * PCOLS <= 512, "TMEM budget");
   static_assert(SMEM <= 232448, "shared memory budget");
   static_assert(NWG * 128 * REG_SOFTMAX + 128 * REG_SERVICE <= NTHREADS * MAXNREG, "register pool");
 };
@@ -249,7 +243,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(QT, C::BKV, 0, 0);  // S = Q K^T : both K-major
     constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(QT, HD, 0, 1);      // O = P V   : A K-major, B (V) MN-major
     const uint32_t sQ = ptx::smem_u32(smem + C::OFF_Q), sK = ptx::smem_u32(smem + C::OFF_K);
-    const uint32_t sV = ptx::smem_u32(smem + C::OFF_V), sP = ptx::smem_u32(smem + C::OFF_P);
+    const uint32_t sV = ptx::smem_u32(smem + C::OFF_V);
 
     auto issue_S = [&](int t, int stage) {
 #pragma unroll
@@ -259,18 +253,13 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         ptx::umma_bf16_ss(tmem + C::S_COL + t * C::BKV, a, b, idesc_s, k != 0);
       }
     };
-    auto issue_PV = [&](int t, int stage, int pbuf, bool accumulate) {
+    auto issue_PV = [&](int t, int stage, bool accumulate) {
 #pragma unroll
       for (int k = 0; k < C::BKV / 16; ++k) {
         // V block: rows = keys (K dim), 64-wide column blocks (N dim) C::BKV*128 bytes apart; 16 keys per step
         const uint64_t b = ptx::umma_desc_sw128(sV + stage * C::V_TILE_BYTES + k * (16 * 128), C::BKV * 128, 1024);
-        if (P_TMEM) {
-          // A = P from tensor memory: lane = query row, 8 columns (16 packed bf16) per step
-          ptx::umma_bf16_ts(tmem + C::O_COL + t * HD, tmem + C::P_COL + t * C::PCOLS + k * 8, b, idesc_o, (accumulate || k != 0) ? 1u : 0u);
-        } else {
-          const uint64_t a = ptx::umma_desc_sw128(sP + (t * 2 + pbuf) * C::P_TILE_BYTES + (k / 4) * (QT * 128) + (k % 4) * 32, 16, 1024);
-          ptx::umma_bf16_ss(tmem + C::O_COL + t * HD, a, b, idesc_o, (accumulate || k != 0) ? 1u : 0u);
-        }
+        // A = P from tensor memory: lane = query row, 8 columns (16 packed bf16) per step
+        ptx::umma_bf16_ts(tmem + C::O_COL + t * HD, tmem + C::P_COL + t * C::PCOLS + k * 8, b, idesc_o, (accumulate || k != 0) ? 1u : 0u);
       }
     };
 
@@ -305,7 +294,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int t = 0; t < n_tiles; ++t) {
         ptx::mbar_wait(&bars->p_ready[t][i & 1], (i >> 1) & 1);
         ptx::tc_fence_after();
-        if (lane == 0) { issue_PV(t, stage, i & 1, i > 0); ptx::umma_commit(&bars->pv_done[t][i & 1]); }
+        if (lane == 0) { issue_PV(t, stage, i > 0); ptx::umma_commit(&bars->pv_done[t][i & 1]); }
         __syncwarp();
       }
       if (lane == 0) ptx::umma_commit(&bars->v_empty[stage]);
@@ -329,7 +318,6 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const uint32_t tS = tmem + lane_addr + C::S_COL + t * C::BKV + h * COLS;
       const uint32_t tO = tmem + lane_addr + C::O_COL + t * HD + h * OCOLS;
       const uint32_t tP = tmem + lane_addr + C::P_COL + t * C::PCOLS;
-      uint8_t* sP0 = smem + C::OFF_P + (t * 2) * C::P_TILE_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
       // SP == 2: the two threads of a row trade their slice maxima through shared memory (bf16, rounded identically on
       // both sides so that they take the same decisions), synchronised by a 64-thread named barrier per (tile, quarter);
       // the slot is double-buffered by iteration parity (the partner may still be reading the previous one).
@@ -375,14 +363,12 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
           for (int c = 0; c < COLS; ++c) if (c >= kv_valid) s[c] = -INFINITY;
         }
-        uint8_t* sP = sP0 + (i & 1) * C::P_TILE_BYTES;
-        // exp2 (packed fp32x2 scale-and-shift), row sum, and P (bf16) straight into shared memory in the K-major
-        // 128B-swizzled layout of the UMMA A operand; returns the row sum of this slice
+        // exp2 (packed fp32x2 scale-and-shift), row sum, and P packed to bf16 pairs and stored to its tensor-memory tile 32
+        // keys at a time (measured alternative: keep all of P in registers and store after the wait for PV(i-1): 714 vs 730)
         auto emit_P = [&](float m_use) -> float {
           const float nmb = -m_use * scale_log2e;
           const unsigned long long sc2 = f2_pack(scale_log2e, scale_log2e), nmb2 = f2_pack(nmb, nmb);
           unsigned long long sum2[2] = {0ull, 0ull};
-#pragma unroll
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < COLS / 8; ++j) {
@@ -399,16 +385,9 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             }
             sum2[0] = f2_add(sum2[0], f2_add(f2_pack(p[0], p[1]), f2_pack(p[4], p[5])));
             sum2[1] = f2_add(sum2[1], f2_add(f2_pack(p[2], p[3]), f2_pack(p[6], p[7])));
-            const int jg = h * (COLS / 8) + j;       // 16-byte chunk within the row of the P tile
-            if (P_TMEM) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) pk[4 * (j & 3) + e] = pack_p<PK>(p[2 * e], p[2 * e + 1]);
-              if ((j & 3) == 3) ptx::tmem_st_32x32b_x16(tP + (jg - 3) * 4, pk);   // 32 keys = 16 packed columns
-            } else {
-              const int kb = jg >> 3, chunk = jg & 7;
-              const uint4 v = make_uint4(pack_p<PK>(p[0], p[1]), pack_p<PK>(p[2], p[3]), pack_p<PK>(p[4], p[5]), pack_p<PK>(p[6], p[7]));
-              *reinterpret_cast<uint4*>(sP + kb * (QT * 128) + ((chunk ^ (r & 7)) << 4)) = v;
-            }
+            for (int e = 0; e < 4; ++e) pk[4 * (j & 3) + e] = pack_p<PK>(p[2 * e], p[2 * e + 1]);
+            if ((j & 3) == 3) ptx::tmem_st_32x32b_x16(tP + (h * (COLS / 8) + j - 3) * 4, pk);   // 32 keys = 16 packed columns
           }
           const unsigned long long tot = f2_add(sum2[0], sum2[1]);
           return f2_lo(tot) + f2_hi(tot);
@@ -419,13 +398,8 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           mx[0] = fmaxf(mx[0], s[c]); mx[1] = fmaxf(mx[1], s[c + 1]); mx[2] = fmaxf(mx[2], s[c + 2]); mx[3] = fmaxf(mx[3], s[c + 3]);
         }
         const float m_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-        if (P_TMEM) {
-          // P is single-buffered in tensor memory: PV(i-1) must have consumed it (this also orders the O rescale below)
-          if (i >= 1) ptx::mbar_wait(&bars->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
-        } else {
-          // the shared-memory P buffer of this parity was last read by PV(i-2)
-          if (i >= 2) ptx::mbar_wait(&bars->pv_done[t][i & 1], ((i - 2) >> 1) & 1);
-        }
+        // P is single-buffered in tensor memory: PV(i-1) must have consumed it (they retire in order, so O is quiescent too)
+        if (i >= 1) ptx::mbar_wait(&bars->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
         ptx::tc_fence_after();
         PH(2);
         float blk_sum;
@@ -439,11 +413,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           const float m_blk = row_max(m_half, i & 1);
           const bool jump = (m_blk - m_ref) * scale_log2e > 8.0f;
           if (__any_sync(0xffffffffu, jump)) {
-            // rescale O in TMEM: every earlier PV product must have retired (they complete in order)
-            if (!P_TMEM) {
-              ptx::mbar_wait(&bars->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
-              ptx::tc_fence_after();
-            }
+            // rescale O in TMEM
             const float alpha = jump ? ex2((m_ref - m_blk) * scale_log2e) : 1.0f;
             if (jump) m_ref = m_blk;
             l_run *= alpha;
@@ -456,15 +426,14 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
               for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
               ptx::tmem_st_32x32b_x16(tO + c, o);
             }
-            ptx::tmem_st_wait();
             blk_sum = emit_P(m_ref);
           }
         }
         l_run += blk_sum;
         PH(3);
-        // p_ready is double-buffered by iteration parity like the P tiles: P(i+2) is only written after PV(i) retired (wait
-        // above), so the softmax warps can never lap the MMA warp on a barrier (parity waits only tell adjacent phases apart).
-        if (P_TMEM) ptx::tmem_st_wait(); else ptx::fence_proxy_async_smem();
+        // p_ready alternates between two barriers by block parity: P(i+1) is only stored after PV(i) retired (wait above), so
+        // the softmax warps can never lap the MMA warp on a barrier (parity waits only tell adjacent phases apart).
+        ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->p_ready[t][i & 1]);

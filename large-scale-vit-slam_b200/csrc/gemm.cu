@@ -7,13 +7,16 @@
 // Replaces the library calls at: UPSTREAM Attention.qkv/proj, Mlp.fc1/fc2,
 // alignment_head.py:242 (project_in), cross_attention.py:55-57,76 (q/k/v/proj), plus the elementwise
 // q_norm/k_norm/RoPE/LayerScale/residual passes that the reference runs as separate ATen kernels.
+#include <cstdlib>
+
 #include "gemm.h"
 #include "host_common.h"
 #include "ptx.cuh"
 #include "tensormap.h"
 
 namespace lsvs {
-int g_gemm_mode = 0;  // 0 auto, 1 force the single-CTA kernel, 2 pair kernel without TMA reduce-add (lsvs_debug_gemm_mode; A/B testing)
+int g_gemm_mode = 0;  // 0 auto, 1 force the single-CTA kernel, 2 pair kernel without TMA reduce-add, 3 pair kernel without B loads (wrong results;
+                      // halves L2->SM bytes: qkv 75.7 -> 70.6 us, i.e. the pair kernel is not L2-bound) (lsvs_debug_gemm_mode; A/B testing)
 namespace {
 
 constexpr int BM = 128;
@@ -469,10 +472,11 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
         ptx::mbar_wait(empty_bar + stage, phase ^ 1);
         if (lane == 0) {
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
-          if (cta == 0) ptx::mbar_expect_tx(full_bar + stage, 2 * L::STAGE_BYTES);  // bytes of both CTAs land here
+          const bool skip_b = (use_tma_reduce & 2) != 0;  // measurement only (lsvs_debug_gemm_mode 3): halves the L2->SM bytes, wrong results
+          if (cta == 0) ptx::mbar_expect_tx(full_bar + stage, skip_b ? 2 * L::A_BYTES : 2 * L::STAGE_BYTES);  // bytes of both CTAs land here
           else ptx::mbar_arrive_remote(full_bar + stage, 0);
           ptx::tma_load_2d_2sm(sa, &tmA, full_bar + stage, kb * BK, m0);
-          ptx::tma_load_2d_2sm(sa + L::A_BYTES, &tmB, full_bar + stage, kb * BK, n0);
+          if (!skip_b) ptx::tma_load_2d_2sm(sa + L::A_BYTES, &tmB, full_bar + stage, kb * BK, n0);
         }
         __syncwarp();
         if (++stage == STAGES2) { stage = 0; phase ^= 1; }
@@ -523,7 +527,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       ptx::tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2;
-      if (L::TRANSPOSE && use_tma_reduce) {
+      if (L::TRANSPOSE && (use_tma_reduce & 1)) {
         epilogue_resid_tma(epi, &tmR, smem + L::TILE_OFFSET + (warp - 2) * L::TILE_BYTES, taddr, m0 + quarter * 32, n0, part * COLS, (part + 1) * COLS);
       } else {
         epilogue_row<BN2, EPI>(epi, sp, taddr, m, n0, m < M, part * COLS, (part + 1) * COLS);
@@ -537,7 +541,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
-  if (L::TRANSPOSE && use_tma_reduce && warp >= 2 && lane == 0) ptx::tma_store_wait<0>();  // reductions issued by this lane are complete
+  if (L::TRANSPOSE && (use_tma_reduce & 1) && warp >= 2 && lane == 0) ptx::tma_store_wait<0>();  // reductions issued by this lane are complete
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();
@@ -546,6 +550,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
 template <int EPI>
 int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const GemmEpilogue& e, cudaStream_t st) {
+  // epilogue warps: 4 (255 registers each) for the LayerNorm+RoPE epilogues, 8 otherwise (16 measured: no gain)
   constexpr int EW = (EPI == EPI_HEADNORM64_BF16 || EPI == EPI_HEADNORM128_BF16) ? 4 : 8;
   auto kern = gemm_bf16_tcgen05_2cta<EPI, EW>;
   static bool configured = false;
@@ -563,6 +568,7 @@ int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K,
     if (!tmR) return LSVS_ECUDA;
     use_red = 1;
   }
+  if (g_gemm_mode == 3) use_red |= 2;
   kern<<<2 * pairs, 64 + 32 * EW, Smem2<EPI>::TOTAL, st>>>(*tmA, *tmB, *tmR, M, N, K, e, use_red);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;

@@ -5,6 +5,9 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "large-scale-vit-slam_b200")]
 import torch
 from lsvs_b200 import ops
 M = 13184
+if os.environ.get("LSVS_GEMM_MODE"):
+    from lsvs_b200 import native
+    native.lib().lsvs_debug_gemm_mode(int(os.environ["LSVS_GEMM_MODE"]))
 def bench(fn_list, reps=30):
     for f in fn_list: f()
     torch.cuda.synchronize()
