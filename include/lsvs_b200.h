@@ -72,7 +72,8 @@ enum { LSVS_EPI_BIAS_BF16 = 0,      /* out bf16 [M,ldo]  = acc + bias           
        LSVS_EPI_BIAS_F32 = 2,       /* out fp32          = acc + bias                                      */
        LSVS_EPI_RESID_F32 = 3,      /* resid fp32 [M,ldr] += gamma * (acc + bias); out2 (optional) = resid */
        LSVS_EPI_HEADNORM64_BF16 = 4,  /* out bf16: per 64-wide head LayerNorm (+RoPE) on q/k columns, bias only on the rest */
-       LSVS_EPI_HEADNORM128_BF16 = 5 };
+       LSVS_EPI_HEADNORM128_BF16 = 5,
+       LSVS_EPI_CONV_BF16 = 6 };    /* internal to lsvs_conv2d_nhwc_bf16: bias + residuals + ReLU + border mask on a padded grid */
 enum { LSVS_ROPE_NONE = 0, LSVS_ROPE_2D = 1, LSVS_ROPE_1D = 2 };
 
 typedef struct lsvs_gemm_epilogue {
@@ -146,6 +147,35 @@ int lsvs_alignment_decode_forward(lsvs_engine* e, const float* align_tokens, int
  * -> pose_enc (B,S,9) of the last refinement iteration. */
 int lsvs_camera_head_forward(lsvs_engine* e, const float* tokens_last, int B, int S, int P, int num_iterations,
                              float* pose_enc, void* stream);
+/* ---- DPT dense-prediction heads (depth_head / point_head) --------------------------------------------
+ * replaces UPSTREAM vggt/heads/dpt_head.py DPTHead.forward (construction featureAligned_vggt.py:28-29, calls :166-168 and
+ * :183-185).  prefix: "depth_head." or "point_head." (state_dict prefix of the parameters pushed
+ * with lsvs_engine_set_param).  Weight layouts expected by lsvs_engine_set_param for these prefixes (rows, cols):
+ *   Conv2d k x k        (oc, ic, k, k)  ->  rows = oc, cols = k*k*ic ordered (ky, kx, ic)
+ *   ConvTranspose2d k=s (ic, oc, k, k)  ->  rows = k*k*oc ordered (ky, kx, oc), cols = ic
+ *   scratch.output_conv2.0: 32 output channels zero-padded to 64 rows (bias to 64); output_conv2.2: (od, 32) fp32.
+ * taps: 4 device pointers to the tapped Aggregator layers 4/11/17/23, each (frames, P, 2048) fp32, P = 5 + (H/14)*(W/14).
+ * pred (frames, H', W', output_dim-1) fp32, conf (frames, H', W') fp32 with H' = 14*(H/14), W' = 14*(W/14);
+ * activation: 0 = exp (depth), 1 = inv_log (points); confidence 1 + exp.  frames_chunk frames are processed at a time
+ * (upstream default 8; results do not depend on it), <= 0: all at once.  bf16 tensor-core convolutions, fp32 accumulate. */
+int lsvs_dpt_head_forward(lsvs_engine* e, const char* prefix, const float* const* taps, int frames, int P, int H, int W,
+                          int output_dim, int activation, float* pred, float* conf, int frames_chunk, void* stream);
+/* convolution on a zero-padded NHWC grid (building block of the DPT head, exported for parity tests):
+ * x (frames*hp*wp, C) bf16 with a one-pixel zero border, w (OC, taps*C) bf16 ordered (ky, kx, c), taps = 1 or 9 (3x3, pad 1),
+ * out = mask(relu?(conv + bias + res1 + res2)) on the same grid (frames*hp*wp, OC); mask_border writes zeros on the border. */
+int lsvs_conv2d_nhwc_bf16(const lsvs_bf16* x, const lsvs_bf16* w, const float* bias, const lsvs_bf16* res1, const lsvs_bf16* res2,
+                          lsvs_bf16* out, int frames, int hp, int wp, int C, int OC, int taps, int relu, int mask_border,
+                          void* stream);
+/* resampling kernels of the DPT head (exported for parity tests).  h, w: input grid; "padded" = one-pixel zero border.
+ *   POS_EMBED      out (frames,h,w,C) += ratio * uv sincos embedding, aspect = W_img / H_img (DPTHead._apply_pos_embed)
+ *   PAD            in (frames,h,w,C) -> out padded (frames,h+2,w+2,C)
+ *   CONVT_SHUFFLE  in (frames*h*w, a*a*C) GEMM output of a ConvTranspose2d(kernel = stride = a) -> out padded (frames,a*h+2,a*w+2,C)
+ *   IM2COL_S2      in (frames,h,w,C) -> out (frames*ho*wo, 9*C) patch matrix of a 3x3 / stride 2 / pad 1 convolution
+ *   BILINEAR       in padded (frames,h+2,w+2,C) -> out padded (frames,a+2,b+2,C), align_corners=True (+ embedding if ratio > 0) */
+enum { LSVS_DPT_POS_EMBED = 0, LSVS_DPT_PAD = 1, LSVS_DPT_CONVT_SHUFFLE = 2, LSVS_DPT_IM2COL_S2 = 3, LSVS_DPT_BILINEAR = 4 };
+int lsvs_dpt_resample(int op, const lsvs_bf16* in, lsvs_bf16* out, int frames, int h, int w, int C, int a, int b, float aspect,
+                      float ratio, void* stream);
+
 /* replaces the pose / Sim(3) composition featureAligned_vggt.py:97-143 and :190-196 (and data.py:12-52,
  * geometry.py:4-37 underneath).  chunk_sim3 (B,1,8), frame_se3 (B,S-1,7), cam_enc (B,S,9) camera-head output,
  * prev_pose_enc (B,S_prev,9) aligned poses of the previous chunk or NULL.

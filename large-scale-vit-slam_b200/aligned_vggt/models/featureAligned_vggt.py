@@ -2,16 +2,17 @@
 merge_results :227): same constructor, forward signature, returned keys and state_dict names.  The Aggregator,
 alignment head, camera head, pose composition and Sim(3) application run as sm_100a kernels behind the C ABI.
 
-Not on this path yet (SURVEY §8f "next"): the DPT depth / point heads and the track head.  Synthetic stand-ins
-for their raw outputs can be passed through `raw_depth` / `raw_points` so that the Sim(3) application
-(:171, :187-207) is exercised exactly as the reference applies it."""
+The DPT depth / point heads (reference :28-29, :166-207) run on the same engine (bf16 tensor-core convolutions).
+Not on this path: the track head (`enable_track` is accepted and ignored, `track_head` stays None —
+the reference's forward never calls it either).  `raw_depth` / `raw_points` (optional) stand in for the DPT outputs,
+e.g. to exercise the Sim(3) application (:171, :187-207) on chosen inputs."""
 import torch
 import torch.nn as nn
 
 from aligned_vggt.heads.alignment_head import AlignmentHead
 from aligned_vggt.utils import alignment as _al
 from lsvs_b200.engine import Engine, pose_chain
-from lsvs_b200.modules import Aggregator, CameraHead
+from lsvs_b200.modules import Aggregator, CameraHead, DPTHead
 
 try:  # the reference mixes in the HF hub loader; keep it when the package is present
     from huggingface_hub import PyTorchModelHubMixin
@@ -31,17 +32,18 @@ class FeatureAlignedVGGT(nn.Module, PyTorchModelHubMixin):
         self.aggregator = Aggregator(img_size=img_size, patch_size=patch_size, embed_dim=embed_dim, depth=depth,
                                      patch_embed_depth=patch_embed_depth, keep_layers=self.intermediate_layer_indices)
         self.camera_head = CameraHead(dim_in=2 * embed_dim) if enable_camera else None
-        # DPT / track heads: SURVEY §8f "next" — not built on this path yet
-        self.point_head = None
-        self.depth_head = None
-        self.track_head = None
+        self.point_head = DPTHead(dim_in=2 * embed_dim, output_dim=4, activation="inv_log", conf_activation="expp1",
+                                  prefix="point_head.") if enable_point else None  # :28
+        self.depth_head = DPTHead(dim_in=2 * embed_dim, output_dim=2, activation="exp", conf_activation="expp1",
+                                  prefix="depth_head.") if enable_depth else None  # :29
+        self.track_head = None  # not on this path (never called by the reference's forward)
         self._requested_heads = dict(point=enable_point, depth=enable_depth, track=enable_track)
         self.alignment_head = AlignmentHead(in_dim=2 * embed_dim, patch_size=patch_size, num_memory_tokens=num_memory_tokens,
                                             temporal_attention=temporal_attention)
         self._bind_children()
 
     def _bind_children(self):
-        for child in (self.aggregator, self.camera_head, self.alignment_head):
+        for child in (self.aggregator, self.camera_head, self.alignment_head, self.point_head, self.depth_head):
             if child is not None:
                 child._bind(self)
         self.__dict__.pop("_native_engine", None)
@@ -49,6 +51,8 @@ class FeatureAlignedVGGT(nn.Module, PyTorchModelHubMixin):
     def set_config(self, cfg):
         """reference :34-46 — called after from_pretrained; re-creates the alignment head (random init)."""
         self.camera_head = self.camera_head if cfg.enable_camera else None
+        self.point_head = self.point_head if cfg.enable_point else None
+        self.depth_head = self.depth_head if cfg.enable_depth else None
         self._requested_heads = dict(point=cfg.enable_point, depth=cfg.enable_depth, track=cfg.enable_track)
         self.enable_memory = cfg.num_memory_tokens > 0
         dev = next(self.aggregator.parameters()).device
@@ -109,12 +113,21 @@ class FeatureAlignedVGGT(nn.Module, PyTorchModelHubMixin):
         if chunk_scale is None:
             chunk_scale = chunk_sim3_enc[..., -1].reshape(B)
 
-        if raw_depth is not None:  # stands in for depth_head(...) until the DPT head is on this path (:166-171)
+        depth_conf = pts_conf = None
+        if raw_depth is None and self.depth_head is not None:  # :166-168
+            raw_depth, depth_conf = self.depth_head(taps, images=images, patch_start_idx=patch_start_idx)
+        if raw_points is None and self.point_head is not None:  # :183-185
+            raw_points, pts_conf = self.point_head(taps, images=images, patch_start_idx=patch_start_idx)
+        if raw_depth is not None:  # :171 depth *= chunk_scale
             depth = _al.scale_depth(raw_depth, chunk_scale)
             _append(predictions, context, "depth", depth)
-        if raw_points is not None:  # stands in for point_head(...) (:183-207)
+            if depth_conf is not None:
+                _append(predictions, context, "depth_conf", depth_conf)
+        if raw_points is not None:  # :187-207 scale, then the chunk's point transform
             pts = _al.apply_sim3_alignment_on_point_maps(raw_points, point_T, chunk_scale) if point_T is not None else raw_points
             _append(predictions, context, "world_points", pts)
+            if pts_conf is not None:
+                _append(predictions, context, "world_points_conf", pts_conf)
         if not self.training:
             _append(predictions, context, "images", images)
         return predictions

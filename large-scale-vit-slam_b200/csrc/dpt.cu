@@ -1,0 +1,259 @@
+// DPT dense-prediction head (UPSTREAM vggt/heads/dpt_head.py; call sites featureAligned_vggt.py:28-29,166,183):
+// resampling / data-movement kernels around the tensor-core convolutions.  The convolutions themselves are GEMMs
+// (csrc/gemm.cu): 1x1 and transposed convolutions directly, 3x3 convolutions as nine row-shifted GEMM k-slabs over a
+// zero-padded NHWC grid (EPI_CONV_BF16).  Everything here is HBM-bound element-wise work: 16-byte accesses, one
+// thread per (pixel, 8 channels).
+#include "dpt.h"
+#include "gemm.h"
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace lsvs {
+namespace {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { f[2 * j] = ptx::bf16_lo(w[j]); f[2 * j + 1] = ptx::bf16_hi(w[j]); }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(ptx::pack_bf16(f[0], f[1]), ptx::pack_bf16(f[2], f[3]), ptx::pack_bf16(f[4], f[5]), ptx::pack_bf16(f[6], f[7]));
+}
+
+// torch.linspace(-span*(n-1)/n, +span*(n-1)/n, n)[i] (symmetric evaluation like ATen)
+__device__ __forceinline__ float uv_coord(int i, int n, float span) {
+  const float end = span * (float)(n - 1) / (float)n, start = -end;
+  if (n == 1) return start;
+  const float step = (end - start) / (float)(n - 1);
+  return i < n / 2 ? start + step * (float)i : end - step * (float)(n - 1 - i);
+}
+// channel c of position_grid_to_embed: [sin(u w_k), cos(u w_k), sin(v w_k), cos(v w_k)], w_k = 100^(-k / (C/4))
+__device__ __forceinline__ float uv_embed(int c, int C, float u, float v) {
+  const int half = C >> 1, quarter = C >> 2;
+  const float coord = c < half ? u : v;
+  const int cc = c < half ? c : c - half;
+  const int k = cc < quarter ? cc : cc - quarter;
+  const float omega = exp2f(-6.643856189774724f * (float)k / (float)quarter);  // log2(100)
+  const float a = coord * omega;
+  return cc < quarter ? sinf(a) : cosf(a);
+}
+__device__ __forceinline__ void uv_spans(float aspect, float& sx, float& sy) {
+  const float diag = sqrtf(aspect * aspect + 1.0f);
+  sx = aspect / diag;
+  sy = 1.0f / diag;
+}
+
+__global__ void pos_embed_kernel(uint4* x, long long total, int h, int w, int C8, float aspect, float ratio) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % C8);
+  const long long pix = i / C8;
+  const int xx = (int)(pix % w), yy = (int)((pix / w) % h);
+  float sx, sy;
+  uv_spans(aspect, sx, sy);
+  const float u = uv_coord(xx, w, sx), v = uv_coord(yy, h, sy);
+  float f[8];
+  unpack8(x[i], f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] += ratio * uv_embed(c8 * 8 + j, C8 * 8, u, v);
+  x[i] = pack8(f);
+}
+
+__global__ void pad_kernel(const uint4* in, uint4* out, long long total, int h, int w, int C8) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % C8);
+  const long long pix = i / C8;
+  const int wp = w + 2, hp = h + 2;
+  const int xp = (int)(pix % wp), yp = (int)((pix / wp) % hp);
+  const long long f = pix / ((long long)wp * hp);
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (xp >= 1 && xp <= w && yp >= 1 && yp <= h) v = in[((f * h + (yp - 1)) * w + (xp - 1)) * C8 + c8];
+  out[i] = v;
+}
+
+__global__ void convt_shuffle_kernel(const uint4* in, const float* bias, uint4* out, long long total, int h, int w, int C8, int k) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % C8);
+  const long long pix = i / C8;
+  const int wp = k * w + 2, hp = k * h + 2;
+  const int xp = (int)(pix % wp), yp = (int)((pix / wp) % hp);
+  const long long f = pix / ((long long)wp * hp);
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (xp >= 1 && xp <= k * w && yp >= 1 && yp <= k * h) {
+    const int oy = yp - 1, ox = xp - 1;
+    const int y = oy / k, ii = oy - y * k, x = ox / k, jj = ox - x * k;
+    v = in[(((f * h + y) * w + x) * (k * k) + ii * k + jj) * C8 + c8];
+    if (bias) {
+      float t[8];
+      unpack8(v, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] += bias[c8 * 8 + j];
+      v = pack8(t);
+    }
+  }
+  out[i] = v;
+}
+
+__global__ void im2col_s2_kernel(const uint4* in, uint4* out, long long total, int h, int w, int ho, int wo, int C8) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % C8);
+  long long r = i / C8;
+  const int tap = (int)(r % 9);
+  r /= 9;
+  const int ox = (int)(r % wo), oy = (int)((r / wo) % ho);
+  const long long f = r / ((long long)wo * ho);
+  const int y = 2 * oy - 1 + tap / 3, x = 2 * ox - 1 + tap % 3;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (y >= 0 && y < h && x >= 0 && x < w) v = in[((f * h + y) * w + x) * C8 + c8];
+  out[i] = v;
+}
+
+__global__ void bilinear_kernel(const uint4* in, uint4* out, long long total, int hi, int wi, int ho, int wo, int C8,
+                                float aspect, float ratio) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % C8);
+  const long long pix = i / C8;
+  const int wpo = wo + 2, hpo = ho + 2, wpi = wi + 2, hpi = hi + 2;
+  const int xp = (int)(pix % wpo), yp = (int)((pix / wpo) % hpo);
+  const long long f = pix / ((long long)wpo * hpo);
+  if (xp < 1 || xp > wo || yp < 1 || yp > ho) { out[i] = make_uint4(0u, 0u, 0u, 0u); return; }
+  const int oy = yp - 1, ox = xp - 1;
+  // align_corners=True (ATen area_pixel_compute_scale / source index)
+  const float sy = ho > 1 ? (float)(hi - 1) / (float)(ho - 1) * (float)oy : 0.f;
+  const float sx = wo > 1 ? (float)(wi - 1) / (float)(wo - 1) * (float)ox : 0.f;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = y0 + (y0 < hi - 1 ? 1 : 0), x1 = x0 + (x0 < wi - 1 ? 1 : 0);
+  const float ly = sy - (float)y0, lx = sx - (float)x0;
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const long long base = f * hpi;
+  float a[8], b[8], c[8], d[8], o[8];
+  unpack8(in[((base + y0 + 1) * wpi + x0 + 1) * C8 + c8], a);
+  unpack8(in[((base + y0 + 1) * wpi + x1 + 1) * C8 + c8], b);
+  unpack8(in[((base + y1 + 1) * wpi + x0 + 1) * C8 + c8], c);
+  unpack8(in[((base + y1 + 1) * wpi + x1 + 1) * C8 + c8], d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = w00 * a[j] + w01 * b[j] + w10 * c[j] + w11 * d[j];
+  if (ratio > 0.f) {
+    float spx, spy;
+    uv_spans(aspect, spx, spy);
+    const float u = uv_coord(ox, wo, spx), v = uv_coord(oy, ho, spy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] += ratio * uv_embed(c8 * 8 + j, C8 * 8, u, v);
+  }
+  out[i] = pack8(o);
+}
+
+// one thread per pixel: 32 input channels (post-ReLU, bf16) x od fp32 weights, then activate_head
+__global__ void final_kernel(const __nv_bfloat16* in, int ldc, const float* w, const float* b, int od, int activation, float* pred,
+                             float* conf, long long total, int H, int W) {
+  __shared__ float sw[4 * 32 + 4];
+  if (threadIdx.x < od * 32) sw[threadIdx.x] = w[threadIdx.x];
+  if (threadIdx.x < od) sw[128 + threadIdx.x] = b[threadIdx.x];
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % W), y = (int)((i / W) % H);
+  const long long f = i / ((long long)W * H);
+  const uint4* src = reinterpret_cast<const uint4*>(in + ((f * (H + 2) + y + 1) * (long long)(W + 2) + x + 1) * ldc);
+  float acc[4] = {sw[128], sw[129], sw[130], sw[131]};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float v[8];
+    unpack8(src[q], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) if (o < od) acc[o] += v[j] * sw[o * 32 + q * 8 + j];
+    }
+  }
+  for (int o = 0; o < od - 1; ++o) {
+    const float t = acc[o];
+    pred[i * (od - 1) + o] = activation == 0 ? expf(t) : copysignf(expm1f(fabsf(t)), t);
+  }
+  conf[i] = 1.0f + expf(acc[od - 1]);
+}
+
+int blocks_for(long long total) { return (int)((total + TPB - 1) / TPB); }
+
+}  // namespace
+
+int dpt_add_pos_embed(void* x, int frames, int h, int w, int C, float aspect, float ratio, cudaStream_t st) {
+  LSVS_CHECK_ARG(x && C % 8 == 0 && C % 4 == 0, "dpt_add_pos_embed: bad arguments");
+  const long long total = (long long)frames * h * w * (C / 8);
+  pos_embed_kernel<<<blocks_for(total), TPB, 0, st>>>(reinterpret_cast<uint4*>(x), total, h, w, C / 8, aspect, ratio);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+int dpt_pad(const void* in, void* out, int frames, int h, int w, int C, cudaStream_t st) {
+  const long long total = (long long)frames * (h + 2) * (w + 2) * (C / 8);
+  pad_kernel<<<blocks_for(total), TPB, 0, st>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), total, h, w, C / 8);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+int dpt_convt_shuffle(const void* in, const float* bias, void* out, int frames, int h, int w, int C, int k, cudaStream_t st) {
+  const long long total = (long long)frames * (k * h + 2) * (k * w + 2) * (C / 8);
+  convt_shuffle_kernel<<<blocks_for(total), TPB, 0, st>>>(reinterpret_cast<const uint4*>(in), bias, reinterpret_cast<uint4*>(out), total, h, w, C / 8, k);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+int dpt_im2col_s2(const void* in, void* out, int frames, int h, int w, int C, cudaStream_t st) {
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const long long total = (long long)frames * ho * wo * 9 * (C / 8);
+  im2col_s2_kernel<<<blocks_for(total), TPB, 0, st>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), total, h, w, ho, wo, C / 8);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+int dpt_bilinear(const void* in, void* out, int frames, int hi, int wi, int ho, int wo, int C, float aspect, float ratio, cudaStream_t st) {
+  const long long total = (long long)frames * (ho + 2) * (wo + 2) * (C / 8);
+  bilinear_kernel<<<blocks_for(total), TPB, 0, st>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), total, hi, wi, ho, wo, C / 8, aspect, ratio);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+int dpt_final(const void* in, int ldc, const float* w, const float* b, int od, int activation, float* pred, float* conf, int frames,
+              int H, int W, cudaStream_t st) {
+  LSVS_CHECK_ARG(od >= 2 && od <= 4 && ldc >= 32 && ldc % 8 == 0, "dpt_final: output_dim must be 2..4");
+  const long long total = (long long)frames * H * W;
+  final_kernel<<<blocks_for(total), TPB, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), ldc, w, b, od, activation, pred, conf, total, H, W);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+
+}  // namespace lsvs
+
+// ---------------------------------------------------------------------------------------------------- C ABI
+extern "C" int lsvs_conv2d_nhwc_bf16(const lsvs_bf16* x, const lsvs_bf16* w, const float* bias, const lsvs_bf16* res1,
+                                     const lsvs_bf16* res2, lsvs_bf16* out, int frames, int hp, int wp, int C, int OC, int taps,
+                                     int relu, int mask_border, void* stream) {
+  using namespace lsvs;
+  LSVS_CHECK_ARG(x && w && out && frames > 0 && hp > 2 && wp > 2, "conv2d: bad arguments");
+  LSVS_CHECK_ARG(taps == 1 || taps == 9, "conv2d: taps must be 1 (1x1) or 9 (3x3, pad 1)");
+  LSVS_CHECK_ARG(C % 64 == 0, "conv2d: input channels must be a multiple of 64");
+  GemmEpilogue e;
+  e.bias = bias; e.out = out; e.ldo = OC;
+  e.conv_taps = taps == 9 ? 9 : 0; e.conv_c = C; e.conv_hp = hp; e.conv_wp = wp; e.conv_relu = relu; e.conv_mask = mask_border;
+  e.res1 = res1; e.res2 = res2;
+  const long long M = (long long)frames * hp * wp;
+  LSVS_CHECK_ARG(M < (1ll << 31), "conv2d: too many pixels for one launch");
+  return gemm_bf16(x, C, w, taps * C, (int)M, OC, taps * C, EPI_CONV_BF16, e, (cudaStream_t)stream);
+}
+
+extern "C" int lsvs_dpt_resample(int op, const lsvs_bf16* in, lsvs_bf16* out, int frames, int h, int w, int C, int a, int b, float aspect,
+                                 float ratio, void* stream) {
+  using namespace lsvs;
+  cudaStream_t st = (cudaStream_t)stream;
+  LSVS_CHECK_ARG(out && frames > 0 && h > 0 && w > 0 && C > 0 && C % 8 == 0, "dpt_resample: bad arguments");
+  switch (op) {
+    case LSVS_DPT_POS_EMBED: return dpt_add_pos_embed(out, frames, h, w, C, aspect, ratio, st);
+    case LSVS_DPT_PAD: LSVS_CHECK_ARG(in, "dpt_resample: null input"); return dpt_pad(in, out, frames, h, w, C, st);
+    case LSVS_DPT_CONVT_SHUFFLE: LSVS_CHECK_ARG(in && a > 0, "dpt_resample: bad stride"); return dpt_convt_shuffle(in, nullptr, out, frames, h, w, C, a, st);
+    case LSVS_DPT_IM2COL_S2: LSVS_CHECK_ARG(in, "dpt_resample: null input"); return dpt_im2col_s2(in, out, frames, h, w, C, st);
+    case LSVS_DPT_BILINEAR: LSVS_CHECK_ARG(in && a > 0 && b > 0, "dpt_resample: bad output size"); return dpt_bilinear(in, out, frames, h, w, a, b, C, aspect, ratio, st);
+    default: return fail(LSVS_EINVAL, "dpt_resample: unknown op %d", op);
+  }
+}

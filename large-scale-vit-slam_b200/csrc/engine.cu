@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "attention.h"
+#include "dpt.h"
 #include "elementwise.h"
 #include "gemm.h"
 #include "host_common.h"
@@ -77,13 +78,13 @@ struct Engine {
   DevBuf rope2d_64, rope2d_128, rope1d_128, ids_q, ids_k;
   int rope_npos2d = 0, rope_npos1d = 0;
   // workspace
-  DevBuf x, xn, qkv, att, h, tmp, im2col, yn, kvb, scratch;
+  DevBuf x, xn, qkv, att, h, tmp, im2col, yn, kvb, scratch, dpt_ws;
   size_t scratch_off = 0;
 
   ~Engine() {
     for (auto& kv : params) { if (kv.second.f32) cudaFree(kv.second.f32); if (kv.second.bf16) cudaFree(kv.second.bf16); }
     for (auto& b : fused) b.release();
-    for (DevBuf* b : {&pos_embed, &rope2d_64, &rope2d_128, &rope1d_128, &ids_q, &ids_k, &x, &xn, &qkv, &att, &h, &tmp, &im2col, &yn, &kvb, &scratch}) b->release();
+    for (DevBuf* b : {&pos_embed, &rope2d_64, &rope2d_128, &rope1d_128, &ids_q, &ids_k, &x, &xn, &qkv, &att, &h, &tmp, &im2col, &yn, &kvb, &scratch, &dpt_ws}) b->release();
   }
 
   const Param* find(const std::string& n) const { auto it = params.find(n); return it == params.end() ? nullptr : &it->second; }
@@ -113,6 +114,8 @@ bool wants_bf16(const std::string& n) {
   if (big_block && (contains(n, "attn.qkv.") || contains(n, "attn.proj.") || contains(n, "attn.q.") || contains(n, "attn.k.") ||
                     contains(n, "attn.v.") || contains(n, "mlp.fc1.") || contains(n, "mlp.fc2.") || contains(n, "patch_embed.proj.")))
     return true;
+  if (contains(n, "depth_head.") || contains(n, "point_head."))  // DPT heads: every convolution except the last 1x1 (fp32 with the activation)
+    return !ends_with(n, "norm.weight") && !contains(n, "output_conv2.2.");
   return n == "alignment_head.project_in.weight";
 }
 
@@ -646,6 +649,141 @@ extern "C" int lsvs_camera_head_forward(lsvs_engine* h, const float* tokens_last
   }
   TRY(combine_rows(pred, 9, nullptr, 0, pose_enc, 9, frames, 9, 7, -1, st));  // activate_pose: T, quat linear; FoV relu
   if (e.scratch_overflow) { e.scratch_overflow = false; return fail(LSVS_ECUDA, "camera_head_forward: scratch under-sized"); }
+  return LSVS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- DPT head
+// UPSTREAM vggt/heads/dpt_head.py DPTHead.forward (depth_head / point_head, featureAligned_vggt.py:166,183).
+// Per frame chunk: LayerNorm of the 4 tapped token maps -> 1x1 projections (+uv position embedding) -> resize
+// (transposed conv x4 / x2, identity, 3x3 stride-2 conv) -> layer_rn 3x3 convs -> 4 refinement stages (residual conv units,
+// bilinear x2, 1x1 out_conv) -> output_conv1 -> bilinear to the image size (+ position embedding) -> output_conv2 ->
+// activation.  The 1x1 out_conv of a fusion block is applied BEFORE its bilinear upsample (both are linear and the
+// interpolation weights sum to one, so the result is the same and the GEMM runs on a quarter of the pixels).
+extern "C" int lsvs_dpt_head_forward(lsvs_engine* h, const char* prefix, const float* const* taps, int frames, int P, int H, int W,
+                                     int output_dim, int activation, float* pred, float* conf, int frames_chunk, void* stream) {
+  Engine& e = *reinterpret_cast<Engine*>(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  LSVS_CHECK_ARG(prefix && taps && pred && conf && frames > 0, "dpt_head_forward: bad arguments");
+  LSVS_CHECK_ARG(output_dim >= 2 && output_dim <= 4 && (activation == 0 || activation == 1), "dpt_head_forward: output_dim 2..4, activation 0 (exp) or 1 (inv_log)");
+  const int ph = H / 14, pw = W / 14, Pp = ph * pw, C = 2048;
+  LSVS_CHECK_ARG(ph > 0 && pw > 0 && P == Pp + 5, "dpt_head_forward: token count %d does not match the %dx%d patch grid (+5)", P, ph, pw);
+  for (int l = 0; l < 4; ++l) LSVS_CHECK_ARG(taps[l], "dpt_head_forward: tap %d is null", l);
+  const std::string pre(prefix);
+  const int oc[4] = {256, 512, 1024, 1024};
+  const int F0 = frames_chunk > 0 ? (frames_chunk < frames ? frames_chunk : frames) : frames;
+  struct Grid { int h, w; long long rows(int F) const { return (long long)F * (h + 2) * (w + 2); } };
+  const Grid g1{4 * ph, 4 * pw}, g2{2 * ph, 2 * pw}, g3{ph, pw}, g4{(ph - 1) / 2 + 1, (pw - 1) / 2 + 1}, g5{8 * ph, 8 * pw}, gF{14 * ph, 14 * pw};
+  const Grid lvl[4] = {g1, g2, g3, g4};
+  // ---- weights
+  const float *nw, *nb;
+  TRY(need_f32(e, pre + "norm.weight", &nw, C)); TRY(need_f32(e, pre + "norm.bias", &nb, C));
+  const __nv_bfloat16 *pw_[4], *rnw[4], *ct0w, *ct1w, *c3w, *oc1w, *oc2w;
+  const float *pb_[4], *ct0b, *ct1b, *c3b, *oc1b, *oc2b, *finw, *finb;
+  for (int l = 0; l < 4; ++l) {
+    TRY(need_bf16(e, pre + "projects." + std::to_string(l) + ".weight", &pw_[l], oc[l], C));
+    TRY(need_f32(e, pre + "projects." + std::to_string(l) + ".bias", &pb_[l], oc[l]));
+    TRY(need_bf16(e, pre + "scratch.layer" + std::to_string(l + 1) + "_rn.weight", &rnw[l], 256, 9 * oc[l]));
+  }
+  TRY(need_bf16(e, pre + "resize_layers.0.weight", &ct0w, 16 * 256, 256)); TRY(need_f32(e, pre + "resize_layers.0.bias", &ct0b, 256));
+  TRY(need_bf16(e, pre + "resize_layers.1.weight", &ct1w, 4 * 512, 512)); TRY(need_f32(e, pre + "resize_layers.1.bias", &ct1b, 512));
+  TRY(need_bf16(e, pre + "resize_layers.3.weight", &c3w, 1024, 9 * 1024)); TRY(need_f32(e, pre + "resize_layers.3.bias", &c3b, 1024));
+  TRY(need_bf16(e, pre + "scratch.output_conv1.weight", &oc1w, 128, 9 * 256)); TRY(need_f32(e, pre + "scratch.output_conv1.bias", &oc1b, 128));
+  TRY(need_bf16(e, pre + "scratch.output_conv2.0.weight", &oc2w, 64, 9 * 128)); TRY(need_f32(e, pre + "scratch.output_conv2.0.bias", &oc2b, 64));
+  TRY(need_f32(e, pre + "scratch.output_conv2.2.weight", &finw, 32LL * output_dim)); TRY(need_f32(e, pre + "scratch.output_conv2.2.bias", &finb, output_dim));
+  struct Rcu { const __nv_bfloat16 *w1, *w2; const float *b1, *b2; };
+  struct Fuse { Rcu u1, u2; const __nv_bfloat16* ow; const float* ob; };
+  Fuse fu[4];
+  for (int r = 0; r < 4; ++r) {
+    const std::string b = pre + "scratch.refinenet" + std::to_string(r + 1) + ".";
+    for (int u = (r == 3 ? 2 : 1); u <= 2; ++u) {
+      Rcu& q = u == 1 ? fu[r].u1 : fu[r].u2;
+      const std::string c = b + "resConfUnit" + std::to_string(u) + ".";
+      TRY(need_bf16(e, c + "conv1.weight", &q.w1, 256, 9 * 256)); TRY(need_f32(e, c + "conv1.bias", &q.b1, 256));
+      TRY(need_bf16(e, c + "conv2.weight", &q.w2, 256, 9 * 256)); TRY(need_f32(e, c + "conv2.bias", &q.b2, 256));
+    }
+    TRY(need_bf16(e, b + "out_conv.weight", &fu[r].ow, 256, 256)); TRY(need_f32(e, b + "out_conv.bias", &fu[r].ob, 256));
+  }
+  // ---- workspace (bf16 elements), bump-allocated
+  const long long rows0 = (long long)F0 * Pp, rows4 = (long long)F0 * g4.h * g4.w;
+  size_t off = 0;
+  auto take = [&](long long elems) { const size_t o = off; off += ((size_t)elems * 2 + 255) & ~size_t(255); return o; };
+  const size_t o_tok = take(rows0 * C), o_proj = take(rows0 * 1024), o_ct = take(rows0 * 4096 > rows4 * 1024 ? rows0 * 4096 : rows4 * 1024),
+               o_col = take(rows4 * 9 * 1024);
+  size_t o_x[4], o_rn[4];
+  for (int l = 0; l < 4; ++l) { o_x[l] = take(lvl[l].rows(F0) * oc[l]); o_rn[l] = take(lvl[l].rows(F0) * 256); }
+  const long long rmax = g1.rows(F0);
+  const size_t o_t = take(rmax * 256), o_a2 = take(rmax * 256), o_o = take(rmax * 256), o_oc = take(rmax * 256);
+  const size_t o_u3 = take(g3.rows(F0) * 256), o_u2 = take(g2.rows(F0) * 256), o_u1 = take(g1.rows(F0) * 256), o_u5 = take(g5.rows(F0) * 256);
+  const size_t o_o1 = take(g5.rows(F0) * 128), o_uf = take(gF.rows(F0) * 128), o_o2 = take(gF.rows(F0) * 64);
+  LSVS_CHECK_ARG(gF.rows(F0) < (1ll << 31), "dpt_head_forward: frame chunk too large");
+  TRY(e.dpt_ws.ensure(off));
+  uint8_t* ws = e.dpt_ws.as<uint8_t>();
+  auto B16 = [&](size_t o) { return reinterpret_cast<__nv_bfloat16*>(ws + o); };
+  const float aspect = (float)W / (float)H;
+
+  auto conv = [&](const __nv_bfloat16* x, const Grid& g, int F, int Cin, const __nv_bfloat16* w, const float* b, int OC, int taps_,
+                  bool relu, const __nv_bfloat16* r1, const __nv_bfloat16* r2, __nv_bfloat16* out) -> int {
+    GemmEpilogue ep;
+    ep.bias = b; ep.out = out; ep.ldo = OC;
+    ep.conv_taps = taps_ == 9 ? 9 : 0; ep.conv_c = Cin; ep.conv_hp = g.h + 2; ep.conv_wp = g.w + 2; ep.conv_relu = relu ? 1 : 0; ep.conv_mask = 1;
+    ep.res1 = r1; ep.res2 = r2;
+    return gemm_bf16(x, Cin, w, taps_ * Cin, (int)g.rows(F), OC, taps_ * Cin, EPI_CONV_BF16, ep, st);
+  };
+  // ResidualConvUnit on a = relu(x) (the fusion blocks use an in-place ReLU, so the skip path carries relu(x)):
+  // out = [relu](conv2(relu(conv1(a))) + a + extra)
+  auto rcu = [&](const Rcu& q, const __nv_bfloat16* a, const Grid& g, int F, const __nv_bfloat16* extra, bool relu_out, __nv_bfloat16* out) -> int {
+    TRY(conv(a, g, F, 256, q.w1, q.b1, 256, 9, true, nullptr, nullptr, B16(o_t)));
+    return conv(B16(o_t), g, F, 256, q.w2, q.b2, 256, 9, relu_out, a, extra, out);
+  };
+
+  for (int f0 = 0; f0 < frames; f0 += F0) {
+    const int F = frames - f0 < F0 ? frames - f0 : F0;
+    const long long r0 = (long long)F * Pp;
+    for (int l = 0; l < 4; ++l) {
+      const float* tap = taps[l] + (size_t)f0 * P * C;
+      TRY(layernorm(tap, C, RowMap{Pp, P, 5}, nw, nb, 1e-5f, B16(o_tok), C, RowMap{}, true, r0, C, st));
+      GemmEpilogue ep;
+      ep.bias = pb_[l]; ep.out = B16(o_proj); ep.ldo = oc[l];
+      TRY(gemm_bf16(B16(o_tok), C, pw_[l], C, (int)r0, oc[l], C, EPI_BIAS_BF16, ep, st));
+      TRY(dpt_add_pos_embed(B16(o_proj), F, ph, pw, oc[l], aspect, 0.1f, st));
+      if (l == 0 || l == 1) {
+        const int k = l == 0 ? 4 : 2;
+        GemmEpilogue ec;
+        ec.out = B16(o_ct); ec.ldo = k * k * oc[l];
+        TRY(gemm_bf16(B16(o_proj), oc[l], l == 0 ? ct0w : ct1w, oc[l], (int)r0, k * k * oc[l], oc[l], EPI_BIAS_BF16, ec, st));
+        TRY(dpt_convt_shuffle(B16(o_ct), l == 0 ? ct0b : ct1b, B16(o_x[l]), F, ph, pw, oc[l], k, st));
+      } else if (l == 2) {
+        TRY(dpt_pad(B16(o_proj), B16(o_x[l]), F, ph, pw, oc[l], st));
+      } else {
+        TRY(dpt_im2col_s2(B16(o_proj), B16(o_col), F, ph, pw, oc[l], st));
+        GemmEpilogue ec;
+        ec.bias = c3b; ec.out = B16(o_ct); ec.ldo = 1024;
+        TRY(gemm_bf16(B16(o_col), 9 * 1024, c3w, 9 * 1024, F * g4.h * g4.w, 1024, 9 * 1024, EPI_BIAS_BF16, ec, st));
+        TRY(dpt_pad(B16(o_ct), B16(o_x[l]), F, g4.h, g4.w, 1024, st));
+      }
+      // layer_rn: 3x3, no bias; its only consumer is a ResidualConvUnit whose in-place ReLU rewrites it, so store relu(.)
+      TRY(conv(B16(o_x[l]), lvl[l], F, oc[l], rnw[l], nullptr, 256, 9, true, nullptr, nullptr, B16(o_rn[l])));
+    }
+    // refinenet4 (no residual input): out_conv(upsample(RCU2(rn4)))
+    TRY(rcu(fu[3].u2, B16(o_rn[3]), g4, F, nullptr, false, B16(o_o)));
+    TRY(conv(B16(o_o), g4, F, 256, fu[3].ow, fu[3].ob, 256, 1, false, nullptr, nullptr, B16(o_oc)));
+    TRY(dpt_bilinear(B16(o_oc), B16(o_u3), F, g4.h, g4.w, g3.h, g3.w, 256, aspect, 0.f, st));
+    const size_t o_up[4] = {o_u1, o_u2, o_u3, 0};
+    for (int r = 2; r >= 0; --r) {
+      const Grid& g = lvl[r];
+      // output = x0 + RCU1(rn_r), then RCU2's in-place ReLU: a2 = relu(conv2(relu(conv1(rn))) + rn + x0)
+      TRY(rcu(fu[r].u1, B16(o_rn[r]), g, F, B16(o_up[r]), true, B16(o_a2)));
+      TRY(rcu(fu[r].u2, B16(o_a2), g, F, nullptr, false, B16(o_o)));
+      TRY(conv(B16(o_o), g, F, 256, fu[r].ow, fu[r].ob, 256, 1, false, nullptr, nullptr, B16(o_oc)));
+      const Grid& gn = r == 0 ? g5 : lvl[r - 1];
+      TRY(dpt_bilinear(B16(o_oc), B16(r == 0 ? o_u5 : o_up[r - 1]), F, g.h, g.w, gn.h, gn.w, 256, aspect, 0.f, st));
+    }
+    TRY(conv(B16(o_u5), g5, F, 256, oc1w, oc1b, 128, 9, false, nullptr, nullptr, B16(o_o1)));
+    TRY(dpt_bilinear(B16(o_o1), B16(o_uf), F, g5.h, g5.w, gF.h, gF.w, 128, aspect, 0.1f, st));
+    TRY(conv(B16(o_uf), gF, F, 128, oc2w, oc2b, 64, 9, true, nullptr, nullptr, B16(o_o2)));
+    TRY(dpt_final(B16(o_o2), 64, finw, finb, output_dim, activation, pred + (size_t)f0 * gF.h * gF.w * (output_dim - 1),
+                  conf + (size_t)f0 * gF.h * gF.w, F, gF.h, gF.w, st));
+  }
   return LSVS_OK;
 }
 

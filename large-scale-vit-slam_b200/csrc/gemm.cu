@@ -154,6 +154,15 @@ __device__ __forceinline__ void head_norm_rope(float* v, const float* __restrict
   }
 }
 
+// EPI_CONV_BF16: k-block -> (channel offset within the tap, A row shifted by the tap offset on the padded grid)
+__device__ __forceinline__ void conv_tap_coords(const GemmEpilogue& e, int& a_k, int& a_row) {
+  if (e.conv_taps == 9) {
+    const int tap = a_k / e.conv_c;
+    a_k -= tap * e.conv_c;
+    a_row += (tap / 3 - 1) * e.conv_wp + (tap % 3 - 1);
+  }
+}
+
 template <int BN, int EPI>
 __device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, const EpiSmem* sp, uint32_t taddr, int m, int n0, bool row_ok, int c_begin = 0, int c_end = BN) {
   if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_F32) {
@@ -177,6 +186,52 @@ __device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, const EpiSme
           for (int i = 0; i < 8; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
         } else {
           store_bf16_row<32>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ldo + n, v);
+        }
+      }
+    }
+  } else if constexpr (EPI == EPI_CONV_BF16) {
+    bool border = false;
+    if (e.conv_mask) {
+      const int rem = m % (e.conv_hp * e.conv_wp);
+      const int yp = rem / e.conv_wp, xp = rem - yp * e.conv_wp;
+      border = (yp == 0) | (yp == e.conv_hp - 1) | (xp == 0) | (xp == e.conv_wp - 1);
+    }
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+      float v[32];
+      __syncwarp();
+      load_acc<32>(taddr + c, v);
+      if (row_ok) {
+        const int n = n0 + c;
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ldo + n;
+        if (border) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(dst)[i] = make_uint4(0u, 0u, 0u, 0u);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 bb = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
+          }
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const void* rp = r == 0 ? e.res1 : e.res2;
+            if (rp) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(rp) + (size_t)m * e.ldo + n);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 u = r4[i];
+                const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { v[8 * i + 2 * j] += ptx::bf16_lo(w[j]); v[8 * i + 2 * j + 1] += ptx::bf16_hi(w[j]); }
+              }
+            }
+          }
+          if (e.conv_relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          store_bf16_row<32>(dst, v);
         }
       }
     }
@@ -297,7 +352,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) {
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           ptx::mbar_expect_tx(full_bar + stage, L::STAGE_BYTES);
-          ptx::tma_load_2d(sa, &tmA, full_bar + stage, kb * BK, m0);
+          int a_k = kb * BK, a_row = m0;
+          if constexpr (EPI == EPI_CONV_BF16) conv_tap_coords(epi, a_k, a_row);
+          ptx::tma_load_2d(sa, &tmA, full_bar + stage, a_k, a_row);
           ptx::tma_load_2d(sa + L::A_BYTES, &tmB, full_bar + stage, kb * BK, n0);
         }
         __syncwarp();
@@ -475,7 +532,9 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const bool skip_b = (use_tma_reduce & 2) != 0;  // measurement only (lsvs_debug_gemm_mode 3): halves the L2->SM bytes, wrong results
           if (cta == 0) ptx::mbar_expect_tx(full_bar + stage, skip_b ? 2 * L::A_BYTES : 2 * L::STAGE_BYTES);  // bytes of both CTAs land here
           else ptx::mbar_arrive_remote(full_bar + stage, 0);
-          ptx::tma_load_2d_2sm(sa, &tmA, full_bar + stage, kb * BK, m0);
+          int a_k = kb * BK, a_row = m0;
+          if constexpr (EPI == EPI_CONV_BF16) conv_tap_coords(epi, a_k, a_row);
+          ptx::tma_load_2d_2sm(sa, &tmA, full_bar + stage, a_k, a_row);
           if (!skip_b) ptx::tma_load_2d_2sm(sa + L::A_BYTES, &tmB, full_bar + stage, kb * BK, n0);
         }
         __syncwarp();
@@ -596,12 +655,24 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
               cudaStream_t st) {
   LSVS_CHECK_ARG(A && W && M > 0 && N > 0 && K > 0, "gemm: null operand or empty shape (M=%d N=%d K=%d)", M, N, K);
   LSVS_CHECK_ARG(K % BK == 0, "gemm: K=%d must be a multiple of %d", K, BK);
-  LSVS_CHECK_ARG(lda >= K && ldw >= K && lda % 8 == 0 && ldw % 8 == 0, "gemm: leading dimensions must be >= K and 16-byte aligned");
+  const bool conv = (epi_kind == EPI_CONV_BF16);
+  int a_cols = K;   // width of the A matrix: K, or the channels of one tap for the shifted-row convolution
+  if (conv) {
+    LSVS_CHECK_ARG(e.out && e.ldo >= N, "gemm: conv epilogue needs out with ldo >= N");
+    LSVS_CHECK_ARG(e.conv_taps == 0 || e.conv_taps == 9, "gemm: conv_taps must be 0 or 9");
+    if (e.conv_taps == 9) {
+      LSVS_CHECK_ARG(e.conv_c > 0 && e.conv_c % BK == 0 && K == 9 * e.conv_c && e.conv_wp > 2, "gemm: bad 3x3 convolution geometry (C=%d, K=%d)", e.conv_c, K);
+      a_cols = e.conv_c;
+    }
+    LSVS_CHECK_ARG(!e.conv_mask || (e.conv_hp > 2 && e.conv_wp > 2 && M % (e.conv_hp * e.conv_wp) == 0), "gemm: border mask needs M = frames * hp * wp");
+  }
+  LSVS_CHECK_ARG(lda >= a_cols && ldw >= K && lda % 8 == 0 && ldw % 8 == 0, "gemm: leading dimensions must be >= K and 16-byte aligned");
   const bool bn256 = (N % 256 == 0);
-  LSVS_CHECK_ARG(bn256 || N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
+  const bool bn64 = conv && N == 64;   // full-resolution DPT output convolution (32 channels padded to 64)
+  LSVS_CHECK_ARG(bn256 || bn64 || N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
   const int BN = bn256 ? 256 : 128;
   const bool pair = bn256 && M > 2 * BM && g_gemm_mode != 1;  // CTA pairs (256x256 tiles) once there are enough rows
-  const CUtensorMap* tmA = tmap_2d_bf16(A, K, M, (uint64_t)lda * 2, BK, BM);
+  const CUtensorMap* tmA = tmap_2d_bf16(A, a_cols, M, (uint64_t)lda * 2, BK, BM);
   const CUtensorMap* tmB = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, pair ? BN2 / 2 : BN);
   if (!tmA || !tmB) return LSVS_ECUDA;
   ProfScope prof(PROF_GEMM, st, 2.0 * M * (double)N * K, 0);
@@ -635,6 +706,14 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
     LSVS_GEMM_CASE(EPI_RESID_F32)
     LSVS_GEMM_CASE(EPI_HEADNORM64_BF16)
     LSVS_GEMM_CASE(EPI_HEADNORM128_BF16)
+    case EPI_CONV_BF16:
+      if (bn64) {
+        const CUtensorMap* tmB64 = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, 64);
+        if (!tmB64) return LSVS_ECUDA;
+        return launch<64, EPI_CONV_BF16>(tmA, tmB64, M, N, K, e, st);
+      }
+      if (pair) return launch2<EPI_CONV_BF16>(tmA, tmB, M, N, K, e, st);
+      return bn256 ? launch<256, EPI_CONV_BF16>(tmA, tmB, M, N, K, e, st) : launch<128, EPI_CONV_BF16>(tmA, tmB, M, N, K, e, st);
     default:
       return fail(LSVS_EINVAL, "gemm: unknown epilogue %d", epi_kind);
   }

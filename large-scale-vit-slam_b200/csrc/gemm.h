@@ -7,7 +7,7 @@ namespace lsvs {
 
 enum { EPI_BIAS_BF16 = LSVS_EPI_BIAS_BF16, EPI_BIAS_GELU_BF16 = LSVS_EPI_BIAS_GELU_BF16, EPI_BIAS_F32 = LSVS_EPI_BIAS_F32,
        EPI_RESID_F32 = LSVS_EPI_RESID_F32, EPI_HEADNORM64_BF16 = LSVS_EPI_HEADNORM64_BF16,
-       EPI_HEADNORM128_BF16 = LSVS_EPI_HEADNORM128_BF16 };
+       EPI_HEADNORM128_BF16 = LSVS_EPI_HEADNORM128_BF16, EPI_CONV_BF16 = LSVS_EPI_CONV_BF16 };
 enum { ROPE_NONE = LSVS_ROPE_NONE, ROPE_2D = LSVS_ROPE_2D, ROPE_1D = LSVS_ROPE_1D };
 
 // same POD as the public struct, with typed pointers
@@ -28,6 +28,14 @@ struct GemmEpilogue {
   const float2* rope_tab = nullptr;  // [pos][n_freq] (cos, sin)
   int tokens_per_frame = 0, n_special = 0, grid_w = 0;  // ROPE_2D: position from the row index
   const int* pos_ids = nullptr; int pos_period = 0;     // ROPE_1D: position = pos_ids[row % pos_period]
+  // EPI_CONV_BF16 — convolution on a zero-padded NHWC grid (csrc/dpt.cu).  A rows are the pixels of the padded grid
+  // [frames][conv_hp][conv_wp], A columns the conv_c input channels.  With conv_taps == 9 the reduction runs over
+  // K = 9 * conv_c and k-block kb reads the A rows shifted by its tap's offset (dy * conv_wp + dx), i.e. the 3x3
+  // convolution is nine shifted 1x1 convolutions accumulated in tensor memory; W is [N][(ky, kx, c)].
+  // out = mask(relu?(acc + bias + res1 + res2)): border pixels of the grid are written as zeros (they are the next
+  // convolution's padding).
+  int conv_taps = 0, conv_c = 0, conv_hp = 0, conv_wp = 0, conv_relu = 0, conv_mask = 0;
+  const void* res1 = nullptr; const void* res2 = nullptr;   // optional bf16 residual inputs, same layout / stride as out
 };
 
 int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epi_kind, const GemmEpilogue& e,

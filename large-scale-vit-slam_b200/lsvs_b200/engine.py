@@ -33,6 +33,20 @@ def interpolate_pos_embed(pos_embed: torch.Tensor, gh: int, gw: int) -> torch.Te
     return torch.cat([pe[0, :1], patch], dim=0).contiguous()
 
 
+def _dpt_weight_layout(name: str, t: torch.Tensor) -> torch.Tensor:
+    """torch conv layouts -> the (rows, cols) layouts of include/lsvs_b200.h (lsvs_dpt_head_forward)."""
+    if not name.endswith((".weight", ".bias")) or ".norm." in name:
+        return t
+    if "resize_layers.0." in name or "resize_layers.1." in name:  # ConvTranspose2d (ic, oc, k, k) -> ((ky, kx, oc), ic)
+        return t.permute(2, 3, 1, 0).reshape(-1, t.shape[0]) if t.dim() == 4 else t
+    if t.dim() == 4:  # Conv2d (oc, ic, k, k) -> (oc, (ky, kx, ic))
+        t = t.permute(0, 2, 3, 1).reshape(t.shape[0], -1)
+    if "output_conv2.0." in name:  # 32 output channels zero-padded to the 64-wide GEMM tile
+        pad = torch.zeros((64 - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        t = torch.cat([t, pad], dim=0)
+    return t
+
+
 class Engine:
     """One native engine per (model, device).  `sync(named_params)` pushes changed parameters."""
 
@@ -71,6 +85,8 @@ class Engine:
             if self._seen.get(name) == key:
                 continue
             t = p.detach()
+            if ".depth_head." in "." + name or ".point_head." in "." + name:
+                t = _dpt_weight_layout(name, t)
             if t.dtype != torch.float32 or not t.is_contiguous():
                 t = t.float().contiguous()
             rows, cols = (t.shape[0], t[0].numel()) if t.dim() >= 2 and name.endswith(".weight") else (0, 0)
@@ -147,6 +163,24 @@ class Engine:
         _n.check(_n.lib().lsvs_alignment_decode_forward(self._h, _n.ptr(tok), _i(B), _i(S), _n.ptr(mem), _n.ptr(sim3), _n.ptr(se3),
                                                         _n.ptr(mem_out), _n.stream_ptr()), "alignment_decode_forward")
         return sim3, se3, mem_out
+
+    def dpt_head_forward(self, prefix: str, taps: Sequence[torch.Tensor], image_hw, output_dim: int, activation: str,
+                         frames_chunk: int = 8):
+        """UPSTREAM DPTHead.forward: 4 tapped layers (B,S,P,2048) -> pred (B,S,H,W,output_dim-1), conf (B,S,H,W)."""
+        B, S, P, C = taps[0].shape
+        H, W = image_hw
+        assert len(taps) == 4 and C == 2048
+        Ho, Wo = 14 * (H // 14), 14 * (W // 14)
+        ts = [t.detach().float().contiguous() for t in taps]
+        dev = ts[0].device
+        pred = torch.empty(B, S, Ho, Wo, output_dim - 1, device=dev)
+        conf = torch.empty(B, S, Ho, Wo, device=dev)
+        ptrs = (_vp * 4)(*[t.data_ptr() for t in ts])
+        act = {"exp": 0, "inv_log": 1}[activation]
+        _n.check(_n.lib().lsvs_dpt_head_forward(self._h, prefix.encode(), ptrs, _i(B * S), _i(P), _i(H), _i(W), _i(output_dim), _i(act),
+                                                _n.ptr(pred), _n.ptr(conf), _i(frames_chunk if frames_chunk else 0), _n.stream_ptr()),
+                 "dpt_head_forward")
+        return pred, conf
 
     def camera_head_forward(self, tokens_last: torch.Tensor, num_iterations: int = 4) -> torch.Tensor:
         B, S, P, C = tokens_last.shape

@@ -79,3 +79,36 @@ class CameraHead(_EngineBound):
 
     def forward(self, aggregated_tokens_list, num_iterations: int = 4):
         return [self._engine().camera_head_forward(aggregated_tokens_list[-1], num_iterations)]
+
+
+class DPTHead(_EngineBound):
+    """UPSTREAM vggt.heads.dpt_head.DPTHead (A.6): forward(aggregated_tokens_list, images, patch_start_idx) ->
+    (pred (B,S,H,W,output_dim-1), conf (B,S,H,W)).  Construction as in featureAligned_vggt.py:28-29; the state_dict keys
+    are facebook/VGGT-1B's `depth_head.*` / `point_head.*` (torch conv layouts; re-laid out when pushed to the engine)."""
+
+    def __init__(self, dim_in=2048, patch_size=14, output_dim=4, activation="inv_log", conf_activation="expp1", features=256,
+                 out_channels=(256, 512, 1024, 1024), intermediate_layer_idx=(4, 11, 17, 23), pos_embed=True,
+                 feature_only=False, down_ratio=1, prefix="point_head."):
+        if not (dim_in == 2048 and patch_size == 14 and features == 256 and tuple(out_channels) == (256, 512, 1024, 1024)
+                and pos_embed and not feature_only and down_ratio == 1 and 2 <= output_dim <= 4):
+            raise ValueError("only the VGGT-1B depth / point DPTHead geometry is built on this path")
+        if activation not in ("exp", "inv_log"):
+            raise ValueError(f"Unknown activation: {activation}")
+        if conf_activation != "expp1":
+            raise ValueError(f"Unknown conf_activation: {conf_activation}")
+        super().__init__(specs.dpt_head_spec(dim_in, output_dim, features, out_channels))
+        self.output_dim, self.activation = output_dim, activation
+        self.intermediate_layer_idx = list(intermediate_layer_idx)
+        self._prefix = prefix
+        specs.init_default_(self)
+
+    def _make_engine(self):
+        return Engine(0, 0, 0, 8, False, False)
+
+    def forward(self, aggregated_tokens_list, images, patch_start_idx: int = 5, frames_chunk_size: int = 8):
+        if patch_start_idx != 5:
+            raise ValueError("DPTHead: patch_start_idx must be 5 (camera token + 4 register tokens)")
+        taps = [aggregated_tokens_list[i] for i in self.intermediate_layer_idx] if len(aggregated_tokens_list) > 4 \
+            else list(aggregated_tokens_list)
+        H, W = images.shape[-2:]
+        return self._engine().dpt_head_forward(self._prefix, taps, (H, W), self.output_dim, self.activation, frames_chunk_size)

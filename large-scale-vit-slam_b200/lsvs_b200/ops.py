@@ -89,3 +89,29 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, batches: int, h
                                           _n.ptr(out), _i(out.stride(0)), _i(batches), _i(heads), _i(head_dim), _i(Lq), _i(Lk),
                                           _f(scale), _n.stream_ptr()), "attention_bf16")
     return out
+
+
+# ---- DPT head building blocks (include/lsvs_b200.h: lsvs_conv2d_nhwc_bf16, lsvs_dpt_resample)
+DPT_POS_EMBED, DPT_PAD, DPT_CONVT_SHUFFLE, DPT_IM2COL_S2, DPT_BILINEAR = range(5)
+
+
+def conv2d_nhwc(x: torch.Tensor, w: torch.Tensor, bias=None, res1=None, res2=None, taps: int = 9, relu: bool = False,
+                mask_border: bool = True) -> torch.Tensor:
+    """x padded NHWC bf16 (frames, hp, wp, C) with a zero border; w bf16 (OC, taps*C) ordered (ky, kx, c)."""
+    frames, hp, wp, C = x.shape
+    OC = w.shape[0]
+    x = _cuda(x, torch.bfloat16, "x"); w = _cuda(w, torch.bfloat16, "w")
+    out = torch.empty(frames, hp, wp, OC, dtype=torch.bfloat16, device=x.device)
+    _n.check(_n.lib().lsvs_conv2d_nhwc_bf16(_vp(_p(x)), _vp(_p(w)), _vp(_p(_cuda(bias, torch.float32, "bias"))),
+                                           _vp(_p(_cuda(res1, torch.bfloat16, "res1"))), _vp(_p(_cuda(res2, torch.bfloat16, "res2"))),
+                                           _vp(_p(out)), _i(frames), _i(hp), _i(wp), _i(C), _i(OC), _i(taps), _i(int(relu)),
+                                           _i(int(mask_border)), _n.stream_ptr()), "conv2d_nhwc_bf16")
+    return out
+
+
+def dpt_resample(op: int, x: torch.Tensor, out: torch.Tensor, frames: int, h: int, w: int, C: int, a: int = 0, b: int = 0,
+                 aspect: float = 1.0, ratio: float = 0.0) -> torch.Tensor:
+    _n.check(_n.lib().lsvs_dpt_resample(_i(op), _vp(_p(_cuda(x, torch.bfloat16, "in"))), _vp(_p(_cuda(out, torch.bfloat16, "out"))),
+                                       _i(frames), _i(h), _i(w), _i(C), _i(a), _i(b), _f(aspect), _f(ratio), _n.stream_ptr()),
+             "dpt_resample")
+    return out

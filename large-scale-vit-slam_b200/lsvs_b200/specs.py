@@ -93,6 +93,31 @@ def alignment_head_spec(in_dim: int = 2048, dim: int = 1024, dec: int = 512, dep
     return s
 
 
+DPT_OUT_CHANNELS = (256, 512, 1024, 1024)
+
+
+def dpt_head_spec(dim_in: int = 2048, output_dim: int = 4, features: int = 256, out_channels=DPT_OUT_CHANNELS) -> Spec:
+    """UPSTREAM vggt DPTHead (facebook/VGGT-1B keys `depth_head.*` / `point_head.*`); conv weights in torch layout."""
+    def conv(n, o, i, k, bias=True):
+        return [(n + ".weight", (o, i, k, k))] + ([(n + ".bias", (o,))] if bias else [])
+    s = _norm("norm", dim_in)
+    for i, c in enumerate(out_channels):
+        s += conv(f"projects.{i}", c, dim_in, 1)
+    s += [("resize_layers.0.weight", (out_channels[0], out_channels[0], 4, 4)), ("resize_layers.0.bias", (out_channels[0],)),
+          ("resize_layers.1.weight", (out_channels[1], out_channels[1], 2, 2)), ("resize_layers.1.bias", (out_channels[1],))]
+    s += conv("resize_layers.3", out_channels[3], out_channels[3], 3)
+    for i, c in enumerate(out_channels):
+        s += conv(f"scratch.layer{i + 1}_rn", features, c, 3, bias=False)
+    for r in (1, 2, 3, 4):
+        s += conv(f"scratch.refinenet{r}.out_conv", features, features, 1)
+        for u in ((1, 2) if r != 4 else (2,)):  # refinenet4 has no residual input (has_residual=False)
+            s += conv(f"scratch.refinenet{r}.resConfUnit{u}.conv1", features, features, 3)
+            s += conv(f"scratch.refinenet{r}.resConfUnit{u}.conv2", features, features, 3)
+    s += conv("scratch.output_conv1", features // 2, features, 3)
+    s += conv("scratch.output_conv2.0", 32, features // 2, 3) + conv("scratch.output_conv2.2", output_dim, 32, 1)
+    return s
+
+
 class ParamTree(nn.Module):
     """Nested parameter container whose state_dict keys are exactly the dotted names of a spec."""
 

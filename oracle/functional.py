@@ -329,3 +329,113 @@ def camera_head_forward(p: Params, prefix: str, tokens_last: torch.Tensor, num_i
         act = torch.cat([pred[..., :3], pred[..., 3:7], F.relu(pred[..., 7:])], dim=-1)
         outs.append(act)
     return outs
+
+
+# ----------------------------------------------------------------------------- DPTHead (A.6)
+# Restated from the public upstream `vggt/heads/dpt_head.py`, `head_act.py`, `heads/utils.py` (upstream is not in the
+# container: behaviour recalled).  Call sites: /root/reference/aligned_vggt/models/
+# featureAligned_vggt.py:28-29 (construction: depth_head = DPTHead(dim_in=2*embed_dim, output_dim=2, activation="exp",
+# conf_activation="expp1"); point_head = DPTHead(dim_in=2*embed_dim, output_dim=4, activation="inv_log",
+# conf_activation="expp1")) and :166-168, :183-185 (forward, fp32: autocast disabled at :103).
+# Recalled-uncertain item (?): the fusion blocks are built with nn.ReLU(inplace=True), so a ResidualConvUnit adds
+# relu(x), not x, on its skip path; `relu_inplace=False` gives the other reading.
+DPT_OUT_CHANNELS = (256, 512, 1024, 1024)
+DPT_FEATURES = 256
+
+
+def make_sincos_pos_embed(embed_dim: int, pos: torch.Tensor, omega_0: float = 100.0) -> torch.Tensor:
+    omega = torch.arange(embed_dim // 2, dtype=torch.double, device=pos.device)
+    omega = 1.0 / omega_0 ** (omega / (embed_dim / 2.0))
+    out = torch.einsum("m,d->md", pos.reshape(-1).double(), omega)
+    return torch.cat([torch.sin(out), torch.cos(out)], dim=1).float()
+
+
+def create_uv_grid(width: int, height: int, aspect_ratio: float, dtype=torch.float32, device=None) -> torch.Tensor:
+    diag = (aspect_ratio ** 2 + 1.0) ** 0.5
+    span_x, span_y = aspect_ratio / diag, 1.0 / diag
+    xs = torch.linspace(-span_x * (width - 1) / width, span_x * (width - 1) / width, steps=width, dtype=dtype, device=device)
+    ys = torch.linspace(-span_y * (height - 1) / height, span_y * (height - 1) / height, steps=height, dtype=dtype, device=device)
+    uu, vv = torch.meshgrid(xs, ys, indexing="xy")
+    return torch.stack((uu, vv), dim=-1)  # (height, width, 2)
+
+
+def dpt_pos_embed(x: torch.Tensor, W: int, H: int, ratio: float = 0.1) -> torch.Tensor:
+    """x (N,C,h,w) + ratio * sincos embedding of the uv grid (x-embedding in channels [0,C/2), y in [C/2,C))."""
+    h, w, C = x.shape[-2], x.shape[-1], x.shape[1]
+    grid = create_uv_grid(w, h, aspect_ratio=W / H, dtype=x.dtype, device=x.device)
+    flat = grid.reshape(-1, 2)
+    emb = torch.cat([make_sincos_pos_embed(C // 2, flat[:, 0]), make_sincos_pos_embed(C // 2, flat[:, 1])], dim=-1)
+    emb = emb.view(h, w, C) * ratio
+    return x + emb.permute(2, 0, 1)[None].to(x.dtype)
+
+
+def _conv(p: Params, name: str, x: torch.Tensor, stride: int = 1, padding: int = 0) -> torch.Tensor:
+    return F.conv2d(x, p[name + ".weight"], p.get(name + ".bias"), stride=stride, padding=padding)
+
+
+def _residual_conv_unit(p: Params, pre: str, x: torch.Tensor, relu_inplace: bool) -> torch.Tensor:
+    a = F.relu(x)
+    out = _conv(p, pre + "conv2", F.relu(_conv(p, pre + "conv1", a, padding=1)), padding=1)
+    return out + (a if relu_inplace else x)
+
+
+def _fusion_block(p: Params, pre: str, x0: torch.Tensor, x1: Optional[torch.Tensor], size, relu_inplace: bool) -> torch.Tensor:
+    out = x0
+    if x1 is not None:  # has_residual
+        out = out + _residual_conv_unit(p, pre + "resConfUnit1.", x1, relu_inplace)
+    out = _residual_conv_unit(p, pre + "resConfUnit2.", out, relu_inplace)
+    if size is None:
+        out = F.interpolate(out, scale_factor=2, mode="bilinear", align_corners=True)
+    else:
+        out = F.interpolate(out, size=tuple(size), mode="bilinear", align_corners=True)
+    return _conv(p, pre + "out_conv", out)
+
+
+def dpt_activate(out: torch.Tensor, activation: str, conf_activation: str):
+    """head_act.activate_head: (N,C,H,W) -> pred (N,H,W,C-1), conf (N,H,W)."""
+    fmap = out.permute(0, 2, 3, 1)
+    xyz, conf = fmap[..., :-1], fmap[..., -1]
+    if activation == "exp":
+        pts = torch.exp(xyz)
+    elif activation == "inv_log":
+        pts = torch.sign(xyz) * torch.expm1(torch.abs(xyz))
+    else:
+        raise ValueError(f"Unknown activation: {activation}")
+    if conf_activation != "expp1":
+        raise ValueError(f"Unknown conf_activation: {conf_activation}")
+    return pts, 1 + conf.exp()
+
+
+def dpt_head_forward(p: Params, prefix: str, taps, image_hw, patch_start_idx: int = 5, activation: str = "inv_log",
+                     conf_activation: str = "expp1", patch_size: int = 14, relu_inplace: bool = True):
+    """taps: the 4 tapped aggregator outputs (layers 4, 11, 17, 23), each (B,S,P,2C).  Returns pred (B,S,H,W,od-1),
+    conf (B,S,H,W).  Per-frame computation, so upstream's frames_chunk_size split does not change the result."""
+    H, W = image_hw
+    B, S = taps[0].shape[:2]
+    ph, pw = H // patch_size, W // patch_size
+    feats = []
+    for i, t in enumerate(taps):
+        x = t[:, :, patch_start_idx:].reshape(B * S, -1, t.shape[-1])
+        x = layer_norm(p, prefix + "norm", x)
+        x = x.permute(0, 2, 1).reshape(B * S, x.shape[-1], ph, pw)
+        x = _conv(p, f"{prefix}projects.{i}", x)
+        x = dpt_pos_embed(x, W, H)
+        if i == 0:
+            x = F.conv_transpose2d(x, p[prefix + "resize_layers.0.weight"], p[prefix + "resize_layers.0.bias"], stride=4)
+        elif i == 1:
+            x = F.conv_transpose2d(x, p[prefix + "resize_layers.1.weight"], p[prefix + "resize_layers.1.bias"], stride=2)
+        elif i == 3:
+            x = _conv(p, prefix + "resize_layers.3", x, stride=2, padding=1)
+        feats.append(x)
+    s = prefix + "scratch."
+    rn = [_conv(p, f"{s}layer{i + 1}_rn", feats[i], padding=1) for i in range(4)]
+    out = _fusion_block(p, s + "refinenet4.", rn[3], None, rn[2].shape[2:], relu_inplace)
+    out = _fusion_block(p, s + "refinenet3.", out, rn[2], rn[1].shape[2:], relu_inplace)
+    out = _fusion_block(p, s + "refinenet2.", out, rn[1], rn[0].shape[2:], relu_inplace)
+    out = _fusion_block(p, s + "refinenet1.", out, rn[0], None, relu_inplace)
+    out = _conv(p, s + "output_conv1", out, padding=1)
+    out = F.interpolate(out, size=(ph * patch_size, pw * patch_size), mode="bilinear", align_corners=True)
+    out = dpt_pos_embed(out, W, H)
+    out = _conv(p, s + "output_conv2.2", F.relu(_conv(p, s + "output_conv2.0", out, padding=1)))
+    pred, conf = dpt_activate(out, activation, conf_activation)
+    return pred.view(B, S, *pred.shape[1:]), conf.view(B, S, *conf.shape[1:])
