@@ -290,6 +290,49 @@ def case_pose_aligned_small():
     save("pose_enc_sim3.npz", enc=enc, T=T, s=s, H=H, W=W, out=ref)
 
 
+def case_model_dpt_small():
+    """FeatureAlignedVGGT with the DPT depth / point heads enabled — the REFERENCE class's own forward (depth scaling :171,
+    point transform :187-207) over the shim's DPTHead — two chained chunks; stored 4x subsampled in H and W."""
+    print("[FeatureAlignedVGGT + DPT heads, depth 1/1, S=3, 56x84, overlap 1]")
+    import json
+    from aligned_vggt.models.featureAligned_vggt import FeatureAlignedVGGT
+    os.environ["VGGT_SHIM_DEPTH"] = "1,1"
+    with torch.device("meta"):
+        model = FeatureAlignedVGGT(enable_point=True, enable_depth=True, enable_track=False)
+    spec = OW.spec_of(model)
+    with open(os.path.join(GOLD, "state_dict_spec_dpt.json"), "w") as f:
+        json.dump({k: list(v) for k, v in spec if k.startswith(("depth_head.", "point_head."))}, f)
+    sd = OW.fill_state_dict(spec, seed=2)
+    model = model.to_empty(device="cpu")
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    taps = (0, 0, 0, 0)
+    model.intermediate_layer_indices = list(taps)
+    S, H, W, ov = 3, 56, 84, 1
+    imgs = [torch.from_numpy(np.random.Generator(np.random.PCG64(400 + i)).random((1, S, 3, H, W), dtype=np.float32)) for i in range(2)]
+    with torch.no_grad():
+        ref1 = model(imgs[0], ov)
+        snap1 = {k: v[-1].clone() for k, v in ref1.items() if k in ("depth", "depth_conf", "world_points", "world_points_conf")}
+        ref2 = model(imgs[1], ov, ref1)
+        snap2 = {k: v[-1].clone() for k, v in ref2.items() if k in ("depth", "depth_conf", "world_points", "world_points_conf")}
+        # restatement: aggregator / head / pose chain as before, DPT through oracle.functional, Sim(3) apply through oracle.aligned
+        outs, ctx = [], None
+        for i in range(2):
+            o = OA.feature_aligned_forward(sd, imgs[i], ov, ctx, depth=1, dino_depth=1, taps=taps)
+            d, dc = OF.dpt_head_forward(sd, "depth_head.", o["taps"], (H, W), activation="exp")
+            p, pc = OF.dpt_head_forward(sd, "point_head.", o["taps"], (H, W), activation="inv_log")
+            o = OA.feature_aligned_forward(sd, imgs[i], ov, ctx, depth=1, dino_depth=1, taps=taps, raw_points=p, raw_depth=d)
+            o["depth_conf"], o["world_points_conf"] = dc, pc
+            outs.append(o)
+            ctx = {"overlap_tokens": o["overlap_tokens"], "memory_tokens": o["memory_tokens"], "pose_enc": o["pose_enc"]}
+    arrs = {"S": S, "H": H, "W": W, "ov": ov, "wsum": OW.checksum(sd), "sub": 4}
+    for ci, (o, r) in enumerate(zip(outs, (snap1, snap2)), 1):
+        for k in ("depth", "depth_conf", "world_points", "world_points_conf"):
+            check(f"dpt c{ci} {k}", o[k], r[k], 5e-4)
+            arrs[f"c{ci}_{k}"] = r[k][:, :, ::4, ::4].contiguous()
+    save("model_dpt_small.npz", **arrs)
+
+
 def case_model_full():
     print("[FeatureAlignedVGGT, full depth, config 1: S=4, 154x518, overlap 1]")
     model, sd = build_reference_model(None)
@@ -305,7 +348,7 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     os.makedirs(GOLD, exist_ok=True)
     cases = {"spec": case_spec, "layers": case_layers, "geometry": case_geometry, "head": case_head, "model_small": case_model_small,
-             "pose_aligned": case_pose_aligned_small}
+             "pose_aligned": case_pose_aligned_small, "model_dpt_small": case_model_dpt_small}
     if args.full:
         cases["model_full"] = case_model_full
     for name, fn in cases.items():

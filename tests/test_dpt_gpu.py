@@ -164,3 +164,29 @@ def test_model_depth_and_points_match_oracle():
     assert rel_l2(out["world_points"][0], ref2["world_points"]) < 5e-2
     assert rel_l2(out["world_points_conf"][0], pc_ref) < 3e-2
     assert float(scale) > 0
+
+
+def test_model_dpt_golden(golden):
+    """two chained chunks against the REFERENCE forward's depth / world_points (tests/golden/model_dpt_small.npz)."""
+    import numpy as np
+    from aligned_vggt.models.featureAligned_vggt import FeatureAlignedVGGT
+    from oracle import weights as OW
+    from parity_util import load_synth_weights
+    g = golden("model_dpt_small.npz")
+    S, H, W, ov, sub = g["S"], g["H"], g["W"], g["ov"], g["sub"]
+    model = FeatureAlignedVGGT(enable_point=True, enable_depth=True, enable_track=False, depth=1, patch_embed_depth=1,
+                               intermediate_layer_indices=(0, 0, 0, 0))
+    sd = load_synth_weights(model, seed=2)
+    assert abs(OW.checksum(sd) - g["wsum"]) < 1e-6 * abs(g["wsum"]), "synthetic weights differ from the golden run"
+    model = model.cuda().eval()
+    p = None
+    for ci in (1, 2):
+        img = torch.from_numpy(np.random.Generator(np.random.PCG64(400 + ci - 1)).random((1, S, 3, H, W), dtype=np.float32))
+        with torch.no_grad():
+            p = model(img.cuda(), ov, p)
+        assert len(p["depth"]) == ci and len(p["world_points_conf"]) == ci  # accumulated per chunk like the reference (:173-181)
+        for k, tol in (("depth", 3e-2), ("depth_conf", 3e-2), ("world_points", 5e-2), ("world_points_conf", 3e-2)):
+            got = p[k][-1][:, :, ::sub, ::sub]
+            ref = torch.as_tensor(g[f"c{ci}_{k}"])
+            assert got.shape == ref.shape, (k, got.shape, ref.shape)
+            assert rel_l2(got, ref) < tol, (ci, k, rel_l2(got, ref))

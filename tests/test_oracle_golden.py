@@ -150,3 +150,27 @@ def test_alignment_head_golden(golden):
     assert o1[3].shape == (1, 1 + ov, P + 1, 1024)
     with pytest.raises(AttributeError):  # the reference's own temporal_attention=False path is broken
         OA.alignment_head_forward(sd, "", tok1, (gh * 14, gw * 14), ov, temporal_attention=False)
+
+
+def test_dpt_model_golden(golden):
+    """oracle DPT restatement + Sim(3) application vs the reference forward's depth / world_points (model_dpt_small.npz:
+    reference FeatureAlignedVGGT :166-207 over the shim DPTHead), two chained chunks."""
+    import numpy as np
+    g = golden("model_dpt_small.npz")
+    S, H, W, ov, sub = g["S"], g["H"], g["W"], g["ov"], g["sub"]
+    from lsvs_b200 import specs
+    spec = [("aggregator." + n, s) for n, s in specs.aggregator_spec(1, 1)] + [("camera_head." + n, s) for n, s in specs.camera_head_spec()] + \
+           [("alignment_head." + n, s) for n, s in specs.alignment_head_spec()] + \
+           [("point_head." + n, s) for n, s in specs.dpt_head_spec(2048, 4)] + [("depth_head." + n, s) for n, s in specs.dpt_head_spec(2048, 2)]
+    sd = OW.fill_state_dict(spec, seed=2)
+    assert abs(OW.checksum(sd) - g["wsum"]) < 1e-6 * abs(g["wsum"])
+    ctx = None
+    for ci in (1, 2):
+        img = torch.from_numpy(np.random.Generator(np.random.PCG64(400 + ci - 1)).random((1, S, 3, H, W), dtype=np.float32))
+        o = OA.feature_aligned_forward(sd, img, ov, ctx, depth=1, dino_depth=1, taps=(0, 0, 0, 0))
+        d, dc = OF.dpt_head_forward(sd, "depth_head.", o["taps"], (H, W), activation="exp")
+        p, pc = OF.dpt_head_forward(sd, "point_head.", o["taps"], (H, W), activation="inv_log")
+        o = OA.feature_aligned_forward(sd, img, ov, ctx, depth=1, dino_depth=1, taps=(0, 0, 0, 0), raw_points=p, raw_depth=d)
+        for k, v in (("depth", o["depth"]), ("depth_conf", dc), ("world_points", o["world_points"]), ("world_points_conf", pc)):
+            close(v[:, :, ::sub, ::sub], g[f"c{ci}_{k}"], 5e-4)
+        ctx = {"overlap_tokens": o["overlap_tokens"], "memory_tokens": o["memory_tokens"], "pose_enc": o["pose_enc"]}

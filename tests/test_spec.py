@@ -28,3 +28,15 @@ def test_default_init_statistics():
     assert abs(float(sd["alpha"]) - 0.1) < 1e-7 and float(sd["gated_update.gate_mlp.2.bias"]) == 0.0
     assert abs(float(sd["frame_blocks.0.ls1.gamma"].mean()) - 0.01) < 1e-8
     assert float(sd["per_frame_alignment_token"].abs().max()) < 1e-4
+
+
+def test_dpt_state_dict_matches_reference():
+    """depth_head.* / point_head.* keys of the reference model (built on the oracle shim's recalled upstream DPTHead tree)."""
+    from aligned_vggt.models.featureAligned_vggt import FeatureAlignedVGGT
+    from conftest import GOLDEN
+    ref = json.load(open(os.path.join(GOLDEN, "state_dict_spec_dpt.json")))
+    with torch.device("meta"):
+        model = FeatureAlignedVGGT(enable_point=True, enable_depth=True, enable_track=False, depth=1, patch_embed_depth=1)
+    mine = {k: list(v.shape) for k, v in model.state_dict().items() if k.startswith(("depth_head.", "point_head."))}
+    assert len(ref) == 124 and set(mine) == set(ref)
+    assert all(mine[k] == ref[k] for k in ref)
