@@ -45,48 +45,75 @@ __device__ __forceinline__ void uv_spans(float aspect, float& sx, float& sy) {
   sy = 1.0f / diag;
 }
 
-__global__ void pos_embed_kernel(uint4* x, long long total, int h, int w, int C8, float aspect, float ratio) {
-  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = (int)(i % C8);
-  const long long pix = i / C8;
-  const int xx = (int)(pix % w), yy = (int)((pix / w) % h);
+// Launch geometry of the resampling kernels: blockIdx.x = row of the (padded) output grid (frame * rows_per_frame + y),
+// blockIdx.y * TPB + threadIdx.x = (x, 8-channel group) within the row — 32-bit index math only.
+// uv position embedding: either from per-axis tables (U [w][C/2], V [h][C/2], already scaled by ratio; engine path) or
+// evaluated in place (tables == nullptr).
+__device__ __forceinline__ void add_embed8(float* f, int c8, int C, int xx, int yy, int w, int h, float aspect, float ratio,
+                                           const float* U, const float* V) {
+  const int c0 = c8 * 8, half = C >> 1;
+  if (U) {
+    const float* t = c0 < half ? U + (size_t)xx * half + c0 : V + (size_t)yy * half + (c0 - half);
+    const float4 a = *reinterpret_cast<const float4*>(t), b = *reinterpret_cast<const float4*>(t + 4);
+    f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+  } else {
+    float sx, sy;
+    uv_spans(aspect, sx, sy);
+    const float u = uv_coord(xx, w, sx), v = uv_coord(yy, h, sy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += ratio * uv_embed(c0 + j, C, u, v);
+  }
+}
+
+__global__ void uv_table_kernel(float* U, float* V, int h, int w, int C, float aspect, float ratio) {
+  const int half = C >> 1;
+  const int i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= (w + h) * half) return;
   float sx, sy;
   uv_spans(aspect, sx, sy);
-  const float u = uv_coord(xx, w, sx), v = uv_coord(yy, h, sy);
+  if (i < w * half) {
+    const int xx = i / half, c = i - xx * half;
+    U[i] = ratio * uv_embed(c, C, uv_coord(xx, w, sx), 0.f);
+  } else {
+    const int k = i - w * half, yy = k / half, c = k - yy * half;
+    V[k] = ratio * uv_embed(half + c, C, 0.f, uv_coord(yy, h, sy));
+  }
+}
+
+__global__ void pos_embed_kernel(uint4* x, int h, int w, int C8, float aspect, float ratio, const float* U, const float* V) {
+  const int idx = blockIdx.y * TPB + threadIdx.x;
+  if (idx >= w * C8) return;
+  const int xx = idx / C8, c8 = idx - xx * C8;
+  const int yy = blockIdx.x % h;
+  uint4* p = x + (size_t)blockIdx.x * w * C8 + idx;
   float f[8];
-  unpack8(x[i], f);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) f[j] += ratio * uv_embed(c8 * 8 + j, C8 * 8, u, v);
-  x[i] = pack8(f);
+  unpack8(*p, f);
+  add_embed8(f, c8, C8 * 8, xx, yy, w, h, aspect, ratio, U, V);
+  *p = pack8(f);
 }
 
-__global__ void pad_kernel(const uint4* in, uint4* out, long long total, int h, int w, int C8) {
-  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = (int)(i % C8);
-  const long long pix = i / C8;
+__global__ void pad_kernel(const uint4* in, uint4* out, int h, int w, int C8) {
   const int wp = w + 2, hp = h + 2;
-  const int xp = (int)(pix % wp), yp = (int)((pix / wp) % hp);
-  const long long f = pix / ((long long)wp * hp);
+  const int idx = blockIdx.y * TPB + threadIdx.x;
+  if (idx >= wp * C8) return;
+  const int xp = idx / C8, c8 = idx - xp * C8;
+  const int f = blockIdx.x / hp, yp = blockIdx.x - f * hp;
   uint4 v = make_uint4(0u, 0u, 0u, 0u);
-  if (xp >= 1 && xp <= w && yp >= 1 && yp <= h) v = in[((f * h + (yp - 1)) * w + (xp - 1)) * C8 + c8];
-  out[i] = v;
+  if (xp >= 1 && xp <= w && yp >= 1 && yp <= h) v = in[(((size_t)f * h + (yp - 1)) * w + (xp - 1)) * C8 + c8];
+  out[(size_t)blockIdx.x * wp * C8 + idx] = v;
 }
 
-__global__ void convt_shuffle_kernel(const uint4* in, const float* bias, uint4* out, long long total, int h, int w, int C8, int k) {
-  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = (int)(i % C8);
-  const long long pix = i / C8;
+__global__ void convt_shuffle_kernel(const uint4* in, const float* bias, uint4* out, int h, int w, int C8, int k) {
   const int wp = k * w + 2, hp = k * h + 2;
-  const int xp = (int)(pix % wp), yp = (int)((pix / wp) % hp);
-  const long long f = pix / ((long long)wp * hp);
+  const int idx = blockIdx.y * TPB + threadIdx.x;
+  if (idx >= wp * C8) return;
+  const int xp = idx / C8, c8 = idx - xp * C8;
+  const int f = blockIdx.x / hp, yp = blockIdx.x - f * hp;
   uint4 v = make_uint4(0u, 0u, 0u, 0u);
   if (xp >= 1 && xp <= k * w && yp >= 1 && yp <= k * h) {
     const int oy = yp - 1, ox = xp - 1;
     const int y = oy / k, ii = oy - y * k, x = ox / k, jj = ox - x * k;
-    v = in[(((f * h + y) * w + x) * (k * k) + ii * k + jj) * C8 + c8];
+    v = in[((((size_t)f * h + y) * w + x) * (k * k) + ii * k + jj) * C8 + c8];
     if (bias) {
       float t[8];
       unpack8(v, t);
@@ -95,34 +122,30 @@ __global__ void convt_shuffle_kernel(const uint4* in, const float* bias, uint4* 
       v = pack8(t);
     }
   }
-  out[i] = v;
+  out[(size_t)blockIdx.x * wp * C8 + idx] = v;
 }
 
-__global__ void im2col_s2_kernel(const uint4* in, uint4* out, long long total, int h, int w, int ho, int wo, int C8) {
-  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = (int)(i % C8);
-  long long r = i / C8;
-  const int tap = (int)(r % 9);
-  r /= 9;
-  const int ox = (int)(r % wo), oy = (int)((r / wo) % ho);
-  const long long f = r / ((long long)wo * ho);
+// blockIdx.x = output pixel row (f, oy), idx = (ox, tap, c8)
+__global__ void im2col_s2_kernel(const uint4* in, uint4* out, int h, int w, int ho, int wo, int C8) {
+  const int idx = blockIdx.y * TPB + threadIdx.x;
+  if (idx >= wo * 9 * C8) return;
+  const int c8 = idx % C8, r = idx / C8, tap = r % 9, ox = r / 9;
+  const int f = blockIdx.x / ho, oy = blockIdx.x - f * ho;
   const int y = 2 * oy - 1 + tap / 3, x = 2 * ox - 1 + tap % 3;
   uint4 v = make_uint4(0u, 0u, 0u, 0u);
-  if (y >= 0 && y < h && x >= 0 && x < w) v = in[((f * h + y) * w + x) * C8 + c8];
-  out[i] = v;
+  if (y >= 0 && y < h && x >= 0 && x < w) v = in[(((size_t)f * h + y) * w + x) * C8 + c8];
+  out[(size_t)blockIdx.x * wo * 9 * C8 + idx] = v;
 }
 
-__global__ void bilinear_kernel(const uint4* in, uint4* out, long long total, int hi, int wi, int ho, int wo, int C8,
-                                float aspect, float ratio) {
-  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = (int)(i % C8);
-  const long long pix = i / C8;
+__global__ void bilinear_kernel(const uint4* in, uint4* out, int hi, int wi, int ho, int wo, int C8, float aspect, float ratio,
+                                const float* U, const float* V) {
   const int wpo = wo + 2, hpo = ho + 2, wpi = wi + 2, hpi = hi + 2;
-  const int xp = (int)(pix % wpo), yp = (int)((pix / wpo) % hpo);
-  const long long f = pix / ((long long)wpo * hpo);
-  if (xp < 1 || xp > wo || yp < 1 || yp > ho) { out[i] = make_uint4(0u, 0u, 0u, 0u); return; }
+  const int idx = blockIdx.y * TPB + threadIdx.x;
+  if (idx >= wpo * C8) return;
+  const int xp = idx / C8, c8 = idx - xp * C8;
+  const int f = blockIdx.x / hpo, yp = blockIdx.x - f * hpo;
+  uint4* dst = out + (size_t)blockIdx.x * wpo * C8 + idx;
+  if (xp < 1 || xp > wo || yp < 1 || yp > ho) { *dst = make_uint4(0u, 0u, 0u, 0u); return; }
   const int oy = yp - 1, ox = xp - 1;
   // align_corners=True (ATen area_pixel_compute_scale / source index)
   const float sy = ho > 1 ? (float)(hi - 1) / (float)(ho - 1) * (float)oy : 0.f;
@@ -131,22 +154,17 @@ __global__ void bilinear_kernel(const uint4* in, uint4* out, long long total, in
   const int y1 = y0 + (y0 < hi - 1 ? 1 : 0), x1 = x0 + (x0 < wi - 1 ? 1 : 0);
   const float ly = sy - (float)y0, lx = sx - (float)x0;
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-  const long long base = f * hpi;
+  const uint4* r0 = in + ((size_t)f * hpi + y0 + 1) * wpi * C8 + c8;
+  const uint4* r1 = in + ((size_t)f * hpi + y1 + 1) * wpi * C8 + c8;
   float a[8], b[8], c[8], d[8], o[8];
-  unpack8(in[((base + y0 + 1) * wpi + x0 + 1) * C8 + c8], a);
-  unpack8(in[((base + y0 + 1) * wpi + x1 + 1) * C8 + c8], b);
-  unpack8(in[((base + y1 + 1) * wpi + x0 + 1) * C8 + c8], c);
-  unpack8(in[((base + y1 + 1) * wpi + x1 + 1) * C8 + c8], d);
+  unpack8(r0[(size_t)(x0 + 1) * C8], a);
+  unpack8(r0[(size_t)(x1 + 1) * C8], b);
+  unpack8(r1[(size_t)(x0 + 1) * C8], c);
+  unpack8(r1[(size_t)(x1 + 1) * C8], d);
 #pragma unroll
   for (int j = 0; j < 8; ++j) o[j] = w00 * a[j] + w01 * b[j] + w10 * c[j] + w11 * d[j];
-  if (ratio > 0.f) {
-    float spx, spy;
-    uv_spans(aspect, spx, spy);
-    const float u = uv_coord(ox, wo, spx), v = uv_coord(oy, ho, spy);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] += ratio * uv_embed(c8 * 8 + j, C8 * 8, u, v);
-  }
-  out[i] = pack8(o);
+  if (ratio > 0.f) add_embed8(o, c8, C8 * 8, ox, oy, wo, ho, aspect, ratio, U, V);
+  *dst = pack8(o);
 }
 
 // one thread per pixel: 32 input channels (post-ReLU, bf16) x od fp32 weights, then activate_head
@@ -180,43 +198,54 @@ __global__ void final_kernel(const __nv_bfloat16* in, int ldc, const float* w, c
 }
 
 int blocks_for(long long total) { return (int)((total + TPB - 1) / TPB); }
+dim3 row_grid(long long rows, int per_row) { return dim3((unsigned)rows, (unsigned)((per_row + TPB - 1) / TPB)); }
 
 }  // namespace
 
-int dpt_add_pos_embed(void* x, int frames, int h, int w, int C, float aspect, float ratio, cudaStream_t st) {
-  LSVS_CHECK_ARG(x && C % 8 == 0 && C % 4 == 0, "dpt_add_pos_embed: bad arguments");
-  const long long total = (long long)frames * h * w * (C / 8);
-  pos_embed_kernel<<<blocks_for(total), TPB, 0, st>>>(reinterpret_cast<uint4*>(x), total, h, w, C / 8, aspect, ratio);
+int dpt_uv_tables(float* U, float* V, int h, int w, int C, float aspect, float ratio, cudaStream_t st) {
+  LSVS_CHECK_ARG(U && V && C % 16 == 0, "dpt_uv_tables: bad arguments");
+  uv_table_kernel<<<blocks_for((long long)(w + h) * (C / 2)), TPB, 0, st>>>(U, V, h, w, C, aspect, ratio);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+int dpt_add_pos_embed(void* x, int frames, int h, int w, int C, float aspect, float ratio, const float* U, const float* V, cudaStream_t st) {
+  LSVS_CHECK_ARG(x && C % 16 == 0, "dpt_add_pos_embed: bad arguments");
+  ProfScope prof(PROF_ELEMENTWISE, st, 0, 4.0 * frames * h * (double)w * C);
+  pos_embed_kernel<<<row_grid((long long)frames * h, w * (C / 8)), TPB, 0, st>>>(reinterpret_cast<uint4*>(x), h, w, C / 8, aspect, ratio, U, V);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
 int dpt_pad(const void* in, void* out, int frames, int h, int w, int C, cudaStream_t st) {
-  const long long total = (long long)frames * (h + 2) * (w + 2) * (C / 8);
-  pad_kernel<<<blocks_for(total), TPB, 0, st>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), total, h, w, C / 8);
+  ProfScope prof(PROF_ELEMENTWISE, st, 0, 2.0 * frames * ((double)h * w + (double)(h + 2) * (w + 2)) * C);
+  pad_kernel<<<row_grid((long long)frames * (h + 2), (w + 2) * (C / 8)), TPB, 0, st>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), h, w, C / 8);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
 int dpt_convt_shuffle(const void* in, const float* bias, void* out, int frames, int h, int w, int C, int k, cudaStream_t st) {
-  const long long total = (long long)frames * (k * h + 2) * (k * w + 2) * (C / 8);
-  convt_shuffle_kernel<<<blocks_for(total), TPB, 0, st>>>(reinterpret_cast<const uint4*>(in), bias, reinterpret_cast<uint4*>(out), total, h, w, C / 8, k);
+  ProfScope prof(PROF_ELEMENTWISE, st, 0, 2.0 * frames * ((double)k * k * h * w + (double)(k * h + 2) * (k * w + 2)) * C);
+  convt_shuffle_kernel<<<row_grid((long long)frames * (k * h + 2), (k * w + 2) * (C / 8)), TPB, 0, st>>>(
+      reinterpret_cast<const uint4*>(in), bias, reinterpret_cast<uint4*>(out), h, w, C / 8, k);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
 int dpt_im2col_s2(const void* in, void* out, int frames, int h, int w, int C, cudaStream_t st) {
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
-  const long long total = (long long)frames * ho * wo * 9 * (C / 8);
-  im2col_s2_kernel<<<blocks_for(total), TPB, 0, st>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), total, h, w, ho, wo, C / 8);
+  ProfScope prof(PROF_ELEMENTWISE, st, 0, 2.0 * frames * ((double)h * w + 9.0 * ho * wo) * C);
+  im2col_s2_kernel<<<row_grid((long long)frames * ho, wo * 9 * (C / 8)), TPB, 0, st>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), h, w, ho, wo, C / 8);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
-int dpt_bilinear(const void* in, void* out, int frames, int hi, int wi, int ho, int wo, int C, float aspect, float ratio, cudaStream_t st) {
-  const long long total = (long long)frames * (ho + 2) * (wo + 2) * (C / 8);
-  bilinear_kernel<<<blocks_for(total), TPB, 0, st>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), total, hi, wi, ho, wo, C / 8, aspect, ratio);
+int dpt_bilinear(const void* in, void* out, int frames, int hi, int wi, int ho, int wo, int C, float aspect, float ratio, const float* U,
+                 const float* V, cudaStream_t st) {
+  ProfScope prof(PROF_ELEMENTWISE, st, 0, 2.0 * frames * ((double)(hi + 2) * (wi + 2) + (double)(ho + 2) * (wo + 2)) * C);
+  bilinear_kernel<<<row_grid((long long)frames * (ho + 2), (wo + 2) * (C / 8)), TPB, 0, st>>>(
+      reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), hi, wi, ho, wo, C / 8, aspect, ratio, U, V);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
 int dpt_final(const void* in, int ldc, const float* w, const float* b, int od, int activation, float* pred, float* conf, int frames,
               int H, int W, cudaStream_t st) {
+  ProfScope prof(PROF_ELEMENTWISE, st, 0, (double)frames * H * W * (64.0 + 4.0 * od));
   LSVS_CHECK_ARG(od >= 2 && od <= 4 && ldc >= 32 && ldc % 8 == 0, "dpt_final: output_dim must be 2..4");
   const long long total = (long long)frames * H * W;
   final_kernel<<<blocks_for(total), TPB, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), ldc, w, b, od, activation, pred, conf, total, H, W);
@@ -249,11 +278,11 @@ extern "C" int lsvs_dpt_resample(int op, const lsvs_bf16* in, lsvs_bf16* out, in
   cudaStream_t st = (cudaStream_t)stream;
   LSVS_CHECK_ARG(out && frames > 0 && h > 0 && w > 0 && C > 0 && C % 8 == 0, "dpt_resample: bad arguments");
   switch (op) {
-    case LSVS_DPT_POS_EMBED: return dpt_add_pos_embed(out, frames, h, w, C, aspect, ratio, st);
+    case LSVS_DPT_POS_EMBED: return dpt_add_pos_embed(out, frames, h, w, C, aspect, ratio, nullptr, nullptr, st);
     case LSVS_DPT_PAD: LSVS_CHECK_ARG(in, "dpt_resample: null input"); return dpt_pad(in, out, frames, h, w, C, st);
     case LSVS_DPT_CONVT_SHUFFLE: LSVS_CHECK_ARG(in && a > 0, "dpt_resample: bad stride"); return dpt_convt_shuffle(in, nullptr, out, frames, h, w, C, a, st);
     case LSVS_DPT_IM2COL_S2: LSVS_CHECK_ARG(in, "dpt_resample: null input"); return dpt_im2col_s2(in, out, frames, h, w, C, st);
-    case LSVS_DPT_BILINEAR: LSVS_CHECK_ARG(in && a > 0 && b > 0, "dpt_resample: bad output size"); return dpt_bilinear(in, out, frames, h, w, a, b, C, aspect, ratio, st);
+    case LSVS_DPT_BILINEAR: LSVS_CHECK_ARG(in && a > 0 && b > 0, "dpt_resample: bad output size"); return dpt_bilinear(in, out, frames, h, w, a, b, C, aspect, ratio, nullptr, nullptr, st);
     default: return fail(LSVS_EINVAL, "dpt_resample: unknown op %d", op);
   }
 }

@@ -7,7 +7,9 @@
 namespace lsvs {
 
 // x[(f,y,x), c] += ratio * sincos_embed(uv grid)  (UPSTREAM DPTHead._apply_pos_embed); x unpadded (frames*h*w, C)
-int dpt_add_pos_embed(void* x, int frames, int h, int w, int C, float aspect, float ratio, cudaStream_t st);
+// U [w][C/2], V [h][C/2] (optional, from dpt_uv_tables, already scaled by ratio) replace the in-kernel sin/cos evaluation
+int dpt_uv_tables(float* U, float* V, int h, int w, int C, float aspect, float ratio, cudaStream_t st);
+int dpt_add_pos_embed(void* x, int frames, int h, int w, int C, float aspect, float ratio, const float* U, const float* V, cudaStream_t st);
 // unpadded (frames,h,w,C) -> padded (frames,h+2,w+2,C)
 int dpt_pad(const void* in, void* out, int frames, int h, int w, int C, cudaStream_t st);
 // ConvTranspose2d(kernel = stride = k) as GEMM output [(f,y,x)][(i,j,c)] (+ bias[c]) -> padded (frames, k*h+2, k*w+2, C)
@@ -17,7 +19,7 @@ int dpt_im2col_s2(const void* in, void* out, int frames, int h, int w, int C, cu
 // bilinear, align_corners=True: padded (frames,hi+2,wi+2,C) -> padded (frames,ho+2,wo+2,C); optionally adds the uv
 // position embedding (ratio > 0) to the result
 int dpt_bilinear(const void* in, void* out, int frames, int hi, int wi, int ho, int wo, int C, float aspect, float ratio,
-                 cudaStream_t st);
+                 const float* U, const float* V, cudaStream_t st);
 // last 1x1 convolution (32 -> od channels, fp32 weights) + activate_head: padded (frames,H+2,W+2,ldc) bf16 ->
 // pred (frames,H,W,od-1) fp32, conf (frames,H,W) fp32.  activation: 0 exp, 1 inv_log; conf: 1 + exp
 int dpt_final(const void* in, int ldc, const float* w, const float* b, int od, int activation, float* pred, float* conf,

@@ -105,7 +105,9 @@ class DPTHead(_EngineBound):
     def _make_engine(self):
         return Engine(0, 0, 0, 8, False, False)
 
-    def forward(self, aggregated_tokens_list, images, patch_start_idx: int = 5, frames_chunk_size: int = 8):
+    def forward(self, aggregated_tokens_list, images, patch_start_idx: int = 5, frames_chunk_size: int = None):
+        """frames_chunk_size: frames per pass (upstream default 8; None = chosen by the engine from a memory budget — the
+        computation is per frame, so the result does not depend on it)."""
         if patch_start_idx != 5:
             raise ValueError("DPTHead: patch_start_idx must be 5 (camera token + 4 register tokens)")
         taps = [aggregated_tokens_list[i] for i in self.intermediate_layer_idx] if len(aggregated_tokens_list) > 4 \

@@ -122,7 +122,8 @@ def test_dpt_head_matches_oracle(H, W, frames, od, activation, prefix):
     taps = [torch.randn(1, frames, P, 2048, generator=g) for _ in range(4)]
     images = torch.zeros(1, frames, 3, H, W)
     with torch.no_grad():
-        pred, conf = head([t.cuda() for t in taps], images=images.cuda(), patch_start_idx=5)
+        # 9 frames with upstream's frames_chunk_size=8 -> two passes of the frame-chunk loop; otherwise the engine's own choice
+        pred, conf = head([t.cuda() for t in taps], images=images.cuda(), patch_start_idx=5, frames_chunk_size=8 if frames > 8 else None)
     torch.cuda.synchronize()
     n_ref = min(frames, 2)  # the fp32 CPU oracle on the first frames (per-frame computation)
     ref_pred, ref_conf = OF.dpt_head_forward(sd, "", [t[:, :n_ref] for t in taps], (H, W), activation=activation)
