@@ -34,12 +34,16 @@ constexpr int KV_STAGES = 4;
 #define LSVS_ATTN_POLY_PAIRS 0  // of every 4 element pairs, this many use the polynomial exp2 path (0 disables; measured slower)
 #endif
 
-template <int HD>
+template <int HD, int NT_>
 struct Cfg {
-  // Two 128-row query tiles per CTA; 128-key blocks at head dim 64, 64-key blocks at head dim 128 (shared memory).
+  // NT_ = 2: two 128-row query tiles per CTA share every K/V block, one CTA per SM (long sequences).
+  // NT_ = 1: one query tile, half the tensor memory and a 2-stage K/V ring so that TWO CTAs fit on an SM: for short
+  //          sequences (frame attention, a few key blocks per CTA) the prologue / epilogue of one CTA hides behind the other.
+  // 128-key blocks at head dim 64, 64-key blocks at head dim 128.
   // (Measured alternative at head dim 64: four tiles x 64-key blocks, i.e. 16 softmax warps: 455 vs 666 TFLOP/s —
   //  the per-block barrier / fence overhead doubles per key and outweighs the extra latency hiding.)
-  static constexpr int NT = 2;                              // query tiles per CTA
+  static constexpr int NT = NT_;                            // query tiles per CTA
+  static constexpr int KVS = (NT_ == 2) ? KV_STAGES : 2;    // K / V ring depth
   static constexpr int BKV = (HD == 64) ? 128 : 64;         // keys per block (UMMA N of S, K of PV)
   // SP softmax warpgroups share one query tile, each thread owning BKV / SP columns of its row: at head dim 64 the
   // softmax is issue / latency bound at 8 warps (2 per SM sub-partition), so the row is split over two threads.
@@ -48,17 +52,17 @@ struct Cfg {
   static constexpr int OCOLS = HD / SP;                     // O columns per softmax thread (rescale / epilogue)
   static constexpr int NWG = NT * SP;                       // softmax warpgroups
   static constexpr int NTHREADS = (NWG + 1) * 128;
-  static constexpr int MAXNREG = (SP == 2) ? 96 : 168;      // launch-time registers / thread (65536 / NTHREADS, multiple of 8)
+  static constexpr int MAXNREG = (SP == 2) ? 96 : (NT_ == 2 ? 168 : 128);  // launch-time registers / thread (register file / resident threads)
   static constexpr int REG_SOFTMAX = (SP == 2) ? 104 : 200; // after setmaxnreg: NWG*128*REG_SOFTMAX + 128*REG_SERVICE <= NTHREADS*MAXNREG
-  static constexpr int REG_SERVICE = (SP == 2) ? 64 : 96;
+  static constexpr int REG_SERVICE = (SP == 2) ? 64 : (NT_ == 2 ? 96 : 56);
   static constexpr int KB = HD / 64;                        // 64-element (128 B) column blocks of the head dim
   static constexpr int Q_TILE_BYTES = QT * HD * 2;
   static constexpr int K_TILE_BYTES = BKV * HD * 2;
   static constexpr int V_TILE_BYTES = BKV * HD * 2;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + NT * Q_TILE_BYTES;
-  static constexpr int OFF_V = OFF_K + KV_STAGES * K_TILE_BYTES;
-  static constexpr int OFF_BAR = OFF_V + KV_STAGES * V_TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + KVS * K_TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_V + KVS * V_TILE_BYTES;
   static constexpr int OFF_X = OFF_BAR + 512;                     // row-max exchange between the SP threads of a row (bf16)
   static constexpr int X_BYTES = (SP == 2) ? 2 * NT * SP * QT * 2 : 0;  // [parity][tile][half][row]
   static constexpr int SMEM = OFF_X + X_BYTES;                    // the dynamic shared window is 1024-aligned (no static smem)
@@ -66,9 +70,9 @@ struct Cfg {
   static constexpr int O_COL = NT * BKV;
   static constexpr int P_COL = O_COL + NT * HD;              // P: bf16 pairs, BKV / 2 columns per tile
   static constexpr int PCOLS = BKV / 2;
-  static constexpr int TMEM_COLS = 512;
-  static_assert(P_COL + NT * PCOLS <= 512, "TMEM budget");
-  static_assert(SMEM <= 232448, "shared memory budget");
+  static constexpr int TMEM_COLS = (NT_ == 2) ? 512 : 256;
+  static_assert(P_COL + NT * PCOLS <= TMEM_COLS, "TMEM budget");
+  static_assert(SMEM <= (NT_ == 2 ? 232448 : 232448 / 2 - 1024), "shared memory budget");
   static_assert(NWG * 128 * REG_SOFTMAX + 128 * REG_SERVICE <= NTHREADS * MAXNREG, "register pool");
 };
 
@@ -121,11 +125,11 @@ __device__ __forceinline__ void ex2_poly2(unsigned long long x2, float& r0, floa
 }
 
 // register re-balancing between the service warpgroup and the softmax warpgroups (setmaxnreg, warpgroup-wide)
-template <int HD> __device__ __forceinline__ void reg_dec() {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg<HD>::REG_SERVICE));
+template <class C> __device__ __forceinline__ void reg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REG_SERVICE));
 }
-template <int HD> __device__ __forceinline__ void reg_inc() {
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg<HD>::REG_SOFTMAX));
+template <class C> __device__ __forceinline__ void reg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::REG_SOFTMAX));
 }
 
 #ifdef LSVS_ATTN_PHASES
@@ -133,7 +137,12 @@ __device__ unsigned long long g_attn_phase[8 * 8];  // [warp][phase] cycle sums 
 #define PH_DECL unsigned ph_t = clock(); unsigned long long ph_acc[6] = {0, 0, 0, 0, 0, 0}
 #define PH(k) do { const unsigned now_ = clock(); ph_acc[k] += now_ - ph_t; ph_t = now_; } while (0)
 #define PH_FLUSH() do { if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) for (int k_ = 0; k_ < 6; ++k_) g_attn_phase[warp * 8 + k_] = ph_acc[k_]; } while (0)
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define MS_ENTRY const unsigned long long ms_t0 = gtime()
+#define MS(k) do { if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == gridDim.z - 1) g_attn_phase[48 + (k)] = gtime() - ms_t0; } while (0)
 #else
+#define MS_ENTRY do {} while (0)
+#define MS(k) do {} while (0)
 #define PH_DECL do {} while (0)
 #define PH(k) do {} while (0)
 #define PH_FLUSH() do {} while (0)
@@ -155,12 +164,14 @@ template <int PK> __device__ __forceinline__ uint32_t pack_p(float lo, float hi)
   return __byte_perm(a, b, 0x7632);
 }
 
-template <int HD, int PK>
-__global__ void __maxnreg__(Cfg<HD>::MAXNREG)
+template <int HD, int NT_>
+__global__ void __maxnreg__((Cfg<HD, NT_>::MAXNREG))
 attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int Lq, int Lk,
                       float scale_log2e, int stagger_cycles) {
-  using C = Cfg<HD>;
+  using C = Cfg<HD, NT_>;
+  constexpr int PK = 0;
+  MS_ENTRY;
   extern __shared__ __align__(1024) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem + C::OFF_BAR);
 
@@ -178,7 +189,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == W_TMA && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
     ptx::mbar_init(&bars->q_full, 1);
-    for (int i = 0; i < KV_STAGES; ++i) {
+    for (int i = 0; i < C::KVS; ++i) {
       ptx::mbar_init(&bars->k_full[i], 1); ptx::mbar_init(&bars->k_empty[i], 1);
       ptx::mbar_init(&bars->v_full[i], 1); ptx::mbar_init(&bars->v_empty[i], 1);
     }
@@ -194,10 +205,11 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
+  MS(0);  // setup done (barriers, TMEM allocation, CTA sync)
 
   if (warp == W_TMA) {
     // ============================================================ TMA producer
-    reg_dec<HD>();
+    reg_dec<C>();
     if (lane == 0) {
       ptx::mbar_expect_tx(&bars->q_full, n_tiles * C::Q_TILE_BYTES);
       for (int t = 0; t < n_tiles; ++t)
@@ -219,11 +231,11 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                            col0 + kb * 64, kv_row0 + i * C::BKV);
       }
       __syncwarp();
-      if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == C::KVS) { stage = 0; phase ^= 1; }
     }
   } else if (warp == W_TMA_V) {
     // ============================================================ TMA producer (V blocks)
-    reg_dec<HD>();
+    reg_dec<C>();
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < n_kv; ++i) {
@@ -235,11 +247,11 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                            col0 + kb * 64, kv_row0 + i * C::BKV);
       }
       __syncwarp();
-      if (++stage == KV_STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == C::KVS) { stage = 0; phase ^= 1; }
     }
   } else if (warp == W_MMA) {
     // ============================================================ MMA issuer
-    reg_dec<HD>();
+    reg_dec<C>();
     constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(QT, C::BKV, 0, 0);  // S = Q K^T : both K-major
     constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(QT, HD, 0, 1);      // O = P V   : A K-major, B (V) MN-major
     const uint32_t sQ = ptx::smem_u32(smem + C::OFF_Q), sK = ptx::smem_u32(smem + C::OFF_K);
@@ -277,7 +289,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       DBG_ITER(i);
       int nstage = stage + 1;
       uint32_t nphase = phase;
-      if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1; }
+      if (nstage == C::KVS) { nstage = 0; nphase ^= 1; }
       if (i + 1 < n_kv) {
         // S_t(i+1) as soon as the softmax warps hold S_t(i) in registers
         ptx::mbar_wait(&bars->k_full[nstage], nphase);
@@ -303,10 +315,10 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       phase = nphase;
     }
   } else if (warp > W_TMA_V) {
-    reg_dec<HD>();  // idle warp of the service warpgroup (setmaxnreg is warpgroup-wide)
+    reg_dec<C>();  // idle warp of the service warpgroup (setmaxnreg is warpgroup-wide)
   } else {
     // ============================================================ softmax / correction / epilogue
-    reg_inc<HD>();
+    reg_inc<C>();
     constexpr int SP = C::SP, COLS = C::COLS, OCOLS = C::OCOLS;
     const int wg = warp >> 2;                  // softmax warpgroup
     const int t = wg / SP;                     // query tile of this warpgroup
@@ -350,6 +362,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         ptx::mbar_wait(&bars->s_full[t], i & 1);
         ptx::tc_fence_after();
         PH(0);
+        if (i == 0) MS(1);  // first S tile ready (Q, K(0) landed, first MMA retired)
         float s[COLS];
 #pragma unroll
         for (int c = 0; c < COLS; c += 32) ptx::tmem_ld_32x32b_x32(tS + c, reinterpret_cast<uint32_t*>(s + c));
@@ -440,6 +453,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         PH(4);
       }
       PH_FLUSH();
+      MS(2);  // key loop done
       // ---- epilogue: O / l -> bf16 -> global
       ptx::mbar_wait(&bars->pv_done[t][(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
       ptx::tc_fence_after();
@@ -473,20 +487,23 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     }
   }
+  MS(3);  // epilogue stores issued
   ptx::tc_fence_before();
   __syncthreads();
+  MS(4);
   if (warp == W_MMA) ptx::tmem_dealloc(tmem, C::TMEM_COLS);
+  MS(5);
 }
 
-template <int HD, int PK>
+template <int HD, int NT_>
 int launch(const AttentionArgs& a, cudaStream_t st) {
-  using C = Cfg<HD>;
+  using C = Cfg<HD, NT_>;
   const size_t rows_q = (size_t)a.batches * a.Lq, rows_k = (size_t)a.batches * a.Lk;
   const CUtensorMap* tq = tmap_2d_bf16(a.q, (uint64_t)a.heads * HD, rows_q, (uint64_t)a.ldq * 2, 64, QT);
   const CUtensorMap* tk = tmap_2d_bf16(a.k, (uint64_t)a.heads * HD, rows_k, (uint64_t)a.ldk * 2, 64, C::BKV);
   const CUtensorMap* tv = tmap_2d_bf16(a.v, (uint64_t)a.heads * HD, rows_k, (uint64_t)a.ldv * 2, 64, C::BKV);
   if (!tq || !tk || !tv) return LSVS_ECUDA;
-  auto kern = attention_fwd_tcgen05<HD, PK>;
+  auto kern = attention_fwd_tcgen05<HD, NT_>;
   static bool configured = false;
   if (!configured) {
     LSVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -512,9 +529,11 @@ int attention_fwd(const AttentionArgs& a, cudaStream_t st) {
   LSVS_CHECK_ARG(a.ldq >= D && a.ldk >= D && a.ldv >= D && a.ldo >= D, "attention: leading dimension smaller than heads*head_dim");
   LSVS_CHECK_ARG(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: leading dimensions must be multiples of 8");
   ProfScope prof(a.Lk >= 2048 ? PROF_ATTENTION_GLOBAL : PROF_ATTENTION, st, 4.0 * a.batches * (double)a.heads * a.Lq * (double)a.Lk * a.head_dim, 0);
-  static const int pk = [] { const char* e = getenv("LSVS_ATTN_PACK"); return e ? atoi(e) : 0; }();
-  if (a.head_dim == 128) return launch<128, 0>(a, st);
-  return pk == 1 ? launch<64, 1>(a, st) : pk == 2 ? launch<64, 2>(a, st) : launch<64, 0>(a, st);
+  // short sequences: one query tile per CTA, two CTAs per SM (fixed per-CTA cost ~10 us vs ~1 us per key block)
+  static const int nt1_max_lk = [] { const char* e = getenv("LSVS_ATTN_NT1_MAX_LK"); return e ? atoi(e) : 1024; }();
+  const bool one_tile = a.Lk <= nt1_max_lk;
+  if (a.head_dim == 128) return one_tile ? launch<128, 1>(a, st) : launch<128, 2>(a, st);
+  return one_tile ? launch<64, 1>(a, st) : launch<64, 2>(a, st);
 }
 
 }  // namespace lsvs
@@ -531,7 +550,7 @@ extern "C" int lsvs_debug_hang_read(int* out257, int* bar_base_offset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out257, ptx::g_lsvs_hang, 257 * sizeof(int));
   cudaMemcpyFromSymbol(out257 + 257, lsvs::g_dbg_iter, 64 * sizeof(int));
-  *bar_base_offset = lsvs::Cfg<64>::OFF_BAR;
+  *bar_base_offset = lsvs::Cfg<64, 2>::OFF_BAR;
   static int zero[257] = {0};
   cudaMemcpyToSymbol(ptx::g_lsvs_hang, zero, sizeof(zero));
   return 0;

@@ -18,6 +18,7 @@ for (B, H, hd, Lq, Lk) in [(1, 16, 64, 13184, 13184), (37, 16, 64, 128, 13184), 
     buf = (ctypes.c_ulonglong * 64)()
     assert lib.lsvs_debug_attn_phases(buf) == 0
     n_kv = -(-Lk // 128)
+    print(json.dumps({"shape": [B, H, Lq, Lk], "milestones_ns (setup, first S, loop done, epilogue, sync, dealloc)": [int(buf[48 + k]) for k in range(6)]}))
     for w in (0, 4):
         ph = [buf[w * 8 + k] / n_kv for k in range(5)]
         print(json.dumps({"shape": [B, H, Lq, Lk], "warp": w, "cycles/iter": round(sum(ph), 1),
