@@ -59,6 +59,47 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(hx, xc * p * rq, hx);
 }
 
+// two elements at a time on the packed fp32x2 pipe (FFMA2 / FMUL2): halves the issue slots of the polynomial — the fc1
+// epilogue is issue-bound (8 or 16 epilogue warps make no difference: 128 x 256 elements x ~21 instructions per tile and SM)
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_dup(float c) { return f2_pack(c, c); }
+__device__ __forceinline__ void gelu_erf2(float& a, float& b) {
+  const float ac = fminf(fmaxf(a * 0.70710678118654752f, -4.0f), 4.0f), bc = fminf(fmaxf(b * 0.70710678118654752f, -4.0f), 4.0f);
+  const unsigned long long xc = f2_pack(ac, bc), x2 = f2_mul(xc, xc);
+  unsigned long long p = f2_fma(x2, f2_dup(-2.72614225801306e-10f), f2_dup(2.77068142495902e-08f));
+  p = f2_fma(x2, p, f2_dup(-2.10102402082508e-06f));
+  p = f2_fma(x2, p, f2_dup(-5.69250639462346e-05f));
+  p = f2_fma(x2, p, f2_dup(-7.34990630326855e-04f));
+  p = f2_fma(x2, p, f2_dup(-2.95459980854025e-03f));
+  p = f2_fma(x2, p, f2_dup(-1.60960333262415e-02f));
+  unsigned long long q = f2_fma(x2, f2_dup(-1.45660718464996e-05f), f2_dup(-2.13374055278905e-04f));
+  q = f2_fma(x2, q, f2_dup(-1.68282697438203e-03f));
+  q = f2_fma(x2, q, f2_dup(-7.37332916720468e-03f));
+  q = f2_fma(x2, q, f2_dup(-1.42647390514189e-02f));
+  float q0, q1, r0, r1;
+  f2_unpack(q, q0, q1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(q0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(q1));
+  const unsigned long long hx = f2_mul(f2_pack(a, b), f2_dup(0.5f));
+  const unsigned long long t = f2_mul(f2_mul(xc, p), f2_pack(r0, r1));
+  f2_unpack(f2_fma(hx, t, hx), a, b);
+}
+
 // ---- epilogue helpers: `v` holds NC consecutive fp32 accumulator columns of one output row ----------
 template <int NC>
 __device__ __forceinline__ void store_bf16_row(__nv_bfloat16* dst, const float* v) {
@@ -79,6 +120,32 @@ __device__ __forceinline__ void load_acc(uint32_t taddr, float* v) {
 #pragma unroll
   for (int c = 0; c < NC; c += 32) ptx::tmem_ld_32x32b_x32(taddr + c, reinterpret_cast<uint32_t*>(v + c));
   ptx::tmem_ld_wait();
+}
+
+// bf16 output through shared memory + TMA store (pair kernel): a lane holding one output row writes 16-byte pieces of 32
+// different rows per store instruction (32 sectors each); staged in a per-warp 32 x 64 tile (128B-swizzled, conflict-free)
+// the same data leaves the SM as one bulk tensor store (measured: qkv GEMM 75.6 us, 61.9 us with the per-lane stores removed).
+struct TmaOut { const CUtensorMap* tm; uint8_t* tile; int m_base; };
+template <int NC>
+__device__ __forceinline__ void store_bf16_tma(const TmaOut& to, const float* v, int n) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int t = 0; t < NC / 64; ++t) {
+    if (lane == 0) ptx::tma_store_wait_read<0>();  // the previous store has finished reading the tile
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float* f = v + t * 64 + 8 * i;
+      *reinterpret_cast<uint4*>(to.tile + lane * 128 + ((i ^ (lane & 7)) << 4)) =
+          make_uint4(ptx::pack_bf16(f[0], f[1]), ptx::pack_bf16(f[2], f[3]), ptx::pack_bf16(f[4], f[5]), ptx::pack_bf16(f[6], f[7]));
+    }
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_2d(to.tm, to.tile, n + t * 64, to.m_base);
+      ptx::tma_store_commit();
+    }
+  }
 }
 
 // Token position of global row m for the 2-D RoPE: frames of `tpf` tokens, the first `nsp` of each are
@@ -163,29 +230,33 @@ __device__ __forceinline__ void conv_tap_coords(const GemmEpilogue& e, int& a_k,
   }
 }
 
-template <int BN, int EPI>
-__device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, const EpiSmem* sp, uint32_t taddr, int m, int n0, bool row_ok, int c_begin = 0, int c_end = BN) {
+template <int BN, int EPI, bool TMA = false>
+__device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, const EpiSmem* sp, uint32_t taddr, int m, int n0, bool row_ok, int c_begin = 0, int c_end = BN,
+                                             const TmaOut* to = nullptr) {
   if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_F32) {
+    constexpr int CH = TMA ? 64 : 32;
 #pragma unroll 1
-    for (int c = c_begin; c < c_end; c += 32) {
-      float v[32];
+    for (int c = c_begin; c < c_end; c += CH) {
+      float v[CH];
       __syncwarp();
-      load_acc<32>(taddr + c, v);
-      if (row_ok) {
+      load_acc<CH>(taddr + c, v);
+      if (row_ok || TMA) {   // TMA: rows past M are computed (garbage) and clipped by the tensor map
         const int n = n0 + c;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < CH; i += 4) {
           const float4 bb = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
           float x0 = v[i] + bb.x, x1 = v[i + 1] + bb.y, x2 = v[i + 2] + bb.z, x3 = v[i + 3] + bb.w;
-          if constexpr (EPI == EPI_BIAS_GELU_BF16) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
+          if constexpr (EPI == EPI_BIAS_GELU_BF16) { gelu_erf2(x0, x1); gelu_erf2(x2, x3); }
           v[i] = x0; v[i + 1] = x1; v[i + 2] = x2; v[i + 3] = x3;
         }
         if constexpr (EPI == EPI_BIAS_F32) {
           float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + (size_t)m * e.ldo + n);
 #pragma unroll
           for (int i = 0; i < 8; ++i) d[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else if constexpr (TMA) {
+          store_bf16_tma<CH>(*to, v, n);
         } else {
-          store_bf16_row<32>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ldo + n, v);
+          if (!e.debug_skip_store || v[0] == 123456.f) store_bf16_row<32>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ldo + n, v);
         }
       }
     }
@@ -283,7 +354,7 @@ __device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, const EpiSme
       float v[HD];
       __syncwarp();
       load_acc<HD>(taddr + c, v);
-      if (!row_ok) continue;  // reconverges at the __syncwarp above / after the loop
+      if (!row_ok && !TMA) continue;  // reconverges at the __syncwarp above / after the loop (TMA: computed and clipped)
       const int n = n0 + c;
       if (n < e.n_q_cols) {
         head_norm_rope<HD>(v, e.bias + n, sp->qn_w, sp->qn_b, e, m);
@@ -296,7 +367,8 @@ __device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, const EpiSme
           v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
         }
       }
-      store_bf16_row<HD>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ldo + n, v);
+      if constexpr (TMA) store_bf16_tma<HD>(*to, v, n);
+      else store_bf16_row<HD>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ldo + n, v);
     }
   }
 }
@@ -427,7 +499,10 @@ struct Smem2 {
   // the fp32-residual epilogue stages 32x32 accumulator blocks in shared memory for TMA reduce-add and gives up one
   // pipeline stage for the staging tiles
   static constexpr bool TRANSPOSE = (EPI == EPI_RESID_F32);
-  static constexpr int STAGES = TRANSPOSE ? 5 : 6;
+  // bf16 outputs are staged the same way (32 x 64 bf16 tile per epilogue warp) for a plain TMA store
+  static constexpr bool TMA_BF16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_HEADNORM64_BF16 || EPI == EPI_HEADNORM128_BF16);
+  static constexpr bool TILES = TRANSPOSE || TMA_BF16;
+  static constexpr int STAGES = TILES ? 5 : 6;
   static constexpr int A_BYTES = BM * BK * 2;          // 16 KB: this CTA's 128 rows
   static constexpr int B_BYTES = (BN2 / 2) * BK * 2;   // 16 KB: this CTA's half of the weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -435,7 +510,7 @@ struct Smem2 {
   static constexpr int PARAM_OFFSET = BAR_OFFSET + 256;
   static constexpr int TILE_OFFSET = (PARAM_OFFSET + 2048 + 1023) / 1024 * 1024;  // 128B-swizzled tiles: 1024-byte aligned
   static constexpr int TILE_BYTES = 32 * 32 * 4;       // per epilogue warp: one 32 x 32 fp32 block
-  static constexpr int TOTAL = TILE_OFFSET + (TRANSPOSE ? 8 * TILE_BYTES : 0) + 1024;
+  static constexpr int TOTAL = TILE_OFFSET + (TILES ? 8 * TILE_BYTES : 0) + 1024;
 };
 
 // resid[m, n] += gamma[n] * (acc[m, n] + bias[n]) without reading the residual in the SM: each warp scales its 32 x 32
@@ -588,6 +663,9 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2;
       if (L::TRANSPOSE && (use_tma_reduce & 1)) {
         epilogue_resid_tma(epi, &tmR, smem + L::TILE_OFFSET + (warp - 2) * L::TILE_BYTES, taddr, m0 + quarter * 32, n0, part * COLS, (part + 1) * COLS);
+      } else if (L::TMA_BF16 && (use_tma_reduce & 4)) {
+        const TmaOut to{&tmR, smem + L::TILE_OFFSET + (warp - 2) * L::TILE_BYTES, m0 + quarter * 32};
+        epilogue_row<BN2, EPI, L::TMA_BF16>(epi, sp, taddr, m, n0, m < M, part * COLS, (part + 1) * COLS, &to);
       } else {
         epilogue_row<BN2, EPI>(epi, sp, taddr, m, n0, m < M, part * COLS, (part + 1) * COLS);
       }
@@ -600,7 +678,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
-  if (L::TRANSPOSE && (use_tma_reduce & 1) && warp >= 2 && lane == 0) ptx::tma_store_wait<0>();  // reductions issued by this lane are complete
+  if (((L::TRANSPOSE && (use_tma_reduce & 1)) || (L::TMA_BF16 && (use_tma_reduce & 4))) && warp >= 2 && lane == 0) ptx::tma_store_wait<0>();  // reductions issued by this lane are complete
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();
@@ -626,6 +704,11 @@ int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K,
     tmR = tmap_2d_f32_box32(e.resid, (uint64_t)N, (uint64_t)M, (uint64_t)e.ldr * 4, 32);
     if (!tmR) return LSVS_ECUDA;
     use_red = 1;
+  }
+  if (Smem2<EPI>::TMA_BF16 && g_gemm_mode != 2 && ((uintptr_t)e.out % 16 == 0) && (e.ldo % 8 == 0)) {
+    tmR = tmap_2d_bf16(e.out, (uint64_t)N, (uint64_t)M, (uint64_t)e.ldo * 2, 64, 32);
+    if (!tmR) return LSVS_ECUDA;
+    use_red |= 4;
   }
   if (g_gemm_mode == 3) use_red |= 2;
   kern<<<2 * pairs, 64 + 32 * EW, Smem2<EPI>::TOTAL, st>>>(*tmA, *tmB, *tmR, M, N, K, e, use_red);
@@ -676,6 +759,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   const CUtensorMap* tmB = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, pair ? BN2 / 2 : BN);
   if (!tmA || !tmB) return LSVS_ECUDA;
   ProfScope prof(PROF_GEMM, st, 2.0 * M * (double)N * K, 0);
+  if (g_gemm_mode == 4) { GemmEpilogue e2 = e; e2.debug_skip_store = 1; const int saved = g_gemm_mode; g_gemm_mode = 0; const int rc = gemm_bf16(A, lda, W, ldw, M, N, K, epi_kind, e2, st); g_gemm_mode = saved; return rc; }
   if (epi_kind == EPI_HEADNORM64_BF16 || epi_kind == EPI_HEADNORM128_BF16) {
     LSVS_CHECK_ARG(e.bias && e.out, "gemm: head-norm epilogue needs bias and out");
     LSVS_CHECK_ARG((e.n_q_cols == 0 || (e.qn_w && e.qn_b)) && (e.n_k_cols == 0 || (e.kn_w && e.kn_b)), "gemm: missing q/k norm weights");
