@@ -199,6 +199,20 @@ int lsvs_irls_umeyama(const float* src, const float* dst, const float* conf_src,
                       float conf_threshold_factor, float delta, int max_iters, float tol, float* R, float* t, float* s,
                       int* status, void* workspace, void* stream);
 
+/* ---- evaluation-side geometry right after the path --------------------------------
+ * replaces unproject_depth_map_to_point_map  aligned_vggt/utils/geometry.py:39-75: depth (frames,H,W) fp32, extrinsics
+ * (frames,3,4) world-to-camera, intrinsics (frames,3,3) -> world_points (frames,H,W,3) = R^T (K^-1 (u,v,1) d) - R^T t. */
+int lsvs_unproject_depth(const float* depth, const float* extrinsics, const float* intrinsics, float* world_points, int frames,
+                         int H, int W, void* stream);
+/* replaces the solver of scale_align_from_depths  aligned_vggt/utils/alignment.py:244-323: per batch element the L1-optimal
+ * scale a = argmin sum_i w_i |a x_i - y_i| = weighted median of y_i / x_i with weights w_i x_i, w_i = mask * conf / max(y, 0.1 *
+ * mean valid depth).  depth_pred, depth_gt, mask (0/1 as fp32), conf: (B, N) fp32; scales: (B) fp32 (made positive).  Radix select
+ * over the ratio bit patterns instead of the reference's sort + cumsum + searchsorted; no host synchronisation.
+ * workspace: lsvs_depth_scale_align_workspace_bytes(B) bytes of device memory. */
+size_t lsvs_depth_scale_align_workspace_bytes(int B);
+int lsvs_depth_scale_align(const float* depth_pred, const float* depth_gt, const float* mask, const float* conf, int B, long long N,
+                           float* scales, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,3 +79,27 @@ def scale_depth(depth: torch.Tensor, scales: torch.Tensor) -> torch.Tensor:
     _n.check(_n.lib().lsvs_scale_rows(_n.ptr(d), _n.ptr(_prep(scales, "scales").reshape(B)), _n.ptr(out), ctypes.c_int(B),
                                       ctypes.c_longlong(d.numel() // B), _n.stream_ptr()), "scale_rows")
     return out
+
+
+def scale_align_from_depths(predictions: dict, batch: dict) -> None:
+    """reference alignment.py:244-323 — one robust L1-optimal scale per batch element from predicted vs ground-truth depth
+    (confidence- and inverse-depth-weighted median of the ratios), applied in place to depth, world points and the pose
+    translations; `predictions["alignment_scales"]` = list of python floats (the reference's `.item()` per batch)."""
+    d_pred, conf = predictions["depth"], predictions["depth_conf"]
+    d_gt, mask = batch["depths"], batch["point_masks"]
+    B, S, H, W, _ = d_pred.shape
+    N = S * H * W
+    x, y = _prep(d_pred, "depth").reshape(B, N), _prep(d_gt, "depths").reshape(B, N)
+    m, c = _prep(mask, "point_masks").reshape(B, N), _prep(conf, "depth_conf").reshape(B, N)
+    lib = _n.lib()
+    lib.lsvs_depth_scale_align_workspace_bytes.restype = ctypes.c_size_t
+    ws = torch.empty(lib.lsvs_depth_scale_align_workspace_bytes(ctypes.c_int(B)), dtype=torch.uint8, device=x.device)
+    scales = torch.empty(B, dtype=torch.float32, device=x.device)
+    _n.check(lib.lsvs_depth_scale_align(_n.ptr(x), _n.ptr(y), _n.ptr(m), _n.ptr(c), ctypes.c_int(B), ctypes.c_longlong(N), _n.ptr(scales),
+                                        _n.ptr(ws), _n.stream_ptr()), "depth_scale_align")
+    predictions["depth"] *= scales[:, None, None, None, None]
+    if "world_points" in predictions:
+        predictions["world_points"] *= scales[:, None, None, None, None]
+    if "pose_enc" in predictions:
+        predictions["pose_enc"][..., :3] *= scales[:, None, None]
+    predictions["alignment_scales"] = [scales[b].item() for b in range(B)]

@@ -451,3 +451,46 @@ def pose_enc_apply_sim3(pose_enc: torch.Tensor, image_hw, T: torch.Tensor, s: to
     extr, intr = OF.pose_encoding_to_extri_intri(pose_enc, image_size_hw=image_hw)
     aligned = apply_sim3_w2c(extr, T, s)
     return OF.extri_intri_to_pose_encoding(aligned, intr, image_size_hw=image_hw)
+
+
+# ----------------------------------------------------------------------------- evaluation-side geometry
+def unproject_depth(depth_map: torch.Tensor, extrinsics: torch.Tensor, intrinsics: torch.Tensor) -> torch.Tensor:
+    """unproject_depth_map_to_point_map — /root/reference/aligned_vggt/utils/geometry.py:39-75.
+    depth (B,S,H,W,1), extrinsics (B,S,3,4) w2c, intrinsics (B,S,3,3) -> (B,S,H,W,3)."""
+    B, S, H, W, _ = depth_map.shape
+    u, v = torch.meshgrid(torch.arange(W), torch.arange(H), indexing="xy")  # geometry.py:152-158
+    pix = torch.stack((u, v, torch.ones_like(u)), dim=-1).float().view(-1, 3)
+    rays = (torch.inverse(intrinsics) @ pix.t()[None, None]).permute(0, 1, 3, 2)  # (B,S,HW,3)
+    cam = rays * depth_map.reshape(B, S, -1, 1)
+    poses = OF.closed_form_inverse_se3(extrinsics.reshape(B * S, 3, 4)).reshape(B, S, 4, 4)
+    world = cam @ poses[..., :3, :3].transpose(-1, -2) + poses[..., None, :3, 3]
+    return world.view(B, S, H, W, 3)
+
+
+def depth_scale_align(d_pred: torch.Tensor, d_gt: torch.Tensor, mask: torch.Tensor, conf: torch.Tensor) -> torch.Tensor:
+    """the solver of scale_align_from_depths — /root/reference/aligned_vggt/utils/alignment.py:259-313: (B,N) each -> scales (B)."""
+    x, y, m, w_conf = d_pred, d_gt, mask.float(), conf
+    N = x.shape[1]
+    sum_valid = m.sum(dim=-1, keepdim=True).clamp_min(1.0)
+    min_depth = 0.1 * ((y * m).sum(dim=-1, keepdim=True) / sum_valid)
+    w = m * w_conf * (1.0 / torch.max(y, min_depth).clamp_min(1e-6))
+    sign = torch.sign(x)
+    sign = torch.where(sign == 0, torch.ones_like(sign), sign)
+    x_pos, y_pos = x * sign, y * sign
+    r = y_pos / x_pos.clamp_min(1e-6)
+    w_eff = w * x_pos
+    r_sorted, idx = torch.sort(r, dim=-1)
+    cumsum = torch.gather(w_eff, -1, idx).cumsum(-1)
+    idx_med = torch.searchsorted(cumsum, 0.5 * cumsum[:, -1:], side="left").clamp(max=N - 1)
+    scales = torch.gather(r_sorted, -1, idx_med).squeeze(-1)
+    scales[scales <= 0] *= -1
+    return scales
+
+
+def convert_dict_lists(chunked: dict, overlap: int) -> dict:
+    """convertDictListsToTensors — /root/reference/aligned_vggt/utils/data.py:54-87 (out of place, tensors only)."""
+    out = {}
+    for k, items in chunked.items():
+        if isinstance(items, list) and torch.is_tensor(items[0]):
+            out[k] = torch.cat([t if i == 0 else t[:, overlap:] for i, t in enumerate(items)], dim=1)
+    return out

@@ -333,6 +333,50 @@ def case_model_dpt_small():
     save("model_dpt_small.npz", **arrs)
 
 
+def case_eval_geometry():
+    """unproject_depth_map_to_point_map, scale_align_from_depths, convertDictListsToTensors of the reference."""
+    print("[evaluation-side geometry]")
+    from aligned_vggt.utils.geometry import unproject_depth_map_to_point_map
+    from aligned_vggt.utils.alignment import scale_align_from_depths
+    from aligned_vggt.utils.data import convertDictListsToTensors
+    B, S, H, W = 2, 3, 10, 14
+    depth = rnd(501, B, S, H, W, 1).abs() + 0.5
+    q = torch.nn.functional.normalize(rnd(502, B, S, 4), dim=-1)
+    extr = torch.cat([OF.quat_to_mat(q), rnd(503, B, S, 3, 1)], dim=-1)
+    intr = torch.zeros(B, S, 3, 3)
+    intr[..., 0, 0] = 20.0 + rnd(504, B, S).abs(); intr[..., 1, 1] = 22.0 + rnd(505, B, S).abs()
+    intr[..., 0, 2] = W / 2; intr[..., 1, 2] = H / 2; intr[..., 2, 2] = 1.0; intr[..., 0, 1] = 0.1
+    ref = unproject_depth_map_to_point_map(depth, extr, intr)
+    check("unproject", OA.unproject_depth(depth, extr, intr), ref, 2e-6)
+    # scale alignment: prediction = gt / true_scale * noise, with outliers, masked pixels, a zero and a negative prediction
+    gt = rnd(506, B, S, H, W, 1).abs() * 3 + 0.2
+    true_scale = torch.tensor([1.7, 0.6]).view(B, 1, 1, 1, 1)
+    pred = gt / true_scale * (1 + 0.05 * rnd(507, B, S, H, W, 1))
+    pred[0, 0, 0, :5] *= 8.0
+    pred[1, 1, 2, 3] = 0.0
+    pred[1, 2, 4, 5] *= -1
+    mask = (rnd(508, B, S, H, W) > -1.0)
+    conf = 1 + rnd(509, B, S, H, W).exp()
+    pts = rnd(510, B, S, H, W, 3)
+    pose = rnd(511, B, S, 9)
+    preds = {"depth": pred.clone(), "depth_conf": conf.clone(), "world_points": pts.clone(), "pose_enc": pose.clone()}
+    scale_align_from_depths(preds, {"depths": gt, "point_masks": mask})
+    sc = torch.tensor(preds["alignment_scales"])
+    mine = OA.depth_scale_align(pred.reshape(B, -1), gt.reshape(B, -1), mask.reshape(B, -1), conf.reshape(B, -1))
+    check("depth scale", mine, sc, 1e-6)
+    print("   scales", sc.tolist())
+    # list merge
+    chunks = {"depth": [rnd(520 + i, 1, 4, 2, 2, 1) for i in range(3)], "pose_enc": [rnd(530 + i, 1, 4, 9) for i in range(3)], "other": [1, 2, 3]}
+    merged = {k: ([t.clone() for t in v] if torch.is_tensor(v[0]) else v) for k, v in chunks.items()}
+    convertDictListsToTensors(merged, 1)
+    mine = OA.convert_dict_lists(chunks, 1)
+    check("merge depth", mine["depth"], merged["depth"], 0)
+    check("merge pose", mine["pose_enc"], merged["pose_enc"], 0)
+    save("eval_geometry.npz", depth=depth, extr=extr, intr=intr, unproj=ref, gt=gt, pred=pred, mask=mask.float(), conf=conf, pts=pts, pose=pose,
+         scales=sc, depth_aligned=preds["depth"], pts_aligned=preds["world_points"], pose_aligned=preds["pose_enc"],
+         merged_depth=merged["depth"], merged_pose=merged["pose_enc"])
+
+
 def case_model_full():
     print("[FeatureAlignedVGGT, full depth, config 1: S=4, 154x518, overlap 1]")
     model, sd = build_reference_model(None)
@@ -348,7 +392,7 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     os.makedirs(GOLD, exist_ok=True)
     cases = {"spec": case_spec, "layers": case_layers, "geometry": case_geometry, "head": case_head, "model_small": case_model_small,
-             "pose_aligned": case_pose_aligned_small, "model_dpt_small": case_model_dpt_small}
+             "pose_aligned": case_pose_aligned_small, "model_dpt_small": case_model_dpt_small, "eval_geometry": case_eval_geometry}
     if args.full:
         cases["model_full"] = case_model_full
     for name, fn in cases.items():

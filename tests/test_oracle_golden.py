@@ -174,3 +174,15 @@ def test_dpt_model_golden(golden):
         for k, v in (("depth", o["depth"]), ("depth_conf", dc), ("world_points", o["world_points"]), ("world_points_conf", pc)):
             close(v[:, :, ::sub, ::sub], g[f"c{ci}_{k}"], 5e-4)
         ctx = {"overlap_tokens": o["overlap_tokens"], "memory_tokens": o["memory_tokens"], "pose_enc": o["pose_enc"]}
+
+
+def test_eval_geometry_golden(golden):
+    """SURVEY §8f rank 3 restatements vs outputs of the reference's unproject_depth_map_to_point_map / scale_align_from_depths /
+    convertDictListsToTensors (tests/golden/eval_geometry.npz)."""
+    g = golden("eval_geometry.npz")
+    t = lambda k: torch.as_tensor(g[k])
+    close(OA.unproject_depth(t("depth"), t("extr"), t("intr")), g["unproj"], 2e-6)
+    B = t("pred").shape[0]
+    sc = OA.depth_scale_align(t("pred").reshape(B, -1), t("gt").reshape(B, -1), t("mask").reshape(B, -1), t("conf").reshape(B, -1))
+    close(sc, g["scales"], 1e-6)
+    close(t("pred") * sc.view(B, 1, 1, 1, 1), g["depth_aligned"], 1e-6)
