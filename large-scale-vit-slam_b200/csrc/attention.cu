@@ -343,10 +343,9 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
         return fmaxf(__bfloat162float(mine), __bfloat162float(xb[par * (C::NT * 2 * QT) + x_other]));
       };
-      // m_ref is the reference maximum used inside exp2; it trails the true running maximum by at most 8 (log2
-      // units) plus the bf16 rounding of the exchanged maxima, so P <= ~2^8 and O / l stay exact after the final
-      // division, while the TMEM rescale of O (and the wait for the previous PV product it needs) only happens on the
-      // rare block where a row's maximum jumps by more.
+      // m_ref is the reference maximum used inside exp2: the maximum of the first key block, raised only when a later
+      // element exceeds it by more than 8 (log2 units), so P <= 2^8 and O / l stay exact after the final division,
+      // while the TMEM rescale of O only happens on the rare block where a row's maximum jumps by more.
       float m_ref = -INFINITY, l_run = 0.f;
       // The exp2 phase of one warp alone already fills the MUFU pipe of its SM sub-partition (ptxas paces it at one MUFU
       // per 8 cycles), so two tiles in lock-step serialise their exp2 phases and then idle the pipe together.  Tile B
@@ -405,41 +404,48 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           const unsigned long long tot = f2_add(sum2[0], sum2[1]);
           return f2_lo(tot) + f2_hi(tot);
         };
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        auto block_max = [&]() -> float {
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int c = 0; c < COLS; c += 4) {
-          mx[0] = fmaxf(mx[0], s[c]); mx[1] = fmaxf(mx[1], s[c + 1]); mx[2] = fmaxf(mx[2], s[c + 2]); mx[3] = fmaxf(mx[3], s[c + 3]);
-        }
-        const float m_half = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+          for (int c = 0; c < COLS; c += 4) {
+            mx[0] = fmaxf(mx[0], s[c]); mx[1] = fmaxf(mx[1], s[c + 1]); mx[2] = fmaxf(mx[2], s[c + 2]); mx[3] = fmaxf(mx[3], s[c + 3]);
+          }
+          return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        };
         // P is single-buffered in tensor memory: PV(i-1) must have consumed it (they retire in order, so O is quiescent too)
         if (i >= 1) ptx::mbar_wait(&bars->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
         ptx::tc_fence_after();
         PH(2);
         float blk_sum;
         if (i == 0) {
-          m_ref = row_max(m_half, 0);
+          m_ref = row_max(block_max(), 0);
           blk_sum = emit_P(m_ref);
         } else {
           // optimistic: exponentiate against the trailing reference maximum (no dependence on this block's maximum, so
-          // the MUFU work starts as soon as S is in registers); redo only if some row's maximum jumped by > 2^8
+          // the MUFU work starts as soon as S is in registers).  The block maximum itself is only needed when a row may have
+          // exceeded the reference by more than 2^8: a row sum <= 2^8 proves that no element did (every p <= its row sum), so
+          // the 128-element max pass is skipped on all other blocks.
           blk_sum = emit_P(m_ref);
-          const float m_blk = row_max(m_half, i & 1);
-          const bool jump = (m_blk - m_ref) * scale_log2e > 8.0f;
-          if (__any_sync(0xffffffffu, jump)) {
-            // rescale O in TMEM
-            const float alpha = jump ? ex2((m_ref - m_blk) * scale_log2e) : 1.0f;
-            if (jump) m_ref = m_blk;
-            l_run *= alpha;
+          const bool suspect = (SP == 2) || !(blk_sum <= 256.0f);  // (split rows: the partner warp must take the same path)
+          if (__any_sync(0xffffffffu, suspect)) {
+            const float m_blk = row_max(block_max(), i & 1);
+            const bool jump = (m_blk - m_ref) * scale_log2e > 8.0f;
+            if (__any_sync(0xffffffffu, jump)) {
+              // rescale O in TMEM, redo P against the new reference
+              const float alpha = jump ? ex2((m_ref - m_blk) * scale_log2e) : 1.0f;
+              if (jump) m_ref = m_blk;
+              l_run *= alpha;
 #pragma unroll
-            for (int c = 0; c < OCOLS; c += 16) {
-              uint32_t o[16];
-              ptx::tmem_ld_32x32b_x16(tO + c, o);
-              ptx::tmem_ld_wait();
+              for (int c = 0; c < OCOLS; c += 16) {
+                uint32_t o[16];
+                ptx::tmem_ld_32x32b_x16(tO + c, o);
+                ptx::tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-              ptx::tmem_st_32x32b_x16(tO + c, o);
+                for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+                ptx::tmem_st_32x32b_x16(tO + c, o);
+              }
+              blk_sum = emit_P(m_ref);
             }
-            blk_sum = emit_P(m_ref);
           }
         }
         l_run += blk_sum;

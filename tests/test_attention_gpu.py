@@ -71,3 +71,27 @@ def test_global_size_properties():
     kf, vf = (t.float().cpu().reshape(L, H, hd).transpose(0, 1) for t in (k, v2))
     ref = torch.softmax(qf @ kf.transpose(1, 2) / 8.0, dim=-1) @ vf
     assert rel_l2(o1[rows].cpu(), ref.transpose(0, 1).reshape(64, D)) < 6e-3
+
+
+@pytest.mark.parametrize("Lk", [700, 2600])  # one-tile (Lk <= 1024) and two-tile kernels
+def test_rising_and_plateau_scores(Lk):
+    """the reference maximum is set by the first key block and only raised when a row sum signals an element 2^8 above it:
+    (a) scores that rise by ~50 per key block (a rescale on every block), (b) a plateau 1.5 above the first block (row sums
+    above 2^8 without any jump: the max pass runs, nothing is rescaled)."""
+    from lsvs_b200 import ops
+    H, hd, Lq = 2, 64, 300
+    D = H * hd
+    g = torch.Generator().manual_seed(Lk)
+    u = torch.nn.functional.normalize(torch.randn(H, hd, generator=g), dim=-1) * 8.0
+    q = (u[None] + 0.05 * torch.randn(Lq, H, hd, generator=g)).reshape(Lq, D).bfloat16()
+    ramp = (torch.arange(Lk).float() * 0.05).view(Lk, 1, 1)
+    k_rise = (u[None] / 8.0 * ramp + 0.05 * torch.randn(Lk, H, hd, generator=g)).reshape(Lk, D).bfloat16()
+    plateau = torch.where(torch.arange(Lk) < 128, 0.0, 1.5).view(Lk, 1, 1)
+    k_plat = (u[None] / 8.0 * plateau + 0.02 * torch.randn(Lk, H, hd, generator=g)).reshape(Lk, D).bfloat16()
+    v = torch.randn(Lk, D, generator=g).bfloat16()
+    for k in (k_rise, k_plat):
+        qf, kf, vf = (t.float().reshape(1, -1, H, hd).transpose(1, 2) for t in (q, k, v))
+        ref = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(Lq, D)
+        out = ops.attention(q.cuda(), k.cuda(), v.cuda(), 1, H, hd, Lq, Lk).cpu()
+        assert torch.isfinite(out.float()).all()
+        assert rel_l2(out, ref) < 8e-3, rel_l2(out, ref)
