@@ -168,7 +168,7 @@ template <int HD, int NT_>
 __global__ void __maxnreg__((Cfg<HD, NT_>::MAXNREG))
 attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int Lq, int Lk,
-                      float scale_log2e, int stagger_cycles) {
+                      float scale_log2e) {
   using C = Cfg<HD, NT_>;
   constexpr int PK = 0;
   MS_ENTRY;
@@ -347,14 +347,6 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       // element exceeds it by more than 8 (log2 units), so P <= 2^8 and O / l stay exact after the final division,
       // while the TMEM rescale of O only happens on the rare block where a row's maximum jumps by more.
       float m_ref = -INFINITY, l_run = 0.f;
-      // The exp2 phase of one warp alone already fills the MUFU pipe of its SM sub-partition (ptxas paces it at one MUFU
-      // per 8 cycles), so two tiles in lock-step serialise their exp2 phases and then idle the pipe together.  Tile B
-      // starts late once; nothing re-synchronises the tiles afterwards, so B's exp2 phase keeps overlapping A's
-      // TMEM-load / max / barrier phase.
-      if (t == 1 && stagger_cycles > 0) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < stagger_cycles) {}
-      }
       PH_DECL;
       for (int i = 0; i < n_kv; ++i) {
         DBG_ITER(i);
@@ -517,9 +509,7 @@ int launch(const AttentionArgs& a, cudaStream_t st) {
   }
   dim3 grid((a.Lq + C::NT * QT - 1) / (C::NT * QT), a.heads, a.batches);
   const float scale_log2e = a.scale * 1.4426950408889634f;
-  static const int stagger = [] { const char* e = getenv("LSVS_ATTN_STAGGER"); return e ? atoi(e) : 0; }();
-  kern<<<grid, C::NTHREADS, C::SMEM, st>>>(*tq, *tk, *tv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, a.Lk, scale_log2e,
-                                           a.Lk >= 4 * C::BKV ? stagger : 0);
+  kern<<<grid, C::NTHREADS, C::SMEM, st>>>(*tq, *tk, *tv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, a.Lk, scale_log2e);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
