@@ -201,10 +201,12 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     ptx::fence_mbar_init();
   }
   if (warp == W_MMA) { ptx::tmem_alloc(&bars->tmem_slot, C::TMEM_COLS); ptx::tmem_relinquish(); }
+  pdl_launch_dependents();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
+  pdl_wait();  // the prologue above overlapped the previous kernel's tail (programmatic dependent launch)
   MS(0);  // setup done (barriers, TMEM allocation, CTA sync)
 
   if (warp == W_TMA) {
@@ -509,7 +511,7 @@ int launch(const AttentionArgs& a, cudaStream_t st) {
   }
   dim3 grid((a.Lq + C::NT * QT - 1) / (C::NT * QT), a.heads, a.batches);
   const float scale_log2e = a.scale * 1.4426950408889634f;
-  kern<<<grid, C::NTHREADS, C::SMEM, st>>>(*tq, *tk, *tv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, a.Lk, scale_log2e);
+  LSVS_CUDA(launch_pdl(kern, grid, dim3(C::NTHREADS), C::SMEM, st, *tq, *tk, *tv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, a.Lk, scale_log2e));
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }

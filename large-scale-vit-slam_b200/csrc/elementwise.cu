@@ -26,6 +26,8 @@ template <int NV, bool OUT_BF16>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long ld_in, RowMap in_map,
                                                         const float* __restrict__ w, const float* __restrict__ b, float eps,
                                                         void* __restrict__ out, long long ld_out, RowMap out_map, long long rows) {
+  pdl_launch_dependents();
+  pdl_wait();  // programmatic dependent launch: the grid may be resident before its predecessor has finished
   const int lane = threadIdx.x & 31;
   const long long m = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= rows) return;
@@ -181,8 +183,8 @@ int layernorm(const float* x, long long ld_in, RowMap in_map, const float* w, co
   const int warps = 8;
   const unsigned grid = (unsigned)((rows + warps - 1) / warps);
 #define LSVS_LN(NV)                                                                                                      \
-  if (out_bf16) layernorm_kernel<NV, true><<<grid, warps * 32, 0, st>>>(x, ld_in, in_map, w, b, eps, out, ld_out, out_map, rows); \
-  else layernorm_kernel<NV, false><<<grid, warps * 32, 0, st>>>(x, ld_in, in_map, w, b, eps, out, ld_out, out_map, rows);
+  if (out_bf16) LSVS_CUDA(launch_pdl(layernorm_kernel<NV, true>, dim3(grid), dim3(warps * 32), 0, st, x, ld_in, in_map, w, b, eps, out, ld_out, out_map, rows)); \
+  else LSVS_CUDA(launch_pdl(layernorm_kernel<NV, false>, dim3(grid), dim3(warps * 32), 0, st, x, ld_in, in_map, w, b, eps, out, ld_out, out_map, rows));
   if (D == 512) { LSVS_LN(4) } else if (D == 1024) { LSVS_LN(8) } else { LSVS_LN(16) }
 #undef LSVS_LN
   LSVS_LAUNCH_CHECK();

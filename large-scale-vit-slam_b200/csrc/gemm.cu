@@ -408,10 +408,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::tmem_alloc(tmem_slot, 2 * BN);
     ptx::tmem_relinquish();
   }
+  pdl_launch_dependents();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -587,11 +589,13 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
     ptx::tmem_alloc_2sm(tmem_slot, 2 * BN2);
     ptx::tmem_relinquish_2sm();
   }
+  pdl_launch_dependents();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -711,7 +715,7 @@ int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K,
     use_red |= 4;
   }
   if (g_gemm_mode == 3) use_red |= 2;
-  kern<<<2 * pairs, 64 + 32 * EW, Smem2<EPI>::TOTAL, st>>>(*tmA, *tmB, *tmR, M, N, K, e, use_red);
+  LSVS_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(64 + 32 * EW), Smem2<EPI>::TOTAL, st, *tmA, *tmB, *tmR, M, N, K, e, use_red));
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
@@ -727,7 +731,7 @@ int launch(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, 
   }
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, NUM_THREADS, L::TOTAL, st>>>(*tmA, *tmB, M, N, K, e);
+  LSVS_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, st, *tmA, *tmB, M, N, K, e));
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
@@ -753,8 +757,19 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   const bool bn256 = (N % 256 == 0);
   const bool bn64 = conv && N == 64;   // full-resolution DPT output convolution (32 channels padded to 64)
   LSVS_CHECK_ARG(bn256 || bn64 || N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
-  const int BN = bn256 ? 256 : 128;
-  const bool pair = bn256 && M > 2 * BM && g_gemm_mode != 1;  // CTA pairs (256x256 tiles) once there are enough rows
+  bool pair = bn256 && M > 2 * BM && g_gemm_mode != 1;  // CTA pairs (256x256 tiles) once there are enough rows
+  bool wide = bn256;                                     // single-CTA kernel: 128x256 tiles, else 128x128
+  if (pair && g_gemm_mode == 0) {
+    // few rows (short chunks: S = 4..8 frames): the 256x256 pair tiles leave SMs idle or waste a whole round; 128x128 single-CTA
+    // tiles do a quarter of the work on half the SMs at ~0.8x the per-tile efficiency
+    static const double penalty = [] { const char* v = getenv("LSVS_GEMM_NARROW_PENALTY"); return v ? atof(v) : 1.25; }();
+    const int sms = num_sms();
+    const long long tiles_pair = (long long)((M + 2 * BM - 1) / (2 * BM)) * (N / BN2);
+    const long long tiles_128 = (long long)((M + BM - 1) / BM) * (N / 128);
+    const long long rounds_pair = (tiles_pair + sms / 2 - 1) / (sms / 2), rounds_128 = (tiles_128 + sms - 1) / sms;
+    if ((double)rounds_128 * 0.5 * penalty < (double)rounds_pair) { pair = false; wide = false; }
+  }
+  const int BN = wide ? 256 : 128;
   const CUtensorMap* tmA = tmap_2d_bf16(A, a_cols, M, (uint64_t)lda * 2, BK, BM);
   const CUtensorMap* tmB = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, pair ? BN2 / 2 : BN);
   if (!tmA || !tmB) return LSVS_ECUDA;
@@ -770,7 +785,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
 #define LSVS_GEMM_CASE(KIND)                                                            \
   case KIND:                                                                            \
     if (pair) return launch2<KIND>(tmA, tmB, M, N, K, e, st);                           \
-    return bn256 ? launch<256, KIND>(tmA, tmB, M, N, K, e, st) : launch<128, KIND>(tmA, tmB, M, N, K, e, st);
+    return wide ? launch<256, KIND>(tmA, tmB, M, N, K, e, st) : launch<128, KIND>(tmA, tmB, M, N, K, e, st);
   // few rows (camera-head trunk, M = frames of one chunk): the job is weight streaming, so spread N over many CTAs
   if (M <= BM && N % 64 == 0 && N / 64 >= 32) {
     const CUtensorMap* tmB64 = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, 64);
@@ -797,7 +812,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
         return launch<64, EPI_CONV_BF16>(tmA, tmB64, M, N, K, e, st);
       }
       if (pair) return launch2<EPI_CONV_BF16>(tmA, tmB, M, N, K, e, st);
-      return bn256 ? launch<256, EPI_CONV_BF16>(tmA, tmB, M, N, K, e, st) : launch<128, EPI_CONV_BF16>(tmA, tmB, M, N, K, e, st);
+      return wide ? launch<256, EPI_CONV_BF16>(tmA, tmB, M, N, K, e, st) : launch<128, EPI_CONV_BF16>(tmA, tmB, M, N, K, e, st);
     default:
       return fail(LSVS_EINVAL, "gemm: unknown epilogue %d", epi_kind);
   }

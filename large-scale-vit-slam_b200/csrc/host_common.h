@@ -3,7 +3,9 @@
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <atomic>
+#include <utility>
 #include "../../include/lsvs_b200.h"
 
 namespace lsvs {
@@ -31,6 +33,30 @@ inline int num_sms() {
   }
   return n;
 }
+
+// ---- programmatic dependent launch ------------------------------------------------------------------------
+// Kernels launched through launch_pdl may become resident while their predecessor in the stream is still draining:
+// their prologue (barrier init, tensor-memory allocation, tensor-map prefetch) and the grid launch latency overlap the
+// predecessor's tail.  Such a kernel executes pdl_wait() (griddepcontrol.wait) before its first global-memory access
+// and pdl_launch_dependents() at its top.  LSVS_PDL=0 in the environment turns the attribute off (A/B measurements).
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* v = getenv("LSVS_PDL"); return !(v && v[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // ---- optional per-kernel-class CUDA-event profiler (bench.py's roofline numbers; off by default) ----------
 enum ProfCat { PROF_GEMM = 0, PROF_ATTENTION = 1, PROF_ELEMENTWISE = 2, PROF_SMALL_F32 = 3, PROF_SIM3 = 4, PROF_ATTENTION_GLOBAL = 5, PROF_NCAT = 6 };
