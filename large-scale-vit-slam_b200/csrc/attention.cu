@@ -1,14 +1,18 @@
 // Fused flash-style attention  O = softmax(Q K^T * scale) V  on tcgen05 / TMEM / TMA (no mask; ragged tails).
 //
-// One CTA owns up to two 128-row query tiles (A, B) of one (batch, head) and streams the K/V blocks once for
-// both.  Warp roles (10 warps):
-//   warp 8      TMA producer: Q tiles once, then K and V blocks through two independent 3-stage rings
-//   warp 9      tcgen05.mma issuer: S_t = Q_t K^T (SS, fp32 in TMEM), O_t += P_t V (SS, P from shared memory)
-//   warps 0-3   softmax for tile A, warps 4-7 softmax for tile B (registers moved to them with setmaxnreg): one thread per query row (TMEM lane), so the
-//               row max / row sum need no shuffles.  exp2 with the softmax scale folded in; running max and sum
-//               in registers; O stays in TMEM and is rescaled in place (tcgen05.ld/st) only when a row max moved.
+// One CTA owns two 128-row query tiles (A, B) of one (batch, head) and streams the K/V blocks once for both (long
+// sequences), or one tile with two CTAs per SM (Lk <= 1024).  Everything the tensor core touches besides Q/K/V lives in
+// tensor memory: S_t (fp32), O_t (fp32) and P_t (bf16 pairs, the A operand of the PV product).  Warp roles, NT = 2:
+//   warps 0-3   softmax for tile A, warps 4-7 for tile B (registers moved to them with setmaxnreg): one thread per query row
+//               (TMEM lane), so row sums need no shuffles.  exp2 with the softmax scale folded in, against a trailing
+//               reference maximum (first block's maximum, raised only when a row sum proves an element 2^8 above it);
+//               O stays in TMEM and is rescaled in place (tcgen05.ld/st) only then.  P goes back with tcgen05.st.
+//   warp 8      TMA producer: Q tiles once, then the K blocks through a 4-stage ring
+//   warp 9      tcgen05.mma issuer: S_t = Q_t K^T (SS form), O_t += P_t V (TS form: A from tensor memory, V MN-major)
+//   warp 10     TMA producer of the V blocks (own ring: a V slot frees late, after PV, and must not delay the next K request)
 // The two tiles ping-pong on the tensor core: while the softmax warps of one tile work, the MMAs of the other
 // run.  S_t(i+1) is issued as soon as the softmax warps have pulled S_t(i) into registers (s_free barrier).
+// Launched with programmatic dependent launch: the prologue overlaps the tail of the previous kernel.
 //
 // Replaces F.scaled_dot_product_attention behind UPSTREAM Attention (Aggregator frame/global/DINO blocks,
 // alignment-head frame blocks alignment_head.py:363, camera-head trunk); q_norm/k_norm/RoPE are already applied
@@ -24,7 +28,7 @@ namespace lsvs {
 namespace {
 
 constexpr int QT = 128;            // query rows per tile (UMMA M)
-// threads = (NT + 1) warpgroups: one softmax warpgroup per query tile, the last one holds the TMA warp, the MMA warp and 2 idle warps
+// threads = (NT + 1) warpgroups: one softmax warpgroup per query tile, the last one holds the K producer, the MMA warp, the V producer and an idle warp
 constexpr int KV_STAGES = 4;
 
 #ifndef LSVS_ATTN_SPLIT64

@@ -1,12 +1,19 @@
-// bf16 GEMM  C[M,N] = A[M,K] . W[N,K]^T  (both operands K-major, i.e. nn.Linear layout) on the 5th-gen
-// tensor cores: TMA (128B swizzle) -> 4-stage shared-memory ring -> tcgen05.mma (cta_group::1, 128xBNx16)
-// accumulating fp32 in TMEM (double-buffered, 2 x BN columns) -> tcgen05.ld epilogue fused with
-//   bias | bias+GELU(erf) | bias+LayerScale+fp32 residual | bias + per-head LayerNorm + RoPE (q,k) .
-// Persistent: one CTA per SM walks tiles n-fastest so that an A row-panel stays in L2 across its N tiles.
+// bf16 GEMM  C[M,N] = A[M,K] . W[N,K]^T  (both operands K-major, i.e. nn.Linear layout) on the 5th-gen tensor cores.
+// Two persistent, warp-specialised kernels (TMA producer warp / single-thread tcgen05.mma issuer / epilogue warps), fp32
+// accumulators double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1:
+//   * gemm_bf16_tcgen05_2cta  CTA pairs (cta_group::2): 256x256 tiles, each CTA loads its 128 A rows and half of the W
+//                             tile; 5-6 stage 32 KB ring; used when M > 256 and N % 256 == 0 (all large GEMMs)
+//   * gemm_bf16_tcgen05<BN>   one CTA, 128 x BN tiles (BN 64 / 128 / 256), 4-stage ring; small M or N
+// Fused epilogues (one thread owns one output row of the tile):
+//   bias | bias+GELU(erf) | bias -> fp32 | bias+LayerScale+fp32 residual (TMA reduce-add) | bias + per-head LayerNorm + RoPE
+//   (q,k) | convolution on a padded NHWC grid (bias + residuals + ReLU + border mask; the producer shifts the A rows per tap).
+// bf16 outputs of the pair kernel are staged in 128B-swizzled shared memory and leave as bulk TMA stores.
+// Tiles are walked n-fastest so that an A row-panel stays in L2 across its N tiles.  Programmatic dependent launch: the
+// prologue (barriers, tensor-memory allocation) overlaps the previous kernel's tail.
 //
 // Replaces the library calls at: UPSTREAM Attention.qkv/proj, Mlp.fc1/fc2,
-// alignment_head.py:242 (project_in), cross_attention.py:55-57,76 (q/k/v/proj), plus the elementwise
-// q_norm/k_norm/RoPE/LayerScale/residual passes that the reference runs as separate ATen kernels.
+// alignment_head.py:242 (project_in), cross_attention.py:55-57,76 (q/k/v/proj), UPSTREAM DPTHead convolutions, plus the
+// elementwise q_norm/k_norm/RoPE/LayerScale/residual passes that the reference runs as separate ATen kernels.
 #include <cstdlib>
 
 #include "gemm.h"
