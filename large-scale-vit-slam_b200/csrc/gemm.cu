@@ -528,7 +528,7 @@ struct Smem2 {
 // clipped by the tensor map.  The row-per-lane read-modify-write it replaces spent its time in long-scoreboard stalls
 // (profiles/: proj GEMM 57 us vs 29 us with a plain bf16 epilogue).
 __device__ __forceinline__ void epilogue_resid_tma(const GemmEpilogue& e, const CUtensorMap* tmR, uint8_t* tile, uint32_t taddr,
-                                                   int m_base, int n0, int c_begin, int c_end) {
+                                                   int m_base, int n0, int c_begin, int c_end, bool with_bias = true) {
   const int lane = threadIdx.x & 31;
 #pragma unroll 1
   for (int c = c_begin; c < c_end; c += 32) {
@@ -539,7 +539,7 @@ __device__ __forceinline__ void epilogue_resid_tma(const GemmEpilogue& e, const 
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 g = e.gamma ? __ldg(reinterpret_cast<const float4*>(e.gamma + n) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
-      const float4 bb = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 bb = (e.bias && with_bias) ? __ldg(reinterpret_cast<const float4*>(e.bias + n) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
       v[4 * i + 0] = g.x * (v[4 * i + 0] + bb.x);
       v[4 * i + 1] = g.y * (v[4 * i + 1] + bb.y);
       v[4 * i + 2] = g.z * (v[4 * i + 2] + bb.z);
@@ -580,8 +580,11 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
   const int n_tiles_n = N / BN2;
   const int n_tiles_m = (M + 2 * BM - 1) / (2 * BM);
-  const int n_tiles = n_tiles_m * n_tiles_n;
-  const int n_kb = K / BK;
+  // split-K (reduce-add residual epilogue only, few tiles): work item = (tile, K slice); every slice adds its partial
+  // gamma * acc into the residual (L2 atomics of the TMA reduce), slice 0 also carries the bias
+  const int splits = (use_tma_reduce >> 8) > 1 ? (use_tma_reduce >> 8) : 1;
+  const int n_tiles = n_tiles_m * n_tiles_n * splits;   // work items
+  const int n_kb = (K / BK) / splits;                   // k-blocks per work item
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -608,10 +611,11 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ------------------------------------------------------------ TMA producer (both CTAs)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+    for (int item = pair; item < n_tiles; item += n_pairs) {
+      const int tile = item / splits, kb0 = (item - tile * splits) * n_kb;
       const int m0 = (tile / n_tiles_n) * (2 * BM) + (int)cta * BM;
       const int n0 = (tile % n_tiles_n) * BN2 + (int)cta * (BN2 / 2);
-      for (int kb = 0; kb < n_kb; ++kb) {
+      for (int kb = kb0; kb < kb0 + n_kb; ++kb) {
         ptx::mbar_wait(empty_bar + stage, phase ^ 1);
         if (lane == 0) {
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
@@ -665,7 +669,8 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
     constexpr int COLS = BN2 / (EW / 4);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = pair; tile < n_tiles; tile += n_pairs) {
+    for (int item = pair; item < n_tiles; item += n_pairs) {
+      const int tile = item / splits, slice = item - tile * splits;
       const int m0 = (tile / n_tiles_n) * (2 * BM) + (int)cta * BM;
       const int n0 = (tile % n_tiles_n) * BN2;
       ptx::mbar_wait(tmem_full + acc, acc_phase);
@@ -673,7 +678,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int m = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2;
       if (L::TRANSPOSE && (use_tma_reduce & 1)) {
-        epilogue_resid_tma(epi, &tmR, smem + L::TILE_OFFSET + (warp - 2) * L::TILE_BYTES, taddr, m0 + quarter * 32, n0, part * COLS, (part + 1) * COLS);
+        epilogue_resid_tma(epi, &tmR, smem + L::TILE_OFFSET + (warp - 2) * L::TILE_BYTES, taddr, m0 + quarter * 32, n0, part * COLS, (part + 1) * COLS, slice == 0);
       } else if (L::TMA_BF16 && (use_tma_reduce & 4)) {
         const TmaOut to{&tmR, smem + L::TILE_OFFSET + (warp - 2) * L::TILE_BYTES, m0 + quarter * 32};
         epilogue_row<BN2, EPI, L::TMA_BF16>(epi, sp, taddr, m, n0, m < M, part * COLS, (part + 1) * COLS, &to);
@@ -708,7 +713,6 @@ int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K,
   }
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * (N / BN2);
   const int max_pairs = num_sms() / 2;
-  const int pairs = tiles < max_pairs ? tiles : max_pairs;
   const CUtensorMap* tmR = tmA;
   int use_red = 0;
   if (EPI == EPI_RESID_F32 && e.out2 == nullptr && g_gemm_mode != 2 && ((uintptr_t)e.resid % 16 == 0) && (e.ldr % 4 == 0)) {
@@ -722,6 +726,14 @@ int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K,
     use_red |= 4;
   }
   if (g_gemm_mode == 3) use_red |= 2;
+  int splits = 1;
+  if ((use_red & 1) && g_gemm_mode == 0) {  // few tiles (short chunks): slice K while all slices still fit in one round of CTA pairs
+    const int n_kb = K / BK;
+    while (splits < 8 && tiles * splits * 2 <= max_pairs && n_kb % (2 * splits) == 0 && n_kb / (2 * splits) >= 4) splits *= 2;
+  }
+  use_red |= splits << 8;
+  const int items = tiles * splits;
+  const int pairs = items < max_pairs ? items : max_pairs;
   LSVS_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(64 + 32 * EW), Smem2<EPI>::TOTAL, st, *tmA, *tmB, *tmR, M, N, K, e, use_red));
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
@@ -766,7 +778,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   LSVS_CHECK_ARG(bn256 || bn64 || N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
   bool pair = bn256 && M > 2 * BM && g_gemm_mode != 1;  // CTA pairs (256x256 tiles) once there are enough rows
   bool wide = bn256;                                     // single-CTA kernel: 128x256 tiles, else 128x128
-  if (pair && g_gemm_mode == 0) {
+  if (pair && g_gemm_mode == 0 && !(epi_kind == EPI_RESID_F32 && e.out2 == nullptr)) {  // (residual GEMMs: pair kernel + split-K instead)
     // few rows (short chunks: S = 4..8 frames): the 256x256 pair tiles leave SMs idle or waste a whole round; 128x128 single-CTA
     // tiles do a quarter of the work on half the SMs at ~0.8x the per-tile efficiency
     static const double penalty = [] { const char* v = getenv("LSVS_GEMM_NARROW_PENALTY"); return v ? atof(v) : 1.25; }();
