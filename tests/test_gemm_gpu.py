@@ -135,3 +135,18 @@ def test_gemm_argument_errors():
     a, w = torch.zeros(4, 100, dtype=torch.bfloat16, device="cuda"), torch.zeros(128, 100, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(ValueError):
         ops.gemm(a, w, ops.EPI_BIAS_BF16)  # K % 64 != 0
+
+
+@pytest.mark.parametrize("M,N,K", [(1648, 1024, 4096), (2060, 1024, 1024), (13184, 1024, 1024), (700, 1024, 2048)])
+def test_gemm_residual_tma_reduce_and_split_k(M, N, K):
+    """LayerScale + residual epilogue of the pair kernel (TMA reduce-add into the fp32 stream), including the short-chunk
+    shapes where K is sliced over CTA pairs (28 / 36 tiles on 74 pairs) and every slice adds its partial; bias counted once."""
+    from lsvs_b200 import ops
+    a, w, bias = mk(M, N, K, seed=M % 97)
+    resid, gamma = rnd(21, M, N), 0.1 * (1 + 0.1 * rnd(22, N))
+    r_dev = resid.cuda()
+    ops.gemm(a.cuda(), w.cuda(), ops.EPI_RESID_F32, bias=bias.cuda(), gamma=gamma.cuda(), resid=r_dev)
+    ref = resid.double() + gamma.double() * (a.double() @ w.double().T + bias.double())
+    assert rel_l2(r_dev.cpu().double(), ref) < 1e-5
+    # the update itself (not hidden behind the residual's magnitude)
+    assert rel_l2(r_dev.cpu().double() - resid.double(), ref - resid.double()) < 1e-4
