@@ -31,12 +31,6 @@ constexpr int QT = 128;            // query rows per tile (UMMA M)
 // threads = (NT + 1) warpgroups: one softmax warpgroup per query tile, the last one holds the K producer, the MMA warp, the V producer and an idle warp
 constexpr int KV_STAGES = 4;
 
-#ifndef LSVS_ATTN_SPLIT64
-#define LSVS_ATTN_SPLIT64 0  // head dim 64: two softmax threads per query row (16 softmax warps); measured 623 vs 658 TFLOP/s
-#endif
-#ifndef LSVS_ATTN_POLY_PAIRS
-#define LSVS_ATTN_POLY_PAIRS 0  // of every 4 element pairs, this many use the polynomial exp2 path (0 disables; measured slower)
-#endif
 
 template <int HD, int NT_>
 struct Cfg {
@@ -49,16 +43,15 @@ struct Cfg {
   static constexpr int NT = NT_;                            // query tiles per CTA
   static constexpr int KVS = (NT_ == 2) ? KV_STAGES : 2;    // K / V ring depth
   static constexpr int BKV = (HD == 64) ? 128 : 64;         // keys per block (UMMA N of S, K of PV)
-  // SP softmax warpgroups share one query tile, each thread owning BKV / SP columns of its row: at head dim 64 the
-  // softmax is issue / latency bound at 8 warps (2 per SM sub-partition), so the row is split over two threads.
-  static constexpr int SP = LSVS_ATTN_SPLIT64 && (HD == 64) ? 2 : 1;
-  static constexpr int COLS = BKV / SP;                     // S columns per softmax thread
-  static constexpr int OCOLS = HD / SP;                     // O columns per softmax thread (rescale / epilogue)
-  static constexpr int NWG = NT * SP;                       // softmax warpgroups
+  // (Measured alternatives, DESIGN.md 5: two threads per softmax row / 16 softmax warps, 701 vs 730 TFLOP/s; a share of the
+  //  exponentials as a degree-3 polynomial on the FMA pipe, 708 vs 730; PRMT instead of F2FP packing, no change.)
+  static constexpr int COLS = BKV;                          // S columns per softmax thread (one thread per query row)
+  static constexpr int OCOLS = HD;                          // O columns per softmax thread (rescale / epilogue)
+  static constexpr int NWG = NT;                            // softmax warpgroups
   static constexpr int NTHREADS = (NWG + 1) * 128;
-  static constexpr int MAXNREG = (SP == 2) ? 96 : (NT_ == 2 ? 168 : 128);  // launch-time registers / thread (register file / resident threads)
-  static constexpr int REG_SOFTMAX = (SP == 2) ? 104 : 200; // after setmaxnreg: NWG*128*REG_SOFTMAX + 128*REG_SERVICE <= NTHREADS*MAXNREG
-  static constexpr int REG_SERVICE = (SP == 2) ? 64 : (NT_ == 2 ? 96 : 56);
+  static constexpr int MAXNREG = NT_ == 2 ? 168 : 128;      // launch-time registers / thread (register file / resident threads)
+  static constexpr int REG_SOFTMAX = 200;                   // after setmaxnreg: NWG*128*REG_SOFTMAX + 128*REG_SERVICE <= NTHREADS*MAXNREG
+  static constexpr int REG_SERVICE = NT_ == 2 ? 96 : 56;
   static constexpr int KB = HD / 64;                        // 64-element (128 B) column blocks of the head dim
   static constexpr int Q_TILE_BYTES = QT * HD * 2;
   static constexpr int K_TILE_BYTES = BKV * HD * 2;
@@ -67,9 +60,7 @@ struct Cfg {
   static constexpr int OFF_K = OFF_Q + NT * Q_TILE_BYTES;
   static constexpr int OFF_V = OFF_K + KVS * K_TILE_BYTES;
   static constexpr int OFF_BAR = OFF_V + KVS * V_TILE_BYTES;
-  static constexpr int OFF_X = OFF_BAR + 512;                     // row-max exchange between the SP threads of a row (bf16)
-  static constexpr int X_BYTES = (SP == 2) ? 2 * NT * SP * QT * 2 : 0;  // [parity][tile][half][row]
-  static constexpr int SMEM = OFF_X + X_BYTES;                    // the dynamic shared window is 1024-aligned (no static smem)
+  static constexpr int SMEM = OFF_BAR + 512;                      // the dynamic shared window is 1024-aligned (no static smem)
   static constexpr int S_COL = 0;                            // TMEM columns: S_A, S_B, O_A, O_B, P_A, P_B
   static constexpr int O_COL = NT * BKV;
   static constexpr int P_COL = O_COL + NT * HD;              // P: bf16 pairs, BKV / 2 columns per tile
@@ -112,22 +103,6 @@ __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsig
   return r;
 }
 
-// exp2 on the FMA/ALU pipes for a share of the elements (the MUFU pipe is the bottleneck at head dim 64):
-// round-to-nearest split x = n + f via the 1.5*2^23 magic add, degree-3 minimax 2^f on [-0.5, 0.5] (max rel. error
-// 7.5e-5, far below the bf16 rounding of P), exponent patched in with an integer add.  Two elements per call.
-__device__ __forceinline__ void ex2_poly2(unsigned long long x2, float& r0, float& r1) {
-  const float MAGIC = 12582912.0f;  // 1.5 * 2^23
-  const unsigned long long xc = f2_pack(fmaxf(f2_lo(x2), -125.0f), fmaxf(f2_hi(x2), -125.0f));
-  const unsigned long long xf = f2_add(xc, f2_pack(MAGIC, MAGIC));
-  const unsigned long long fi = f2_add(xf, f2_pack(-MAGIC, -MAGIC));
-  const unsigned long long fr = f2_fma(fi, f2_pack(-1.0f, -1.0f), xc);
-  unsigned long long p = f2_fma(f2_pack(0.055171654f, 0.055171654f), fr, f2_pack(0.24261113f, 0.24261113f));
-  p = f2_fma(p, fr, f2_pack(0.69326097f, 0.69326097f));
-  p = f2_fma(p, fr, f2_pack(0.99992806f, 0.99992806f));
-  r0 = __int_as_float(__float_as_int(f2_lo(p)) + (__float_as_int(f2_lo(xf)) << 23));
-  r1 = __int_as_float(__float_as_int(f2_hi(p)) + (__float_as_int(f2_hi(xf)) << 23));
-}
-
 // register re-balancing between the service warpgroup and the softmax warpgroups (setmaxnreg, warpgroup-wide)
 template <class C> __device__ __forceinline__ void reg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REG_SERVICE));
@@ -159,22 +134,12 @@ __device__ int g_dbg_iter[64];
 #define DBG_ITER(i) do {} while (0)
 #endif
 
-// P (fp32) -> packed bf16 pair.  PK 0: cvt.rn.bf16x2.f32 (F2FP); 1: truncation with one PRMT; 2: round-half-up with two
-// integer adds + PRMT (exp2 outputs are positive and finite, so the carry never reaches the sign / inf patterns).
-template <int PK> __device__ __forceinline__ uint32_t pack_p(float lo, float hi) {
-  if (PK == 0) return ptx::pack_bf16(lo, hi);
-  uint32_t a = __float_as_uint(lo), b = __float_as_uint(hi);
-  if (PK == 2) { a += 0x8000u; b += 0x8000u; }
-  return __byte_perm(a, b, 0x7632);
-}
-
 template <int HD, int NT_>
 __global__ void __maxnreg__((Cfg<HD, NT_>::MAXNREG))
 attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int Lq, int Lk,
                       float scale_log2e) {
   using C = Cfg<HD, NT_>;
-  constexpr int PK = 0;
   MS_ENTRY;
   extern __shared__ __align__(1024) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem + C::OFF_BAR);
@@ -198,8 +163,8 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       ptx::mbar_init(&bars->v_full[i], 1); ptx::mbar_init(&bars->v_empty[i], 1);
     }
     for (int t = 0; t < NT; ++t) {
-      ptx::mbar_init(&bars->s_full[t], 1); ptx::mbar_init(&bars->s_free[t], 4 * C::SP);
-      ptx::mbar_init(&bars->p_ready[t][0], 4 * C::SP); ptx::mbar_init(&bars->p_ready[t][1], 4 * C::SP);
+      ptx::mbar_init(&bars->s_full[t], 1); ptx::mbar_init(&bars->s_free[t], 4);
+      ptx::mbar_init(&bars->p_ready[t][0], 4); ptx::mbar_init(&bars->p_ready[t][1], 4);
       ptx::mbar_init(&bars->pv_done[t][0], 1); ptx::mbar_init(&bars->pv_done[t][1], 1);
     }
     ptx::fence_mbar_init();
@@ -325,30 +290,15 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   } else {
     // ============================================================ softmax / correction / epilogue
     reg_inc<C>();
-    constexpr int SP = C::SP, COLS = C::COLS, OCOLS = C::OCOLS;
-    const int wg = warp >> 2;                  // softmax warpgroup
-    const int t = wg / SP;                     // query tile of this warpgroup
-    const int h = wg % SP;                     // which COLS-wide slice of the key block (and OCOLS-wide slice of O) it owns
+    constexpr int COLS = C::COLS, OCOLS = C::OCOLS;
+    const int t = warp >> 2;                   // query tile of this softmax warpgroup
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;         // query row within the tile == TMEM lane
     if (t < n_tiles) {
       const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-      const uint32_t tS = tmem + lane_addr + C::S_COL + t * C::BKV + h * COLS;
-      const uint32_t tO = tmem + lane_addr + C::O_COL + t * HD + h * OCOLS;
+      const uint32_t tS = tmem + lane_addr + C::S_COL + t * C::BKV;
+      const uint32_t tO = tmem + lane_addr + C::O_COL + t * HD;
       const uint32_t tP = tmem + lane_addr + C::P_COL + t * C::PCOLS;
-      // SP == 2: the two threads of a row trade their slice maxima through shared memory (bf16, rounded identically on
-      // both sides so that they take the same decisions), synchronised by a 64-thread named barrier per (tile, quarter);
-      // the slot is double-buffered by iteration parity (the partner may still be reading the previous one).
-      __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(smem + C::OFF_X);
-      const int x_mine = (t * 2 + h) * QT + r, x_other = (t * 2 + (h ^ 1)) * QT + r;
-      const int pair_bar = 1 + t * 4 + quarter;
-      auto row_max = [&](float m_half, int par) -> float {
-        if (SP == 1) return m_half;
-        const __nv_bfloat16 mine = __float2bfloat16_rn(m_half);
-        xb[par * (C::NT * 2 * QT) + x_mine] = mine;
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        return fmaxf(__bfloat162float(mine), __bfloat162float(xb[par * (C::NT * 2 * QT) + x_other]));
-      };
       // m_ref is the reference maximum used inside exp2: the maximum of the first key block, raised only when a later
       // element exceeds it by more than 8 (log2 units), so P <= 2^8 and O / l stay exact after the final division,
       // while the TMEM rescale of O only happens on the rare block where a row's maximum jumps by more.
@@ -368,7 +318,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->s_free[t]);
-        const int kv_valid = Lk - i * C::BKV - h * COLS;  // keys of this slice inside the sequence
+        const int kv_valid = Lk - i * C::BKV;  // keys of this block inside the sequence
         if (kv_valid < COLS) {
 #pragma unroll
           for (int c = 0; c < COLS; ++c) if (c >= kv_valid) s[c] = -INFINITY;
@@ -386,18 +336,14 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
               const unsigned long long x = f2_fma(f2_pack(s[8 * j + e], s[8 * j + e + 1]), sc2, nmb2);
-              if (HD == 64 && e / 2 < LSVS_ATTN_POLY_PAIRS) {
-                ex2_poly2(x, p[e], p[e + 1]);
-              } else {
-                p[e] = ex2(f2_lo(x));
-                p[e + 1] = ex2(f2_hi(x));
-              }
+              p[e] = ex2(f2_lo(x));
+              p[e + 1] = ex2(f2_hi(x));
             }
             sum2[0] = f2_add(sum2[0], f2_add(f2_pack(p[0], p[1]), f2_pack(p[4], p[5])));
             sum2[1] = f2_add(sum2[1], f2_add(f2_pack(p[2], p[3]), f2_pack(p[6], p[7])));
 #pragma unroll
-            for (int e = 0; e < 4; ++e) pk[4 * (j & 3) + e] = pack_p<PK>(p[2 * e], p[2 * e + 1]);
-            if ((j & 3) == 3) ptx::tmem_st_32x32b_x16(tP + (h * (COLS / 8) + j - 3) * 4, pk);   // 32 keys = 16 packed columns
+            for (int e = 0; e < 4; ++e) pk[4 * (j & 3) + e] = ptx::pack_bf16(p[2 * e], p[2 * e + 1]);
+            if ((j & 3) == 3) ptx::tmem_st_32x32b_x16(tP + (j - 3) * 4, pk);   // 32 keys = 16 packed columns
           }
           const unsigned long long tot = f2_add(sum2[0], sum2[1]);
           return f2_lo(tot) + f2_hi(tot);
@@ -416,7 +362,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         PH(2);
         float blk_sum;
         if (i == 0) {
-          m_ref = row_max(block_max(), 0);
+          m_ref = block_max();
           blk_sum = emit_P(m_ref);
         } else {
           // optimistic: exponentiate against the trailing reference maximum (no dependence on this block's maximum, so
@@ -424,9 +370,9 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           // exceeded the reference by more than 2^8: a row sum <= 2^8 proves that no element did (every p <= its row sum), so
           // the 128-element max pass is skipped on all other blocks.
           blk_sum = emit_P(m_ref);
-          const bool suspect = (SP == 2) || !(blk_sum <= 256.0f);  // (split rows: the partner warp must take the same path)
+          const bool suspect = !(blk_sum <= 256.0f);
           if (__any_sync(0xffffffffu, suspect)) {
-            const float m_blk = row_max(block_max(), i & 1);
+            const float m_blk = block_max();
             const bool jump = (m_blk - m_ref) * scale_log2e > 8.0f;
             if (__any_sync(0xffffffffu, jump)) {
               // rescale O in TMEM, redo P against the new reference
@@ -461,16 +407,9 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       // ---- epilogue: O / l -> bf16 -> global
       ptx::mbar_wait(&bars->pv_done[t][(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
       ptx::tc_fence_after();
-      if (SP == 2) {
-        // total row sum = sum of the two slice sums; the Q tile of this query tile is dead once its last S product retired
-        float* lx = reinterpret_cast<float*>(smem + C::OFF_Q + t * C::Q_TILE_BYTES);
-        lx[h * QT + r] = l_run;
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        l_run += lx[(h ^ 1) * QT + r];
-      }
       const float inv_l = 1.0f / l_run;
       const int q_local = q0 + t * QT + r;
-      __nv_bfloat16* dst = O + (size_t)(batch * (size_t)Lq + q_local) * ldo + col0 + h * OCOLS;
+      __nv_bfloat16* dst = O + (size_t)(batch * (size_t)Lq + q_local) * ldo + col0;
 #pragma unroll
       for (int c = 0; c < OCOLS; c += 32) {
         uint32_t o[32];
