@@ -88,7 +88,9 @@ typedef struct lsvs_gemm_epilogue {
 
 int lsvs_gemm_bf16(const lsvs_bf16* A, int lda, const lsvs_bf16* W, int ldw, int M, int N, int K, int epilogue_kind,
                    const lsvs_gemm_epilogue* epilogue, void* stream);
-/* A/B switch for measurements: 0 = auto (CTA-pair 256x256 tiles when M > 256 and N % 256 == 0), 1 = single-CTA kernel only */
+/* A/B switch for measurements: 0 = auto (CTA-pair 256x256 tiles when M > 256 and N % 256 == 0), 1 = single-CTA kernel only,
+ * 2 = pair kernel with per-lane epilogue stores (no TMA store / reduce-add), 3 = pair kernel without the W-operand loads (wrong
+ * results; halves the L2->SM bytes to test for a bandwidth bound) */
 int lsvs_debug_gemm_mode(int mode);
 /* cos/sin table used by the RoPE epilogues: tab[p][j] = (cos, sin)(p * base^(-2j/(2*n_freq))), p < n_pos.
  * (rope.py:46-58; fp32 angles)  `tab` holds n_pos*n_freq*2 floats. */

@@ -263,7 +263,7 @@ __device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, const EpiSme
         } else if constexpr (TMA) {
           store_bf16_tma<CH>(*to, v, n);
         } else {
-          if (!e.debug_skip_store || v[0] == 123456.f) store_bf16_row<32>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ldo + n, v);
+          store_bf16_row<32>(reinterpret_cast<__nv_bfloat16*>(e.out) + (size_t)m * e.ldo + n, v);
         }
       }
     }
@@ -793,7 +793,6 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   const CUtensorMap* tmB = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, pair ? BN2 / 2 : BN);
   if (!tmA || !tmB) return LSVS_ECUDA;
   ProfScope prof(PROF_GEMM, st, 2.0 * M * (double)N * K, 0);
-  if (g_gemm_mode == 4) { GemmEpilogue e2 = e; e2.debug_skip_store = 1; const int saved = g_gemm_mode; g_gemm_mode = 0; const int rc = gemm_bf16(A, lda, W, ldw, M, N, K, epi_kind, e2, st); g_gemm_mode = saved; return rc; }
   if (epi_kind == EPI_HEADNORM64_BF16 || epi_kind == EPI_HEADNORM128_BF16) {
     LSVS_CHECK_ARG(e.bias && e.out, "gemm: head-norm epilogue needs bias and out");
     LSVS_CHECK_ARG((e.n_q_cols == 0 || (e.qn_w && e.qn_b)) && (e.n_k_cols == 0 || (e.kn_w && e.kn_b)), "gemm: missing q/k norm weights");

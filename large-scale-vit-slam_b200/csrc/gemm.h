@@ -35,7 +35,6 @@ struct GemmEpilogue {
   // out = mask(relu?(acc + bias + res1 + res2)): border pixels of the grid are written as zeros (they are the next
   // convolution's padding).
   int conv_taps = 0, conv_c = 0, conv_hp = 0, conv_wp = 0, conv_relu = 0, conv_mask = 0;
-  int debug_skip_store = 0;      // measurement only (lsvs_debug_gemm_mode 4): bf16 epilogues compute but do not store
   const void* res1 = nullptr; const void* res2 = nullptr;   // optional bf16 residual inputs, same layout / stride as out
 };
 
