@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
                                                          const float* __restrict__ b, float* __restrict__ y, long long ldy, int M,
                                                          int N, int K, int in_act, int out_act, const float* __restrict__ gamma,
                                                          int residual) {
+  pdl_launch_dependents();
+  pdl_wait();  // programmatic dependent launch (host_common.h)
   const int lane = threadIdx.x & 31;
   const int n0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * LIN_NW;
   const int m0 = blockIdx.y * LIN_MT;
@@ -106,6 +108,8 @@ __global__ void __launch_bounds__(256) linear_f32_tiled_kernel(const float* __re
                                                                const float* __restrict__ b, float* __restrict__ y, long long ldy,
                                                                int M, int N, int K, int in_act, int out_act,
                                                                const float* __restrict__ gamma, int residual) {
+  pdl_launch_dependents();
+  pdl_wait();  // programmatic dependent launch (host_common.h)
   static_assert(MS * KS == 8, "8 warps");
   constexpr int NC = 8, RW = 8;  // columns per block, rows per warp
   __shared__ float red[KS][MS * RW][NC];
@@ -167,6 +171,8 @@ __global__ void __launch_bounds__(256) linear_f32_tiled_kernel(const float* __re
 // Lane holds elements e = lane + 32*j, so rotate-half partners (e, e + hd/2) sit in the same lane.
 template <int HD>
 __global__ void __launch_bounds__(128) attn_small_kernel(SmallAttnArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();  // programmatic dependent launch (host_common.h)
   constexpr int EPL = HD / 32;
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -231,6 +237,8 @@ __global__ void __launch_bounds__(128) attn_small_kernel(SmallAttnArgs a) {
 // ---- alignment decode helpers (D = 512 per token) ------------------------------------------------
 // mean over the S rows of each batch element of the row L2 norm (alignment_head.py:469).  One block per batch.
 __global__ void __launch_bounds__(256) mean_row_norm_kernel(const float* __restrict__ x, int S, int D, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();  // programmatic dependent launch (host_common.h)
   __shared__ float part[8];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc = 0.f;
@@ -260,6 +268,8 @@ __global__ void __launch_bounds__(128) memory_prepare_kernel(const float* __rest
                                                              const float* __restrict__ alpha, const float* __restrict__ mean_norm,
                                                              float* __restrict__ kv, float* __restrict__ directional, int S, int NM,
                                                              int D) {
+  pdl_launch_dependents();
+  pdl_wait();  // programmatic dependent launch (host_common.h)
   __shared__ float red[4];
   const int b = blockIdx.x, j = blockIdx.y;
   if (j == NM) {  // copy tokens
@@ -292,6 +302,8 @@ __global__ void __launch_bounds__(128) memory_prepare_kernel(const float* __rest
 // GatedUpdate stage 1 (gated_update.py:55-60): u = ||update||; inp[b,i] = [update, mem_i*u, mean_i(mem)*u]; also mem*u.
 __global__ void __launch_bounds__(128) gu_prepare_kernel(const float* __restrict__ mem, const float* __restrict__ upd,
                                                          float* __restrict__ inp, float* __restrict__ mem_scaled, int NM, int D) {
+  pdl_launch_dependents();
+  pdl_wait();  // programmatic dependent launch (host_common.h)
   __shared__ float red[4];
   const int b = blockIdx.x, i = blockIdx.y;
   const float* u = upd + (size_t)b * D;
@@ -317,6 +329,8 @@ __global__ void __launch_bounds__(128) gu_prepare_kernel(const float* __restrict
 // stage 2: gate_in[b,i] = [delta - mem, mem_scaled]  (:66-69)
 __global__ void __launch_bounds__(128) gu_gate_input_kernel(const float* __restrict__ deltas, const float* __restrict__ mem,
                                                             const float* __restrict__ mem_scaled, float* __restrict__ gate_in, int D) {
+  pdl_launch_dependents();
+  pdl_wait();  // programmatic dependent launch (host_common.h)
   const size_t r = blockIdx.x;
   for (int k = threadIdx.x; k < D; k += blockDim.x) {
     gate_in[r * 2 * D + k] = deltas[r * D + k] - mem[r * D + k];
@@ -327,6 +341,8 @@ __global__ void __launch_bounds__(128) gu_gate_input_kernel(const float* __restr
 // stage 3: orthogonalise the difference against the memory row, normalise, apply gate, normalise (:72-78)
 __global__ void __launch_bounds__(128) gu_finish_kernel(const float* __restrict__ gate_in, const float* __restrict__ mem,
                                                         const float* __restrict__ gate, float* __restrict__ out, int D) {
+  pdl_launch_dependents();
+  pdl_wait();  // programmatic dependent launch (host_common.h)
   __shared__ float red[4];
   __shared__ float bc;
   const size_t r = blockIdx.x;
@@ -357,6 +373,8 @@ __global__ void __launch_bounds__(128) gu_finish_kernel(const float* __restrict_
 // camera head: x = gate * (adaLN(tok) * (1 + scale) + shift) + tok   with (shift, scale, gate) = chunk3(mod)
 __global__ void __launch_bounds__(256) modulate_kernel(const float* __restrict__ normed, const float* __restrict__ tok,
                                                        const float* __restrict__ mod, float* __restrict__ out, long long rows, int D) {
+  pdl_launch_dependents();
+  pdl_wait();  // programmatic dependent launch (host_common.h)
   const long long total = rows * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / D;
@@ -371,6 +389,8 @@ __global__ void __launch_bounds__(256) modulate_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) combine_rows_kernel(const float* __restrict__ a, long long lda, const float* __restrict__ b,
                                                            long long ldb, float* __restrict__ out, long long ldo, long long rows, int cols,
                                                            int relu_from, int exp_col) {
+  pdl_launch_dependents();
+  pdl_wait();  // programmatic dependent launch (host_common.h)
   const long long total = rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols;
@@ -397,12 +417,12 @@ int linear_f32(const float* x, long long ldx, const float* W, const float* b, fl
   const bool vec = (K % 4 == 0) && (ldx % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)W % 16 == 0);
   if (vec && M > 8) {
     dim3 g2((N + 7) / 8, (M + 31) / 32);
-    linear_f32_tiled_kernel<4, 2><<<g2, 256, 0, st>>>(x, ldx, W, b, y, ldy, M, N, K, in_act, out_act, gamma, residual ? 1 : 0);
+    LSVS_CUDA(launch_pdl(linear_f32_tiled_kernel<4, 2>, dim3(g2), dim3(256), 0, st, x, ldx, W, b, y, ldy, M, N, K, in_act, out_act, gamma, residual ? 1 : 0));
   } else if (vec) {
     dim3 g2((N + 7) / 8, 1);
-    linear_f32_tiled_kernel<1, 8><<<g2, 256, 0, st>>>(x, ldx, W, b, y, ldy, M, N, K, in_act, out_act, gamma, residual ? 1 : 0);
+    LSVS_CUDA(launch_pdl(linear_f32_tiled_kernel<1, 8>, dim3(g2), dim3(256), 0, st, x, ldx, W, b, y, ldy, M, N, K, in_act, out_act, gamma, residual ? 1 : 0));
   } else {
-    linear_f32_kernel<false><<<grid, 256, 0, st>>>(x, ldx, W, b, y, ldy, M, N, K, in_act, out_act, gamma, residual ? 1 : 0);
+    LSVS_CUDA(launch_pdl(linear_f32_kernel<false>, dim3(grid), dim3(256), 0, st, x, ldx, W, b, y, ldy, M, N, K, in_act, out_act, gamma, residual ? 1 : 0));
   }
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
@@ -413,48 +433,48 @@ int attn_small_f32(const SmallAttnArgs& a, cudaStream_t st) {
   LSVS_CHECK_ARG(a.hd == 64 || a.hd == 128, "attn_small: head_dim %d unsupported", a.hd);
   ProfScope prof(PROF_SMALL_F32, st, 0, 0);
   const int total = a.B * a.H * a.Nq;
-  if (a.hd == 64) attn_small_kernel<64><<<(total + 3) / 4, 128, 0, st>>>(a);
-  else attn_small_kernel<128><<<(total + 3) / 4, 128, 0, st>>>(a);
+  if (a.hd == 64) LSVS_CUDA(launch_pdl(attn_small_kernel<64>, dim3((total + 3) / 4), dim3(128), 0, st, a));
+  else LSVS_CUDA(launch_pdl(attn_small_kernel<128>, dim3((total + 3) / 4), dim3(128), 0, st, a));
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
 
 int mean_row_norm(const float* x, int B, int S, int D, float* out, cudaStream_t st) {
-  mean_row_norm_kernel<<<B, 256, 0, st>>>(x, S, D, out);
+  LSVS_CUDA(launch_pdl(mean_row_norm_kernel, dim3(B), dim3(256), 0, st, x, S, D, out));
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
 
 int memory_prepare(const float* tokens, const float* mem_param, const float* mem_in, const float* frame_init, const float* alpha,
                    const float* mean_norm, float* kv, float* directional, int B, int S, int NM, int D, cudaStream_t st) {
-  memory_prepare_kernel<<<dim3(B, NM + 1), 128, 0, st>>>(tokens, mem_param, mem_in, frame_init, alpha, mean_norm, kv, directional, S, NM, D);
+  LSVS_CUDA(launch_pdl(memory_prepare_kernel, dim3(dim3(B, NM + 1)), dim3(128), 0, st, tokens, mem_param, mem_in, frame_init, alpha, mean_norm, kv, directional, S, NM, D));
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
 
 int gu_prepare(const float* mem, const float* upd, float* inp, float* mem_scaled, int B, int NM, int D, cudaStream_t st) {
-  gu_prepare_kernel<<<dim3(B, NM), 128, 0, st>>>(mem, upd, inp, mem_scaled, NM, D);
+  LSVS_CUDA(launch_pdl(gu_prepare_kernel, dim3(dim3(B, NM)), dim3(128), 0, st, mem, upd, inp, mem_scaled, NM, D));
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
 int gu_gate_input(const float* deltas, const float* mem, const float* mem_scaled, float* gate_in, int rows, int D, cudaStream_t st) {
-  gu_gate_input_kernel<<<rows, 128, 0, st>>>(deltas, mem, mem_scaled, gate_in, D);
+  LSVS_CUDA(launch_pdl(gu_gate_input_kernel, dim3(rows), dim3(128), 0, st, deltas, mem, mem_scaled, gate_in, D));
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
 int gu_finish(const float* gate_in, const float* mem, const float* gate, float* out, int rows, int D, cudaStream_t st) {
-  gu_finish_kernel<<<rows, 128, 0, st>>>(gate_in, mem, gate, out, D);
+  LSVS_CUDA(launch_pdl(gu_finish_kernel, dim3(rows), dim3(128), 0, st, gate_in, mem, gate, out, D));
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
 int modulate(const float* normed, const float* tok, const float* mod, float* out, long long rows, int D, cudaStream_t st) {
-  modulate_kernel<<<nblk(rows * D), 256, 0, st>>>(normed, tok, mod, out, rows, D);
+  LSVS_CUDA(launch_pdl(modulate_kernel, dim3(nblk(rows * D)), dim3(256), 0, st, normed, tok, mod, out, rows, D));
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
 int combine_rows(const float* a, long long lda, const float* b, long long ldb, float* out, long long ldo, long long rows, int cols,
                  int relu_from, int exp_col, cudaStream_t st) {
-  combine_rows_kernel<<<nblk(rows * cols), 256, 0, st>>>(a, lda, b, ldb, out, ldo, rows, cols, relu_from, exp_col);
+  LSVS_CUDA(launch_pdl(combine_rows_kernel, dim3(nblk(rows * cols)), dim3(256), 0, st, a, lda, b, ldb, out, ldo, rows, cols, relu_from, exp_col));
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
