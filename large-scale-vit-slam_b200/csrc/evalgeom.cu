@@ -4,6 +4,8 @@
 // The reference materialises pixel grids, rays, homogeneous copies and a full sort of S*H*W ratios; here the unprojection is one
 // pass (4 B read + 12 B written per pixel) and the weighted median is a 4-pass radix select over the ratio bit patterns
 // (24 B read per pixel and pass, no sort, no host synchronisation).
+#include <cstdint>
+
 #include "host_common.h"
 
 namespace {
@@ -33,9 +35,52 @@ __device__ __forceinline__ Cam load_cam(const float* __restrict__ E, const float
   return c;
 }
 
-// one thread per pixel; grid.y = frame
+// A warp handles 128 consecutive pixels of one frame per step: each lane reads 4 depths (one 16-byte load), computes its 4
+// points and stages the 12 floats in shared memory so that the float3 output leaves as three fully coalesced 16-byte stores
+// per lane (same regrouping as the Sim(3) kernel, csrc/sim3.cu).  grid.y = frame; H*W % 4 == 0 on this path.
 __global__ void __launch_bounds__(TPB) unproject_kernel(const float* __restrict__ depth, const float* __restrict__ extr,
                                                         const float* __restrict__ intr, float* __restrict__ out, int H, int W) {
+  __shared__ Cam cam;
+  __shared__ float4 slab[TPB / 32][96];
+  const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) cam = load_cam(extr + (size_t)f * 12, intr + (size_t)f * 9);
+  __syncthreads();
+  const int n = H * W, chunks = (n + 127) >> 7;
+  const float* dsrc = depth + (size_t)f * n;
+  float4* dst4 = reinterpret_cast<float4*>(out + (size_t)f * n * 3);
+  float* sl = reinterpret_cast<float*>(slab[w]);
+  for (int c = blockIdx.x * (TPB / 32) + w; c < chunks; c += gridDim.x * (TPB / 32)) {
+    const int p0 = (c << 7) + 4 * lane;
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p0 + 3 < n) { const float4 v = __ldg(reinterpret_cast<const float4*>(dsrc + p0)); d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+    else { for (int j = 0; j < 4; ++j) if (p0 + j < n) d[j] = __ldg(dsrc + p0 + j); }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int p = p0 + j, v = p / W, u = p - v * W;
+      // ray = K^-1 (u, v, 1); cam = ray * depth; world = R^T cam - R^T t
+      const float fu = (float)u, fv = (float)v;
+      const float rx = (cam.kinv[0] * fu + cam.kinv[1] * fv + cam.kinv[2]) * d[j];
+      const float ry = (cam.kinv[3] * fu + cam.kinv[4] * fv + cam.kinv[5]) * d[j];
+      const float rz = (cam.kinv[6] * fu + cam.kinv[7] * fv + cam.kinv[8]) * d[j];
+      sl[12 * lane + 3 * j + 0] = cam.r[0] * rx + cam.r[1] * ry + cam.r[2] * rz + cam.t[0];
+      sl[12 * lane + 3 * j + 1] = cam.r[3] * rx + cam.r[4] * ry + cam.r[5] * rz + cam.t[1];
+      sl[12 * lane + 3 * j + 2] = cam.r[6] * rx + cam.r[7] * ry + cam.r[8] * rz + cam.t[2];
+    }
+    __syncwarp();
+    const long long base4 = (long long)c * 96;       // float4 index of this chunk's first output
+    const long long end4 = ((long long)n * 3) >> 2;  // H*W % 4 == 0: the frame's output is a whole number of float4
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const long long i4 = base4 + 32 * k + lane;
+      if (i4 < end4) dst4[i4] = slab[w][32 * k + lane];
+    }
+    __syncwarp();
+  }
+}
+
+// pixel-per-thread variant for H*W % 4 != 0 (frames then lose 16-byte alignment)
+__global__ void __launch_bounds__(TPB) unproject_scalar_kernel(const float* __restrict__ depth, const float* __restrict__ extr,
+                                                               const float* __restrict__ intr, float* __restrict__ out, int H, int W) {
   __shared__ Cam cam;
   const int f = blockIdx.y;
   if (threadIdx.x == 0) cam = load_cam(extr + (size_t)f * 12, intr + (size_t)f * 9);
@@ -44,7 +89,6 @@ __global__ void __launch_bounds__(TPB) unproject_kernel(const float* __restrict_
   if (p >= H * W) return;
   const int v = p / W, u = p - v * W;
   const float d = __ldg(depth + (size_t)f * H * W + p);
-  // ray = K^-1 (u, v, 1); cam = ray * depth; world = R^T cam - R^T t
   const float fu = (float)u, fv = (float)v;
   const float rx = (cam.kinv[0] * fu + cam.kinv[1] * fv + cam.kinv[2]) * d;
   const float ry = (cam.kinv[3] * fu + cam.kinv[4] * fv + cam.kinv[5]) * d;
@@ -200,8 +244,16 @@ extern "C" int lsvs_unproject_depth(const float* depth, const float* extrinsics,
   LSVS_CHECK_ARG(depth && extrinsics && intrinsics && world_points && frames > 0 && H > 0 && W > 0, "unproject_depth: bad arguments");
   LSVS_CHECK_ARG(frames <= 65535, "unproject_depth: more than 65535 frames in one call");
   lsvs::ProfScope prof(lsvs::PROF_SIM3, (cudaStream_t)stream, 0, 16.0 * frames * H * (double)W);
-  dim3 grid((H * W + TPB - 1) / TPB, frames);
-  unproject_kernel<<<grid, TPB, 0, (cudaStream_t)stream>>>(depth, extrinsics, intrinsics, world_points, H, W);
+  const int n = H * W;
+  if ((n & 3) == 0 && ((uintptr_t)depth % 16 == 0) && ((uintptr_t)world_points % 16 == 0)) {
+    const int chunks = (n + 127) >> 7, per_cta = TPB / 32;
+    int bx = (chunks + per_cta - 1) / per_cta;
+    const int cap = (lsvs::num_sms() * 8 + frames - 1) / frames;
+    if (bx > cap) bx = cap < 1 ? 1 : cap;
+    unproject_kernel<<<dim3(bx, frames), TPB, 0, (cudaStream_t)stream>>>(depth, extrinsics, intrinsics, world_points, H, W);
+  } else {
+    unproject_scalar_kernel<<<dim3((n + TPB - 1) / TPB, frames), TPB, 0, (cudaStream_t)stream>>>(depth, extrinsics, intrinsics, world_points, H, W);
+  }
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }

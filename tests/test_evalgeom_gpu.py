@@ -79,3 +79,21 @@ def test_convert_dict_lists_matches_reference(golden):
     convertDictListsToTensors(chunks, 1)
     assert torch.equal(chunks["depth"].cpu(), torch.as_tensor(g["merged_depth"])) and torch.equal(chunks["pose_enc"].cpu(), torch.as_tensor(g["merged_pose"]))
     assert chunks["other"] == [1, 2, 3]
+
+
+@pytest.mark.parametrize("H,W", [(7, 9), (12, 20), (33, 128)])
+def test_unproject_ragged_sizes_vs_oracle(H, W):
+    """H*W not a multiple of 4 (pixel-per-thread kernel), partial 128-pixel chunks, and whole chunks."""
+    from aligned_vggt.utils.geometry import unproject_depth_map_to_point_map
+    from oracle import aligned as OA
+    from oracle import functional as OF
+    B, S = 2, 3
+    g = torch.Generator().manual_seed(H * W)
+    depth = torch.rand(B, S, H, W, 1, generator=g) * 10 + 0.1
+    q = torch.nn.functional.normalize(torch.randn(B, S, 4, generator=g), dim=-1)
+    extr = torch.cat([OF.quat_to_mat(q), torch.randn(B, S, 3, 1, generator=g)], dim=-1)
+    K = torch.zeros(B, S, 3, 3)
+    K[..., 0, 0] = 30.0; K[..., 1, 1] = 31.0; K[..., 0, 2] = W / 2; K[..., 1, 2] = H / 2; K[..., 2, 2] = 1.0; K[..., 0, 1] = 0.2
+    ref = OA.unproject_depth(depth, extr, K)
+    out = unproject_depth_map_to_point_map(depth.cuda(), extr.cuda(), K.cuda()).cpu()
+    assert float((out - ref).abs().max()) < 1e-5 * float(ref.abs().max())
