@@ -10,7 +10,8 @@ and memory) -> camera head -> pose/Sim(3) composition -> Sim(3) applied to a syn
 frames per chunk); frame-forwards/sec is reported next to it.
 
 N > 1: chunks of one sequence are dealt round-robin to the ranks for the Aggregator; the last-layer tokens travel
-over NCCL to the rank that runs the sequential alignment chain (lsvs_b200/scheduler.py).
+over NVLink (copy engines into CUDA-IPC mailboxes; torch.distributed p2p as the alternative) to the rank that runs the
+sequential alignment chain (lsvs_b200/scheduler.py).
 """
 import argparse
 import json
@@ -180,7 +181,8 @@ def run_b200(args):
     if world > 1:
         from lsvs_b200.scheduler import model_pipeline
         fwd, bwd = dist.new_group(), dist.new_group()  # separate communicators: token traffic never queues behind result packets
-        pipe = model_pipeline(model, OVERLAP, S_CHUNK, H, W, rank, world, dev, head_cost=args.head_cost, fwd_group=fwd, bwd_group=bwd)
+        pipe = model_pipeline(model, OVERLAP, S_CHUNK, H, W, rank, world, dev, head_cost=args.head_cost, fwd_group=fwd, bwd_group=bwd,
+                              transport=args.transport, lag=args.lag, defer_chain=not args.no_defer)
 
         def step_fn(i):  # one round: every owner rank encodes one chunk, rank 0 chains the heads
             pipe.step((imgs[i % n_bufs], raw_pts, raw_dep) if pipe.owns() else None)
@@ -357,11 +359,13 @@ def run_b200(args):
                            "frames_per_chunk": S_CHUNK, "overlap": OVERLAP, "image_hw": [H, W], "output_frames_per_step": frames_per_step,
                            "frame_forwards_per_s": (S_CHUNK * args.steps / (ms / 1e3)) if world == 1 else None,
                            "l2_policy": "per-step working set (~0.4 GB activations + 2.5 GB weights) exceeds the 126 MB L2; 4 rotating input buffers",
-                           "parallelism": f"chunks dealt over {world} GPU(s); alignment chain on rank 0 (per-GPU work fixed as N grows)"},
+                           "parallelism": f"chunks dealt over {world} GPU(s); alignment chain on rank 0 (per-GPU work fixed as N grows)"
+                           + (f"; transport: {pipe.tx.name}; apply lag {pipe.lag}; head_cost {args.head_cost}" if world > 1 else "")},
                 "clocks": clocks.summary(), "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
                 "kernel_classes": prof_detail}
         print(json.dumps(line), flush=True)
     if world > 1:
+        pipe.tx.close()
         dist.destroy_process_group()
 
 
@@ -372,7 +376,10 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--head-cost", type=float, default=0.12, help="alignment-head time / aggregator time (rank-0 load balancing)")
+    ap.add_argument("--head-cost", type=float, default=0.085, help="alignment-head time / aggregator time (rank-0 load balancing; measured 0.081)")
+    ap.add_argument("--transport", default="auto", choices=["auto", "peer", "dist"], help="N>1: CUDA-IPC peer mailboxes or torch.distributed p2p")
+    ap.add_argument("--lag", type=int, default=2, help="N>1: chunks an owner keeps in flight before it needs a Sim(3) packet")
+    ap.add_argument("--no-defer", action="store_true", help="N>1: rank 0 chains a round's heads in the same round (A/B)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

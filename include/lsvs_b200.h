@@ -215,6 +215,29 @@ size_t lsvs_depth_scale_align_workspace_bytes(int B);
 int lsvs_depth_scale_align(const float* depth_pred, const float* depth_gt, const float* mask, const float* conf, int B, long long N,
                            float* scales, void* workspace, void* stream);
 
+/* ---- peer mailboxes over NVLink (transport of the chunk scheduler) -------------------------
+ * replaces the per-chunk hand-over of the reference's sequential loop (training/training_metrics.py:636-657: one process,
+ * the previous chunk's predictions are simply passed to the next call) once chunks are dealt to several GPUs: the
+ * owner's last-layer tokens + camera encodings go to the alignment rank, the decoded Sim(3) packet comes back.
+ * Buffers are plain cudaMalloc memory shared between the per-GPU processes of one box through CUDA IPC; payloads move
+ * with the copy engines, a sequence number published by lsvs_peer_signal / awaited by lsvs_peer_wait orders them.
+ * No SM is held while waiting for a peer (unlike an NCCL send/recv kernel), no host synchronisation.
+ *   lsvs_peer_alloc    zero-initialised device buffer that can be exported (synchronises the device once)
+ *   lsvs_peer_export   64-byte handle to hand to another process;  lsvs_peer_open maps it there (peer access enabled lazily)
+ *   lsvs_peer_put      dst (local or mapped peer memory) <- src, `bytes` bytes, in stream order
+ *   lsvs_peer_signal   *flag <- value with system-scope release, after everything earlier in the stream
+ *   lsvs_peer_wait     the stream continues once (int)(*flag - value) >= 0; after timeout_s seconds *status (device word,
+ *                      local) is set to 1 and the stream continues, so a lost peer surfaces as an error, not as a hang */
+#define LSVS_PEER_HANDLE_BYTES 64
+int lsvs_peer_alloc(size_t bytes, void** ptr);
+int lsvs_peer_free(void* ptr);
+int lsvs_peer_export(const void* ptr, unsigned char* handle64);
+int lsvs_peer_open(const unsigned char* handle64, void** ptr);
+int lsvs_peer_close(void* ptr);
+int lsvs_peer_put(void* dst, const void* src, size_t bytes, void* stream);
+int lsvs_peer_signal(unsigned* flag, unsigned value, void* stream);
+int lsvs_peer_wait(const unsigned* flag, unsigned value, unsigned* status, double timeout_s, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

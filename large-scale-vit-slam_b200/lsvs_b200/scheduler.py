@@ -6,14 +6,16 @@ images, so chunks are dealt to ranks; the alignment head of chunk k needs the pr
 aligned poses of chunk k-1, so it runs as one sequential chain on the alignment rank (rank 0).  The only data-path
 exchange is point-to-point: owner -> rank 0 carries the chunk's last-layer tokens (bf16, which is what the head's
 first GEMM consumes) and the 9-d camera encodings; rank 0 -> owner carries the decoded Sim(3) packet (< 3 KB).  The
-owner then applies the Sim(3) to its own depth / point maps, one round late, so that the chain on rank 0 overlaps
-the next round's Aggregator work everywhere else.
+owner then applies the Sim(3) to its own depth / point maps `lag` chunks late, so that the chain on rank 0 overlaps
+the following rounds' Aggregator work everywhere else.
 
 Because rank 0 also pays for every chunk's head, it is given proportionally fewer Aggregator chunks
 (`head_cost` = head time / aggregator time): with world*head_cost >= 1 it only aligns.
 
-The transport is torch.distributed isend/irecv: NCCL over NVLink on GPUs, gloo on CPU tensors in the unit tests
-(tests/test_scheduler.py drives this file with stand-in stage functions).
+Transport: on GPUs, CUDA-IPC mailboxes in the receiver's HBM filled by the copy engines over NVLink and ordered by
+sequence flags (PeerTransport; include/lsvs_b200.h lsvs_peer_*), because a pending NCCL send/recv kernel busy-waits on
+SMs that the persistent encoder kernels need; torch.distributed isend/irecv (DistTransport) remains for gloo on CPU
+tensors (tests/test_scheduler.py drives this file with stand-in stage functions) and as the multi-node option.
 """
 from collections import deque
 from typing import Callable, List, Optional
@@ -57,26 +59,270 @@ def round_owners(round_idx: int, world: int, head_cost: float) -> List[int]:
     return ([0] if takes else []) + list(range(1, world))
 
 
+# ------------------------------------------------------------------------------------------------ transports
+class DistTransport:
+    """Owner <-> alignment-rank exchange over torch.distributed isend/irecv: gloo on CPU tensors (unit tests) or NCCL.
+    On GPUs prefer PeerTransport: an unmatched NCCL send/recv kernel keeps SMs busy-waiting next to the persistent
+    encoder kernels (see csrc/peer.cu)."""
+
+    name = "torch.distributed p2p"
+
+    def __init__(self, rank, world, tokens_like, cam_like, packet_numel, fwd_group=None, bwd_group=None, device=None):
+        self.rank, self.world = rank, world
+        self.tokens_like, self.cam_like, self.packet_numel = tokens_like, cam_like, packet_numel
+        self.fwd, self.bwd, self.device = fwd_group, bwd_group, device
+        self._packets = {}          # owner side: seq -> (work, buffer)
+        self._inflight = deque()    # (work handles, tensors) of sends that must stay alive
+
+    def _retire(self, keep):
+        while len(self._inflight) > keep:
+            works, _tensors = self._inflight.popleft()
+            for w in works:
+                w.wait()
+
+    # owner side
+    def send_chunk(self, seq, tokens, cam):
+        w1 = dist.isend(tokens, dst=0, group=self.fwd)
+        w2 = dist.isend(cam, dst=0, group=self.fwd)
+        self._inflight.append(([w1, w2], (tokens, cam)))
+        packet = torch.empty(self.packet_numel, dtype=torch.float32, device=cam.device)
+        self._packets[seq] = (dist.irecv(packet, src=0, group=self.bwd), packet)
+        self._retire(keep=4)
+
+    def recv_packet(self, seq):
+        work, packet = self._packets.pop(seq)
+        work.wait()
+        return packet
+
+    # alignment-rank side
+    def recv_chunk(self, owner, seq):
+        t, c = self.tokens_like(), self.cam_like()
+        w1 = dist.irecv(t, src=owner, group=self.fwd)
+        w2 = dist.irecv(c, src=owner, group=self.fwd)
+        w1.wait()
+        w2.wait()
+        return t, c
+
+    def send_packet(self, owner, seq, packet):
+        self._inflight.append(([dist.isend(packet, dst=owner, group=self.bwd)], (packet,)))
+        self._retire(keep=2 * self.world)
+
+    def finish(self):
+        self._retire(keep=0)
+
+    def close(self):
+        pass
+
+
+def _align256(n: int) -> int:
+    return (n + 255) // 256 * 256
+
+
+class _RawCudaBytes:
+    """Exposes raw device memory to torch (zero copy) through the CUDA array interface."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerTransport:
+    """Owner <-> alignment-rank exchange through CUDA-IPC mailboxes in the *receiver's* HBM (include/lsvs_b200.h, lsvs_peer_*):
+    payloads are pushed over NVLink by the copy engines and ordered by sequence numbers, so no SM is ever held waiting
+    for a peer and nobody rendezvous.
+
+    Layout.  Rank 0 owns one inbox per owner rank: [flag | slots x (cam, tokens)]; every owner rank owns one mailbox:
+    [flag | slots x packet].  Flags hold `number of messages published so far`.  A slot is reused every `slots`
+    messages; that is safe when slots >= lag + 1 (lag = how many of its own chunks an owner keeps in flight before it
+    waits for a packet), because receiving packet k proves that rank 0 has consumed chunk k, and an owner waits for
+    packet seq - lag - 1 (stream order) before it overwrites anything belonging to message seq - slots."""
+
+    name = "CUDA-IPC peer mailboxes (copy engines + sequence flags)"
+
+    def __init__(self, rank, world, tokens_shape, tokens_dtype, cam_shape, packet_numel, device, group=None, slots=3, timeout_s=120.0):
+        import ctypes
+        from . import native
+        self.rank, self.world, self.slots, self.timeout_s, self.device = rank, world, slots, float(timeout_s), device
+        self.tokens_shape, self.tokens_dtype, self.cam_shape, self.packet_numel = tuple(tokens_shape), tokens_dtype, tuple(cam_shape), packet_numel
+        self._ct, self._native, self._lib = ctypes, native, native.lib()
+        self._lib.lsvs_peer_wait.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
+        self._lib.lsvs_peer_signal.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p]
+        self._lib.lsvs_peer_put.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+        self._lib.lsvs_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+        self.tok_bytes = int(torch.tensor([], dtype=tokens_dtype).element_size())
+        for d in self.tokens_shape:
+            self.tok_bytes *= d
+        self.cam_bytes = 4
+        for d in self.cam_shape:
+            self.cam_bytes *= d
+        self.cam_stride = _align256(self.cam_bytes)
+        self.chunk_stride = self.cam_stride + _align256(self.tok_bytes)
+        self.packet_stride = _align256(4 * packet_numel)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self._local, self._mapped = {}, {}     # peer rank -> base pointer (local allocation / mapped remote allocation)
+        # two collective phases, each followed by an exchange of outcomes, so that a failure on one rank (IPC not
+        # permitted, out of memory) raises on every rank instead of leaving the others waiting
+        handles, err = {}, None
+        try:
+            if rank == 0:
+                for o in range(1, world):
+                    self._local[o] = self._alloc(256 + slots * self.chunk_stride)
+                    handles[o] = self._export(self._local[o])
+            else:
+                self._local[0] = self._alloc(256 + slots * self.packet_stride)
+                handles[0] = self._export(self._local[0])
+        except Exception as e:  # noqa: BLE001
+            err = f"rank {rank}: {e}"
+        table = [None] * world
+        dist.all_gather_object(table, (handles, err), group=group)
+        self._raise_any([t[1] for t in table])
+        try:
+            if rank == 0:
+                for o in range(1, world):
+                    self._mapped[o] = self._open(table[o][0][0])
+            else:
+                self._mapped[0] = self._open(table[0][0][rank])
+        except Exception as e:  # noqa: BLE001
+            err = f"rank {rank}: {e}"
+        outcome = [None] * world
+        dist.all_gather_object(outcome, err, group=group)
+        self._raise_any(outcome)
+        self._views, self._zero_copy = {}, True
+
+    def _raise_any(self, errors):
+        errors = [e for e in errors if e]
+        if errors:
+            for p in self._local.values():
+                self._lib.lsvs_peer_free(self._ct.c_void_p(p))
+            self._local = {}
+            raise self._native.NativeError("peer mailbox setup failed: " + "; ".join(errors))
+
+    # -- raw memory helpers -----------------------------------------------------------------------
+    def _alloc(self, nbytes):
+        p = self._ct.c_void_p()
+        self._native.check(self._lib.lsvs_peer_alloc(nbytes, self._ct.byref(p)), "lsvs_peer_alloc")
+        return int(p.value)
+
+    def _export(self, ptr):
+        buf = (self._ct.c_ubyte * 64)()
+        self._native.check(self._lib.lsvs_peer_export(self._ct.c_void_p(ptr), buf), "lsvs_peer_export")
+        return bytes(buf)
+
+    def _open(self, handle):
+        p = self._ct.c_void_p()
+        buf = (self._ct.c_ubyte * 64).from_buffer_copy(handle)
+        self._native.check(self._lib.lsvs_peer_open(buf, self._ct.byref(p)), "lsvs_peer_open")
+        return int(p.value)
+
+    def _put(self, dst, src_tensor, nbytes):
+        self._native.check(self._lib.lsvs_peer_put(dst, src_tensor.data_ptr(), nbytes, self._native.stream_ptr()), "lsvs_peer_put")
+
+    def _signal(self, flag, value):
+        self._native.check(self._lib.lsvs_peer_signal(flag, value & 0xFFFFFFFF, self._native.stream_ptr()), "lsvs_peer_signal")
+
+    def _wait(self, flag, value):
+        self._native.check(self._lib.lsvs_peer_wait(flag, value & 0xFFFFFFFF, self.status.data_ptr(), self.timeout_s,
+                                                    self._native.stream_ptr()), "lsvs_peer_wait")
+
+    def _read(self, ptr, nbytes, dtype, shape, private=False):
+        """Torch tensor over local mailbox memory: a zero-copy alias (a private copy if `private`); if this torch build
+        cannot alias raw device memory, a copy-engine copy into a fresh tensor, in stream order."""
+        if self._zero_copy:
+            try:
+                key = (ptr, dtype)
+                if key not in self._views:
+                    raw = torch.as_tensor(_RawCudaBytes(ptr, nbytes), device=self.device)
+                    if raw.data_ptr() != ptr:
+                        raise RuntimeError("torch copied the mailbox instead of aliasing it")
+                    self._views[key] = raw.view(dtype).view(shape)
+                return self._views[key].clone() if private else self._views[key]
+            except Exception as e:  # noqa: BLE001
+                import sys
+                print(f"[lsvs_b200] mailbox views fall back to staged copies: {e}", file=sys.stderr, flush=True)
+                self._zero_copy = False
+        out = torch.empty(shape, dtype=dtype, device=self.device)
+        self._native.check(self._lib.lsvs_peer_put(out.data_ptr(), ptr, nbytes, self._native.stream_ptr()), "lsvs_peer_put")
+        return out
+
+    # -- owner side ------------------------------------------------------------------------------
+    def send_chunk(self, seq, tokens, cam):
+        assert tokens.is_contiguous() and cam.is_contiguous() and tokens.dtype == self.tokens_dtype and cam.dtype == torch.float32
+        assert tuple(tokens.shape) == self.tokens_shape and tuple(cam.shape) == self.cam_shape, "chunk shape differs from the mailbox layout"
+        base = self._mapped[0] + 256 + (seq % self.slots) * self.chunk_stride
+        self._put(base, cam, self.cam_bytes)
+        self._put(base + self.cam_stride, tokens, self.tok_bytes)
+        self._signal(self._mapped[0], seq + 1)
+
+    def recv_packet(self, seq):
+        self._wait(self._local[0], seq + 1)
+        ptr = self._local[0] + 256 + (seq % self.slots) * self.packet_stride
+        return self._read(ptr, 4 * self.packet_numel, torch.float32, (self.packet_numel,), private=True)
+
+    # -- alignment-rank side ---------------------------------------------------------------------
+    def recv_chunk(self, owner, seq):
+        self._wait(self._local[owner], seq + 1)
+        base = self._local[owner] + 256 + (seq % self.slots) * self.chunk_stride
+        cam = self._read(base, self.cam_bytes, torch.float32, self.cam_shape)
+        tokens = self._read(base + self.cam_stride, self.tok_bytes, self.tokens_dtype, self.tokens_shape)
+        return tokens, cam
+
+    def send_packet(self, owner, seq, packet):
+        assert packet.is_contiguous() and packet.dtype == torch.float32 and packet.numel() == self.packet_numel
+        self._put(self._mapped[owner] + 256 + (seq % self.slots) * self.packet_stride, packet, 4 * self.packet_numel)
+        self._signal(self._mapped[owner], seq + 1)
+
+    def finish(self):
+        """Host-synchronising health check: raises if any wait on a peer timed out."""
+        if int(self.status.item()) != 0:
+            raise self._native.NativeError(f"rank {self.rank}: a peer did not publish its message within {self.timeout_s} s")
+
+    def close(self, group=None):
+        """Collective: unmap the peers' buffers, then free the local ones."""
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        for p in self._mapped.values():
+            self._lib.lsvs_peer_close(self._ct.c_void_p(p))
+        self._mapped, self._views = {}, {}
+        dist.barrier(group=group)
+        for p in self._local.values():
+            self._lib.lsvs_peer_free(self._ct.c_void_p(p))
+        self._local = {}
+
+
+# ------------------------------------------------------------------------------------------------ pipeline
 class ChunkPipeline:
     """SPMD driver: every rank calls step() once per round with the inputs of the chunk it owns in that round
     (or None).  Stage functions:
         encode_fn(inputs)                -> (tokens, cam)      context-free part (Aggregator + camera head)
         align_fn(tokens, cam, ctx)       -> (packet, new_ctx)  sequential part, rank 0 only; packet is a flat fp32 tensor
         apply_fn(packet, inputs)         -> result             owner side (Sim(3) application)
-    `tokens_like()` / `cam_like()` (fresh receive buffers) and `packet_numel` describe the transfers."""
+
+    Timing structure.  `defer_chain`: rank 0 runs the alignment chain of round r-1 at the start of round r, when those
+    tokens have long arrived, and only then encodes its own chunk of round r, so its stream never idles waiting for the
+    other ranks' encoders.  `lag`: an owner applies the Sim(3) packet of its chunk k only while stepping chunk k+lag, so a
+    round in which rank 0 both encodes and aligns (longer than everybody else's) is absorbed instead of stalling the
+    owners.  Results are independent of both (tests/test_scheduler.py compares with the sequential loop bit for bit)."""
 
     def __init__(self, encode_fn: Callable, align_fn: Callable, apply_fn: Callable, rank: int, world: int, *,
                  head_cost: float = 0.1, packet_numel: int = 0, tokens_like: Callable = None, cam_like: Callable = None,
-                 device=None, fwd_group=None, bwd_group=None):
+                 device=None, fwd_group=None, bwd_group=None, transport=None, lag: int = 2, defer_chain: bool = True):
         self.encode_fn, self.align_fn, self.apply_fn = encode_fn, align_fn, apply_fn
         self.rank, self.world, self.head_cost = rank, world, head_cost
-        self.packet_numel, self.tokens_like, self.cam_like = packet_numel, tokens_like, cam_like
         self.device = device
-        self.fwd, self.bwd = fwd_group, bwd_group
+        if transport is None and world > 1:
+            transport = DistTransport(rank, world, tokens_like, cam_like, packet_numel, fwd_group, bwd_group, device)
+        self.tx = transport
+        if lag < 1:
+            raise ValueError("lag must be >= 1")
+        if getattr(transport, "slots", lag + 1) < lag + 1:
+            raise ValueError(f"transport has {transport.slots} slots; lag {lag} needs {lag + 1}")
+        self.lag, self.defer = lag, defer_chain
         self.round = 0
         self.ctx = None
-        self.pending = deque()   # (work, packet buffer, inputs) awaiting their Sim(3) packet
-        self.inflight = deque()  # (work handles, tensors) of sends that must stay alive
+        self.seq = 0                      # owner side: chunks this rank has encoded
+        self.pending = deque()            # owner side: (seq, inputs) awaiting their Sim(3) packet
+        self._own = {}                    # rank 0: round -> (tokens, cam, inputs) of its own chunk, until chained
+        self._oseq = [0] * world          # rank 0: chunks received per owner
+        self._chained = 0                 # rank 0: rounds [0, _chained) have been through the chain
         self.results = []
 
     # -- bookkeeping -----------------------------------------------------------------------------
@@ -89,59 +335,55 @@ class ChunkPipeline:
     def chunks_in_rounds(self, n_rounds: int, start: int = 0) -> int:
         return sum(len(round_owners(j, self.world, self.head_cost)) for j in range(start, start + n_rounds))
 
-    def _retire_sends(self, keep: int):
-        while len(self.inflight) > keep:
-            works, _tensors = self.inflight.popleft()
-            for w in works:
-                w.wait()
-
     def _apply_ready(self, keep: int):
         while len(self.pending) > keep:
-            work, packet, inputs = self.pending.popleft()
-            if work is not None:
-                work.wait()
-            self.results.append(self.apply_fn(packet, inputs))
+            seq, inputs = self.pending.popleft()
+            self.results.append(self.apply_fn(self.tx.recv_packet(seq), inputs))
+
+    def _chain_through(self, last_round: int):
+        """Rank 0: run the alignment chain for every not yet chained round <= last_round, chunks in order."""
+        while self._chained <= last_round:
+            r = self._chained
+            for o in round_owners(r, self.world, self.head_cost):
+                if o == 0:
+                    t, c, inputs = self._own.pop(r)
+                else:
+                    t, c = self.tx.recv_chunk(o, self._oseq[o])
+                packet, self.ctx = self.align_fn(t, c, self.ctx)
+                if o == 0:
+                    self.results.append(self.apply_fn(packet, inputs))
+                else:
+                    self.tx.send_packet(o, self._oseq[o], packet)
+                    self._oseq[o] += 1
+            self._chained += 1
 
     # -- one round -------------------------------------------------------------------------------
     def step(self, inputs):
-        owners = self.owners()
-        mine = self.rank in owners
+        mine = self.rank in self.owners()
         if mine and inputs is None:
             raise ValueError(f"rank {self.rank} owns a chunk in round {self.round} but got no inputs")
-        tokens = cam = None
+        if self.rank == 0 and self.defer:
+            self._chain_through(self.round - 1)
         if mine:
             tokens, cam = self.encode_fn(inputs)
-        if self.rank == 0:
-            for o in owners:
-                if o == 0:
-                    t, c = tokens, cam
-                else:
-                    t, c = self.tokens_like(), self.cam_like()
-                    w1 = dist.irecv(t, src=o, group=self.fwd)
-                    w2 = dist.irecv(c, src=o, group=self.fwd)
-                    w1.wait()
-                    w2.wait()
-                packet, self.ctx = self.align_fn(t, c, self.ctx)
-                if o == 0:
-                    self.pending.append((None, packet, inputs))
-                else:
-                    w = dist.isend(packet, dst=o, group=self.bwd)
-                    self.inflight.append(([w], (packet,)))
-        elif mine:
-            w1 = dist.isend(tokens, dst=0, group=self.fwd)
-            w2 = dist.isend(cam, dst=0, group=self.fwd)
-            self.inflight.append(([w1, w2], (tokens, cam)))
-            packet = torch.empty(self.packet_numel, dtype=torch.float32, device=cam.device)
-            wr = dist.irecv(packet, src=0, group=self.bwd)
-            self.pending.append((wr, packet, inputs))
-        # apply the previous round's packet now (this round's encode is already queued ahead of the wait)
-        self._apply_ready(keep=1)
-        self._retire_sends(keep=2 * self.world)
+            if self.rank == 0:
+                self._own[self.round] = (tokens, cam, inputs)
+            else:
+                self.tx.send_chunk(self.seq, tokens, cam)
+                self.pending.append((self.seq, inputs))
+                self.seq += 1
+        if self.rank == 0 and not self.defer:
+            self._chain_through(self.round)
+        # owners: apply the packet of the chunk encoded `lag` chunks ago (this round's encode is already queued ahead of it)
+        self._apply_ready(keep=self.lag)
         self.round += 1
 
     def flush(self):
+        if self.rank == 0:
+            self._chain_through(self.round - 1)
         self._apply_ready(keep=0)
-        self._retire_sends(keep=0)
+        if self.tx is not None:
+            self.tx.finish()
         out, self.results = self.results, []
         return out
 
@@ -195,8 +437,23 @@ class ModelStages:
         return out
 
 
-def model_pipeline(model, num_overlap: int, S: int, H: int, W: int, rank: int, world: int, device, head_cost: float = 0.1,
-                   fwd_group=None, bwd_group=None) -> ChunkPipeline:
+def model_pipeline(model, num_overlap: int, S: int, H: int, W: int, rank: int, world: int, device, head_cost: float = 0.085,
+                   fwd_group=None, bwd_group=None, transport: str = "auto", lag: int = 2, defer_chain: bool = True,
+                   handshake_group=None) -> ChunkPipeline:
+    """transport: "peer" (CUDA-IPC mailboxes, one box), "dist" (torch.distributed isend/irecv) or "auto" (peer, and
+    torch.distributed only if every rank agrees that the mailboxes could not be set up)."""
     st = ModelStages(model, num_overlap, S, H, W, device)
+    tx = None
+    if world > 1 and transport in ("auto", "peer"):
+        try:
+            tx = PeerTransport(rank, world, (1, S, st.P, 2048), torch.bfloat16, (1, S, 9), st.packet_numel, device,
+                               group=handshake_group, slots=lag + 1)
+        except Exception as e:  # noqa: BLE001  (raised on every rank together, see PeerTransport.__init__)
+            if transport == "peer":
+                raise
+            import sys
+            print(f"[lsvs_b200] peer mailboxes unavailable, using torch.distributed p2p: {e}", file=sys.stderr, flush=True)
+    if world > 1 and tx is None:
+        tx = DistTransport(rank, world, st.tokens_like, st.cam_like, st.packet_numel, fwd_group, bwd_group, device)
     return ChunkPipeline(st.encode, st.align, st.apply, rank, world, head_cost=head_cost, packet_numel=st.packet_numel,
-                         tokens_like=st.tokens_like, cam_like=st.cam_like, device=device, fwd_group=fwd_group, bwd_group=bwd_group)
+                         device=device, transport=tx, lag=lag, defer_chain=defer_chain)

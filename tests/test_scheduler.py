@@ -66,12 +66,13 @@ def _inputs(k):
     return (torch.randn(4, 5, generator=g), torch.randn(3, generator=g))
 
 
-def _worker(rank, world, port, head_cost, n_rounds, q):
+def _worker(rank, world, port, head_cost, n_rounds, q, lag=2, defer=True):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     fwd, bwd = dist.new_group(), dist.new_group()
     pipe = sch.ChunkPipeline(_encode, _align, _apply, rank, world, head_cost=head_cost, packet_numel=4,
-                             tokens_like=lambda: torch.empty(4, 5), cam_like=lambda: torch.empty(1, 1), fwd_group=fwd, bwd_group=bwd)
+                             tokens_like=lambda: torch.empty(4, 5), cam_like=lambda: torch.empty(1, 1), fwd_group=fwd, bwd_group=bwd,
+                             lag=lag, defer_chain=defer)
     k = 0
     for j in range(n_rounds):
         owners = pipe.owners()
@@ -93,13 +94,15 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,head_cost", [(2, 0.1), (3, 0.4), (2, 0.6)])
-def test_pipeline_equals_sequential_gloo(world, head_cost):
+@pytest.mark.parametrize("world,head_cost,lag,defer", [(2, 0.1, 2, True), (3, 0.4, 2, True), (2, 0.6, 1, False), (3, 0.2, 3, True),
+                                                       (2, 0.3, 1, True), (3, 0.1, 2, False)])
+def test_pipeline_equals_sequential_gloo(world, head_cost, lag, defer):
+    """Every (lag, deferred-chain) setting only moves work in time: same results as the sequential loop, bit for bit."""
     n_rounds = 7
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, head_cost, n_rounds, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, head_cost, n_rounds, q, lag, defer)) for r in range(world)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=120) for _ in range(world))
@@ -113,3 +116,87 @@ def test_pipeline_equals_sequential_gloo(world, head_cost):
         for a, b in zip(mine, got[r]):
             assert torch.allclose(a, b, atol=0, rtol=0)
     assert sum(len(v) for v in got.values()) == len(ref) == sum(len(sch.round_owners(j, world, head_cost)) for j in range(n_rounds))
+
+
+def test_pipeline_single_rank_and_argument_errors():
+    """world 1 needs no transport: the deferred chain hands results back one round late, flush() returns the rest."""
+    pipe = sch.ChunkPipeline(_encode, _align, _apply, 0, 1)
+    outs = []
+    for k in range(4):
+        pipe.step(_inputs(k))
+        outs += pipe.results
+        pipe.results = []
+        assert len(outs) == k          # chunk k is chained at the start of round k+1
+    outs += pipe.flush()
+    ref = [v for _, v in _sequential(4, 1, 0.1)]
+    assert len(outs) == 4 and all(torch.equal(a, b) for a, b in zip(outs, ref))
+    with pytest.raises(ValueError):
+        sch.ChunkPipeline(_encode, _align, _apply, 0, 1, lag=0)
+    with pytest.raises(ValueError):
+        sch.ChunkPipeline(_encode, _align, _apply, 0, 1).step(None)
+
+    class FewSlots:
+        slots = 2
+    with pytest.raises(ValueError):
+        sch.ChunkPipeline(_encode, _align, _apply, 1, 2, transport=FewSlots(), lag=2)
+
+
+# ---- GPU: the CUDA-IPC mailbox transport (csrc/peer.cu) between two processes ------------------------------------------
+def _peer_worker(rank, world, port, n_rounds, q, lag):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)      # handshake only; payloads go through the mailboxes
+    dev = torch.device("cuda", rank % torch.cuda.device_count())
+    torch.cuda.set_device(dev)
+    try:
+        tx = sch.PeerTransport(rank, world, (4, 5), torch.float32, (1, 1), 4, dev, slots=lag + 1, timeout_s=60.0)
+        pipe = sch.ChunkPipeline(_encode, _align, _apply, rank, world, head_cost=0.2, transport=tx, lag=lag)
+        k = 0
+        for j in range(n_rounds):
+            mine = None
+            for o in pipe.owners():
+                if o == rank:
+                    mine = tuple(t.to(dev) for t in _inputs(k))
+                k += 1
+            pipe.step(mine)
+        res = [r.cpu() for r in pipe.flush()]
+        tx.close()
+        q.put((rank, res, None))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, None, repr(e)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lag", [1, 2])
+def test_peer_mailboxes_two_processes(lag):
+    """Two processes (two GPUs if the box has them, else both on cuda:0) exchange chunks and packets through the IPC
+    mailboxes for more rounds than there are slots; results equal the sequential loop on the same device."""
+    world, n_rounds = 2, 11
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, n_rounds, q, lag)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        rank, res, err = q.get(timeout=300)
+        assert err is None, f"rank {rank}: {err}"
+        got[rank] = res
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    dev = torch.device("cuda", 0)
+    ctx_, ref, k = None, {0: [], 1: []}, 0
+    for j in range(n_rounds):
+        for o in sch.round_owners(j, world, 0.2):
+            inp = tuple(t.to(dev) for t in _inputs(k))
+            t, c = _encode(inp)
+            packet, ctx_ = _align(t, c, ctx_)
+            ref[o].append(_apply(packet, inp).cpu())
+            k += 1
+    for r in range(world):
+        assert len(got[r]) == len(ref[r]) > 0
+        for a, b in zip(got[r], ref[r]):
+            assert torch.equal(a, b)
