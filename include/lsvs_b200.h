@@ -185,6 +185,19 @@ int lsvs_dpt_resample(int op, const lsvs_bf16* in, lsvs_bf16* out, int frames, i
 int lsvs_pose_chain(const float* chunk_sim3, const float* frame_se3, const float* cam_enc, const float* prev_pose_enc,
                     int S_prev, int overlap, int B, int S, int H, int W, float* pose_enc_out, float* point_T,
                     float* scale_out, void* stream);
+/* the same composition when the caller passes ground-truth poses (sample modes chunk_gt / two_chunks, run_model.py:332,
+ * training_metrics.py:645).  gt_poses (B,S,gt_rows,4) world-to-camera, gt_rows 3 (padded with [0 0 0 1] like
+ * poseAligned_wrapped_vggt.py:86-87) or 4.  gt_mode is a bit set:
+ *   LSVS_GT_MEAN   with a previous chunk, gt_poses[:,0] replaces the averaged overlap transform
+ *                  (featureAligned_vggt.py:123-124, poseAligned_wrapped_vggt.py:108-109);
+ *   LSVS_GT_SCALE  S > 1: the camera translations (and scale_out, which the caller applies to depth / point maps) are multiplied by
+ *                  |sum x.y / sum x.x| over the re-based predicted positions x and the first-frame-centred gt positions y
+ *                  (poseAligned_wrapped_vggt.py:84-104 with scale_lse_solver, alignment.py:113-129; a CPU numpy round trip there). */
+#define LSVS_GT_MEAN 1
+#define LSVS_GT_SCALE 2
+int lsvs_pose_chain_gt(const float* chunk_sim3, const float* frame_se3, const float* cam_enc, const float* prev_pose_enc,
+                       int S_prev, int overlap, int B, int S, int H, int W, const float* gt_poses, int gt_rows, int gt_mode,
+                       float* pose_enc_out, float* point_T, float* scale_out, void* stream);
 /* replaces pointAligned_wrapped_vggt.py:113-122: pose_enc (B,S,9) -> extrinsics -> apply_sim3_alignment_on_w2c (alignment.py:528)
  * -> pose_enc (B,S,9), FoV entries passed through the reference's tan/atan round trip. */
 int lsvs_pose_enc_apply_sim3(const float* pose_enc, const float* T, const float* s, float* out, int B, int S, int H, int W, void* stream);

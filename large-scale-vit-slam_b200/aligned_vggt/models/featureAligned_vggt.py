@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from aligned_vggt.heads.alignment_head import AlignmentHead
 from aligned_vggt.utils import alignment as _al
-from lsvs_b200.engine import Engine, pose_chain
+from lsvs_b200.engine import GT_MEAN, Engine, pose_chain
 from lsvs_b200.modules import Aggregator, CameraHead, DPTHead
 
 try:  # the reference mixes in the HF hub loader; keep it when the package is present
@@ -73,8 +73,6 @@ class FeatureAlignedVGGT(nn.Module, PyTorchModelHubMixin):
     def forward(self, images: torch.Tensor, num_overlap: int, context: dict = None, gt_poses: torch.Tensor = None,
                 raw_depth=None, raw_points=None) -> dict:
         """images (B,S,3,H,W) in [0,1] -> predictions dict with the reference's keys (:60-71)."""
-        if gt_poses is not None:
-            raise NotImplementedError("gt_poses (sample_mode chunk_gt / two_chunks) is a training-time path outside this build")
         B, S, C, H, W = images.shape
         predictions = {}
         tokens_list, patch_start_idx = self.aggregator(images)
@@ -94,7 +92,13 @@ class FeatureAlignedVGGT(nn.Module, PyTorchModelHubMixin):
         if self.camera_head is not None:
             cam_enc = self.camera_head(taps)[-1]
             prev = context["pose_enc"][-1] if context is not None else None
-            aligned_pose_enc, point_T, chunk_scale = pose_chain(chunk_sim3_enc, frame_se3_enc, cam_enc, prev, overlap, (H, W))
+            gt, gt_mode = None, 0
+            if gt_poses is not None and context is not None:  # :123-124 mean_camera_transform = gt_poses[:, :1]
+                if tuple(gt_poses.shape[-2:]) != (4, 4):     # the reference's matmul with the (B,S,4,4) chain fails on (3,4) here
+                    raise RuntimeError(f"gt_poses must be (B,S,4,4) homogeneous world-to-camera matrices, got {tuple(gt_poses.shape)}")
+                gt, gt_mode = gt_poses, GT_MEAN
+            aligned_pose_enc, point_T, chunk_scale = pose_chain(chunk_sim3_enc, frame_se3_enc, cam_enc, prev, overlap, (H, W),
+                                                                gt_poses=gt, gt_mode=gt_mode)
             predictions["overlap_tokens"] = overlap_tokens
             if context is None:
                 predictions["pose_enc"] = [aligned_pose_enc]

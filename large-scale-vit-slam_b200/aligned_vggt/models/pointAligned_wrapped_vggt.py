@@ -2,8 +2,9 @@
 (:14-157) and its IRLS weighted-Umeyama solver (:159-305).  Aggregator / camera head run in the native engine, the
 Sim(3) estimation in csrc/umeyama.cu (no host round trips inside the IRLS loop), its application in csrc/sim3.cu.
 
-The DPT point / depth heads are outside this path: pass their raw outputs through `raw_points`,
-`raw_points_conf`, `raw_depth` until they are built."""
+The DPT point / depth heads (:19-20, :69-72, :130-133) run on the engine like the feature-aligned model's; `raw_points`,
+`raw_points_conf`, `raw_depth`, `raw_depth_conf` (optional) stand in for their outputs.  `gt_poses` is accepted and
+unused, as in the reference."""
 import ctypes
 from typing import Optional, Tuple
 
@@ -13,7 +14,7 @@ import torch.nn as nn
 from aligned_vggt.utils.alignment import apply_sim3_alignment_on_point_maps, scale_depth
 from lsvs_b200 import native as _n
 from lsvs_b200.engine import Engine, pose_enc_apply_sim3
-from lsvs_b200.modules import Aggregator, CameraHead
+from lsvs_b200.modules import Aggregator, CameraHead, DPTHead
 
 try:
     from huggingface_hub import PyTorchModelHubMixin
@@ -68,13 +69,25 @@ class VGGT(nn.Module, PyTorchModelHubMixin):
         self.aggregator = Aggregator(img_size=img_size, patch_size=patch_size, embed_dim=embed_dim, depth=depth,
                                      patch_embed_depth=patch_embed_depth, keep_layers=self.intermediate_layer_indices)
         self.camera_head = CameraHead(dim_in=2 * embed_dim) if enable_camera else None
-        self.point_head = self.depth_head = self.track_head = None  # DPT / track heads: SURVEY §8f, not on this path yet
-        for child in (self.aggregator, self.camera_head):
+        self.point_head = DPTHead(dim_in=2 * embed_dim, output_dim=4, activation="inv_log", conf_activation="expp1",
+                                  prefix="point_head.") if enable_point else None  # :19
+        self.depth_head = DPTHead(dim_in=2 * embed_dim, output_dim=2, activation="exp", conf_activation="expp1",
+                                  prefix="depth_head.") if enable_depth else None  # :20
+        self.track_head = None  # never called by the reference's forward; not built
+        self._bind_children()
+
+    def _bind_children(self):
+        for child in (self.aggregator, self.camera_head, self.point_head, self.depth_head):
             if child is not None:
                 child._bind(self)
+        self.__dict__.pop("_native_engine", None)
 
     def set_config(self, cfg):
+        """reference :25-32."""
         self.camera_head = self.camera_head if cfg.enable_camera else None
+        self.point_head = self.point_head if cfg.enable_point else None
+        self.depth_head = self.depth_head if cfg.enable_depth else None
+        self._bind_children()
 
     def _engine(self) -> Engine:
         eng = self.__dict__.get("_native_engine")
@@ -89,11 +102,15 @@ class VGGT(nn.Module, PyTorchModelHubMixin):
         """reference :34-157."""
         B, S, C, H, W = images.shape
         predictions = {}
-        tokens_list, _ = self.aggregator(images)
+        tokens_list, patch_start_idx = self.aggregator(images)
         taps = [tokens_list[i] for i in self.intermediate_layer_indices]
         del tokens_list
         alignment_transform = batch_scales = None
-        if raw_points is not None:  # stands in for self.point_head(...) (:69-72)
+        if raw_points is None and self.point_head is not None:  # :69-72
+            raw_points, raw_points_conf = self.point_head(taps, images=images, patch_start_idx=patch_start_idx)
+        if raw_depth is None and self.depth_head is not None:  # :130-133
+            raw_depth, raw_depth_conf = self.depth_head(taps, images=images, patch_start_idx=patch_start_idx)
+        if raw_points is not None:
             pts3d, pts3d_conf = raw_points, raw_points_conf
             if context is not None:
                 ctx_pts = context["world_points"][-1][:, -num_overlap:].to(pts3d.device)
@@ -118,7 +135,7 @@ class VGGT(nn.Module, PyTorchModelHubMixin):
             if alignment_transform is not None:  # :113-122
                 pose_enc = pose_enc_apply_sim3(pose_enc, alignment_transform, batch_scales, (H, W))
             _append(predictions, context, "pose_enc", pose_enc)
-        if raw_depth is not None:  # stands in for self.depth_head(...) (:130-138)
+        if raw_depth is not None:  # :135-138
             depth = scale_depth(raw_depth, batch_scales) if batch_scales is not None else raw_depth
             _append(predictions, context, "depth", depth)
             _append(predictions, context, "depth_conf", raw_depth_conf)

@@ -814,6 +814,14 @@ extern "C" int lsvs_pose_chain(const float* chunk_sim3, const float* frame_se3, 
                           (cudaStream_t)stream);
 }
 
+extern "C" int lsvs_pose_chain_gt(const float* chunk_sim3, const float* frame_se3, const float* cam_enc, const float* prev_pose_enc,
+                                  int S_prev, int overlap, int B, int S, int H, int W, const float* gt_poses, int gt_rows, int gt_mode,
+                                  float* pose_enc_out, float* point_T, float* scale_out, void* stream) {
+  LSVS_CHECK_ARG(gt_poses != nullptr, "pose_chain_gt: gt_poses is null");
+  return lsvs::pose_chain(chunk_sim3, frame_se3, cam_enc, prev_pose_enc, S_prev, overlap, B, S, H, W, pose_enc_out, point_T, scale_out,
+                          (cudaStream_t)stream, gt_poses, gt_rows, gt_mode);
+}
+
 extern "C" int lsvs_alignment_decode_forward(lsvs_engine* h, const float* align_tokens, int B, int S, const float* memory_in,
                                              float* chunk_sim3, float* frame_se3, float* memory_out, void* stream) {
   Engine& e = *reinterpret_cast<Engine*>(h);

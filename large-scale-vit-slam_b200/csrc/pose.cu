@@ -97,27 +97,51 @@ __device__ void top_eigvec4(double A[4][4], float* out) {
 
 constexpr int MAX_OVERLAP = 128;
 
+__device__ M4 load_gt(const float* g, int rows) {  // (rows,4) world-to-camera, rows 3 -> padded with [0 0 0 1] (poseAligned...:86-87)
+  M4 o;
+  for (int i = 0; i < rows * 4; ++i) o.m[i] = g[i];
+  if (rows == 3) { o.m[12] = 0; o.m[13] = 0; o.m[14] = 0; o.m[15] = 1; }
+  return o;
+}
+
 __global__ void __launch_bounds__(128) pose_chain_kernel(const float* __restrict__ chunk_sim3, const float* __restrict__ frame_se3,
                                                          const float* __restrict__ cam_enc, const float* __restrict__ prev_enc, int S_prev,
                                                          int overlap, int S, int H, int W, float* __restrict__ pose_out,
-                                                         float* __restrict__ point_T, float* __restrict__ scale_out) {
+                                                         float* __restrict__ point_T, float* __restrict__ scale_out,
+                                                         const float* __restrict__ gt, int gt_rows, int gt_mode) {
   __shared__ M4 chunk_se3, ident, mean_T, pf0;
   __shared__ float cam_enc7[MAX_OVERLAP][7];
+  __shared__ float scale_sh;
   const int b = blockIdx.x;
   const float* cs = chunk_sim3 + (size_t)b * 8;
-  const float scale = cs[7];
+  const float* gtb = gt ? gt + (size_t)b * S * gt_rows * 4 : nullptr;
   if (threadIdx.x == 0) {
     chunk_se3 = enc_to_mat(cs, true);                                   // pose_encoding_to_extri (data.py:33-52)
     M4 e0 = enc_to_mat(cam_enc + (size_t)b * S * 9, false);              // upstream pose_encoding_to_extri_intri
     ident = inv_se3(e0);                                                 // featureAligned_vggt.py:114
-    scale_out[b] = scale;
+    float sc = cs[7];
+    if (gtb && (gt_mode & LSVS_GT_SCALE) && S > 1) {                     // poseAligned_wrapped_vggt.py:84-104 + scale_lse_solver
+      const M4 centering = inv_se3(load_gt(gtb, gt_rows));               // (alignment.py:113-129): |sum x.y / sum x.x| over the
+      double dots = 0, norms = 0;                                        // re-based predicted / first-frame-centred gt positions
+      for (int s = 0; s < S; ++s) {
+        const M4 g = mul(load_gt(gtb + (size_t)s * gt_rows * 4, gt_rows), centering);
+        const M4 e = mul(enc_to_mat(cam_enc + ((size_t)b * S + s) * 9, false), ident);
+        dots += (double)e.m[3] * g.m[3] + (double)e.m[7] * g.m[7] + (double)e.m[11] * g.m[11];
+        norms += (double)e.m[3] * e.m[3] + (double)e.m[7] * e.m[7] + (double)e.m[11] * e.m[11];
+      }
+      sc *= (float)fabs(dots / norms);
+    }
+    scale_sh = sc;
+    scale_out[b] = sc;
   }
   __syncthreads();
+  const float scale = scale_sh;
+  const bool gt_mean = gtb && (gt_mode & LSVS_GT_MEAN) && prev_enc;      // featureAligned_vggt.py:123-124, poseAligned...:108-109
   // re-based, scaled camera extrinsics of every frame (:116-119)
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
     M4 e = mul(enc_to_mat(cam_enc + ((size_t)b * S + s) * 9, false), ident);
     e.m[3] *= scale; e.m[7] *= scale; e.m[11] *= scale;
-    if (prev_enc && s < overlap) {                                       // :126-128
+    if (prev_enc && !gt_mean && s < overlap) {                           // :126-128
       const M4 ctx = enc_to_mat(prev_enc + ((size_t)b * S_prev + (S_prev - overlap + s)) * 9, true);
       const M4 ct = mul(inv_se3(e), ctx);
       if (overlap > 1) {                                                 // extri_to_pose_encoding (data.py:12-30)
@@ -135,6 +159,8 @@ __global__ void __launch_bounds__(128) pose_chain_kernel(const float* __restrict
   if (threadIdx.x == 0) {
     if (!prev_enc) {
       for (int i = 0; i < 16; ++i) mean_T.m[i] = (i % 5 == 0) ? 1.f : 0.f;
+    } else if (gt_mean) {
+      mean_T = load_gt(gtb, gt_rows);
     } else if (overlap > 1) {                                            // averagePoseEncodings (geometry.py:4-37)
       float avg[7] = {0, 0, 0, 0, 0, 0, 0};
       double A[4][4] = {};
@@ -206,12 +232,16 @@ int pose_enc_apply_sim3(const float* enc, const float* T, const float* s, float*
 }
 
 int pose_chain(const float* chunk_sim3, const float* frame_se3, const float* cam_enc, const float* prev_pose_enc, int S_prev,
-               int overlap, int B, int S, int H, int W, float* pose_enc_out, float* point_T, float* scale_out, cudaStream_t st) {
+               int overlap, int B, int S, int H, int W, float* pose_enc_out, float* point_T, float* scale_out, cudaStream_t st,
+               const float* gt_poses, int gt_rows, int gt_mode) {
   LSVS_CHECK_ARG(chunk_sim3 && cam_enc && pose_enc_out && point_T && scale_out && B > 0 && S > 0, "pose_chain: bad arguments");
   LSVS_CHECK_ARG(S == 1 || frame_se3, "pose_chain: frame_se3 missing");
-  LSVS_CHECK_ARG(!prev_pose_enc || (overlap >= 1 && overlap <= MAX_OVERLAP && overlap <= S && overlap <= S_prev),
+  const bool averaged = prev_pose_enc && !(gt_poses && (gt_mode & LSVS_GT_MEAN));
+  LSVS_CHECK_ARG(!averaged || (overlap >= 1 && overlap <= MAX_OVERLAP && overlap <= S && overlap <= S_prev),
                  "pose_chain: overlap %d out of range (S=%d, previous chunk %d)", overlap, S, S_prev);
-  pose_chain_kernel<<<B, 128, 0, st>>>(chunk_sim3, frame_se3, cam_enc, prev_pose_enc, S_prev, overlap, S, H, W, pose_enc_out, point_T, scale_out);
+  LSVS_CHECK_ARG(!gt_poses || gt_rows == 3 || gt_rows == 4, "pose_chain: gt_poses must be (B,S,3,4) or (B,S,4,4)");
+  pose_chain_kernel<<<B, 128, 0, st>>>(chunk_sim3, frame_se3, cam_enc, prev_pose_enc, S_prev, overlap, S, H, W, pose_enc_out, point_T,
+                                       scale_out, gt_poses, gt_rows, gt_poses ? gt_mode : 0);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }

@@ -31,7 +31,8 @@ int combine_rows(const float* a, long long lda, const float* b, long long ldb, f
 
 // Pose / Sim(3) composition of one chunk (featureAligned_vggt.py:97-143,190-196).  See csrc/pose.cu.
 int pose_chain(const float* chunk_sim3, const float* frame_se3, const float* cam_enc, const float* prev_pose_enc, int S_prev,
-               int overlap, int B, int S, int H, int W, float* pose_enc_out, float* point_T, float* scale_out, cudaStream_t st);
+               int overlap, int B, int S, int H, int W, float* pose_enc_out, float* point_T, float* scale_out, cudaStream_t st,
+               const float* gt_poses = nullptr, int gt_rows = 4, int gt_mode = 0);
 
 int pose_enc_apply_sim3(const float* enc, const float* T, const float* s, float* out, int B, int S, int H, int W, cudaStream_t st);
 // IRLS weighted Umeyama (csrc/umeyama.cu); status: 0 ok, 1 = total weight too small

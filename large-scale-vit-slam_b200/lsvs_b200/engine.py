@@ -191,10 +191,14 @@ class Engine:
         return out
 
 
+GT_MEAN, GT_SCALE = 1, 2   # LSVS_GT_MEAN / LSVS_GT_SCALE of include/lsvs_b200.h
+
+
 def pose_chain(chunk_sim3: torch.Tensor, frame_se3: torch.Tensor, cam_enc: torch.Tensor, prev_pose_enc: Optional[torch.Tensor],
-               overlap: int, image_hw):
+               overlap: int, image_hw, gt_poses: Optional[torch.Tensor] = None, gt_mode: int = 0):
     """Pose / Sim(3) composition of one chunk (featureAligned_vggt.py:97-143, :190-196) in one kernel.
-    Returns (aligned pose_enc (B,S,9), point transform (B,4,4), chunk scale (B,))."""
+    Returns (aligned pose_enc (B,S,9), point transform (B,4,4), chunk scale (B,)).
+    gt_poses (B,S,3|4,4) + gt_mode (GT_MEAN | GT_SCALE): the ground-truth variants of the chain (lsvs_pose_chain_gt)."""
     B, S, _ = cam_enc.shape
     dev = cam_enc.device
     H, W = image_hw
@@ -209,6 +213,14 @@ def pose_chain(chunk_sim3: torch.Tensor, frame_se3: torch.Tensor, cam_enc: torch
     pose = torch.empty(B, S, 9, device=dev)
     pt = torch.empty(B, 4, 4, device=dev)
     sc = torch.empty(B, device=dev)
+    if gt_poses is not None and gt_mode:
+        gt = gt_poses.detach().to(dev, torch.float32).contiguous()
+        if gt.dim() != 4 or gt.shape[0] != B or gt.shape[1] != S or gt.shape[-1] != 4 or gt.shape[-2] not in (3, 4):
+            raise ValueError(f"gt_poses must be (B,S,3,4) or (B,S,4,4) with B={B}, S={S}; got {tuple(gt.shape)}")
+        _n.check(_n.lib().lsvs_pose_chain_gt(_n.ptr(cs), _n.ptr(fs), _n.ptr(ce), _n.ptr(prev), _i(S_prev), _i(overlap), _i(B), _i(S),
+                                             _i(H), _i(W), _n.ptr(gt), _i(gt.shape[-2]), _i(gt_mode), _n.ptr(pose), _n.ptr(pt),
+                                             _n.ptr(sc), _n.stream_ptr()), "pose_chain_gt")
+        return pose, pt, sc
     _n.check(_n.lib().lsvs_pose_chain(_n.ptr(cs), _n.ptr(fs), _n.ptr(ce), _n.ptr(prev), _i(S_prev), _i(overlap), _i(B), _i(S),
                                       _i(H), _i(W), _n.ptr(pose), _n.ptr(pt), _n.ptr(sc), _n.stream_ptr()), "pose_chain")
     return pose, pt, sc

@@ -358,10 +358,19 @@ def compose_alignment(chunk_sim3: torch.Tensor, frame_se3: torch.Tensor):
     return torch.cat([chunk_se3, per_frame], dim=1), chunk_sim3[..., -1]
 
 
+def scale_lse(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """scale_lse_solver — /root/reference/aligned_vggt/utils/alignment.py:113-129: |sum(x*y) / sum(x**2)|, (n,3) each."""
+    assert x.shape == y.shape, "x shape not equal to y shape"
+    return ((x * y).sum() / (x ** 2).sum()).abs()
+
+
 def pose_chain(pose_enc_cam: torch.Tensor, image_hw, per_frame_se3: torch.Tensor, scale: torch.Tensor,
-               prev_pose_enc: Optional[torch.Tensor], overlap: int):
-    """featureAligned_vggt.py:106-143 (gt_poses=None).  Returns (aligned_pose_enc (B,S,9),
-    per_frame_se3 incl. mean transform (B,S,4,4), point_identity_alignment (B,4,4))."""
+               prev_pose_enc: Optional[torch.Tensor], overlap: int, gt_mean: Optional[torch.Tensor] = None,
+               gt_scale_poses: Optional[torch.Tensor] = None):
+    """featureAligned_vggt.py:106-143.  Returns (aligned_pose_enc (B,S,9), per_frame_se3 incl. mean transform (B,S,4,4),
+    point_identity_alignment (B,4,4)).  gt_mean (B,1,4,4): `mean_camera_transform = gt_poses[:,:1]` (:123-124, only looked at
+    with a previous chunk).  gt_scale_poses (B,S,4,4) padded gt: the pose-aligned baseline's position-scale alignment
+    (poseAligned_wrapped_vggt.py:84-104); the per-batch scales are then returned as a fourth value."""
     B = pose_enc_cam.shape[0]
     extr3, intr = OF.pose_encoding_to_extri_intri(pose_enc_cam, image_size_hw=image_hw)
     extr = F.pad(extr3, (0, 0, 0, 1))
@@ -370,7 +379,14 @@ def pose_chain(pose_enc_cam: torch.Tensor, image_hw, per_frame_se3: torch.Tensor
     point_identity = extr[:, 0].clone()
     extr = extr @ ident.view(B, 1, 4, 4)
     extr[:, :, :3, 3] *= scale.view(B, 1, 1)
-    if prev_pose_enc is not None:
+    batch_scales = None
+    if gt_scale_poses is not None and extr.shape[1] > 1:
+        centred = gt_scale_poses @ OF.closed_form_inverse_se3(gt_scale_poses[:, 0]).view(B, 1, 4, 4)
+        batch_scales = torch.stack([scale_lse(extr[b, :, :3, 3], centred[b, :, :3, 3]) for b in range(B)])
+        extr[:, :, :3, 3] *= batch_scales.view(B, 1, 1)
+    if prev_pose_enc is not None and gt_mean is not None:
+        mean_T = gt_mean.to(extr)
+    elif prev_pose_enc is not None:
         ctx = pose_encoding_to_extri(prev_pose_enc[:, -overlap:])
         cam_T = inv_se3(extr[:, :overlap]) @ ctx
         if overlap > 1:
@@ -382,6 +398,8 @@ def pose_chain(pose_enc_cam: torch.Tensor, image_hw, per_frame_se3: torch.Tensor
     per_frame_se3 = per_frame_se3 @ mean_T
     aligned = extr @ per_frame_se3
     enc = OF.extri_intri_to_pose_encoding(aligned, intr, image_size_hw=image_hw)
+    if gt_scale_poses is not None:
+        return enc, per_frame_se3, point_identity, batch_scales
     return enc, per_frame_se3, point_identity
 
 
@@ -395,8 +413,8 @@ def point_transform(per_frame_se3: torch.Tensor, point_identity: torch.Tensor, h
 def feature_aligned_forward(p: Params, images: torch.Tensor, num_overlap: int, context: Optional[dict] = None, *,
                             raw_points: Optional[torch.Tensor] = None, raw_depth: Optional[torch.Tensor] = None,
                             depth: int = 24, dino_depth: int = 24, taps=(4, 11, 17, 23), depth_aa: int = 4,
-                            num_memory_tokens: int = 8, amp: bool = False) -> dict:
-    """FeatureAlignedVGGT.forward (eval, gt_poses=None, enable_camera=True) — featureAligned_vggt.py:48-225.
+                            num_memory_tokens: int = 8, amp: bool = False, gt_poses: Optional[torch.Tensor] = None) -> dict:
+    """FeatureAlignedVGGT.forward (eval, enable_camera=True) — featureAligned_vggt.py:48-225.
     The DPT heads are out of scope: ``raw_points`` (B,S,H,W,3) / ``raw_depth`` (B,S,H,W,1)
     stand in for their outputs so the Sim(3) application can be checked.  Returns this chunk's tensors
     (not the accumulated lists) plus the context entries needed by the next chunk."""
@@ -415,7 +433,8 @@ def feature_aligned_forward(p: Params, images: torch.Tensor, num_overlap: int, c
         num_memory_tokens=num_memory_tokens, amp=amp)
     per_frame, scale = compose_alignment(chunk_sim3, frame_se3)
     cam_enc = OF.camera_head_forward(p, "camera_head.", taps_t[-1])[-1]
-    pose_enc, per_frame, pt_ident = pose_chain(cam_enc, (H, W), per_frame, scale, prev_pose, overlap)
+    pose_enc, per_frame, pt_ident = pose_chain(cam_enc, (H, W), per_frame, scale, prev_pose, overlap,
+                                               gt_mean=None if gt_poses is None else gt_poses[:, :1])
     out = {"taps": taps_t, "chunk_sim3_alignment_enc": chunk_sim3, "frame_se3_alignment_enc": frame_se3,
            "memory_tokens": memory, "overlap_tokens": overlap_tokens, "pose_enc": pose_enc, "camera_pose_enc": cam_enc}
     if raw_depth is not None:
@@ -428,21 +447,56 @@ def feature_aligned_forward(p: Params, images: torch.Tensor, num_overlap: int, c
 
 
 def pose_aligned_forward(p: Params, images: torch.Tensor, num_overlap: int, context: Optional[dict] = None, *,
-                         raw_points: Optional[torch.Tensor] = None, depth: int = 24, dino_depth: int = 24,
-                         taps=(4, 11, 17, 23)) -> dict:
-    """pose-aligned baseline VGGT.forward (eval, gt_poses=None) — aligned_vggt/models/poseAligned_wrapped_vggt.py:36-204.
-    Same chain as the feature-aligned model with identity learned alignment and unit scale (:107-130, :171-187)."""
+                         raw_points: Optional[torch.Tensor] = None, raw_depth: Optional[torch.Tensor] = None, depth: int = 24,
+                         dino_depth: int = 24, taps=(4, 11, 17, 23), gt_poses: Optional[torch.Tensor] = None) -> dict:
+    """pose-aligned baseline VGGT.forward (eval) — aligned_vggt/models/poseAligned_wrapped_vggt.py:36-204.
+    Same chain as the feature-aligned model with identity learned alignment and unit scale (:107-130, :171-187);
+    gt_poses (B,S,3,4): position-scale alignment + gt chunk transform (:84-109), scale applied to depth / points (:144-147, :166-169).
+    raw_points / raw_depth stand in for (or are) the DPT head outputs."""
     B, S, _, H, W = images.shape
     toks, _ = OF.aggregator_forward(p, "aggregator.", images, depth=depth, dino_depth=dino_depth, keep=taps)
     cam_enc = OF.camera_head_forward(p, "camera_head.", toks[taps[-1]])[-1]
     eye = torch.eye(4).view(1, 1, 4, 4).expand(B, S, -1, -1)
     prev = context["pose_enc"] if context is not None else None
-    pose_enc, per_frame, pt_ident = pose_chain(cam_enc, (H, W), eye, torch.ones(B, 1), prev, num_overlap)
-    out = {"pose_enc": pose_enc, "camera_pose_enc": cam_enc}
+    batch_scales = None
+    if gt_poses is not None:
+        gt4 = F.pad(gt_poses, (0, 0, 0, 1))
+        gt4[:, :, 3, 3] = 1.0
+        pose_enc, per_frame, pt_ident, batch_scales = pose_chain(cam_enc, (H, W), eye, torch.ones(B, 1), prev, num_overlap,
+                                                                 gt_mean=gt4[:, :1], gt_scale_poses=gt4)
+    else:
+        pose_enc, per_frame, pt_ident = pose_chain(cam_enc, (H, W), eye, torch.ones(B, 1), prev, num_overlap)
+    s = torch.ones(B) if batch_scales is None else batch_scales
+    out = {"pose_enc": pose_enc, "camera_pose_enc": cam_enc, "taps": [toks[i].float() for i in taps], "batch_scales": s}
+    if raw_depth is not None:
+        out["depth"] = raw_depth * s.view(B, 1, 1, 1, 1)
     if raw_points is not None:
         Tp = point_transform(per_frame, pt_ident, context is not None)
-        out["world_points"] = apply_sim3_points(raw_points, Tp, torch.ones(B))
+        out["world_points"] = apply_sim3_points(raw_points, Tp, s)
         out["point_transform"] = Tp
+    return out
+
+
+def point_aligned_forward(p: Params, images: torch.Tensor, num_overlap: int, context: Optional[dict] = None, *,
+                          raw_points: torch.Tensor, raw_points_conf: torch.Tensor, raw_depth: Optional[torch.Tensor] = None,
+                          depth: int = 24, dino_depth: int = 24, taps=(4, 11, 17, 23)) -> dict:
+    """point-aligned baseline VGGT.forward (eval) — aligned_vggt/models/pointAligned_wrapped_vggt.py:34-157: IRLS Umeyama of
+    the overlap point maps onto the previous chunk's aligned ones (:74-99), applied to points (:100), poses (:113-122) and
+    depth (:135-138).  context: {"world_points", "world_points_conf"} of the previous chunk (aligned)."""
+    B, S, _, H, W = images.shape
+    toks, _ = OF.aggregator_forward(p, "aggregator.", images, depth=depth, dino_depth=dino_depth, keep=taps)
+    cam_enc = OF.camera_head_forward(p, "camera_head.", toks[taps[-1]])[-1]
+    T = torch.eye(4).repeat(B, 1, 1)
+    s = torch.ones(B)
+    if context is not None:
+        for b in range(B):
+            r, t, sc = irls_umeyama(raw_points[b, :num_overlap], context["world_points"][b, -num_overlap:],
+                                    raw_points_conf[b, :num_overlap], context["world_points_conf"][b, -num_overlap:])
+            T[b, :3, :3], T[b, :3, 3], s[b] = r, t, sc
+    out = {"world_points": apply_sim3_points(raw_points, T, s), "world_points_conf": raw_points_conf,
+           "pose_enc": pose_enc_apply_sim3(cam_enc, (H, W), T, s), "transform": T, "scales": s}
+    if raw_depth is not None:
+        out["depth"] = raw_depth * s.view(B, 1, 1, 1, 1)
     return out
 
 

@@ -333,6 +333,106 @@ def case_model_dpt_small():
     save("model_dpt_small.npz", **arrs)
 
 
+def _synth_gt_poses(seed, S, rows):
+    """(1,S,rows,4) world-to-camera matrices of a slowly moving camera (rotation a few degrees per frame)."""
+    q = torch.nn.functional.normalize(torch.tensor([0.0, 0.0, 0.0, 1.0]) + 0.05 * rnd(seed, S, 4), dim=-1)
+    g = torch.eye(4).repeat(S, 1, 1)
+    g[:, :3, :3] = OF.quat_to_mat(q)
+    g[:, :3, 3] = rnd(seed + 1, S, 3, scale=0.5) + torch.arange(S).view(S, 1) * torch.tensor([0.3, 0.0, 1.0])
+    return g[None, :, :rows].contiguous()
+
+
+def case_baselines_gt_dpt():
+    """The gt_poses variants (sample modes chunk_gt / two_chunks) and the two baseline wrappers WITH their DPT heads: outputs of
+    the reference classes' own forwards over the shim, two chained chunks whose overlap frames are the same images."""
+    print("[gt_poses paths + baseline wrappers with DPT heads, depth 1/1, S=4, 56x84, overlap 2]")
+    import json
+    from aligned_vggt.models.featureAligned_vggt import FeatureAlignedVGGT
+    from aligned_vggt.models.pointAligned_wrapped_vggt import VGGT as PointVGGT
+    from aligned_vggt.models.poseAligned_wrapped_vggt import VGGT as PoseVGGT
+    os.environ["VGGT_SHIM_DEPTH"] = "1,1"
+    taps = (0, 0, 0, 0)
+    S, H, W, ov, sub = 4, 56, 84, 2, 4
+    imgs = [torch.from_numpy(np.random.Generator(np.random.PCG64(500 + i)).random((1, S, 3, H, W), dtype=np.float32)) for i in range(2)]
+    imgs[1][:, :ov] = imgs[0][:, -ov:]
+    arrs = {"S": S, "H": H, "W": W, "ov": ov, "sub": sub}
+
+    def build(cls, seed, **kw):
+        with torch.device("meta"):
+            m = cls(enable_track=False, **kw)
+        spec = OW.spec_of(m)
+        sd = OW.fill_state_dict(spec, seed=seed)
+        m = m.to_empty(device="cpu")
+        m.load_state_dict(sd, strict=True)
+        m.eval()
+        m.intermediate_layer_indices = list(taps)
+        return m, sd, spec
+
+    # (a) feature-aligned, gt_poses (1,S,4,4) given with the second chunk
+    model, sd, _ = build(FeatureAlignedVGGT, 0, enable_point=False, enable_depth=False)
+    gt4 = [_synth_gt_poses(600 + 10 * i, S, 4) for i in range(2)]
+    r1 = model(imgs[0], ov, None, gt_poses=gt4[0])
+    e1 = r1["pose_enc"][-1].clone()
+    r2 = model(imgs[1], ov, r1, gt_poses=gt4[1])
+    e2 = r2["pose_enc"][-1].clone()
+    o1 = OA.feature_aligned_forward(sd, imgs[0], ov, None, depth=1, dino_depth=1, taps=taps, gt_poses=gt4[0])
+    ctx = {"overlap_tokens": o1["overlap_tokens"], "memory_tokens": o1["memory_tokens"], "pose_enc": o1["pose_enc"]}
+    pts = rnd(620, 1, S, H, W, 3, scale=5.0)
+    o2 = OA.feature_aligned_forward(sd, imgs[1], ov, ctx, depth=1, dino_depth=1, taps=taps, gt_poses=gt4[1], raw_points=pts)
+    check("feature-aligned gt c1 pose_enc", o1["pose_enc"], e1, 5e-4)
+    check("feature-aligned gt c2 pose_enc", o2["pose_enc"], e2, 5e-4)
+    arrs.update(fa_wsum=OW.checksum(sd), fa_gt1=gt4[0], fa_gt2=gt4[1], fa_c1_pose_enc=e1, fa_c2_pose_enc=e2)
+
+    # (b) pose-aligned with DPT heads: plain, and with gt_poses (1,S,3,4) on both chunks
+    model, sd, spec = build(PoseVGGT, 2, enable_point=True, enable_depth=True)
+    with open(os.path.join(GOLD, "state_dict_spec_baselines.json"), "w") as f:
+        json.dump({k: list(v) for k, v in spec}, f)
+    arrs["pa_wsum"] = OW.checksum(sd)
+    gt3 = [_synth_gt_poses(640 + 10 * i, S, 3) for i in range(2)]
+    keys = ("pose_enc", "depth", "depth_conf", "world_points", "world_points_conf")
+    for tag, gts in (("pa", (None, None)), ("pagt", gt3)):
+        r1 = model(imgs[0], ov, None, gt_poses=None if gts[0] is None else gts[0].clone())
+        s1 = {k: r1[k][-1].clone() for k in keys}
+        r2 = model(imgs[1], ov, r1, gt_poses=None if gts[1] is None else gts[1].clone())
+        s2 = {k: r2[k][-1].clone() for k in keys}
+        ctx = None
+        for ci, (img, snap, gt) in enumerate(((imgs[0], s1, gts[0]), (imgs[1], s2, gts[1])), 1):
+            o = OA.pose_aligned_forward(sd, img, ov, ctx, depth=1, dino_depth=1, taps=taps, gt_poses=gt)
+            d, dc = OF.dpt_head_forward(sd, "depth_head.", o["taps"], (H, W), activation="exp")
+            pp, pc = OF.dpt_head_forward(sd, "point_head.", o["taps"], (H, W), activation="inv_log")
+            o = OA.pose_aligned_forward(sd, img, ov, ctx, depth=1, dino_depth=1, taps=taps, gt_poses=gt, raw_points=pp, raw_depth=d)
+            ctx = {"pose_enc": o["pose_enc"]}
+            for k, v in (("pose_enc", o["pose_enc"]), ("depth", o["depth"]), ("depth_conf", dc), ("world_points", o["world_points"]),
+                         ("world_points_conf", pc)):
+                check(f"{tag} c{ci} {k}", v, snap[k], 5e-4)
+                arrs[f"{tag}_c{ci}_{k}"] = snap[k] if k == "pose_enc" else snap[k][:, :, ::sub, ::sub].contiguous()
+            if gt is not None:
+                arrs[f"{tag}_gt{ci}"] = gt
+                arrs[f"{tag}_c{ci}_scale"] = o["batch_scales"]
+
+    # (c) point-aligned with DPT heads (same weights as (b): identical parameter tree)
+    model, sd_c, _ = build(PointVGGT, 2, enable_point=True, enable_depth=True)
+    assert OW.checksum(sd_c) == OW.checksum(sd)
+    r1 = model(imgs[0], ov, None)
+    s1 = {k: r1[k][-1].clone() for k in keys}
+    r2 = model(imgs[1], ov, r1)
+    s2 = {k: r2[k][-1].clone() for k in keys}
+    ctx = None
+    for ci, (img, snap) in enumerate(((imgs[0], s1), (imgs[1], s2)), 1):
+        tp = OA.pose_aligned_forward(sd, img, ov, None, depth=1, dino_depth=1, taps=taps)["taps"]
+        d, dc = OF.dpt_head_forward(sd, "depth_head.", tp, (H, W), activation="exp")
+        pp, pc = OF.dpt_head_forward(sd, "point_head.", tp, (H, W), activation="inv_log")
+        o = OA.point_aligned_forward(sd, img, ov, ctx, raw_points=pp, raw_points_conf=pc, raw_depth=d, depth=1, dino_depth=1, taps=taps)
+        ctx = {"world_points": o["world_points"], "world_points_conf": pc}
+        for k, v in (("pose_enc", o["pose_enc"]), ("depth", o["depth"]), ("depth_conf", dc), ("world_points", o["world_points"]),
+                     ("world_points_conf", pc)):
+            check(f"point-aligned c{ci} {k}", v, snap[k], 2e-3)
+            arrs[f"pt_c{ci}_{k}"] = snap[k] if k == "pose_enc" else snap[k][:, :, ::sub, ::sub].contiguous()
+        arrs[f"pt_c{ci}_scale"] = o["scales"]
+        arrs[f"pt_c{ci}_T"] = o["transform"]
+    save("model_baselines_gt_dpt.npz", **arrs)
+
+
 def case_eval_geometry():
     """unproject_depth_map_to_point_map, scale_align_from_depths, convertDictListsToTensors of the reference."""
     print("[evaluation-side geometry]")
@@ -392,7 +492,8 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     os.makedirs(GOLD, exist_ok=True)
     cases = {"spec": case_spec, "layers": case_layers, "geometry": case_geometry, "head": case_head, "model_small": case_model_small,
-             "pose_aligned": case_pose_aligned_small, "model_dpt_small": case_model_dpt_small, "eval_geometry": case_eval_geometry}
+             "pose_aligned": case_pose_aligned_small, "model_dpt_small": case_model_dpt_small, "eval_geometry": case_eval_geometry,
+             "baselines_gt_dpt": case_baselines_gt_dpt}
     if args.full:
         cases["model_full"] = case_model_full
     for name, fn in cases.items():

@@ -125,3 +125,77 @@ def test_point_aligned_model_chain():
     m = pose_metrics(p2["pose_enc"][1], ref)
     assert m["trans_rel"] < TRANS_REL and m["rot_deg"] < ROT_DEG, m
     assert torch.equal(p2["pose_enc"][0], cam1)
+
+
+# ---- gt_poses variants and the baseline wrappers with their DPT heads (tests/golden/model_baselines_gt_dpt.npz: outputs of the
+# ---- reference classes' own forwards; two chained chunks whose overlap frames are the same images) -------------------------
+def _gt_dpt_images(g):
+    import numpy as np
+    S, H, W, ov = g["S"], g["H"], g["W"], g["ov"]
+    imgs = [torch.from_numpy(np.random.Generator(np.random.PCG64(500 + i)).random((1, S, 3, H, W), dtype=np.float32)) for i in range(2)]
+    imgs[1][:, :ov] = imgs[0][:, -ov:]
+    return imgs
+
+
+def _check_pose(e, ref, what):
+    m = pose_metrics(e, ref)   # bf16 encoder + camera trunk vs the fp32 reference run: calibration band of tests/test_model_gpu.py
+    assert m["trans_rel"] < 1e-2 and m["rot_deg"] < 1.0, (what, m)
+
+
+def test_feature_aligned_gt_poses_golden(golden):
+    from aligned_vggt.models.featureAligned_vggt import FeatureAlignedVGGT
+    g = golden("model_baselines_gt_dpt.npz")
+    model = FeatureAlignedVGGT(enable_point=False, enable_depth=False, enable_track=False, depth=1, patch_embed_depth=1,
+                               intermediate_layer_indices=(0, 0, 0, 0))
+    sd = load_synth_weights(model, seed=0)
+    assert abs(OW.checksum(sd) - g["fa_wsum"]) < 1e-6 * abs(g["fa_wsum"])
+    model = model.cuda().eval()
+    imgs, ov = _gt_dpt_images(g), g["ov"]
+    p1 = model(imgs[0].cuda(), ov, None, gt_poses=g["fa_gt1"].cuda())
+    _check_pose(p1["pose_enc"][-1], g["fa_c1_pose_enc"], "c1")
+    ctx_plain = {k: (list(v) if isinstance(v, list) else v) for k, v in p1.items()}
+    p2 = model(imgs[1].cuda(), ov, p1, gt_poses=g["fa_gt2"])          # CPU gt tensor: moved like the reference's .to(extr)
+    _check_pose(p2["pose_enc"][-1], g["fa_c2_pose_enc"], "c2")
+    p2_plain = model(imgs[1].cuda(), ov, ctx_plain)
+    assert float((p2_plain["pose_enc"][-1] - p2["pose_enc"][-1]).abs().max()) > 1e-2
+
+
+@pytest.mark.parametrize("tag", ["pa", "pagt"])
+def test_pose_aligned_with_dpt_heads_golden(golden, tag):
+    from aligned_vggt.models.poseAligned_wrapped_vggt import VGGT
+    g = golden("model_baselines_gt_dpt.npz")
+    sub, ov = g["sub"], g["ov"]
+    model = VGGT(enable_track=False, depth=1, patch_embed_depth=1, intermediate_layer_indices=(0, 0, 0, 0))
+    sd = load_synth_weights(model, seed=2)
+    assert abs(OW.checksum(sd) - g["pa_wsum"]) < 1e-6 * abs(g["pa_wsum"])
+    model = model.cuda().eval()
+    imgs = _gt_dpt_images(g)
+    p = None
+    for ci in (1, 2):
+        gt = g[f"pagt_gt{ci}"].cuda() if tag == "pagt" else None
+        p = model(imgs[ci - 1].cuda(), ov, p, gt_poses=gt)
+        assert len(p["depth"]) == ci and len(p["world_points"]) == ci
+        _check_pose(p["pose_enc"][-1], g[f"{tag}_c{ci}_pose_enc"], (tag, ci))
+        for k, tol in (("depth", 3e-2), ("depth_conf", 3e-2), ("world_points", 5e-2), ("world_points_conf", 3e-2)):
+            got, ref = p[k][-1][:, :, ::sub, ::sub], g[f"{tag}_c{ci}_{k}"]
+            assert got.shape == ref.shape and rel_l2(got, ref) < tol, (tag, ci, k, rel_l2(got, ref))
+    if tag == "pagt":
+        with pytest.raises(RuntimeError):   # the reference pads one row: only (B,S,3,4) works there
+            model(imgs[0].cuda(), ov, None, gt_poses=torch.eye(4).expand(1, g["S"], 4, 4).cuda())
+
+
+def test_point_aligned_with_dpt_heads_golden(golden):
+    from aligned_vggt.models.pointAligned_wrapped_vggt import VGGT
+    g = golden("model_baselines_gt_dpt.npz")
+    sub, ov = g["sub"], g["ov"]
+    model = VGGT(enable_track=False, depth=1, patch_embed_depth=1, intermediate_layer_indices=(0, 0, 0, 0))
+    load_synth_weights(model, seed=2)
+    model = model.cuda().eval()
+    imgs = _gt_dpt_images(g)
+    p = None
+    for ci in (1, 2):
+        p = model(imgs[ci - 1].cuda(), ov, p)
+        _check_pose(p["pose_enc"][-1], g[f"pt_c{ci}_pose_enc"], ci)
+        for k, tol in (("depth", 3e-2), ("depth_conf", 3e-2), ("world_points", 5e-2), ("world_points_conf", 3e-2)):
+            got, ref = p[k][-1][:, :, ::sub, ::sub], g[f"pt_c{ci}_{k}"]
+            assert got.shape == ref.shape and rel_l2(got, ref) < tol, (ci, k, rel_l2(got, ref))

@@ -210,8 +210,9 @@ def test_model_state_and_errors():
     p2 = model(img.cuda(), 1)
     d = (p2["chunk_sim3_alignment_enc"] - p1["chunk_sim3_alignment_enc"]).cpu()[0, 0]
     assert torch.allclose(d[:7], torch.ones(7), atol=1e-4)
-    with pytest.raises(NotImplementedError):
-        model(img.cuda(), 1, gt_poses=torch.zeros(1, 2, 3, 4))
+    model(img.cuda(), 1, gt_poses=torch.zeros(1, 2, 3, 4))          # first chunk: gt_poses is not looked at (:122-124)
+    with pytest.raises(RuntimeError):                                # with context the reference's matmul needs (B,S,4,4)
+        model(img.cuda(), 1, p2, gt_poses=torch.zeros(1, 2, 3, 4))
     # S <= num_overlap: overlap falls back to S-1 (featureAligned_vggt.py:93)
     p3 = model(img.cuda(), 5)
     assert p3["overlap_tokens"].shape[1] == 2

@@ -186,3 +186,60 @@ def test_eval_geometry_golden(golden):
     sc = OA.depth_scale_align(t("pred").reshape(B, -1), t("gt").reshape(B, -1), t("mask").reshape(B, -1), t("conf").reshape(B, -1))
     close(sc, g["scales"], 1e-6)
     close(t("pred") * sc.view(B, 1, 1, 1, 1), g["depth_aligned"], 1e-6)
+
+
+def _gt_dpt_images(g):
+    S, H, W, ov = g["S"], g["H"], g["W"], g["ov"]
+    imgs = [torch.from_numpy(np.random.Generator(np.random.PCG64(500 + i)).random((1, S, 3, H, W), dtype=np.float32)) for i in range(2)]
+    imgs[1][:, :ov] = imgs[0][:, -ov:]
+    return imgs
+
+
+def test_gt_poses_and_baselines_with_dpt_golden(golden):
+    """gt_poses variants (featureAligned_vggt.py:123-124, poseAligned_wrapped_vggt.py:84-109,:144-169) and the baseline wrappers
+    with their DPT heads (pose-aligned :132-195, point-aligned :69-138) vs the reference classes' own outputs."""
+    g = golden("model_baselines_gt_dpt.npz")
+    S, H, W, ov, sub = g["S"], g["H"], g["W"], g["ov"], g["sub"]
+    imgs = _gt_dpt_images(g)
+    from lsvs_b200 import specs
+    base = [("aggregator." + n, s) for n, s in specs.aggregator_spec(1, 1)] + [("camera_head." + n, s) for n, s in specs.camera_head_spec()]
+    kw = dict(depth=1, dino_depth=1, taps=(0, 0, 0, 0))
+    # (a) feature-aligned with gt_poses (B,S,4,4)
+    sd = OW.fill_state_dict(base + [("alignment_head." + n, s) for n, s in specs.alignment_head_spec()], seed=0)
+    assert abs(OW.checksum(sd) - g["fa_wsum"]) < 1e-6 * abs(g["fa_wsum"])
+    o1 = OA.feature_aligned_forward(sd, imgs[0], ov, None, gt_poses=g["fa_gt1"], **kw)
+    ctx = {"overlap_tokens": o1["overlap_tokens"], "memory_tokens": o1["memory_tokens"], "pose_enc": o1["pose_enc"]}
+    o2 = OA.feature_aligned_forward(sd, imgs[1], ov, ctx, gt_poses=g["fa_gt2"], **kw)
+    close(o1["pose_enc"], g["fa_c1_pose_enc"], 5e-4)
+    close(o2["pose_enc"], g["fa_c2_pose_enc"], 5e-4)
+    o2_plain = OA.feature_aligned_forward(sd, imgs[1], ov, ctx, **kw)
+    assert float((o2_plain["pose_enc"] - o2["pose_enc"]).abs().max()) > 1e-2  # the gt transform really replaces the averaged one
+    # (b) pose-aligned with DPT heads, without and with gt_poses (B,S,3,4); (c) point-aligned with DPT heads
+    sd = OW.fill_state_dict(base + [("point_head." + n, s) for n, s in specs.dpt_head_spec(2048, 4)]
+                            + [("depth_head." + n, s) for n, s in specs.dpt_head_spec(2048, 2)], seed=2)
+    assert abs(OW.checksum(sd) - g["pa_wsum"]) < 1e-6 * abs(g["pa_wsum"])
+    dpt = []
+    for img in imgs:  # the heads depend only on the chunk's own images
+        tp = OA.pose_aligned_forward(sd, img, ov, None, **kw)["taps"]
+        dpt.append(OF.dpt_head_forward(sd, "depth_head.", tp, (H, W), activation="exp") + OF.dpt_head_forward(sd, "point_head.", tp, (H, W), activation="inv_log"))
+    for tag in ("pa", "pagt"):
+        ctx = None
+        for ci in (1, 2):
+            d, dc, pp, pc = dpt[ci - 1]
+            gt = g[f"pagt_gt{ci}"] if tag == "pagt" else None
+            o = OA.pose_aligned_forward(sd, imgs[ci - 1], ov, ctx, gt_poses=gt, raw_points=pp, raw_depth=d, **kw)
+            ctx = {"pose_enc": o["pose_enc"]}
+            close(o["pose_enc"], g[f"{tag}_c{ci}_pose_enc"], 5e-4)
+            close(o["depth"][:, :, ::sub, ::sub], g[f"{tag}_c{ci}_depth"], 5e-4)
+            close(o["world_points"][:, :, ::sub, ::sub], g[f"{tag}_c{ci}_world_points"], 5e-4)
+            if gt is not None:
+                close(o["batch_scales"], g[f"pagt_c{ci}_scale"], 1e-5)
+    ctx = None
+    for ci in (1, 2):
+        d, dc, pp, pc = dpt[ci - 1]
+        o = OA.point_aligned_forward(sd, imgs[ci - 1], ov, ctx, raw_points=pp, raw_points_conf=pc, raw_depth=d, **kw)
+        ctx = {"world_points": o["world_points"], "world_points_conf": pc}
+        close(o["pose_enc"], g[f"pt_c{ci}_pose_enc"], 2e-3)
+        close(o["world_points"][:, :, ::sub, ::sub], g[f"pt_c{ci}_world_points"], 2e-3)
+        close(o["depth"][:, :, ::sub, ::sub], g[f"pt_c{ci}_depth"], 2e-3)
+        close(o["scales"], g[f"pt_c{ci}_scale"], 1e-4)

@@ -39,7 +39,7 @@ def _encode(inputs):
 
 
 def _align(tokens, cam, ctx):
-    prev = torch.zeros(1) if ctx is None else ctx["state"]
+    prev = torch.zeros(1, device=tokens.device) if ctx is None else ctx["state"]
     state = 0.5 * prev + tokens.mean().reshape(1) + cam.reshape(1)   # depends on every earlier chunk, in order
     packet = torch.cat([state, tokens.flatten()[:3]])
     return packet, {"state": state}
@@ -161,8 +161,10 @@ def _peer_worker(rank, world, port, n_rounds, q, lag):
         res = [r.cpu() for r in pipe.flush()]
         tx.close()
         q.put((rank, res, None))
-    except Exception as e:  # noqa: BLE001
-        q.put((rank, None, repr(e)))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, None, traceback.format_exc()))
+        return
     dist.barrier()
     dist.destroy_process_group()
 
@@ -180,13 +182,18 @@ def test_peer_mailboxes_two_processes(lag):
     for p in procs:
         p.start()
     got = {}
-    for _ in range(world):
-        rank, res, err = q.get(timeout=300)
-        assert err is None, f"rank {rank}: {err}"
-        got[rank] = res
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        for _ in range(world):
+            rank, res, err = q.get(timeout=120)
+            assert err is None, f"rank {rank}: {err}"
+            got[rank] = res
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:          # a failed rank must not leave its peer spinning on a mailbox
+            if p.is_alive():
+                p.terminate()
     dev = torch.device("cuda", 0)
     ctx_, ref, k = None, {0: [], 1: []}, 0
     for j in range(n_rounds):

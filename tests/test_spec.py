@@ -40,3 +40,23 @@ def test_dpt_state_dict_matches_reference():
     mine = {k: list(v.shape) for k, v in model.state_dict().items() if k.startswith(("depth_head.", "point_head."))}
     assert len(ref) == 124 and set(mine) == set(ref)
     assert all(mine[k] == ref[k] for k in ref)
+
+
+def test_baseline_wrappers_state_dict_matches_reference():
+    """pose-aligned / point-aligned `VGGT` with their DPT heads: keys and shapes of the reference classes
+    (poseAligned_wrapped_vggt.py:16-25, pointAligned_wrapped_vggt.py:14-22; enable_track=False)."""
+    from aligned_vggt.models.pointAligned_wrapped_vggt import VGGT as PointVGGT
+    from aligned_vggt.models.poseAligned_wrapped_vggt import VGGT as PoseVGGT
+    from conftest import GOLDEN
+    ref = json.load(open(os.path.join(GOLDEN, "state_dict_spec_baselines.json")))
+    for cls in (PoseVGGT, PointVGGT):
+        with torch.device("meta"):
+            model = cls(enable_track=False, depth=1, patch_embed_depth=1)
+        mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+        assert set(mine) == set(ref), (cls, sorted(set(mine) ^ set(ref))[:5])
+        assert all(mine[k] == ref[k] for k in ref)
+
+        class Cfg:
+            enable_camera, enable_point, enable_depth, enable_track = True, False, True, False
+        model.set_config(Cfg)
+        assert model.point_head is None and model.depth_head is not None and model.camera_head is not None
