@@ -1,4 +1,4 @@
-"""Drop-in for the hot-path part of the reference's aligned_vggt/utils/alignment.py (:491-594).
+"""Drop-in for the hot-path part of the reference's aligned_vggt/utils/alignment.py (:244-323, :428-594).
 
 Same function names, argument meaning and error behaviour; the arithmetic runs in liblsvs_b200.so
 (csrc/sim3.cu) on the tensors' CUDA device.  No CPU fallback: CPU tensors raise.
@@ -79,6 +79,45 @@ def scale_depth(depth: torch.Tensor, scales: torch.Tensor) -> torch.Tensor:
     _n.check(_n.lib().lsvs_scale_rows(_n.ptr(d), _n.ptr(_prep(scales, "scales").reshape(B)), _n.ptr(out), ctypes.c_int(B),
                                       ctypes.c_longlong(d.numel() // B), _n.stream_ptr()), "scale_rows")
     return out
+
+
+def _as_device_f32(x, device) -> torch.Tensor:
+    """numpy array / python scalars / tensor -> fp32 tensor on `device` (the reference does torch.from_numpy(...).float().to(device))."""
+    return torch.as_tensor(x).to(device=device, dtype=torch.float32)
+
+
+def apply_sim3_alignment(alignment_transforms, alignment_scales, pose_encodings: torch.Tensor, images_size: tuple,
+                         points: torch.Tensor = None, depths: torch.Tensor = None) -> tuple:
+    """reference alignment.py:449-489.  alignment_transforms (B,4,4) and alignment_scales (B,) numpy arrays (tensors accepted);
+    pose_encodings (B,S,9) -> aligned (w2c -> Sim(3) in camera-to-world space -> encoding, one kernel); points (B,S,H,W,3)
+    transformed; depths (B,S,H,W,1) scaled IN PLACE like the reference's `depths *= ...`."""
+    dev = pose_encodings.device
+    T = _as_device_f32(alignment_transforms, dev)
+    s = _as_device_f32(alignment_scales, dev)
+    B = T.shape[0]
+    from lsvs_b200.engine import pose_enc_apply_sim3
+    pose_encodings = pose_enc_apply_sim3(pose_encodings, T, s.reshape(B), images_size)
+    if points is not None:
+        points = apply_sim3_alignment_on_point_maps(points, T, s.reshape(B))
+    if depths is not None:
+        if depths.dtype == torch.float32 and depths.is_contiguous() and depths.is_cuda:
+            _n.check(_n.lib().lsvs_scale_rows(_n.ptr(depths), _n.ptr(s.reshape(B).contiguous()), _n.ptr(depths), ctypes.c_int(B),
+                                              ctypes.c_longlong(depths.numel() // B), _n.stream_ptr()), "scale_rows")
+        else:
+            depths.copy_(scale_depth(depths, s))
+    return pose_encodings, points, depths
+
+
+def apply_sim3_alignment_on_dict(pred: dict, images_size: tuple, alignment_poses, alignment_scales) -> None:
+    """reference alignment.py:428-447: Sim(3) applied to pred["pose_enc"], and to "world_points" / "depth" when present."""
+    pose, pts, dep = apply_sim3_alignment(alignment_poses, alignment_scales, pred["pose_enc"], images_size,
+                                          pred["world_points"] if "world_points" in pred else None,
+                                          pred["depth"] if "depth" in pred else None)
+    pred["pose_enc"] = pose
+    if "world_points" in pred:
+        pred["world_points"] = pts
+    if "depth" in pred:
+        pred["depth"] = dep
 
 
 def scale_align_from_depths(predictions: dict, batch: dict) -> None:

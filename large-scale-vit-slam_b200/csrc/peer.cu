@@ -31,7 +31,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 
 // Returns when (int)(*flag - value) >= 0.  On timeout sets *status = 1 and returns (the stream keeps going and the host
-// reports the failure at the next lsvs_peer_status check) instead of hanging the device.
+// reads the status word at its next flush) instead of hanging the device.
 __global__ void peer_wait_kernel(const unsigned* flag, unsigned value, unsigned* status, unsigned long long timeout_ns) {
   if (threadIdx.x != 0) return;
   const unsigned long long t0 = global_ns();

@@ -507,6 +507,15 @@ def pose_enc_apply_sim3(pose_enc: torch.Tensor, image_hw, T: torch.Tensor, s: to
     return OF.extri_intri_to_pose_encoding(aligned, intr, image_size_hw=image_hw)
 
 
+def apply_sim3_alignment(T: torch.Tensor, s: torch.Tensor, pose_enc: torch.Tensor, image_hw, points: Optional[torch.Tensor] = None,
+                         depths: Optional[torch.Tensor] = None):
+    """apply_sim3_alignment — /root/reference/aligned_vggt/utils/alignment.py:449-489 (out of place)."""
+    B = T.shape[0]
+    return (pose_enc_apply_sim3(pose_enc, image_hw, T, s),
+            None if points is None else apply_sim3_points(points, T, s),
+            None if depths is None else depths * s.view(B, 1, 1, 1, 1))
+
+
 # ----------------------------------------------------------------------------- evaluation-side geometry (SURVEY §8f rank 3)
 def unproject_depth(depth_map: torch.Tensor, extrinsics: torch.Tensor, intrinsics: torch.Tensor) -> torch.Tensor:
     """unproject_depth_map_to_point_map — /root/reference/aligned_vggt/utils/geometry.py:39-75.

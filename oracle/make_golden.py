@@ -433,6 +433,28 @@ def case_baselines_gt_dpt():
     save("model_baselines_gt_dpt.npz", **arrs)
 
 
+def case_sim3_dict():
+    """apply_sim3_alignment / apply_sim3_alignment_on_dict (alignment.py:428-489), real reference functions."""
+    print("[apply_sim3_alignment_on_dict]")
+    from aligned_vggt.utils.alignment import apply_sim3_alignment_on_dict
+    B, S, H, W = 2, 3, 28, 42
+    q = rnd(21, B, 4)
+    T = torch.eye(4).repeat(B, 1, 1)
+    T[:, :3, :3] = OF.quat_to_mat(q / q.norm(dim=-1, keepdim=True))
+    T[:, :3, 3] = rnd(22, B, 3, scale=3.0)
+    s = torch.tensor([0.6, 2.3])
+    enc = torch.cat([rnd(23, B, S, 3), torch.nn.functional.normalize(rnd(24, B, S, 4), dim=-1),
+                     0.5 + 0.3 * torch.rand(B, S, 2, generator=torch.Generator().manual_seed(25))], -1)
+    pts, dep = rnd(26, B, S, H, W, 3, scale=5.0), rnd(27, B, S, H, W, 1).abs() + 0.1
+    pred = {"pose_enc": enc.clone(), "world_points": pts.clone(), "depth": dep.clone()}
+    apply_sim3_alignment_on_dict(pred, (H, W), T.numpy(), s.numpy())
+    o = OA.apply_sim3_alignment(T, s, enc, (H, W), pts, dep)
+    for k, v in zip(("pose_enc", "world_points", "depth"), o):
+        check(f"sim3 dict {k}", v, pred[k], 1e-5)
+    save("sim3_dict.npz", T=T, s=s, enc=enc, pts=pts, dep=dep, H=H, W=W, out_pose_enc=pred["pose_enc"], out_world_points=pred["world_points"],
+         out_depth=pred["depth"])
+
+
 def case_eval_geometry():
     """unproject_depth_map_to_point_map, scale_align_from_depths, convertDictListsToTensors of the reference."""
     print("[evaluation-side geometry]")
@@ -493,7 +515,7 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     cases = {"spec": case_spec, "layers": case_layers, "geometry": case_geometry, "head": case_head, "model_small": case_model_small,
              "pose_aligned": case_pose_aligned_small, "model_dpt_small": case_model_dpt_small, "eval_geometry": case_eval_geometry,
-             "baselines_gt_dpt": case_baselines_gt_dpt}
+             "baselines_gt_dpt": case_baselines_gt_dpt, "sim3_dict": case_sim3_dict}
     if args.full:
         cases["model_full"] = case_model_full
     for name, fn in cases.items():

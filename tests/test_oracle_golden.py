@@ -243,3 +243,12 @@ def test_gt_poses_and_baselines_with_dpt_golden(golden):
         close(o["world_points"][:, :, ::sub, ::sub], g[f"pt_c{ci}_world_points"], 2e-3)
         close(o["depth"][:, :, ::sub, ::sub], g[f"pt_c{ci}_depth"], 2e-3)
         close(o["scales"], g[f"pt_c{ci}_scale"], 1e-4)
+
+
+def test_sim3_dict_golden(golden):
+    """apply_sim3_alignment (alignment.py:449-489) restatement vs the reference function's outputs."""
+    g = golden("sim3_dict.npz")
+    pose, pts, dep = OA.apply_sim3_alignment(g["T"], g["s"], g["enc"], (g["H"], g["W"]), g["pts"], g["dep"])
+    close(pose, g["out_pose_enc"], 1e-5)
+    close(pts, g["out_world_points"], 1e-5)
+    close(dep, g["out_depth"], 1e-6)

@@ -88,3 +88,21 @@ def test_depth_scale_and_poses():
     assert rel(got, OA.apply_sim3_w2c(extr, T, s)) < TOL
     c2w = OA.inv_se3(extr)
     assert rel(A.apply_sim3_alignment_on_c2w(c2w.cuda(), T.cuda(), s.cuda()).cpu(), OA.apply_sim3_c2w(c2w, T, s)) < TOL
+
+
+def test_apply_sim3_alignment_on_dict_golden(golden):
+    """reference alignment.py:428-489: numpy transforms / scales, pose encodings + points + depth (depth in place)."""
+    from aligned_vggt.utils import alignment as A
+    from parity_util import ROT_DEG, TRANS_REL, pose_metrics, scalar_rel
+    g = golden("sim3_dict.npz")
+    dep = g["dep"].cuda()
+    pred = {"pose_enc": g["enc"].cuda(), "world_points": g["pts"].cuda(), "depth": dep}
+    A.apply_sim3_alignment_on_dict(pred, (g["H"], g["W"]), g["T"].numpy(), g["s"].numpy())
+    m = pose_metrics(pred["pose_enc"], g["out_pose_enc"])
+    assert m["trans_rel"] < TRANS_REL and m["rot_deg"] < ROT_DEG and scalar_rel(pred["pose_enc"][..., 7:], g["out_pose_enc"][..., 7:]) < 1e-5
+    assert float((pred["world_points"].cpu() - g["out_world_points"]).abs().max()) <= 1e-5 * float(g["out_world_points"].abs().max())
+    assert pred["depth"].data_ptr() == dep.data_ptr()                       # scaled in place like `depths *= ...` (:487)
+    assert float((dep.cpu() - g["out_depth"]).abs().max()) <= 1e-6 * float(g["out_depth"].abs().max())
+    only_pose = {"pose_enc": g["enc"].cuda()}
+    A.apply_sim3_alignment_on_dict(only_pose, (g["H"], g["W"]), g["T"].numpy(), g["s"].numpy())
+    assert set(only_pose) == {"pose_enc"} and torch.equal(only_pose["pose_enc"], pred["pose_enc"])
