@@ -455,5 +455,9 @@ def model_pipeline(model, num_overlap: int, S: int, H: int, W: int, rank: int, w
             print(f"[lsvs_b200] peer mailboxes unavailable, using torch.distributed p2p: {e}", file=sys.stderr, flush=True)
     if world > 1 and tx is None:
         tx = DistTransport(rank, world, st.tokens_like, st.cam_like, st.packet_numel, fwd_group, bwd_group, device)
+        if torch.device(device).type == "cuda":
+            # NCCL serialises eager point-to-point calls per communicator; only the original schedule (chain in the same
+            # round, packet needed one chunk later) has been measured to run on it
+            lag, defer_chain = 1, False
     return ChunkPipeline(st.encode, st.align, st.apply, rank, world, head_cost=head_cost, packet_numel=st.packet_numel,
                          device=device, transport=tx, lag=lag, defer_chain=defer_chain)
