@@ -180,9 +180,18 @@ def run_b200(args):
 
     if world > 1:
         from lsvs_b200.scheduler import model_pipeline
-        fwd, bwd = dist.new_group(), dist.new_group()  # separate communicators: token traffic never queues behind result packets
-        pipe = model_pipeline(model, OVERLAP, S_CHUNK, H, W, rank, world, dev, head_cost=args.head_cost, fwd_group=fwd, bwd_group=bwd,
-                              transport=args.transport, lag=args.lag, defer_chain=not args.no_defer)
+        kw = dict(head_cost=args.head_cost, lag=args.lag, defer_chain=not args.no_defer)
+        pipe = None
+        if args.transport in ("auto", "peer"):
+            try:  # a failure here is raised on every rank together (PeerTransport.__init__), so all ranks take the same branch
+                pipe = model_pipeline(model, OVERLAP, S_CHUNK, H, W, rank, world, dev, transport="peer", **kw)
+            except Exception as e:  # noqa: BLE001
+                if args.transport == "peer":
+                    raise
+                print(f"[bench] peer mailboxes unavailable ({e}); using torch.distributed p2p", file=sys.stderr, flush=True)
+        if pipe is None:
+            fwd, bwd = dist.new_group(), dist.new_group()  # separate communicators: token traffic never queues behind result packets
+            pipe = model_pipeline(model, OVERLAP, S_CHUNK, H, W, rank, world, dev, fwd_group=fwd, bwd_group=bwd, transport="dist", **kw)
 
         def step_fn(i):  # one round: every owner rank encodes one chunk, rank 0 chains the heads
             pipe.step((imgs[i % n_bufs], raw_pts, raw_dep) if pipe.owns() else None)
