@@ -26,6 +26,20 @@ def test_argument_errors_without_gpu():
         native.check(rc, "sim3_apply_points")
 
 
+def test_new_entry_points_reject_null_arguments():
+    """lsvs_peer_* / lsvs_pose_chain_gt validate their arguments before touching CUDA."""
+    from lsvs_b200 import native
+    lib = native.lib()
+    assert lib.lsvs_peer_put(None, None, ctypes.c_size_t(16), None) == -1
+    assert lib.lsvs_peer_signal(None, ctypes.c_uint(1), None) == -1
+    assert lib.lsvs_peer_wait(None, ctypes.c_uint(1), None, ctypes.c_double(1.0), None) == -1
+    assert lib.lsvs_peer_alloc(ctypes.c_size_t(0), None) == -1
+    assert lib.lsvs_peer_free(None) == 0 and lib.lsvs_peer_close(None) == 0
+    z = ctypes.c_int(1)
+    rc = lib.lsvs_pose_chain_gt(None, None, None, None, z, z, z, z, z, z, None, ctypes.c_int(3), ctypes.c_int(3), None, None, None, None)
+    assert rc == -1 and b"gt_poses" in lib.lsvs_last_error()
+
+
 def test_no_cpu_fallback():
     import torch
     from aligned_vggt.utils import alignment as A

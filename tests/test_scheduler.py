@@ -170,11 +170,12 @@ def _peer_worker(rank, world, port, n_rounds, q, lag):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("lag", [1, 2])
-def test_peer_mailboxes_two_processes(lag):
-    """Two processes (two GPUs if the box has them, else both on cuda:0) exchange chunks and packets through the IPC
-    mailboxes for more rounds than there are slots; results equal the sequential loop on the same device."""
-    world, n_rounds = 2, 11
+@pytest.mark.parametrize("world,lag", [(2, 1), (2, 2), (3, 2), (4, 2)])
+def test_peer_mailboxes_between_processes(world, lag):
+    """`world` processes (spread over the box's GPUs, sharing cuda:0 if there is only one) exchange chunks and packets through
+    the IPC mailboxes for more rounds than there are slots; results equal the sequential loop on the same device.  world > 2:
+    several owner ranks, i.e. one inbox per owner on rank 0."""
+    n_rounds = 11
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -195,7 +196,7 @@ def test_peer_mailboxes_two_processes(lag):
             if p.is_alive():
                 p.terminate()
     dev = torch.device("cuda", 0)
-    ctx_, ref, k = None, {0: [], 1: []}, 0
+    ctx_, ref, k = None, {r: [] for r in range(world)}, 0
     for j in range(n_rounds):
         for o in sch.round_owners(j, world, 0.2):
             inp = tuple(t.to(dev) for t in _inputs(k))
