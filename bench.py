@@ -143,6 +143,68 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------- B200 arm
+class HostIO:
+    """End-to-end leg: pinned-host inputs and outputs staged over PCIe on a side stream, ordered against the compute stream
+    by events, so the copies of step i overlap the kernels of step i-1 / i+1 instead of sitting between them."""
+
+    def __init__(self, dev, host_imgs, n_slots=3):
+        self.copy = torch.cuda.Stream(device=dev)
+        self.host_imgs = host_imgs
+        self.dev_in = [torch.empty(host_imgs[0].shape, dtype=host_imgs[0].dtype, device=dev) for _ in range(n_slots)]
+        self.in_ready = [None] * n_slots   # H2D into the slot finished (recorded on the copy stream)
+        self.in_free = [None] * n_slots    # the step that read the slot finished (recorded on the compute stream)
+        self.host_out = {}
+        self.inflight = []                 # (copy-done event, source tensors) of the last device->host batches
+        self.k = 0
+
+    def upload(self):
+        """Enqueue this step's host->device input copy; returns (slot, device tensor valid on the compute stream)."""
+        j = self.k % len(self.dev_in)
+        with torch.cuda.stream(self.copy):
+            if self.in_free[j] is not None:
+                self.copy.wait_event(self.in_free[j])
+            self.dev_in[j].copy_(self.host_imgs[self.k % len(self.host_imgs)], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy)
+        self.in_ready[j] = ev
+        self.k += 1
+        torch.cuda.current_stream().wait_event(ev)
+        return j, self.dev_in[j]
+
+    def release(self, j):
+        """Call once the step that reads slot j is enqueued on the compute stream."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.in_free[j] = ev
+
+    def download(self, named):
+        """Device->host copies of (name, tensor) results once the compute stream has produced them; returns the bytes.
+        The source tensors are kept referenced until their copy has completed (cheaper than Tensor.record_stream, which makes
+        the caching allocator fall back to cudaMalloc while the blocks are in limbo)."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        nbytes = 0
+        named = list(named)
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(ev)
+            for k, t in named:
+                if k not in self.host_out or self.host_out[k].shape != t.shape:
+                    self.host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                self.host_out[k].copy_(t, non_blocking=True)
+                nbytes += t.numel() * t.element_size()
+            done = torch.cuda.Event()
+            done.record(self.copy)
+        self.inflight.append((done, [t for _, t in named]))
+        while len(self.inflight) > 2:
+            old_done, _tensors = self.inflight.pop(0)
+            old_done.synchronize()   # normally long complete: two newer batches have been issued since
+        return nbytes
+
+    def drain(self):
+        """The compute stream waits for every copy issued so far (call before the closing timing event)."""
+        torch.cuda.current_stream().wait_stream(self.copy)
+
+
 def trim_context(pred):
     """Keep only what the next chunk needs (the reference moves older chunks to the CPU, training_metrics.py:650)."""
     ctx = {}
@@ -211,6 +273,11 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if world > 1:
+        # every rank runs its encode path once before the warm-up rounds: with few warm-up rounds rank 0 (which encodes only in
+        # a share of the rounds) would otherwise meet its first Aggregator pass -- workspace allocation, kernel module loads --
+        # inside the timed region
+        pipe.encode_fn((imgs[0], raw_pts, raw_dep))
     for i in range(args.warmup):
         step_fn(i)
     barrier()
@@ -246,20 +313,19 @@ def run_b200(args):
     # ---- end to end through the public module API with HOST buffers (pinned), H2D + D2H inside the timed region
     e2e = None
     if world > 1:
-        host_img = torch.rand(1, S_CHUNK, 3, H, W).pin_memory()
-        host_out = {}
+        io = HostIO(dev, [torch.rand(1, S_CHUNK, 3, H, W).pin_memory() for _ in range(2)])
+        host_img = io.host_imgs[0]
 
         def e2e_round():
-            mine = pipe.owns()
-            pipe.step((host_img.to(dev, non_blocking=True), raw_pts, raw_dep) if mine else None)
+            if pipe.owns():
+                j, x = io.upload()
+                pipe.step((x, raw_pts, raw_dep))
+                io.release(j)
+            else:
+                pipe.step(None)
             nbytes = 0
             for res in pipe.results:  # chunks whose Sim(3) packet arrived: copy their outputs to the host
-                for k in ("pose_enc", "world_points", "depth"):
-                    t = res[k]
-                    if k not in host_out:
-                        host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-                    host_out[k].copy_(t, non_blocking=True)
-                    nbytes += t.numel() * t.element_size()
+                nbytes += io.download([(k, res[k]) for k in ("pose_enc", "world_points", "depth")])
             pipe.results.clear()
             return nbytes
         start_round = pipe.round
@@ -272,6 +338,7 @@ def run_b200(args):
         d2h_total = 0
         for _ in range(args.steps):
             d2h_total += e2e_round()
+        io.drain()
         b.record()
         barrier()
         t = torch.tensor([a.elapsed_time(b)], device=dev)
@@ -283,28 +350,17 @@ def run_b200(args):
         e2e = {"value": n_chunks_e2e * (S_CHUNK - OVERLAP) / (float(t.item()) / 1e3), "unit": "frames/s",
                "h2d_bytes_per_step": host_img.numel() * 4 * n_chunks_e2e / args.steps, "d2h_bytes_per_step": float(bt.item()) / args.steps}
     if world == 1:
-        host_imgs = [torch.rand(1, S_CHUNK, 3, H, W).pin_memory() for _ in range(2)]
+        io = HostIO(dev, [torch.rand(1, S_CHUNK, 3, H, W).pin_memory() for _ in range(2)])
+        host_imgs = io.host_imgs
         keep = ("pose_enc", "world_points", "depth")
-        host_out = {}
         state["ctx"] = trim_context(model(imgs[0], OVERLAP, None, raw_depth=raw_dep, raw_points=raw_pts))
 
         def e2e_step(i):
-            x = host_imgs[i % 2].to(dev, non_blocking=True)
+            j, x = io.upload()
             pred = model(x, OVERLAP, state["ctx"], raw_depth=raw_dep, raw_points=raw_pts)
-            d2h = 0
-            for k in keep:
-                t = pred[k][-1]
-                if k not in host_out:
-                    host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-                host_out[k].copy_(t, non_blocking=True)
-                d2h += t.numel() * t.element_size()
-            for k in ("chunk_sim3_alignment_enc", "frame_se3_alignment_enc"):
-                t = pred[k]
-                host_out.setdefault(k, torch.empty(t.shape, dtype=t.dtype).pin_memory())
-                if host_out[k].shape != t.shape:
-                    host_out[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-                host_out[k].copy_(t, non_blocking=True)
-                d2h += t.numel() * t.element_size()
+            io.release(j)
+            d2h = io.download([(k, pred[k][-1]) for k in keep]
+                              + [(k, pred[k]) for k in ("chunk_sim3_alignment_enc", "frame_se3_alignment_enc")])
             state["ctx"] = trim_context(pred)
             return d2h
         for i in range(max(1, min(args.warmup, 2))):
@@ -315,6 +371,7 @@ def run_b200(args):
         a.record()
         for i in range(args.steps):
             d2h_bytes = e2e_step(i)
+        io.drain()
         b.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
