@@ -18,7 +18,7 @@ SMs that the persistent encoder kernels need; torch.distributed isend/irecv (Dis
 tensors (tests/test_scheduler.py drives this file with stand-in stage functions) and as the multi-node option.
 """
 from collections import deque
-from typing import Callable, List, Optional
+from typing import Callable, List, Optional, Sequence
 
 import torch
 import torch.distributed as dist
@@ -80,23 +80,25 @@ class DistTransport:
             for w in works:
                 w.wait()
 
-    # owner side
-    def send_chunk(self, seq, tokens, cam):
+    # owner side (shapes: None = the fixed full-size chunk; otherwise the shapes of a shorter chunk, e.g. a sequence's tail)
+    def send_chunk(self, seq, tokens, cam, packet_numel=None):
         w1 = dist.isend(tokens, dst=0, group=self.fwd)
         w2 = dist.isend(cam, dst=0, group=self.fwd)
         self._inflight.append(([w1, w2], (tokens, cam)))
-        packet = torch.empty(self.packet_numel, dtype=torch.float32, device=cam.device)
+        packet = torch.empty(packet_numel or self.packet_numel, dtype=torch.float32, device=cam.device)
         self._packets[seq] = (dist.irecv(packet, src=0, group=self.bwd), packet)
         self._retire(keep=4)
 
-    def recv_packet(self, seq):
+    def recv_packet(self, seq, packet_numel=None):
         work, packet = self._packets.pop(seq)
         work.wait()
         return packet
 
     # alignment-rank side
-    def recv_chunk(self, owner, seq):
+    def recv_chunk(self, owner, seq, tokens_shape=None, cam_shape=None):
         t, c = self.tokens_like(), self.cam_like()
+        if tokens_shape is not None:
+            t, c = t.new_empty(tokens_shape), c.new_empty(cam_shape)
         w1 = dist.irecv(t, src=owner, group=self.fwd)
         w2 = dist.irecv(c, src=owner, group=self.fwd)
         w1.wait()
@@ -131,7 +133,8 @@ class PeerTransport:
     for a peer and nobody rendezvous.
 
     Layout.  Rank 0 owns one inbox per owner rank: [flag | slots x (cam, tokens)]; every owner rank owns one mailbox:
-    [flag | slots x packet].  Flags hold `number of messages published so far`.  A slot is reused every `slots`
+    [flag | slots x packet]; slots are sized for the largest chunk, a shorter chunk (a sequence's tail) fills a prefix.
+    Flags hold `number of messages published so far`.  A slot is reused every `slots`
     messages; that is safe when slots >= lag + 1 (lag = how many of its own chunks an owner keeps in flight before it
     waits for a packet), because receiving packet k proves that rank 0 has consumed chunk k, and an owner waits for
     packet seq - lag - 1 (stream order) before it overwrites anything belonging to message seq - slots."""
@@ -228,7 +231,7 @@ class PeerTransport:
         cannot alias raw device memory, a copy-engine copy into a fresh tensor, in stream order."""
         if self._zero_copy:
             try:
-                key = (ptr, dtype)
+                key = (ptr, dtype, tuple(shape))
                 if key not in self._views:
                     raw = torch.as_tensor(_RawCudaBytes(ptr, nbytes), device=self.device)
                     if raw.data_ptr() != ptr:
@@ -243,31 +246,45 @@ class PeerTransport:
         self._native.check(self._lib.lsvs_peer_put(out.data_ptr(), ptr, nbytes, self._native.stream_ptr()), "lsvs_peer_put")
         return out
 
+    @staticmethod
+    def _nbytes(shape, itemsize):
+        n = itemsize
+        for d in shape:
+            n *= d
+        return n
+
     # -- owner side ------------------------------------------------------------------------------
-    def send_chunk(self, seq, tokens, cam):
+    def send_chunk(self, seq, tokens, cam, packet_numel=None):
         assert tokens.is_contiguous() and cam.is_contiguous() and tokens.dtype == self.tokens_dtype and cam.dtype == torch.float32
-        assert tuple(tokens.shape) == self.tokens_shape and tuple(cam.shape) == self.cam_shape, "chunk shape differs from the mailbox layout"
+        tok_bytes, cam_bytes = tokens.numel() * tokens.element_size(), cam.numel() * 4
+        assert 0 < tok_bytes <= self.tok_bytes and 0 < cam_bytes <= self.cam_bytes, "chunk larger than the mailbox slot"
         base = self._mapped[0] + 256 + (seq % self.slots) * self.chunk_stride
-        self._put(base, cam, self.cam_bytes)
-        self._put(base + self.cam_stride, tokens, self.tok_bytes)
+        self._put(base, cam, cam_bytes)
+        self._put(base + self.cam_stride, tokens, tok_bytes)
         self._signal(self._mapped[0], seq + 1)
 
-    def recv_packet(self, seq):
+    def recv_packet(self, seq, packet_numel=None):
+        n = packet_numel or self.packet_numel
+        assert n <= self.packet_numel
         self._wait(self._local[0], seq + 1)
         ptr = self._local[0] + 256 + (seq % self.slots) * self.packet_stride
-        return self._read(ptr, 4 * self.packet_numel, torch.float32, (self.packet_numel,), private=True)
+        return self._read(ptr, 4 * n, torch.float32, (n,), private=True)
 
     # -- alignment-rank side ---------------------------------------------------------------------
-    def recv_chunk(self, owner, seq):
+    def recv_chunk(self, owner, seq, tokens_shape=None, cam_shape=None):
+        tokens_shape, cam_shape = tuple(tokens_shape or self.tokens_shape), tuple(cam_shape or self.cam_shape)
+        tok_bytes = self._nbytes(tokens_shape, self.tok_bytes // max(1, self._nbytes(self.tokens_shape, 1)))
+        cam_bytes = self._nbytes(cam_shape, 4)
+        assert tok_bytes <= self.tok_bytes and cam_bytes <= self.cam_bytes
         self._wait(self._local[owner], seq + 1)
         base = self._local[owner] + 256 + (seq % self.slots) * self.chunk_stride
-        cam = self._read(base, self.cam_bytes, torch.float32, self.cam_shape)
-        tokens = self._read(base + self.cam_stride, self.tok_bytes, self.tokens_dtype, self.tokens_shape)
+        cam = self._read(base, cam_bytes, torch.float32, cam_shape)
+        tokens = self._read(base + self.cam_stride, tok_bytes, self.tokens_dtype, tokens_shape)
         return tokens, cam
 
     def send_packet(self, owner, seq, packet):
-        assert packet.is_contiguous() and packet.dtype == torch.float32 and packet.numel() == self.packet_numel
-        self._put(self._mapped[owner] + 256 + (seq % self.slots) * self.packet_stride, packet, 4 * self.packet_numel)
+        assert packet.is_contiguous() and packet.dtype == torch.float32 and packet.numel() <= self.packet_numel
+        self._put(self._mapped[owner] + 256 + (seq % self.slots) * self.packet_stride, packet, 4 * packet.numel())
         self._signal(self._mapped[owner], seq + 1)
 
     def finish(self):
@@ -304,7 +321,11 @@ class ChunkPipeline:
 
     def __init__(self, encode_fn: Callable, align_fn: Callable, apply_fn: Callable, rank: int, world: int, *,
                  head_cost: float = 0.1, packet_numel: int = 0, tokens_like: Callable = None, cam_like: Callable = None,
-                 device=None, fwd_group=None, bwd_group=None, transport=None, lag: int = 2, defer_chain: bool = True):
+                 device=None, fwd_group=None, bwd_group=None, transport=None, lag: int = 2, defer_chain: bool = True,
+                 chunk_frames: Optional[Sequence[int]] = None, shapes_of: Optional[Callable] = None):
+        """chunk_frames: frames of every chunk of a finite sequence, in chunk order (generate_chunks); the last round is then cut
+        to the chunks that remain, and chunks may differ in length (the short tail chunk, data.py:196-203) if
+        shapes_of(frames) -> (tokens shape, cam shape, packet numel) is given."""
         self.encode_fn, self.align_fn, self.apply_fn = encode_fn, align_fn, apply_fn
         self.rank, self.world, self.head_cost = rank, world, head_cost
         self.device = device
@@ -316,42 +337,70 @@ class ChunkPipeline:
         if getattr(transport, "slots", lag + 1) < lag + 1:
             raise ValueError(f"transport has {transport.slots} slots; lag {lag} needs {lag + 1}")
         self.lag, self.defer = lag, defer_chain
+        self.chunk_frames = None if chunk_frames is None else [int(f) for f in chunk_frames]
+        self.shapes_of = shapes_of
+        self._starts = [0]                # _starts[r] = global index of the first chunk of round r
         self.round = 0
         self.ctx = None
         self.seq = 0                      # owner side: chunks this rank has encoded
-        self.pending = deque()            # owner side: (seq, inputs) awaiting their Sim(3) packet
+        self.pending = deque()            # owner side: (seq, inputs, global chunk index) awaiting their Sim(3) packet
         self._own = {}                    # rank 0: round -> (tokens, cam, inputs) of its own chunk, until chained
         self._oseq = [0] * world          # rank 0: chunks received per owner
         self._chained = 0                 # rank 0: rounds [0, _chained) have been through the chain
         self.results = []
+        self.result_chunks = []           # global chunk index of every entry of `results`
 
     # -- bookkeeping -----------------------------------------------------------------------------
+    def chunk_start(self, round_idx: int) -> int:
+        """Global index of the first chunk of round `round_idx` (chunks are dealt round by round, owners in rank order)."""
+        while len(self._starts) <= round_idx:
+            r = len(self._starts) - 1
+            self._starts.append(self._starts[r] + len(self.owners(r)))
+        return self._starts[round_idx]
+
     def owners(self, round_idx: Optional[int] = None) -> List[int]:
-        return round_owners(self.round if round_idx is None else round_idx, self.world, self.head_cost)
+        r = self.round if round_idx is None else round_idx
+        ow = round_owners(r, self.world, self.head_cost)
+        if self.chunk_frames is not None:
+            ow = ow[:max(0, len(self.chunk_frames) - self.chunk_start(r))]
+        return ow
 
     def owns(self, round_idx: Optional[int] = None) -> bool:
         return self.rank in self.owners(round_idx)
 
+    def done(self) -> bool:
+        """Finite sequences: every chunk has been dealt."""
+        return self.chunk_frames is not None and self.chunk_start(self.round) >= len(self.chunk_frames)
+
     def chunks_in_rounds(self, n_rounds: int, start: int = 0) -> int:
-        return sum(len(round_owners(j, self.world, self.head_cost)) for j in range(start, start + n_rounds))
+        return self.chunk_start(start + n_rounds) - self.chunk_start(start)
+
+    def _shapes(self, k: int):
+        if self.chunk_frames is None or self.shapes_of is None:
+            return None, None, None
+        return self.shapes_of(self.chunk_frames[k])
 
     def _apply_ready(self, keep: int):
         while len(self.pending) > keep:
-            seq, inputs = self.pending.popleft()
-            self.results.append(self.apply_fn(self.tx.recv_packet(seq), inputs))
+            seq, inputs, k = self.pending.popleft()
+            self.results.append(self.apply_fn(self.tx.recv_packet(seq, self._shapes(k)[2]), inputs))
+            self.result_chunks.append(k)
 
     def _chain_through(self, last_round: int):
         """Rank 0: run the alignment chain for every not yet chained round <= last_round, chunks in order."""
         while self._chained <= last_round:
             r = self._chained
-            for o in round_owners(r, self.world, self.head_cost):
+            for idx, o in enumerate(self.owners(r)):
+                k = self.chunk_start(r) + idx
                 if o == 0:
                     t, c, inputs = self._own.pop(r)
                 else:
-                    t, c = self.tx.recv_chunk(o, self._oseq[o])
+                    tshape, cshape, _ = self._shapes(k)
+                    t, c = self.tx.recv_chunk(o, self._oseq[o], tshape, cshape)
                 packet, self.ctx = self.align_fn(t, c, self.ctx)
                 if o == 0:
                     self.results.append(self.apply_fn(packet, inputs))
+                    self.result_chunks.append(k)
                 else:
                     self.tx.send_packet(o, self._oseq[o], packet)
                     self._oseq[o] += 1
@@ -359,18 +408,20 @@ class ChunkPipeline:
 
     # -- one round -------------------------------------------------------------------------------
     def step(self, inputs):
-        mine = self.rank in self.owners()
+        owners = self.owners()
+        mine = self.rank in owners
         if mine and inputs is None:
             raise ValueError(f"rank {self.rank} owns a chunk in round {self.round} but got no inputs")
         if self.rank == 0 and self.defer:
             self._chain_through(self.round - 1)
         if mine:
+            k = self.chunk_start(self.round) + owners.index(self.rank)
             tokens, cam = self.encode_fn(inputs)
             if self.rank == 0:
                 self._own[self.round] = (tokens, cam, inputs)
             else:
-                self.tx.send_chunk(self.seq, tokens, cam)
-                self.pending.append((self.seq, inputs))
+                self.tx.send_chunk(self.seq, tokens, cam, self._shapes(k)[2])
+                self.pending.append((self.seq, inputs, k))
                 self.seq += 1
         if self.rank == 0 and not self.defer:
             self._chain_through(self.round)
@@ -378,14 +429,33 @@ class ChunkPipeline:
         self._apply_ready(keep=self.lag)
         self.round += 1
 
-    def flush(self):
+    def flush(self, with_chunk_ids: bool = False):
         if self.rank == 0:
             self._chain_through(self.round - 1)
         self._apply_ready(keep=0)
         if self.tx is not None:
             self.tx.finish()
-        out, self.results = self.results, []
-        return out
+        out, ids = self.results, self.result_chunks
+        self.results, self.result_chunks = [], []
+        return list(zip(ids, out)) if with_chunk_ids else out
+
+
+def run_sequence(pipe: ChunkPipeline, load_chunk: Callable[[int], tuple]):
+    """The reference's chunk loop (training/run_model.py:326-338, training_metrics.py:636-657) over a finite sequence on
+    every rank of the pipeline: `pipe` was built with chunk_frames = [len(c) for c in generate_chunks(...)], load_chunk(k)
+    returns the stage inputs of chunk k and is only called on the rank that owns it.  Returns [(chunk index, result)] of the
+    chunks this rank owns, in chunk order."""
+    if pipe.chunk_frames is None:
+        raise ValueError("run_sequence needs a pipeline built with chunk_frames")
+    out = []
+    while not pipe.done():
+        owners = pipe.owners()
+        mine = pipe.chunk_start(pipe.round) + owners.index(pipe.rank) if pipe.rank in owners else None
+        pipe.step(load_chunk(mine) if mine is not None else None)
+        out += list(zip(pipe.result_chunks, pipe.results))
+        pipe.results, pipe.result_chunks = [], []
+    out += pipe.flush(with_chunk_ids=True)
+    return sorted(out, key=lambda kv: kv[0])
 
 
 # ------------------------------------------------------------------------------------------------ model binding
@@ -397,6 +467,10 @@ class ModelStages:
         self.model, self.ov, self.S, self.H, self.W, self.device = model, num_overlap, S, H, W, device
         self.P = 5 + (H // 14) * (W // 14)
         self.packet_numel = 1 + 16 + S * 9 + 8 + (S - 1) * 7
+
+    def shapes_of(self, frames: int):
+        """(tokens shape, camera-encoding shape, packet numel) of a chunk of `frames` frames."""
+        return (1, frames, self.P, 2048), (1, frames, 9), 1 + 16 + frames * 9 + 8 + (frames - 1) * 7
 
     def tokens_like(self):
         return torch.empty(1, self.S, self.P, 2048, dtype=torch.bfloat16, device=self.device)
@@ -426,7 +500,7 @@ class ModelStages:
 
     def apply(self, packet, inputs):
         from aligned_vggt.utils import alignment as al
-        S = self.S
+        S = inputs[0].shape[1]
         scale, T = packet[0:1], packet[1:17].view(1, 4, 4)
         out = {"pose_enc": packet[17:17 + S * 9].view(1, S, 9), "chunk_sim3_alignment_enc": packet[17 + S * 9:25 + S * 9].view(1, 1, 8),
                "frame_se3_alignment_enc": packet[25 + S * 9:].view(1, S - 1, 7)}
@@ -439,9 +513,10 @@ class ModelStages:
 
 def model_pipeline(model, num_overlap: int, S: int, H: int, W: int, rank: int, world: int, device, head_cost: float = 0.085,
                    fwd_group=None, bwd_group=None, transport: str = "auto", lag: int = 2, defer_chain: bool = True,
-                   handshake_group=None) -> ChunkPipeline:
+                   handshake_group=None, chunk_frames: Optional[Sequence[int]] = None) -> ChunkPipeline:
     """transport: "peer" (CUDA-IPC mailboxes, one box), "dist" (torch.distributed isend/irecv) or "auto" (peer, and
-    torch.distributed only if every rank agrees that the mailboxes could not be set up)."""
+    torch.distributed only if every rank agrees that the mailboxes could not be set up).  S = frames of the largest chunk;
+    chunk_frames = per-chunk frame counts of a finite sequence (see run_sequence), None = endless rounds of S-frame chunks."""
     st = ModelStages(model, num_overlap, S, H, W, device)
     tx = None
     if world > 1 and transport in ("auto", "peer"):
@@ -460,4 +535,5 @@ def model_pipeline(model, num_overlap: int, S: int, H: int, W: int, rank: int, w
             # round, packet needed one chunk later) has been measured to run on it
             lag, defer_chain = 1, False
     return ChunkPipeline(st.encode, st.align, st.apply, rank, world, head_cost=head_cost, packet_numel=st.packet_numel,
-                         device=device, transport=tx, lag=lag, defer_chain=defer_chain)
+                         device=device, transport=tx, lag=lag, defer_chain=defer_chain, chunk_frames=chunk_frames,
+                         shapes_of=st.shapes_of if chunk_frames is not None else None)

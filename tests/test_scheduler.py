@@ -208,3 +208,112 @@ def test_peer_mailboxes_between_processes(world, lag):
         assert len(got[r]) == len(ref[r]) > 0
         for a, b in zip(got[r], ref[r]):
             assert torch.equal(a, b)
+
+
+# ---- finite sequence with a short tail chunk (generate_chunks' last chunk, data.py:196-203): run_sequence ------------------
+FRAMES = [4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 2]     # 11 chunks; with 3 ranks the last round is cut to the chunks that remain
+
+
+def _shapes_of(frames):
+    return (frames, 5), (1, 1), 1 + frames
+
+
+def _inputs_fr(k, dev="cpu"):
+    g = torch.Generator().manual_seed(1000 + k)
+    return (torch.randn(FRAMES[k], 5, generator=g).to(dev), torch.randn(3, generator=g).to(dev))
+
+
+def _align_var(tokens, cam, ctx):
+    prev = torch.zeros(1, device=tokens.device) if ctx is None else ctx["state"]
+    state = 0.5 * prev + tokens.mean().reshape(1) + cam.reshape(1)
+    return torch.cat([state, tokens[:, 0]]), {"state": state}     # packet length follows the chunk length
+
+
+def _apply_var(packet, inputs):
+    assert packet.numel() == 1 + inputs[0].shape[0]
+    return packet[0] * inputs[1] + packet[1:].sum()
+
+
+def _sequence_reference(dev="cpu"):
+    ctx, out = None, []
+    for k in range(len(FRAMES)):
+        inp = _inputs_fr(k, dev)
+        t, c = _encode(inp)
+        packet, ctx = _align_var(t, c, ctx)
+        out.append(_apply_var(packet, inp).cpu())
+    return out
+
+
+def _sequence_worker(rank, world, port, q, use_peer):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        kw = dict(head_cost=0.2, lag=2, chunk_frames=FRAMES, shapes_of=_shapes_of)
+        if use_peer:
+            dev = torch.device("cuda", rank % torch.cuda.device_count())
+            torch.cuda.set_device(dev)
+            tx = sch.PeerTransport(rank, world, (4, 5), torch.float32, (1, 1), 5, dev, slots=3, timeout_s=60.0)
+            pipe = sch.ChunkPipeline(_encode, _align_var, _apply_var, rank, world, transport=tx, **kw)
+        else:
+            dev = "cpu"
+            pipe = sch.ChunkPipeline(_encode, _align_var, _apply_var, rank, world, packet_numel=5, tokens_like=lambda: torch.empty(4, 5),
+                                     cam_like=lambda: torch.empty(1, 1), **kw)
+        res = sch.run_sequence(pipe, lambda k: _inputs_fr(k, dev))
+        if use_peer:
+            tx.close()
+        q.put((rank, [(k, v.cpu().numpy()) for k, v in res], None))     # numpy: no fd hand-over that could outlive this process
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, None, traceback.format_exc()))
+        return
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _check_sequence(world, use_peer):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sequence_worker, args=(r, world, port, q, use_peer)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    try:
+        for _ in range(world):
+            rank, res, err = q.get(timeout=120)
+            assert err is None, f"rank {rank}: {err}"
+            got[rank] = res
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+    ref = _sequence_reference("cuda" if use_peer else "cpu")
+    seen = sorted(k for res in got.values() for k, _ in res)
+    assert seen == list(range(len(FRAMES)))                       # every chunk exactly once, tail included
+    for res in got.values():
+        assert [k for k, _ in res] == sorted(k for k, _ in res)
+        for k, v in res:
+            assert torch.equal(torch.from_numpy(v), ref[k]), k
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_run_sequence_with_short_tail_gloo(world):
+    _check_sequence(world, use_peer=False)
+
+
+@pytest.mark.gpu
+def test_run_sequence_with_short_tail_peer_mailboxes():
+    _check_sequence(3, use_peer=True)
+
+
+def test_finite_sequence_bookkeeping():
+    pipe = sch.ChunkPipeline(_encode, _align_var, _apply_var, 1, 3, transport=object(), head_cost=0.2, chunk_frames=FRAMES, shapes_of=_shapes_of)
+    dealt = [pipe.owners(r) for r in range(6)]
+    assert sum(len(o) for o in dealt) == len(FRAMES) and dealt[-1] == [] and len(dealt[-2]) <= 3
+    assert pipe.chunk_start(0) == 0 and pipe.chunks_in_rounds(6) == len(FRAMES)
+    assert pipe._shapes(10) == ((2, 5), (1, 1), 3)
+    with pytest.raises(ValueError):
+        sch.run_sequence(sch.ChunkPipeline(_encode, _align, _apply, 0, 1), lambda k: None)
