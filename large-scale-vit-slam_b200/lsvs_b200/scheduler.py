@@ -141,16 +141,22 @@ class PeerTransport:
 
     name = "CUDA-IPC peer mailboxes (copy engines + sequence flags)"
 
-    def __init__(self, rank, world, tokens_shape, tokens_dtype, cam_shape, packet_numel, device, group=None, slots=3, timeout_s=120.0):
+    def __init__(self, rank, world, tokens_shape, tokens_dtype, cam_shape, packet_numel, device, group=None, slots=3, timeout_s=120.0,
+                 backend=None):
+        """backend: object with lib() / stream_ptr() / check() / NativeError like lsvs_b200.native (the default); the CPU unit
+        tests pass an emulation of the lsvs_peer_* calls over shared host memory to exercise this class without a GPU."""
         import ctypes
         from . import native
+        native = backend or native
+        self._on_cuda = torch.device(device).type == "cuda"
         self.rank, self.world, self.slots, self.timeout_s, self.device = rank, world, slots, float(timeout_s), device
         self.tokens_shape, self.tokens_dtype, self.cam_shape, self.packet_numel = tuple(tokens_shape), tokens_dtype, tuple(cam_shape), packet_numel
         self._ct, self._native, self._lib = ctypes, native, native.lib()
-        self._lib.lsvs_peer_wait.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
-        self._lib.lsvs_peer_signal.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p]
-        self._lib.lsvs_peer_put.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
-        self._lib.lsvs_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+        if backend is None:  # ctypes prototypes of the entry points called with plain Python integers
+            self._lib.lsvs_peer_wait.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
+            self._lib.lsvs_peer_signal.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p]
+            self._lib.lsvs_peer_put.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+            self._lib.lsvs_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
         self.tok_bytes = int(torch.tensor([], dtype=tokens_dtype).element_size())
         for d in self.tokens_shape:
             self.tok_bytes *= d
@@ -189,7 +195,7 @@ class PeerTransport:
         outcome = [None] * world
         dist.all_gather_object(outcome, err, group=group)
         self._raise_any(outcome)
-        self._views, self._zero_copy = {}, True
+        self._views, self._zero_copy = {}, self._on_cuda
 
     def _raise_any(self, errors):
         errors = [e for e in errors if e]
@@ -294,7 +300,8 @@ class PeerTransport:
 
     def close(self, group=None):
         """Collective: unmap the peers' buffers, then free the local ones."""
-        torch.cuda.synchronize()
+        if self._on_cuda:
+            torch.cuda.synchronize()
         dist.barrier(group=group)
         for p in self._mapped.values():
             self._lib.lsvs_peer_close(self._ct.c_void_p(p))

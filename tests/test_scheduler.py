@@ -83,7 +83,7 @@ def _worker(rank, world, port, head_cost, n_rounds, q, lag=2, defer=True):
             k += 1
         pipe.step(mine)
     res = pipe.flush()
-    q.put((rank, [r.clone() for r in res]))
+    q.put((rank, [r.numpy().copy() for r in res]))     # numpy: nothing that needs this process alive when the parent unpickles
     dist.barrier()
     dist.destroy_process_group()
 
@@ -114,7 +114,7 @@ def test_pipeline_equals_sequential_gloo(world, head_cost, lag, defer):
         mine = [v for o, v in ref if o == r]
         assert len(mine) == len(got[r])
         for a, b in zip(mine, got[r]):
-            assert torch.allclose(a, b, atol=0, rtol=0)
+            assert torch.equal(a, torch.from_numpy(b))
     assert sum(len(v) for v in got.values()) == len(ref) == sum(len(sch.round_owners(j, world, head_cost)) for j in range(n_rounds))
 
 
@@ -142,13 +142,22 @@ def test_pipeline_single_rank_and_argument_errors():
 
 
 # ---- GPU: the CUDA-IPC mailbox transport (csrc/peer.cu) between two processes ------------------------------------------
-def _peer_worker(rank, world, port, n_rounds, q, lag):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)      # handshake only; payloads go through the mailboxes
+def _peer_device(rank, mock):
+    """CUDA device of this rank and the backend of the mailbox calls (None = liblsvs_b200.so); mock: host memory emulation."""
+    if mock:
+        import mock_peer
+        return torch.device("cpu"), mock_peer
     dev = torch.device("cuda", rank % torch.cuda.device_count())
     torch.cuda.set_device(dev)
+    return dev, None
+
+
+def _peer_worker(rank, world, port, n_rounds, q, lag, mock=False):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)      # handshake only; payloads go through the mailboxes
     try:
-        tx = sch.PeerTransport(rank, world, (4, 5), torch.float32, (1, 1), 4, dev, slots=lag + 1, timeout_s=60.0)
+        dev, backend = _peer_device(rank, mock)
+        tx = sch.PeerTransport(rank, world, (4, 5), torch.float32, (1, 1), 4, dev, slots=lag + 1, timeout_s=60.0, backend=backend)
         pipe = sch.ChunkPipeline(_encode, _align, _apply, rank, world, head_cost=0.2, transport=tx, lag=lag)
         k = 0
         for j in range(n_rounds):
@@ -158,7 +167,7 @@ def _peer_worker(rank, world, port, n_rounds, q, lag):
                     mine = tuple(t.to(dev) for t in _inputs(k))
                 k += 1
             pipe.step(mine)
-        res = [r.cpu() for r in pipe.flush()]
+        res = [r.cpu().numpy() for r in pipe.flush()]
         tx.close()
         q.put((rank, res, None))
     except Exception:  # noqa: BLE001
@@ -169,17 +178,12 @@ def _peer_worker(rank, world, port, n_rounds, q, lag):
     dist.destroy_process_group()
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("world,lag", [(2, 1), (2, 2), (3, 2), (4, 2)])
-def test_peer_mailboxes_between_processes(world, lag):
-    """`world` processes (spread over the box's GPUs, sharing cuda:0 if there is only one) exchange chunks and packets through
-    the IPC mailboxes for more rounds than there are slots; results equal the sequential loop on the same device.  world > 2:
-    several owner ranks, i.e. one inbox per owner on rank 0."""
+def _check_peer_mailboxes(world, lag, mock):
     n_rounds = 11
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, n_rounds, q, lag)) for r in range(world)]
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, n_rounds, q, lag, mock)) for r in range(world)]
     for p in procs:
         p.start()
     got = {}
@@ -195,7 +199,7 @@ def test_peer_mailboxes_between_processes(world, lag):
         for p in procs:          # a failed rank must not leave its peer spinning on a mailbox
             if p.is_alive():
                 p.terminate()
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cpu") if mock else torch.device("cuda", 0)
     ctx_, ref, k = None, {r: [] for r in range(world)}, 0
     for j in range(n_rounds):
         for o in sch.round_owners(j, world, 0.2):
@@ -207,7 +211,23 @@ def test_peer_mailboxes_between_processes(world, lag):
     for r in range(world):
         assert len(got[r]) == len(ref[r]) > 0
         for a, b in zip(got[r], ref[r]):
-            assert torch.equal(a, b)
+            assert torch.equal(torch.from_numpy(a), b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,lag", [(2, 1), (2, 2), (3, 2), (4, 2)])
+def test_peer_mailboxes_between_processes(world, lag):
+    """`world` processes (spread over the box's GPUs, sharing cuda:0 if there is only one) exchange chunks and packets through
+    the IPC mailboxes for more rounds than there are slots; results equal the sequential loop on the same device.  world > 2:
+    several owner ranks, i.e. one inbox per owner on rank 0."""
+    _check_peer_mailboxes(world, lag, mock=False)
+
+
+@pytest.mark.parametrize("world,lag", [(2, 1), (3, 2)])
+def test_peer_mailbox_protocol_on_host_memory(world, lag):
+    """The same exchange with the lsvs_peer_* calls emulated over shared host memory (tests/mock_peer.py): layout, slot reuse and
+    flag arithmetic of PeerTransport in the CPU suite."""
+    _check_peer_mailboxes(world, lag, mock=True)
 
 
 # ---- finite sequence with a short tail chunk (generate_chunks' last chunk, data.py:196-203): run_sequence ------------------
@@ -244,15 +264,14 @@ def _sequence_reference(dev="cpu"):
     return out
 
 
-def _sequence_worker(rank, world, port, q, use_peer):
+def _sequence_worker(rank, world, port, q, use_peer, mock=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         kw = dict(head_cost=0.2, lag=2, chunk_frames=FRAMES, shapes_of=_shapes_of)
         if use_peer:
-            dev = torch.device("cuda", rank % torch.cuda.device_count())
-            torch.cuda.set_device(dev)
-            tx = sch.PeerTransport(rank, world, (4, 5), torch.float32, (1, 1), 5, dev, slots=3, timeout_s=60.0)
+            dev, backend = _peer_device(rank, mock)
+            tx = sch.PeerTransport(rank, world, (4, 5), torch.float32, (1, 1), 5, dev, slots=3, timeout_s=60.0, backend=backend)
             pipe = sch.ChunkPipeline(_encode, _align_var, _apply_var, rank, world, transport=tx, **kw)
         else:
             dev = "cpu"
@@ -270,11 +289,11 @@ def _sequence_worker(rank, world, port, q, use_peer):
     dist.destroy_process_group()
 
 
-def _check_sequence(world, use_peer):
+def _check_sequence(world, use_peer, mock=False):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_sequence_worker, args=(r, world, port, q, use_peer)) for r in range(world)]
+    procs = [ctx.Process(target=_sequence_worker, args=(r, world, port, q, use_peer, mock)) for r in range(world)]
     for p in procs:
         p.start()
     got = {}
@@ -290,7 +309,7 @@ def _check_sequence(world, use_peer):
         for p in procs:
             if p.is_alive():
                 p.terminate()
-    ref = _sequence_reference("cuda" if use_peer else "cpu")
+    ref = _sequence_reference("cuda" if use_peer and not mock else "cpu")
     seen = sorted(k for res in got.values() for k, _ in res)
     assert seen == list(range(len(FRAMES)))                       # every chunk exactly once, tail included
     for res in got.values():
@@ -307,6 +326,10 @@ def test_run_sequence_with_short_tail_gloo(world):
 @pytest.mark.gpu
 def test_run_sequence_with_short_tail_peer_mailboxes():
     _check_sequence(3, use_peer=True)
+
+
+def test_run_sequence_with_short_tail_mailbox_protocol_on_host_memory():
+    _check_sequence(3, use_peer=True, mock=True)
 
 
 def test_finite_sequence_bookkeeping():
