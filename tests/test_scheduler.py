@@ -386,3 +386,26 @@ def test_finite_sequence_bookkeeping():
     assert pipe._shapes(10) == ((2, 5), (1, 1), 3)
     with pytest.raises(ValueError):
         sch.run_sequence(sch.ChunkPipeline(_encode, _align, _apply, 0, 1), lambda k: None)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_config4_dealing(world):
+    """BASELINE config 4 (1000 frames, 32-frame chunks, 8 overlap): 42 chunks, every output frame exactly once, each chunk dealt to
+    exactly one rank; with 8 ranks the alignment rank encodes in about a third of the rounds (head_cost 0.085)."""
+    chunks = sch.generate_chunks(1000, "chunk_overlap", 32, 8)
+    frames = [len(c) for c in chunks]
+    assert len(chunks) == 42 and frames[-1] == 16 and sum(frames) == 1328
+    new = [c if i == 0 else c[8:] for i, c in enumerate(chunks)]
+    assert [f for c in new for f in c] == list(range(1000))
+    pipe = sch.ChunkPipeline(_encode, _align, _apply, 0, world, transport=object() if world > 1 else None, head_cost=0.085,
+                             chunk_frames=frames)
+    dealt, r = [], 0
+    while pipe.chunk_start(r) < len(frames):
+        dealt.append(pipe.owners(r))
+        r += 1
+    assert sum(len(o) for o in dealt) == 42 and pipe.owners(r) == []
+    per_rank = [sum(o.count(k) for o in dealt) for k in range(world)]
+    assert sum(per_rank) == 42 and all(n > 0 for n in per_rank)
+    if world == 8:
+        assert per_rank[0] in (1, 2) and max(per_rank[1:]) - min(per_rank[1:]) <= 1     # rank 0 mostly aligns
+    assert pipe.shapes_of is None and pipe._shapes(41) == (None, None, None)
