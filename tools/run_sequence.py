@@ -26,6 +26,7 @@ ap.add_argument("--chunk", type=int, default=32)
 ap.add_argument("--overlap", type=int, default=8)
 ap.add_argument("--hw", type=int, nargs=2, default=[154, 518])
 ap.add_argument("--head-cost", type=float, default=0.085)
+ap.add_argument("--check", action="store_true", help="rank 0 re-runs the sequence alone and compares every chunk's aligned poses")
 args = ap.parse_args()
 
 world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
@@ -52,8 +53,11 @@ def load_chunk(k):
     return torch.rand(1, S, 3, H, W, device=dev, generator=g), pts[:, :S].contiguous(), dep[:, :S].contiguous()
 
 
-def one_pass():
-    pipe = model_pipeline(model, args.overlap, S_max, H, W, rank, world, dev, head_cost=args.head_cost, chunk_frames=frames_of)
+def one_pass(solo=False):
+    r, w = (0, 1) if solo else (rank, world)
+    pipe = model_pipeline(model, args.overlap, S_max, H, W, r, w, dev, head_cost=args.head_cost, chunk_frames=frames_of)
+    if solo:
+        return 0.0, run_sequence(pipe, load_chunk)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -77,8 +81,21 @@ if world > 1:
     dist.all_gather_object(table, owned)
     owned = sorted(k for t in table for k in t)
 assert owned == list(range(len(chunks))), "every chunk must come back exactly once"
+max_dev = None
+if args.check and world > 1:
+    # the sharded run must reproduce the sequential chunk loop: same poses for every chunk (split-K reduce-adds make the encoder
+    # reproducible only to rounding, hence a tolerance instead of bit equality)
+    mine = [(k, r["pose_enc"].cpu()) for k, r in res]
+    table = [None] * world
+    dist.all_gather_object(table, mine)
+    if rank == 0:
+        got = dict(kv for t in table for kv in t)
+        _, solo = one_pass(solo=True)
+        max_dev = max(float((got[k] - r["pose_enc"].cpu()).abs().max()) for k, r in solo)
+        assert max_dev < 1e-3, f"sharded run deviates from the sequential loop: {max_dev}"
+    dist.barrier()
 if rank == 0:
-    print(json.dumps({"config": f"{args.frames} frames, {args.chunk}-frame chunks, {args.overlap} overlap, {H}x{W}", "n_gpus": world,
+    print(json.dumps({"max_pose_enc_deviation_vs_sequential": max_dev, "config": f"{args.frames} frames, {args.chunk}-frame chunks, {args.overlap} overlap, {H}x{W}", "n_gpus": world,
                       "chunks": len(chunks), "tail_chunk_frames": frames_of[-1], "seconds": ms / 1e3,
                       "output_frames_per_s": args.frames / (ms / 1e3), "frame_forwards_per_s": sum(frames_of) / (ms / 1e3)}), flush=True)
 if world > 1:
