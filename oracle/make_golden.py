@@ -433,6 +433,38 @@ def case_baselines_gt_dpt():
     save("model_baselines_gt_dpt.npz", **arrs)
 
 
+def case_model_ragged():
+    """Chunks of different length through the REFERENCE FeatureAlignedVGGT with context: a full chunk, a shorter tail chunk
+    (generate_chunks' last chunk, data.py:196-203) and a chunk no longer than num_overlap (overlap falls back to S-1, :93)."""
+    print("[FeatureAlignedVGGT, ragged chunks S = 4, 3, 2 with overlap 2, depth 1/1, 56x84]")
+    from aligned_vggt.models.featureAligned_vggt import FeatureAlignedVGGT
+    os.environ["VGGT_SHIM_DEPTH"] = "1,1"
+    with torch.device("meta"):
+        model = FeatureAlignedVGGT(enable_point=False, enable_depth=False, enable_track=False)
+    sd = OW.fill_state_dict(OW.spec_of(model), seed=0)
+    model = model.to_empty(device="cpu")
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    taps = (0, 0, 0, 0)
+    model.intermediate_layer_indices = list(taps)
+    H, W, ov, lens = 56, 84, 2, (4, 3, 2)
+    imgs = [torch.from_numpy(np.random.Generator(np.random.PCG64(700 + i)).random((1, S, 3, H, W), dtype=np.float32)) for i, S in enumerate(lens)]
+    arrs = {"H": H, "W": W, "ov": ov, "lens": np.array(lens), "wsum": OW.checksum(sd)}
+    ref, ctx = None, None
+    for ci, img in enumerate(imgs, 1):
+        ref = model(img, ov, ref)
+        snap = {"pose_enc": ref["pose_enc"][-1], "memory_tokens": ref["memory_tokens"][-1], "overlap_tokens": ref["overlap_tokens"],
+                "chunk_sim3_alignment_enc": ref["chunk_sim3_alignment_enc"][:, -1:],
+                "frame_se3_alignment_enc": ref["frame_se3_alignment_enc"][:, -(img.shape[1] - 1):]}
+        o = OA.feature_aligned_forward(sd, img, ov, ctx, depth=1, dino_depth=1, taps=taps)
+        ctx = {"overlap_tokens": o["overlap_tokens"], "memory_tokens": o["memory_tokens"], "pose_enc": o["pose_enc"]}
+        for k, v in snap.items():
+            check(f"ragged c{ci} {k}", o[k], v, 5e-4)
+            arrs[f"c{ci}_{k}"] = v[..., ::8].contiguous() if k == "overlap_tokens" else v.clone()
+    arrs["sample_stride"] = 8
+    save("model_ragged_small.npz", **arrs)
+
+
 def case_sim3_dict():
     """apply_sim3_alignment / apply_sim3_alignment_on_dict (alignment.py:428-489), real reference functions."""
     print("[apply_sim3_alignment_on_dict]")
@@ -515,7 +547,7 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     cases = {"spec": case_spec, "layers": case_layers, "geometry": case_geometry, "head": case_head, "model_small": case_model_small,
              "pose_aligned": case_pose_aligned_small, "model_dpt_small": case_model_dpt_small, "eval_geometry": case_eval_geometry,
-             "baselines_gt_dpt": case_baselines_gt_dpt, "sim3_dict": case_sim3_dict}
+             "baselines_gt_dpt": case_baselines_gt_dpt, "sim3_dict": case_sim3_dict, "model_ragged": case_model_ragged}
     if args.full:
         cases["model_full"] = case_model_full
     for name, fn in cases.items():

@@ -252,3 +252,24 @@ def test_sim3_dict_golden(golden):
     close(pose, g["out_pose_enc"], 1e-5)
     close(pts, g["out_world_points"], 1e-5)
     close(dep, g["out_depth"], 1e-6)
+
+
+def test_ragged_chunks_golden(golden):
+    """Chunks of 4, 3 and 2 frames chained with overlap 2 (short tail chunk; S <= num_overlap -> overlap S-1,
+    featureAligned_vggt.py:93) vs the reference model's outputs."""
+    g = golden("model_ragged_small.npz")
+    from lsvs_b200 import specs
+    spec = [("aggregator." + n, s) for n, s in specs.aggregator_spec(1, 1)] + [("camera_head." + n, s) for n, s in specs.camera_head_spec()] + \
+           [("alignment_head." + n, s) for n, s in specs.alignment_head_spec()]
+    sd = OW.fill_state_dict(spec, seed=0)
+    assert abs(OW.checksum(sd) - g["wsum"]) < 1e-6 * abs(g["wsum"])
+    H, W, ov, st = g["H"], g["W"], g["ov"], g["sample_stride"]
+    ctx = None
+    for ci, S in enumerate(g["lens"].tolist(), 1):
+        img = torch.from_numpy(np.random.Generator(np.random.PCG64(700 + ci - 1)).random((1, S, 3, H, W), dtype=np.float32))
+        o = OA.feature_aligned_forward(sd, img, ov, ctx, depth=1, dino_depth=1, taps=(0, 0, 0, 0))
+        ctx = {"overlap_tokens": o["overlap_tokens"], "memory_tokens": o["memory_tokens"], "pose_enc": o["pose_enc"]}
+        assert o["overlap_tokens"].shape[1] == 1 + min(ov, S - 1) and o["frame_se3_alignment_enc"].shape == (1, S - 1, 7)
+        for k in ("pose_enc", "memory_tokens", "chunk_sim3_alignment_enc", "frame_se3_alignment_enc"):
+            close(o[k], g[f"c{ci}_{k}"], 5e-4)
+        close(o["overlap_tokens"][..., ::st], g[f"c{ci}_overlap_tokens"], 5e-4)
