@@ -232,42 +232,6 @@ def test_peer_mailboxes_between_processes(world, lag):
     _check_peer_mailboxes(world, lag, mock=False)
 
 
-@pytest.mark.gpu
-def test_peer_primitives_single_process():
-    """lsvs_peer_* on one GPU, one stream, no cross-kernel waiting: copy-engine put into an exportable buffer, publish, a wait
-    that is already satisfied, and the bounded wait for a message that never comes (reported through the status word)."""
-    import ctypes
-    from lsvs_b200 import native
-    lib = native.lib()
-    lib.lsvs_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
-    lib.lsvs_peer_put.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
-    lib.lsvs_peer_signal.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p]
-    lib.lsvs_peer_wait.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
-    p = ctypes.c_void_p()
-    native.check(lib.lsvs_peer_alloc(4096, ctypes.byref(p)), "alloc")
-    base = int(p.value)
-    try:
-        src = torch.arange(256, dtype=torch.float32, device="cuda")
-        out = torch.empty(256, dtype=torch.float32, device="cuda")
-        status = torch.zeros(1, dtype=torch.int32, device="cuda")
-        st = native.stream_ptr()
-        native.check(lib.lsvs_peer_put(base + 256, src.data_ptr(), 1024, st), "put")
-        native.check(lib.lsvs_peer_signal(base, 3, st), "signal")
-        native.check(lib.lsvs_peer_wait(base, 3, status.data_ptr(), 5.0, st), "wait")   # published: returns at once
-        native.check(lib.lsvs_peer_wait(base, 2, status.data_ptr(), 5.0, st), "wait")   # an older message: satisfied too
-        native.check(lib.lsvs_peer_put(out.data_ptr(), base + 256, 1024, st), "put")
-        torch.cuda.synchronize()
-        assert torch.equal(out, src) and int(status.item()) == 0
-        native.check(lib.lsvs_peer_wait(base, 4, status.data_ptr(), 0.05, st), "wait")  # never published: gives up after 50 ms
-        torch.cuda.synchronize()
-        assert int(status.item()) == 1
-        handle = (ctypes.c_ubyte * 64)()
-        native.check(lib.lsvs_peer_export(ctypes.c_void_p(base), handle), "export")
-        assert any(handle)
-    finally:
-        lib.lsvs_peer_free(ctypes.c_void_p(base))
-
-
 @pytest.mark.parametrize("world,lag", [(2, 1), (3, 2)])
 def test_peer_mailbox_protocol_on_host_memory(world, lag):
     """The same exchange with the lsvs_peer_* calls emulated over shared host memory (tests/mock_peer.py): layout, slot reuse and
