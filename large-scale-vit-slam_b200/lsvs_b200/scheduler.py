@@ -468,12 +468,14 @@ def run_sequence(pipe: ChunkPipeline, load_chunk: Callable[[int], tuple]):
 # ------------------------------------------------------------------------------------------------ model binding
 class ModelStages:
     """Stage functions of ChunkPipeline for a FeatureAlignedVGGT drop-in (batch size 1 per chunk).
-    inputs = (images (1,S,3,H,W), raw_points (1,S,H,W,3) | None, raw_depth (1,S,H,W,1) | None)."""
+    inputs = (images (1,S,3,H,W), raw_points (1,S,H,W,3) | None, raw_depth (1,S,H,W,1) | None); with None and a model that has its
+    DPT heads, the owner computes the maps itself (results then also carry world_points_conf / depth_conf)."""
 
     def __init__(self, model, num_overlap: int, S: int, H: int, W: int, device):
         self.model, self.ov, self.S, self.H, self.W, self.device = model, num_overlap, S, H, W, device
         self.P = 5 + (H // 14) * (W // 14)
         self.packet_numel = 1 + 16 + S * 9 + 8 + (S - 1) * 7
+        self._maps = {}   # id(inputs) -> DPT head outputs of a chunk whose packet has not arrived yet
 
     def shapes_of(self, frames: int):
         """(tokens shape, camera-encoding shape, packet numel) of a chunk of `frames` frames."""
@@ -487,9 +489,20 @@ class ModelStages:
 
     def encode(self, inputs):
         images = inputs[0]
-        tokens_list, _ = self.model.aggregator(images)
-        last = tokens_list[self.model.intermediate_layer_indices[-1]]
-        cam = self.model.camera_head([last])[-1]
+        m = self.model
+        tokens_list, patch_start_idx = m.aggregator(images)
+        taps = [tokens_list[i] for i in m.intermediate_layer_indices]
+        last = taps[-1]
+        cam = m.camera_head([last])[-1]
+        # DPT heads of the model (featureAligned_vggt.py:166-168, :183-185) run on the chunk's owner when no stand-in maps are given;
+        # their outputs wait here for the chunk's Sim(3) packet
+        maps = {}
+        if inputs[2] is None and getattr(m, "depth_head", None) is not None:
+            maps["depth"], maps["depth_conf"] = m.depth_head(taps, images=images, patch_start_idx=patch_start_idx)
+        if inputs[1] is None and getattr(m, "point_head", None) is not None:
+            maps["points"], maps["points_conf"] = m.point_head(taps, images=images, patch_start_idx=patch_start_idx)
+        if maps:
+            self._maps[id(inputs)] = maps
         return last.to(torch.bfloat16), cam
 
     def align(self, tokens, cam, ctx):
@@ -511,10 +524,16 @@ class ModelStages:
         scale, T = packet[0:1], packet[1:17].view(1, 4, 4)
         out = {"pose_enc": packet[17:17 + S * 9].view(1, S, 9), "chunk_sim3_alignment_enc": packet[17 + S * 9:25 + S * 9].view(1, 1, 8),
                "frame_se3_alignment_enc": packet[25 + S * 9:].view(1, S - 1, 7)}
-        if inputs[1] is not None:
-            out["world_points"] = al.apply_sim3_alignment_on_point_maps(inputs[1], T, scale)
-        if inputs[2] is not None:
-            out["depth"] = al.scale_depth(inputs[2], scale)
+        maps = self._maps.pop(id(inputs), {})
+        pts = inputs[1] if inputs[1] is not None else maps.get("points")
+        dep = inputs[2] if inputs[2] is not None else maps.get("depth")
+        if pts is not None:
+            out["world_points"] = al.apply_sim3_alignment_on_point_maps(pts, T, scale)
+        if dep is not None:
+            out["depth"] = al.scale_depth(dep, scale)
+        for src, dst in (("points_conf", "world_points_conf"), ("depth_conf", "depth_conf")):
+            if src in maps:
+                out[dst] = maps[src]
         return out
 
 

@@ -373,3 +373,49 @@ def test_config4_dealing(world):
     if world == 8:
         assert per_rank[0] in (1, 2) and max(per_rank[1:]) - min(per_rank[1:]) <= 1     # rank 0 mostly aligns
     assert pipe.shapes_of is None and pipe._shapes(41) == (None, None, None)
+
+
+def test_model_stages_run_dpt_heads_on_the_owner(monkeypatch):
+    """ModelStages with a stand-in model: without raw maps the owner runs the model's DPT heads at encode time and applies the
+    chunk's Sim(3) to their outputs when the packet arrives; with raw maps given the heads are not called."""
+    from aligned_vggt.utils import alignment as al
+    monkeypatch.setattr(al, "apply_sim3_alignment_on_point_maps", lambda p, T, s: p * s.view(-1, 1, 1, 1, 1) + T[:, :3, 3].view(-1, 1, 1, 1, 3))
+    monkeypatch.setattr(al, "scale_depth", lambda d, s: d * s.view(-1, 1, 1, 1, 1))
+    S, H, W = 3, 28, 42
+    calls = []
+
+    class Head:
+        def __init__(self, c):
+            self.c = c
+
+        def __call__(self, taps, images, patch_start_idx):
+            calls.append(self.c)
+            return torch.full((1, S, H, W, self.c), float(self.c)), torch.ones(1, S, H, W)
+
+    class Model:
+        intermediate_layer_indices = [0, 0, 0, 1]
+        depth_head, point_head = Head(1), Head(3)
+
+        def aggregator(self, images):
+            return [torch.zeros(1, S, 11, 2048), torch.ones(1, S, 11, 2048)], 5
+
+        def camera_head(self, toks):
+            return [torch.zeros(1, S, 9)]
+
+    st = sch.ModelStages(Model(), 1, S, H, W, "cpu")
+    assert st.shapes_of(2) == ((1, 2, 11, 2048), (1, 2, 9), 1 + 16 + 18 + 8 + 7)
+    packet = torch.zeros(st.packet_numel)
+    packet[0] = 2.0                                      # scale
+    packet[1:17] = torch.eye(4).flatten()
+    packet[4] = 0.5                                      # T[0, 3]: x translation
+    inputs = (torch.zeros(1, S, 3, H, W), None, None)
+    tok, cam = st.encode(inputs)
+    assert tok.dtype == torch.bfloat16 and float(tok.float().mean()) == 1.0 and sorted(calls) == [1, 3] and len(st._maps) == 1
+    out = st.apply(packet, inputs)
+    assert st._maps == {} and set(out) >= {"world_points", "depth", "world_points_conf", "depth_conf", "pose_enc"}
+    assert torch.equal(out["depth"], torch.full((1, S, H, W, 1), 2.0)) and float(out["world_points"][..., 0].mean()) == 6.5
+    calls.clear()
+    given = (torch.zeros(1, S, 3, H, W), torch.ones(1, S, H, W, 3), torch.ones(1, S, H, W, 1))
+    st.encode(given)
+    out = st.apply(packet, given)
+    assert calls == [] and "world_points_conf" not in out and float(out["depth"].mean()) == 2.0
