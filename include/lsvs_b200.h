@@ -5,7 +5,7 @@
  * (ruppelb/Large-Scale-ViT-SLAM) is pure PyTorch, so "what its FFI would bind" are the module
  * forwards / free functions on the hot path; each entry point cites the reference
  * interface it replaces.  The Python mirror of those interfaces (large-scale-vit-slam_b200/aligned_vggt)
- * binds this header through ctypes (large-scale-vit-slam_b200/_native.py); INTEGRATION.md shows the
+ * binds this header through ctypes (large-scale-vit-slam_b200/lsvs_b200/native.py); INTEGRATION.md shows the
  * reference-side stub.
  *
  * Conventions
