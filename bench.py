@@ -416,6 +416,16 @@ def run_b200(args):
         cpu_baseline = {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
                         "sample": "one 4-frame chunk (BASELINE config 1: 518x154, full depth, first chunk) through the fp32 oracle port"}
 
+    attention = None
+    try:  # BASELINE.json's metric also names the attention tensor-pipe share of the bf16 peak: report it beside the roofline object
+        if prof_detail and prof_detail.get("attention_tcgen05_global", {}).get("tflops"):
+            pk = peaks()
+            tf = prof_detail["attention_tcgen05_global"]["tflops"]
+            attention = {"kernel": "attention_tcgen05_global", "tflops": tf, "frac_of_bf16_peak_sustained": tf / pk["bf16_tflops_sustained"],
+                         "frac_of_bf16_peak_burst": tf / pk["bf16_tflops"], "ms_per_step": prof_detail["attention_tcgen05_global"]["ms_per_step"]}
+    except Exception:  # noqa: BLE001  (never lose the bench line over an annotation)
+        attention = None
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -428,7 +438,7 @@ def run_b200(args):
                            "parallelism": f"chunks dealt over {world} GPU(s); alignment chain on rank 0 (per-GPU work fixed as N grows)"
                            + (f"; transport: {pipe.tx.name}; apply lag {pipe.lag}; head_cost {args.head_cost}" if world > 1 else "")},
                 "clocks": clocks.summary(), "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "kernel_classes": prof_detail}
+                "attention": attention, "kernel_classes": prof_detail}
         print(json.dumps(line), flush=True)
     if world > 1:
         pipe.tx.close()
