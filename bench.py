@@ -349,6 +349,18 @@ def run_b200(args):
         pipe.flush()
         e2e = {"value": n_chunks_e2e * (S_CHUNK - OVERLAP) / (float(t.item()) / 1e3), "unit": "frames/s",
                "h2d_bytes_per_step": host_img.numel() * 4 * n_chunks_e2e / args.steps, "d2h_bytes_per_step": float(bt.item()) / args.steps}
+    # ---- N > 1: integrity of the transport on this box (untimed): one patterned message per owner and direction, compared bit for bit
+    transport_check = None
+    if world > 1:
+        try:
+            from lsvs_b200.scheduler import mailbox_self_check
+            chk = mailbox_self_check(pipe)
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] mailbox self-check did not complete on rank {rank}: {e}", file=sys.stderr, flush=True)
+            chk = False
+        flag = torch.tensor([-1 if chk is None else int(bool(chk))], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        transport_check = {-1: None, 0: "MISMATCH", 1: "bit-exact"}[int(flag.item())]
     if world == 1:
         io = HostIO(dev, [torch.rand(1, S_CHUNK, 3, H, W).pin_memory() for _ in range(2)])
         host_imgs = io.host_imgs
@@ -438,7 +450,7 @@ def run_b200(args):
                            "parallelism": f"chunks dealt over {world} GPU(s); alignment chain on rank 0 (per-GPU work fixed as N grows)"
                            + (f"; transport: {pipe.tx.name}; apply lag {pipe.lag}; head_cost {args.head_cost}" if world > 1 else "")},
                 "clocks": clocks.summary(), "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "attention": attention, "kernel_classes": prof_detail}
+                "attention": attention, "transport_check": transport_check, "kernel_classes": prof_detail}
         print(json.dumps(line), flush=True)
     if world > 1:
         pipe.tx.close()

@@ -447,6 +447,39 @@ class ChunkPipeline:
         return list(zip(ids, out)) if with_chunk_ids else out
 
 
+def mailbox_self_check(pipe: ChunkPipeline) -> Optional[bool]:
+    """Integrity check of the mailbox transport, to be called by every rank right after pipe.flush(): each owner pushes one more
+    full-size chunk message filled with a known bit pattern, rank 0 compares every element and answers with a patterned packet
+    that the owner compares in turn.  True / False = everything this rank received was / was not bit-exact (host-synchronising);
+    None when the pipeline does not run on PeerTransport."""
+    tx = pipe.tx
+    if not isinstance(tx, PeerTransport):
+        return None
+
+    def pattern(shape, dtype, salt):  # integers below 251: exact in bf16 as well
+        n = 1
+        for d in shape:
+            n *= d
+        return ((torch.arange(n, device=tx.device) + salt) % 251).to(dtype).view(tuple(shape))
+
+    ok = True
+    if pipe.rank == 0:
+        for o in range(1, pipe.world):
+            seq = pipe._oseq[o]
+            t, c = tx.recv_chunk(o, seq)
+            ok = ok and torch.equal(t, pattern(tx.tokens_shape, tx.tokens_dtype, 7 * o + seq % 5))
+            ok = ok and torch.equal(c, pattern(tx.cam_shape, torch.float32, 3 * o + 1))
+            tx.send_packet(o, seq, pattern((tx.packet_numel,), torch.float32, 11 * o))
+            pipe._oseq[o] += 1
+    else:
+        seq, o = pipe.seq, pipe.rank
+        tx.send_chunk(seq, pattern(tx.tokens_shape, tx.tokens_dtype, 7 * o + seq % 5), pattern(tx.cam_shape, torch.float32, 3 * o + 1))
+        ok = torch.equal(tx.recv_packet(seq), pattern((tx.packet_numel,), torch.float32, 11 * o))
+        pipe.seq += 1
+    tx.finish()
+    return bool(ok)
+
+
 def run_sequence(pipe: ChunkPipeline, load_chunk: Callable[[int], tuple]):
     """The reference's chunk loop (training/run_model.py:326-338, training_metrics.py:636-657) over a finite sequence on
     every rank of the pipeline: `pipe` was built with chunk_frames = [len(c) for c in generate_chunks(...)], load_chunk(k)

@@ -288,7 +288,11 @@ def _sequence_worker(rank, world, port, q, use_peer, mock=False):
                                      cam_like=lambda: torch.empty(1, 1), **kw)
         res = sch.run_sequence(pipe, lambda k: _inputs_fr(k, dev))
         if use_peer:
+            assert sch.mailbox_self_check(pipe) is True          # one more patterned message per owner and direction
+            assert sch.mailbox_self_check(pipe) is True          # (repeatable: sequence numbers and slots move on)
             tx.close()
+        else:
+            assert sch.mailbox_self_check(pipe) is None
         q.put((rank, [(k, v.cpu().numpy()) for k, v in res], None))     # numpy: no fd hand-over that could outlive this process
     except Exception:  # noqa: BLE001
         import traceback
@@ -419,3 +423,53 @@ def test_model_stages_run_dpt_heads_on_the_owner(monkeypatch):
     st.encode(given)
     out = st.apply(packet, given)
     assert calls == [] and "world_points_conf" not in out and float(out["depth"].mean()) == 2.0
+
+
+def _self_check_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dev, backend = _peer_device(rank, mock=True)
+        tx = sch.PeerTransport(rank, world, (4, 5), torch.float32, (1, 1), 4, dev, slots=3, timeout_s=30.0, backend=backend)
+        pipe = sch.ChunkPipeline(_encode, _align, _apply, rank, world, head_cost=0.2, transport=tx)
+        clean = sch.mailbox_self_check(pipe)
+        if rank == 2:                                   # rank 2 damages one element of its next chunk message
+            send = tx.send_chunk
+
+            def damaged(seq, tokens, cam, packet_numel=None):
+                tokens = tokens.clone()
+                tokens.view(-1)[7] += 1.0
+                return send(seq, tokens, cam, packet_numel)
+            tx.send_chunk = damaged
+        q.put((rank, (clean, sch.mailbox_self_check(pipe)), None))
+        tx.close()
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, None, traceback.format_exc()))
+        return
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_mailbox_self_check_detects_a_damaged_message():
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_self_check_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    try:
+        for _ in range(world):
+            rank, res, err = q.get(timeout=120)
+            assert err is None, f"rank {rank}: {err}"
+            got[rank] = res
+        for p in procs:
+            p.join(timeout=60)
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+    assert got[0] == (True, False)                      # rank 0 sees the damaged chunk of rank 2
+    assert got[1] == (True, True) and got[2] == (True, True)
