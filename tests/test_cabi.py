@@ -46,3 +46,20 @@ def test_no_cpu_fallback():
     from lsvs_b200 import native
     with pytest.raises(native.NativeError):
         A.apply_sim3_alignment_on_point_maps(torch.zeros(1, 1, 2, 2, 3), torch.eye(4)[None], torch.ones(1))
+
+
+def test_documents_name_only_exported_entry_points():
+    """Every lsvs_* entry point that INTEGRATION.md / DESIGN.md / README.md mention is declared in include/lsvs_b200.h."""
+    import os
+    import re
+    from lsvs_b200 import native
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    declared = set(native.declared_symbols())
+    families = ("lsvs_peer_", "lsvs_sim3_apply_", "lsvs_dpt_", "lsvs_engine_")       # documents also use family prefixes / wildcards
+    for doc in ("INTEGRATION.md", "DESIGN.md", "README.md"):
+        text = open(os.path.join(root, doc)).read()
+        for name in set(re.findall(r"\blsvs_[a-z0-9_]+\b", text)):
+            if name in declared or name.startswith("lsvs_b200") or name in ("lsvs_engine", "lsvs_bf16", "lsvs_gemm_epilogue", "lsvs_engine_config"):
+                continue
+            assert any(name == f or name == f.rstrip("_") or (name.startswith(f) and any(d.startswith(name) for d in declared)) for f in families) \
+                or any(d.startswith(name) for d in declared), f"{doc} mentions {name}, which include/lsvs_b200.h does not declare"
