@@ -88,10 +88,9 @@ typedef struct lsvs_gemm_epilogue {
 
 int lsvs_gemm_bf16(const lsvs_bf16* A, int lda, const lsvs_bf16* W, int ldw, int M, int N, int K, int epilogue_kind,
                    const lsvs_gemm_epilogue* epilogue, void* stream);
-/* A/B switch for measurements: 0 = auto (CTA-pair 256x256 tiles when M > 256 and N % 256 == 0), 1 = single-CTA kernel only,
- * 2 = pair kernel with per-lane epilogue stores (no TMA store / reduce-add), 3 = pair kernel without the W-operand loads (wrong
- * results; halves the L2->SM bytes to test for a bandwidth bound) */
-int lsvs_debug_gemm_mode(int mode);
+/* Determinism: results are bit-reproducible from run to run except for the residual GEMMs (LSVS_EPI_RESID_F32) of SHORT chunks
+ * (fewer than 37 output tiles, i.e. about 4-8 frames of 518x154), where K is sliced over idle CTA pairs and the slices are added
+ * into the fp32 residual by L2 atomics in arrival order.  LSVS_DETERMINISTIC=1 in the environment disables the slicing. */
 /* cos/sin table used by the RoPE epilogues: tab[p][j] = (cos, sin)(p * base^(-2j/(2*n_freq))), p < n_pos.
  * (rope.py:46-58; fp32 angles)  `tab` holds n_pos*n_freq*2 floats. */
 int lsvs_rope_table(float* tab, int n_pos, int n_freq, float base, void* stream);
@@ -146,9 +145,10 @@ int lsvs_alignment_head_forward(lsvs_engine* e, const float* tokens, int B, int 
 int lsvs_alignment_decode_forward(lsvs_engine* e, const float* align_tokens, int B, int S, const float* memory_in,
                                   float* chunk_sim3, float* frame_se3, float* memory_out, void* stream);
 /* replaces UPSTREAM vggt CameraHead.forward (call site featureAligned_vggt.py:106): tokens_last (B,S,P,2048)
- * -> pose_enc (B,S,9) of the last refinement iteration. */
+ * -> pose_enc (B,S,9) of the last refinement iteration; pose_enc_iters (optional, NULL to skip): (num_iterations,B,S,9), the
+ * activated encoding after every iteration (UPSTREAM returns that list; the reference reads only [-1], :109). */
 int lsvs_camera_head_forward(lsvs_engine* e, const float* tokens_last, int B, int S, int P, int num_iterations,
-                             float* pose_enc, void* stream);
+                             float* pose_enc, float* pose_enc_iters, void* stream);
 /* ---- DPT dense-prediction heads (depth_head / point_head) --------------------------------------------
  * replaces UPSTREAM vggt/heads/dpt_head.py DPTHead.forward (construction featureAligned_vggt.py:28-29, calls :166-168 and
  * :183-185).  prefix: "depth_head." or "point_head." (state_dict prefix of the parameters pushed
@@ -238,9 +238,15 @@ int lsvs_depth_scale_align(const float* depth_pred, const float* depth_gt, const
  *   lsvs_peer_alloc    zero-initialised device buffer that can be exported (synchronises the device once)
  *   lsvs_peer_export   64-byte handle to hand to another process;  lsvs_peer_open maps it there (peer access enabled lazily)
  *   lsvs_peer_put      dst (local or mapped peer memory) <- src, `bytes` bytes, in stream order
- *   lsvs_peer_signal   *flag <- value with system-scope release, after everything earlier in the stream
- *   lsvs_peer_wait     the stream continues once (int)(*flag - value) >= 0; after timeout_s seconds *status (device word,
- *                      local) is set to 1 and the stream continues, so a lost peer surfaces as an error, not as a hang */
+ * A mailbox starts with a two-word header: flag[0] = sequence number, flag[1] = poison.  `status` is the calling rank's health
+ * word — device memory or pinned (mapped) host memory, so that the host can poll it without synchronising: 0 healthy, 1 one of
+ * this rank's waits timed out, 2 a peer published poison.
+ *   lsvs_peer_signal   flag[0] <- value with system-scope release, after everything earlier in the stream; if *status != 0
+ *                      (status may be NULL) it publishes flag[1] <- 1 instead: a rank that lost a message never hands results
+ *                      computed from stale mailboxes to its peers
+ *   lsvs_peer_wait     the stream continues once (int)(flag[0] - value) >= 0; it gives up — the stream continues, nothing
+ *                      hangs — when flag[1] != 0 (*status <- 2), after timeout_s seconds (*status <- 1), or at once when
+ *                      *status is already non-zero */
 #define LSVS_PEER_HANDLE_BYTES 64
 int lsvs_peer_alloc(size_t bytes, void** ptr);
 int lsvs_peer_free(void* ptr);
@@ -248,7 +254,7 @@ int lsvs_peer_export(const void* ptr, unsigned char* handle64);
 int lsvs_peer_open(const unsigned char* handle64, void** ptr);
 int lsvs_peer_close(void* ptr);
 int lsvs_peer_put(void* dst, const void* src, size_t bytes, void* stream);
-int lsvs_peer_signal(unsigned* flag, unsigned value, void* stream);
+int lsvs_peer_signal(unsigned* flag, unsigned value, const unsigned* status, void* stream);
 int lsvs_peer_wait(const unsigned* flag, unsigned value, unsigned* status, double timeout_s, void* stream);
 
 #ifdef __cplusplus

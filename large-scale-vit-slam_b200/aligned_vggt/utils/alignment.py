@@ -1,10 +1,15 @@
-"""Drop-in for the hot-path part of the reference's aligned_vggt/utils/alignment.py (:244-323, :428-594).
+"""Drop-in for the reference's aligned_vggt/utils/alignment.py: every public name of that module.
 
-Same function names, argument meaning and error behaviour; the arithmetic runs in liblsvs_b200.so
-(csrc/sim3.cu) on the tensors' CUDA device.  No CPU fallback: CPU tensors raise.
+Hot-path part (:244-323 weighted-median depth scale, :428-594 Sim(3) application): same function names, argument meaning and
+error behaviour; the arithmetic runs in liblsvs_b200.so (csrc/sim3.cu, csrc/evalgeom.cu) on the tensors' CUDA device.  No CPU
+fallback there: CPU tensors raise.
+Evaluation-side solvers on a few hundred camera positions / a masked point subset (:6-129 `umeyama`, `methodOfHorn`,
+`scale_lse_solver`; :131-242, :325-426 the ground-truth aligners that `alignAndConvertOutputs` dispatches to): host glue in
+numpy / torch like the reference's, their results applied through the kernels above.
 """
 import ctypes
 
+import numpy as np
 import torch
 
 from lsvs_b200 import native as _n
@@ -142,3 +147,131 @@ def scale_align_from_depths(predictions: dict, batch: dict) -> None:
     if "pose_enc" in predictions:
         predictions["pose_enc"][..., :3] *= scales[:, None, None]
     predictions["alignment_scales"] = [scales[b].item() for b in range(B)]
+
+
+# ------------------------------------------------------------------------------------------------ evaluation-side solvers
+def _kabsch(cov: np.ndarray):
+    """SVD of a 3x3 cross-covariance -> (proper rotation U S V^T, singular values, S diagonal)."""
+    u, d, vt = np.linalg.svd(cov)
+    sign = np.ones(cov.shape[0])
+    if np.linalg.det(u) * np.linalg.det(vt) < 0.0:
+        sign[-1] = -1.0
+    return (u * sign) @ vt, d, sign
+
+
+def umeyama(x: np.ndarray, y: np.ndarray) -> tuple:
+    """reference :6-59.  Least-squares Sim(m) with y ~ c r x + t (Umeyama 1991).  x, y (m,n) -> r (m,m), t (m,), c."""
+    assert x.shape == y.shape, "x shape not equal to y shape"
+    n = x.shape[1]
+    mx, my = x.mean(axis=1), y.mean(axis=1)
+    xc, yc = x - mx[:, None], y - my[:, None]
+    r, d, sign = _kabsch(yc @ xc.T / n)
+    c = float((d * sign).sum() / ((xc ** 2).sum() / n))
+    return r, my - c * (r @ mx), c
+
+
+def methodOfHorn(model: np.ndarray, data: np.ndarray, align_scale: bool = True) -> tuple:
+    """reference :61-111 (closed-form trajectory alignment, evaluate_ate_scale).  model, data (3,n) -> rot (3,3), trans (3,), s."""
+    assert model.shape == data.shape, "model shape not equal to data shape"
+    model, data = np.asarray(model, dtype=np.float64), np.asarray(data, dtype=np.float64)
+    mc, dc = model - model.mean(1, keepdims=True), data - data.mean(1, keepdims=True)
+    rot, _, _ = _kabsch(dc @ mc.T)
+    s = float(((rot @ mc) * dc).sum() / (mc ** 2).sum()) if align_scale else 1.0
+    trans = data.mean(1) - s * (rot @ model.mean(1))
+    return rot, trans, np.asarray(s)
+
+
+def scale_lse_solver(x: np.ndarray, y: np.ndarray) -> float:
+    """reference :113-129.  argmin_s |s x - y|^2, made positive.  x, y (n,3)."""
+    assert x.shape == y.shape, "x shape not equal to y shape"
+    return np.abs(np.sum(x * y) / np.sum(x ** 2))
+
+
+def _positions(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy()
+
+
+def _scale_maps_(predictions: dict, index, factor) -> None:
+    for key in ("depth", "world_points"):
+        if key in predictions:
+            predictions[key][index] *= factor
+
+
+def per_frame_scale_alignment_from_poses(predictions: dict, batch: dict) -> None:
+    """reference :131-165: one least-squares scale per frame from the camera translations (frame 0 keeps 1.0), applied in place to
+    pose translations, depth and world points.  `alignment_scales` holds the last batch element's list, as in the reference."""
+    B, S = batch["extrinsics"].shape[:2]
+    gt, pr = _positions(batch["extrinsics"][..., :3, 3]), _positions(predictions["pose_enc"][..., :3])
+    for b in range(B):
+        frame_scales = [1.0 if s == 0 else scale_lse_solver(pr[b, s], gt[b, s]) for s in range(S)]
+        for s, f in enumerate(frame_scales):
+            predictions["pose_enc"][b, s, :3] *= f
+            _scale_maps_(predictions, (b, s), f)
+    predictions["alignment_scales"] = frame_scales
+
+
+def per_chunk_scale_alignment_from_poses(predictions: dict, batch: dict) -> None:
+    """reference :167-203: chunked (list-valued) predictions / batch; one scale per (chunk, batch element)."""
+    out = []
+    for c in range(len(batch["extrinsics"])):
+        gt, pr = _positions(batch["extrinsics"][c][..., :3, 3]), _positions(predictions["pose_enc"][c][..., :3])
+        scales = [scale_lse_solver(pr[b], gt[b]) for b in range(gt.shape[0])]
+        for b, f in enumerate(scales):
+            predictions["pose_enc"][c][b, :, :3] *= f
+            for key in ("depth", "world_points"):
+                if key in predictions:
+                    predictions[key][c][b, ...] *= f
+        out.append(torch.tensor(scales))
+    predictions["alignment_scales_per_chunk"] = out
+
+
+def scale_alignment_from_poses(predictions: dict, batch: dict, seq_width: int = -1) -> None:
+    """reference :206-242: one scale per batch element from the first `seq_width` frames' translations (-1 = all)."""
+    B = batch["extrinsics"].shape[0]
+    if seq_width == -1:
+        seq_width = batch["extrinsics"].shape[1]
+    gt, pr = _positions(batch["extrinsics"][:, :seq_width, :3, 3]), _positions(predictions["pose_enc"][:, :seq_width, :3])
+    scales = [scale_lse_solver(pr[b], gt[b]) for b in range(B)]
+    for b, f in enumerate(scales):
+        predictions["pose_enc"][b, :, :3] *= f
+        _scale_maps_(predictions, (b, Ellipsis), f)
+    predictions["alignment_scales"] = scales
+
+
+def _sim3_matrices(solutions):
+    T = np.tile(np.eye(4), (len(solutions), 1, 1))
+    for b, (r, t, _) in enumerate(solutions):
+        T[b, :3, :3], T[b, :3, 3] = r, t
+    return T, np.array([c for _, _, c in solutions])
+
+
+def umeyama_alignment_from_poses(predictions: dict, batch: dict, seq_width: int) -> None:
+    """reference :325-370: Sim(3) between predicted and ground-truth camera centres of the first `seq_width` frames (Umeyama),
+    applied to pose encodings, world points and depth through apply_sim3_alignment."""
+    from lsvs_b200 import posemath as pm
+    B = batch["extrinsics"].shape[0]
+    hw = tuple(batch["images"].shape[-2:])
+    gt_c = _positions(pm.inverse_se3(batch["extrinsics"][:, :seq_width].float())[..., :3, 3])
+    pred_extr, _ = pm.pose_encoding_to_extri_intri(predictions["pose_enc"][:, :seq_width].float(), hw)
+    pr_c = _positions(pm.inverse_se3(pred_extr)[..., :3, 3])
+    T, c = _sim3_matrices([umeyama(pr_c[b].T, gt_c[b].T) for b in range(B)])
+    pose, pts, dep = apply_sim3_alignment(T, c, predictions["pose_enc"], hw, predictions.get("world_points"), predictions.get("depth"))
+    predictions["pose_enc"] = pose
+    if "world_points" in predictions:
+        predictions["world_points"] = pts
+    if "depth" in predictions:
+        predictions["depth"] = dep
+
+
+def umeyama_alignment_from_points(pred_points, pred_confidence, target_points, target_point_mask, confidence_threshold: int) -> tuple:
+    """reference :372-426: per batch element, Umeyama between the predicted and target points that are valid in the target mask and
+    at least at the `confidence_threshold` percentile of predicted confidence.  Returns (poses (B,4,4), scales (B,)) numpy arrays.
+    (Like the reference, the selected (n,3) arrays are reshaped — not transposed — to (3,n) before the solve.)"""
+    as_np = lambda a: a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    pred_points, pred_confidence, target_points, target_point_mask = map(as_np, (pred_points, pred_confidence, target_points, target_point_mask))
+    sols = []
+    for b in range(pred_points.shape[0]):
+        conf = pred_confidence[b]
+        keep = (target_point_mask[b] > 0) & (conf >= np.percentile(conf, confidence_threshold)) & (conf > 1e-5)
+        sols.append(umeyama(pred_points[b][keep].reshape(3, -1), target_points[b][keep].reshape(3, -1)))
+    return _sim3_matrices(sols)

@@ -45,8 +45,10 @@ extern "C" int lsvs_attention_bf16(const lsvs_bf16* q, int ldq, const lsvs_bf16*
   return lsvs::attention_fwd(a, (cudaStream_t)stream);
 }
 
+#ifdef LSVS_MEASURE   // measurement builds only: the product ABI has no switch that changes results
 namespace lsvs { extern int g_gemm_mode; }
 extern "C" int lsvs_debug_gemm_mode(int mode) {
   lsvs::g_gemm_mode = mode;
   return LSVS_OK;
 }
+#endif

@@ -606,7 +606,7 @@ extern "C" int lsvs_alignment_head_forward(lsvs_engine* h, const float* tokens, 
 
 // ================================================================================================ CameraHead
 extern "C" int lsvs_camera_head_forward(lsvs_engine* h, const float* tokens_last, int B, int S, int P, int num_iterations,
-                                        float* pose_enc, void* stream) {
+                                        float* pose_enc, float* pose_enc_iters, void* stream) {
   Engine& e = *reinterpret_cast<Engine*>(h);
   cudaStream_t st = (cudaStream_t)stream;
   LSVS_CHECK_ARG(e.finalized && e.cfg.with_camera_head, "camera_head_forward: engine has no camera head / not finalized");
@@ -646,6 +646,8 @@ extern "C" int lsvs_camera_head_forward(lsvs_engine* h, const float* tokens_last
     TRY(linear_f32(bh, C / 2, b2w, b2b, delta, 9, frames, 9, C / 2, ACT_NONE, ACT_NONE, nullptr, false, st));
     if (it == 0) TRY(combine_rows(delta, 9, nullptr, 0, pred, 9, frames, 9, -1, -1, st));
     else TRY(combine_rows(pred, 9, delta, 9, pred, 9, frames, 9, -1, -1, st));
+    // UPSTREAM returns the activated encoding of every refinement iteration (the reference only reads the last, :109)
+    if (pose_enc_iters) TRY(combine_rows(pred, 9, nullptr, 0, pose_enc_iters + (size_t)it * frames * 9, 9, frames, 9, 7, -1, st));
   }
   TRY(combine_rows(pred, 9, nullptr, 0, pose_enc, 9, frames, 9, 7, -1, st));  // activate_pose: T, quat linear; FoV relu
   if (e.scratch_overflow) { e.scratch_overflow = false; return fail(LSVS_ECUDA, "camera_head_forward: scratch under-sized"); }

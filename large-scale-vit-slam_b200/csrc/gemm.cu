@@ -22,8 +22,22 @@
 #include "tensormap.h"
 
 namespace lsvs {
-int g_gemm_mode = 0;  // 0 auto, 1 force the single-CTA kernel, 2 pair kernel without TMA reduce-add, 3 pair kernel without B loads (wrong results;
-                      // halves L2->SM bytes: qkv 75.7 -> 70.6 us, i.e. the pair kernel is not L2-bound) (lsvs_debug_gemm_mode; A/B testing)
+// Kernel-selection switch for A/B measurements: 0 auto, 1 force the single-CTA kernel, 2 pair kernel without TMA store / reduce-add,
+// 3 pair kernel without B loads (WRONG results; halves L2->SM bytes: qkv 75.7 -> 70.6 us, i.e. the pair kernel is not L2-bound).
+// It only exists in measurement builds (LSVS_NVCC_DEFINES="-DLSVS_MEASURE", entry point lsvs_debug_gemm_mode in capi_gemm.cu);
+// the product library compiles the switch away.
+#ifdef LSVS_MEASURE
+int g_gemm_mode = 0;
+#else
+constexpr int g_gemm_mode = 0;
+#endif
+// Split-K over the TMA reduce-add epilogue (short chunks only: fewer residual-GEMM tiles than CTA pairs) adds the K slices'
+// partial sums into the fp32 residual with L2 atomics in arrival order, so those outputs can differ in the last bit from run to
+// run.  LSVS_DETERMINISTIC=1 in the environment keeps one slice per tile (bit-reproducible, slower on 4-8 frame chunks).
+static bool deterministic() {
+  static const bool on = [] { const char* v = getenv("LSVS_DETERMINISTIC"); return v && atoi(v) != 0; }();
+  return on;
+}
 namespace {
 
 constexpr int BM = 128;
@@ -619,7 +633,11 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
         ptx::mbar_wait(empty_bar + stage, phase ^ 1);
         if (lane == 0) {
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
-          const bool skip_b = (use_tma_reduce & 2) != 0;  // measurement only (lsvs_debug_gemm_mode 3): halves the L2->SM bytes, wrong results
+#ifdef LSVS_MEASURE
+          const bool skip_b = (use_tma_reduce & 2) != 0;  // lsvs_debug_gemm_mode 3: halves the L2->SM bytes, wrong results
+#else
+          constexpr bool skip_b = false;
+#endif
           if (cta == 0) ptx::mbar_expect_tx(full_bar + stage, skip_b ? 2 * L::A_BYTES : 2 * L::STAGE_BYTES);  // bytes of both CTAs land here
           else ptx::mbar_arrive_remote(full_bar + stage, 0);
           int a_k = kb * BK, a_row = m0;
@@ -728,7 +746,7 @@ int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K,
   }
   if (g_gemm_mode == 3) use_red |= 2;
   int splits = 1;
-  if ((use_red & 1) && g_gemm_mode == 0) {  // few tiles (short chunks): slice K while all slices still fit in one round of CTA pairs
+  if ((use_red & 1) && g_gemm_mode == 0 && !deterministic()) {  // few tiles (short chunks): slice K while all slices still fit in one round of CTA pairs
     const int n_kb = K / BK;
     while (splits < 8 && tiles * splits * 2 <= max_pairs && n_kb % (2 * splits) == 0 && n_kb / (2 * splits) >= 4) splits *= 2;
   }

@@ -13,8 +13,16 @@
 
 namespace {
 
-__global__ void peer_signal_kernel(unsigned* flag, unsigned value) {
+// A mailbox header is two words: flag[0] = sequence number (messages published so far), flag[1] = poison (non-zero once the
+// publishing rank has seen a failure).  `status` is the caller's health word (device or pinned host memory): 0 = healthy,
+// 1 = a wait of this rank timed out, 2 = a peer published poison.
+__global__ void peer_signal_kernel(unsigned* flag, unsigned value, const volatile unsigned* status) {
   __threadfence_system();
+  if (status != nullptr && *status != 0u) {
+    // this rank's inputs may be stale (an earlier wait gave up): tell the consumer instead of publishing results built on them
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag + 1), "r"(1u) : "memory");
+    return;
+  }
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
 }
 
@@ -30,19 +38,20 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-// Returns when (int)(*flag - value) >= 0.  On timeout sets *status = 1 and returns (the stream keeps going and the host
-// reads the status word at its next flush) instead of hanging the device.
-__global__ void peer_wait_kernel(const unsigned* flag, unsigned value, unsigned* status, unsigned long long timeout_ns) {
+// Returns when (int)(flag[0] - value) >= 0.  Gives up — the stream keeps going, nothing hangs — when the producer has published
+// poison (*status = 2), after `timeout_ns` (*status = 1), or at once if *status is already non-zero (a failed rank does not
+// wait a full timeout per message again).  Every later lsvs_peer_signal of this rank then publishes poison, so one lost peer
+// stops the whole group within a message instead of letting it compute on stale mailboxes.
+__global__ void peer_wait_kernel(const unsigned* flag, unsigned value, volatile unsigned* status, unsigned long long timeout_ns) {
   if (threadIdx.x != 0) return;
+  if (*status != 0u) return;
   const unsigned long long t0 = global_ns();
   unsigned backoff = 32;
   while ((int)(ld_acquire_sys(flag) - value) < 0) {
+    if (ld_acquire_sys(flag + 1) != 0u) { *status = 2u; __threadfence_system(); return; }
     __nanosleep(backoff);
     if (backoff < 2048) backoff *= 2;
-    if (global_ns() - t0 > timeout_ns) {
-      atomicExch(status, 1u);
-      return;
-    }
+    if (global_ns() - t0 > timeout_ns) { *status = 1u; __threadfence_system(); return; }
   }
 }
 
@@ -98,9 +107,9 @@ extern "C" int lsvs_peer_put(void* dst, const void* src, size_t bytes, void* str
   return LSVS_OK;
 }
 
-extern "C" int lsvs_peer_signal(unsigned* flag, unsigned value, void* stream) {
+extern "C" int lsvs_peer_signal(unsigned* flag, unsigned value, const unsigned* status, void* stream) {
   LSVS_CHECK_ARG(flag != nullptr, "lsvs_peer_signal: null flag");
-  peer_signal_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(flag, value);
+  peer_signal_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(flag, value, status);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }

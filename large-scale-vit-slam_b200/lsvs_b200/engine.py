@@ -182,13 +182,16 @@ class Engine:
                  "dpt_head_forward")
         return pred, conf
 
-    def camera_head_forward(self, tokens_last: torch.Tensor, num_iterations: int = 4) -> torch.Tensor:
+    def camera_head_forward(self, tokens_last: torch.Tensor, num_iterations: int = 4, all_iterations: bool = False):
+        """(B,S,P,2048) -> pose_enc (B,S,9) of the last iteration, or with `all_iterations` the list of every iteration's
+        activated encoding (UPSTREAM CameraHead.forward's return value)."""
         B, S, P, C = tokens_last.shape
         tok = tokens_last.detach().float().contiguous()
         out = torch.empty(B, S, 9, device=tok.device)
+        iters = torch.empty(num_iterations, B, S, 9, device=tok.device) if all_iterations else None
         _n.check(_n.lib().lsvs_camera_head_forward(self._h, _n.ptr(tok), _i(B), _i(S), _i(P), _i(num_iterations), _n.ptr(out),
-                                                   _n.stream_ptr()), "camera_head_forward")
-        return out
+                                                   _n.ptr(iters), _n.stream_ptr()), "camera_head_forward")
+        return list(iters.unbind(0)) if all_iterations else out
 
 
 GT_MEAN, GT_SCALE = 1, 2   # LSVS_GT_MEAN / LSVS_GT_SCALE of include/lsvs_b200.h

@@ -61,8 +61,8 @@ class Aggregator(_EngineBound):
 
 
 class CameraHead(_EngineBound):
-    """UPSTREAM vggt.heads.camera_head.CameraHead (A.5): forward(list of tapped layers) -> list with the pose
-    encodings (B,S,9); this path computes only the last refinement iteration (the reference uses [-1] only,
+    """UPSTREAM vggt.heads.camera_head.CameraHead (A.5): forward(list of tapped layers, num_iterations=4) -> list of
+    `num_iterations` activated pose encodings (B,S,9), one per refinement iteration (the reference reads [-1],
     featureAligned_vggt.py:109)."""
     _prefix = "camera_head."
 
@@ -78,7 +78,7 @@ class CameraHead(_EngineBound):
         return Engine(0, 0, 0, 8, False, True)
 
     def forward(self, aggregated_tokens_list, num_iterations: int = 4):
-        return [self._engine().camera_head_forward(aggregated_tokens_list[-1], num_iterations)]
+        return self._engine().camera_head_forward(aggregated_tokens_list[-1], num_iterations, all_iterations=True)
 
 
 class DPTHead(_EngineBound):

@@ -26,7 +26,8 @@ import torch.distributed as dist
 
 # ------------------------------------------------------------------------------------------------ chunk indices
 def generate_chunks(num_frames: int, mode: str, seq_width: int, overlap: int) -> List[List[int]]:
-    """Drop-in for aligned_vggt/utils/data.py:155-207 (deterministic modes)."""
+    """Drop-in for aligned_vggt/utils/data.py:155-207.  "two_chunks" (:192-204) draws from the `random` module like the
+    reference: a random non-empty proper subset of the frames, in sampling order, and the remaining frames in index order."""
     out: List[List[int]] = []
     if mode == "chunk_gt":
         for i in range(0, num_frames - seq_width + 1, seq_width):
@@ -44,6 +45,15 @@ def generate_chunks(num_frames: int, mode: str, seq_width: int, overlap: int) ->
                 out.append(list(range(len(out) * step, num_frames)))
     elif mode == "all":
         out = [list(range(num_frames))]
+    elif mode == "two_chunks":
+        if num_frames < 2:
+            raise ValueError("Number of frames must be at least 2 for two_chunks mode.")
+        if num_frames == 2:
+            return [[0, 1]]
+        import random
+        first = random.sample(range(num_frames), random.randint(1, num_frames - 1))
+        taken = set(first)
+        out = [first, [i for i in range(num_frames) if i not in taken]]
     else:
         raise ValueError(f"Unknown sequence generation mode: {mode}")
     return out
@@ -154,7 +164,7 @@ class PeerTransport:
         self._ct, self._native, self._lib = ctypes, native, native.lib()
         if backend is None:  # ctypes prototypes of the entry points called with plain Python integers
             self._lib.lsvs_peer_wait.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
-            self._lib.lsvs_peer_signal.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p]
+            self._lib.lsvs_peer_signal.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p]
             self._lib.lsvs_peer_put.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
             self._lib.lsvs_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
         self.tok_bytes = int(torch.tensor([], dtype=tokens_dtype).element_size())
@@ -166,7 +176,10 @@ class PeerTransport:
         self.cam_stride = _align256(self.cam_bytes)
         self.chunk_stride = self.cam_stride + _align256(self.tok_bytes)
         self.packet_stride = _align256(4 * packet_numel)
-        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        # health word (include/lsvs_b200.h): pinned host memory on a GPU, so that step() can read it without a device sync
+        self.status = torch.zeros(1, dtype=torch.int32)
+        if self._on_cuda:
+            self.status = self.status.pin_memory()
         self._local, self._mapped = {}, {}     # peer rank -> base pointer (local allocation / mapped remote allocation)
         # two collective phases, each followed by an exchange of outcomes, so that a failure on one rank (IPC not
         # permitted, out of memory) raises on every rank instead of leaving the others waiting
@@ -226,7 +239,8 @@ class PeerTransport:
         self._native.check(self._lib.lsvs_peer_put(dst, src_tensor.data_ptr(), nbytes, self._native.stream_ptr()), "lsvs_peer_put")
 
     def _signal(self, flag, value):
-        self._native.check(self._lib.lsvs_peer_signal(flag, value & 0xFFFFFFFF, self._native.stream_ptr()), "lsvs_peer_signal")
+        self._native.check(self._lib.lsvs_peer_signal(flag, value & 0xFFFFFFFF, self.status.data_ptr(), self._native.stream_ptr()),
+                           "lsvs_peer_signal")
 
     def _wait(self, flag, value):
         self._native.check(self._lib.lsvs_peer_wait(flag, value & 0xFFFFFFFF, self.status.data_ptr(), self.timeout_s,
@@ -293,10 +307,21 @@ class PeerTransport:
         self._put(self._mapped[owner] + 256 + (seq % self.slots) * self.packet_stride, packet, 4 * packet.numel())
         self._signal(self._mapped[owner], seq + 1)
 
+    def poll(self):
+        """Non-blocking health check (a plain read of the pinned status word): raises once a wait of this rank has given up — from
+        then on this rank publishes poison instead of results (lsvs_peer_signal), so its peers raise within one message too.  The
+        word is cleared when the error is raised; the transport itself must be rebuilt (its sequence numbers are out of step)."""
+        code = int(self.status[0])
+        if code != 0:
+            self.status[0] = 0
+            why = {1: f"a peer did not publish its message within {self.timeout_s} s", 2: "a peer reported a failure (poisoned mailbox)"}
+            raise self._native.NativeError(f"rank {self.rank}: {why.get(code, f'transport status {code}')}")
+
     def finish(self):
-        """Host-synchronising health check: raises if any wait on a peer timed out."""
-        if int(self.status.item()) != 0:
-            raise self._native.NativeError(f"rank {self.rank}: a peer did not publish its message within {self.timeout_s} s")
+        """Host-synchronising health check: waits for the stream's pending waits, then raises like poll()."""
+        if self._on_cuda:
+            torch.cuda.current_stream().synchronize()
+        self.poll()
 
     def close(self, group=None):
         """Collective: unmap the peers' buffers, then free the local ones."""
@@ -435,6 +460,8 @@ class ChunkPipeline:
         # owners: apply the packet of the chunk encoded `lag` chunks ago (this round's encode is already queued ahead of it)
         self._apply_ready(keep=self.lag)
         self.round += 1
+        if self.tx is not None and hasattr(self.tx, "poll"):
+            self.tx.poll()  # a timed-out / poisoned mailbox surfaces within a round, not at the end of the sequence
 
     def flush(self, with_chunk_ids: bool = False):
         if self.rank == 0:

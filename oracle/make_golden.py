@@ -531,6 +531,73 @@ def case_eval_geometry():
          merged_depth=merged["depth"], merged_pose=merged["pose_enc"])
 
 
+def case_host_glue():
+    """Host-side glue of data.py / geometry.py / alignment.py that training/{run_model,training_metrics,loss}.py import
+    (tests/test_dropin_surface.py checks the drop-in's own versions against these reference outputs)."""
+    print("[host glue: data.py / geometry.py / alignment.py]")
+    import random
+    from aligned_vggt.utils import alignment as RA
+    from aligned_vggt.utils import data as RD
+    from aligned_vggt.utils import geometry as RG
+    out = {}
+    B, S, H, W = 2, 5, 6, 8
+    q = rnd(40, B, S, 4)
+    extr = torch.cat([OF.quat_to_mat(q), rnd(41, B, S, 3, 1, scale=2.0)], dim=-1)          # (B,S,3,4) world-to-camera
+    out["extr"] = extr
+    out["rel_next"] = RG.compute_relative_poses(extr)
+    out["rel_prev3"] = RG.compute_relative_poses(extr, 3, False)
+    wp = rnd(42, B, S, H, W, 3, scale=4.0)
+    K = torch.zeros(B, S, 3, 3)
+    K[..., 0, 0], K[..., 1, 1], K[..., 0, 2], K[..., 1, 2], K[..., 2, 2] = 300.0, 320.0, W / 2, H / 2, 1.0
+    pix, valid = RG.project_world_points_to_pixels(wp, extr, K)
+    out.update(wp=wp, K=K, pix=pix, pix_valid=valid.float())
+    # data.py: normalisation of a data-loader batch
+    masks = (rnd(43, B, S, H, W) > -0.5)
+    cam_pts, depths = rnd(44, B, S, H, W, 3, scale=3.0), rnd(45, B, S, H, W).abs() + 0.5
+    ne, nc, nw, nd = RD.normalize_camera_extrinsics_and_points_batch(extr, cam_pts, wp, depths, True, masks)
+    out.update(masks=masks.float(), cam_pts=cam_pts, depths=depths, norm_extr=ne, norm_cam=nc, norm_world=nw, norm_depths=nd)
+    ne2, _, nw2, _ = RD.normalize_camera_extrinsics_and_points_batch(extr, cam_pts, wp, depths, False, masks)
+    out.update(norm_extr_noscale=ne2, norm_world_noscale=nw2)
+    # chunk_batch + two_chunks
+    batch = {"images": rnd(46, B, 11, 3, 4, 4), "ids": torch.arange(B * 11).view(B, 11), "name": "not a tensor"}
+    idx = RD.generate_chunks(11, "chunk_overlap", 5, 1)
+    cb = RD.chunk_batch(batch, idx)
+    assert sorted(cb.keys()) == ["ids", "images"]
+    out["chunk_ids_last"] = cb["ids"][-1]
+    random.seed(7)
+    tc = [RD.generate_chunks(n, "two_chunks", 4, 1) for n in (2, 3, 9, 9)]
+    out["two_chunks_flat"] = np.array([i for chunks in tc for c in chunks for i in c + [-1]])
+    # alignment.py: closed-form solvers
+    g = np.random.Generator(np.random.PCG64(47))
+    x = g.standard_normal((3, 40))
+    Rg = OF.quat_to_mat(rnd(48, 4)).double().numpy()
+    y = 1.7 * Rg @ x + np.array([[0.3], [-1.0], [2.0]]) + 0.01 * g.standard_normal((3, 40))
+    r, t, c = RA.umeyama(x, y)
+    rh, th, sh = RA.methodOfHorn(x, y)
+    rh1, th1, sh1 = RA.methodOfHorn(x, y, align_scale=False)
+    out.update(um_x=x, um_y=y, um_r=r, um_t=t, um_c=c, horn_r=rh, horn_t=th, horn_s=sh, horn_t_noscale=th1,
+               lse=RA.scale_lse_solver(x.T, y.T))
+    # alignment.py: ground-truth scale aligners (in place on clones)
+    def preds():
+        return {"pose_enc": torch.cat([rnd(49, B, S, 3), rnd(50, B, S, 4), torch.full((B, S, 2), 0.8)], -1),
+                "depth": rnd(51, B, S, H, W, 1).abs() + 0.3, "world_points": rnd(52, B, S, H, W, 3)}
+    gtb = {"extrinsics": extr}
+    for name, fn in (("sfp", lambda p: RA.scale_alignment_from_poses(p, gtb)), ("sfp3", lambda p: RA.scale_alignment_from_poses(p, gtb, 3)),
+                     ("pfs", lambda p: RA.per_frame_scale_alignment_from_poses(p, gtb))):
+        p = preds()
+        fn(p)
+        out.update({f"{name}_pose": p["pose_enc"], f"{name}_depth": p["depth"], f"{name}_points": p["world_points"],
+                    f"{name}_scales": np.array(p["alignment_scales"], dtype=np.float64)})
+    pc = {k: [v[:, :3].clone(), v[:, 2:].clone()] for k, v in preds().items()}
+    RA.per_chunk_scale_alignment_from_poses(pc, {"extrinsics": [extr[:, :3], extr[:, 2:]]})
+    out.update(pcs_pose1=pc["pose_enc"][1], pcs_depth0=pc["depth"][0], pcs_scales=torch.stack(pc["alignment_scales_per_chunk"]))
+    conf = 1 + torch.exp(rnd(53, B, S, H, W))
+    tgt = 0.9 * wp @ torch.from_numpy(Rg).float().T + 0.5
+    Tp, cp = RA.umeyama_alignment_from_points(wp[:, :3], conf[:, :3], tgt[:, :3], masks[:, :3], confidence_threshold=50.0)
+    out.update(ufp_conf=conf, ufp_tgt=tgt, ufp_T=Tp, ufp_c=cp)
+    save("host_glue.npz", **out)
+
+
 def case_model_full():
     print("[FeatureAlignedVGGT, full depth, config 1: S=4, 154x518, overlap 1]")
     model, sd = build_reference_model(None)
@@ -547,7 +614,8 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     cases = {"spec": case_spec, "layers": case_layers, "geometry": case_geometry, "head": case_head, "model_small": case_model_small,
              "pose_aligned": case_pose_aligned_small, "model_dpt_small": case_model_dpt_small, "eval_geometry": case_eval_geometry,
-             "baselines_gt_dpt": case_baselines_gt_dpt, "sim3_dict": case_sim3_dict, "model_ragged": case_model_ragged}
+             "baselines_gt_dpt": case_baselines_gt_dpt, "sim3_dict": case_sim3_dict, "model_ragged": case_model_ragged,
+             "host_glue": case_host_glue}
     if args.full:
         cases["model_full"] = case_model_full
     for name, fn in cases.items():

@@ -45,15 +45,24 @@ class _Lib:
         ctypes.memmove(int(dst), int(src), int(nbytes))
         return 0
 
-    def lsvs_peer_signal(self, flag, value, stream):
+    def lsvs_peer_signal(self, flag, value, status, stream):
+        if status and ctypes.c_int32.from_address(int(status)).value != 0:
+            ctypes.c_uint32.from_address(int(flag) + 4).value = 1   # poison instead of the sequence number
+            return 0
         ctypes.c_uint32.from_address(int(flag)).value = int(value)
         return 0
 
     def lsvs_peer_wait(self, flag, value, status, timeout_s, stream):
+        st = ctypes.c_int32.from_address(int(status))
+        if st.value != 0:
+            return 0
         t0 = time.time()
         while ((ctypes.c_uint32.from_address(int(flag)).value - int(value)) & 0xFFFFFFFF) >= 0x80000000:
+            if ctypes.c_uint32.from_address(int(flag) + 4).value != 0:
+                st.value = 2
+                return 0
             if time.time() - t0 > timeout_s:
-                ctypes.c_int32.from_address(int(status)).value = 1
+                st.value = 1
                 return 0
             time.sleep(0.0005)
         return 0

@@ -1,0 +1,246 @@
+"""The drop-in `aligned_vggt` package must offer the reference-side import surface: everything
+/root/reference/training/{run_model,training_metrics,loss}.py import from `aligned_vggt.*` has to resolve with the drop-in AHEAD of
+the reference on sys.path, and the host-side glue it re-implements must reproduce the reference's outputs
+(tests/golden/host_glue.npz, written by `python -m oracle.make_golden --only host_glue` from the reference's own functions)."""
+import ast
+import importlib
+import os
+import random
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG, ROOT
+
+REFERENCE = "/root/reference"
+needs_reference = pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "training")),
+                                     reason="reference checkout not present (GPU box): the import-surface check runs in the build container")
+
+
+# ------------------------------------------------------------------------------------------------ import surface
+_IMPORT_SCRIPT = r"""
+import ast, importlib, sys, types
+pkg, shim, ref = sys.argv[1:4]
+sys.path[:0] = [pkg, shim, ref]          # drop-in first, then the restated upstream `vggt`, then the reference checkout
+
+class _Stub(types.ModuleType):            # third-party packages that are not installed here (hydra, lightning, viser, ...)
+    __path__ = []
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return type(name, (), {"__init__": lambda self, *a, **k: None, "__call__": lambda self, *a, **k: None})
+
+class _Finder:
+    ROOTS = ("hydra", "omegaconf", "lightning", "iopath", "certifi", "viser", "cv2", "pytorch3d", "torchmetrics", "trimesh",
+             "matplotlib", "onnxruntime")
+    EXTRA = ("vggt.visual_util", "vggt.training.train_utils.freeze", "vggt.training.data")
+    def find_spec(self, name, path=None, target=None):
+        if name.split(".")[0] in self.ROOTS or any(name == e or name.startswith(e + ".") for e in self.EXTRA):
+            import importlib.machinery
+            return importlib.machinery.ModuleSpec(name, self)
+        return None
+    def create_module(self, spec):
+        return _Stub(spec.name)
+    def exec_module(self, module):
+        pass
+sys.meta_path.append(_Finder())
+
+import aligned_vggt
+assert aligned_vggt.__path__[0].startswith(pkg), aligned_vggt.__path__
+checked = []
+for f in ("training/run_model.py", "training/training_metrics.py", "training/loss.py"):
+    tree = ast.parse(open(f"{ref}/{f}").read())
+    for node in tree.body:
+        if isinstance(node, ast.ImportFrom) and node.module and node.module.split(".")[0] == "aligned_vggt":
+            m = importlib.import_module(node.module)
+            for a in node.names:
+                getattr(m, a.name)
+                checked.append(f"{node.module}.{a.name}")
+# the whole import block of run_model.py (first statement that is not an import ends it)
+src = open(f"{ref}/training/run_model.py").read()
+block = []
+for node in ast.parse(src).body:
+    if not isinstance(node, (ast.Import, ast.ImportFrom)):
+        break
+    block.append(ast.get_source_segment(src, node))
+exec("\n".join(block), {})
+# the Hydra targets resolve to the drop-in classes
+for target in ("aligned_vggt.models.featureAligned_vggt.FeatureAlignedVGGT", "aligned_vggt.models.poseAligned_wrapped_vggt.VGGT",
+               "aligned_vggt.models.pointAligned_wrapped_vggt.VGGT", "aligned_vggt.heads.alignment_head.AlignmentHead"):
+    mod, cls = target.rsplit(".", 1)
+    m = importlib.import_module(mod)
+    assert m.__file__.startswith(pkg), m.__file__
+    getattr(m, cls)
+# modules the drop-in does not provide fall through to the reference's own files
+from aligned_vggt.layers.gated_update import GatedUpdate
+import aligned_vggt.layers.gated_update as gu, aligned_vggt.utils.visualization as vis
+assert gu.__file__.startswith(ref) and vis.__file__.startswith(ref), (gu.__file__, vis.__file__)
+print("RESOLVED", len(checked), " ".join(sorted(set(checked))))
+"""
+
+
+@needs_reference
+def test_reference_side_imports_resolve_against_the_dropin():
+    out = subprocess.run([sys.executable, "-c", _IMPORT_SCRIPT, PKG, os.path.join(ROOT, "oracle", "vggt_shim"), REFERENCE],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("RESOLVED")][0]
+    for name in ("alignAndConvertOutputs", "chunk_batch", "normalize_camera_extrinsics_and_points_batch", "pose_encoding_to_extri",
+                 "moveDictListItemToCPU", "generate_chunks", "unproject_depth_map_to_point_map", "viser_wrapper", "compute_relative_poses"):
+        assert name in line, f"{name} not exercised: {line}"
+
+
+def test_public_names_of_the_reference_utils_modules_exist():
+    """Frozen list of the reference's public names in utils/{data,alignment,geometry}.py (so the check also runs without /root/reference)."""
+    names = {
+        "aligned_vggt.utils.data": ["extri_to_pose_encoding", "pose_encoding_to_extri", "convertDictListsToTensors", "moveDictListItemToCPU",
+                                    "alignAndConvertOutputs", "generate_chunks", "chunk_batch", "check_valid_tensor",
+                                    "normalize_camera_extrinsics_and_points_batch", "apply_sim3_alignment_on_dict", "umeyama"],
+        "aligned_vggt.utils.alignment": ["umeyama", "methodOfHorn", "scale_lse_solver", "per_frame_scale_alignment_from_poses",
+                                         "per_chunk_scale_alignment_from_poses", "scale_alignment_from_poses", "scale_align_from_depths",
+                                         "umeyama_alignment_from_poses", "umeyama_alignment_from_points", "apply_sim3_alignment_on_dict",
+                                         "apply_sim3_alignment", "apply_sim3_alignment_on_point_maps", "apply_sim3_alignment_on_w2c",
+                                         "apply_sim3_alignment_on_c2w"],
+        "aligned_vggt.utils.geometry": ["averagePoseEncodings", "unproject_depth_map_to_point_map", "project_world_points_to_pixels",
+                                        "compute_relative_poses", "generate_3D_pixel_grid"],
+    }
+    for mod, fns in names.items():
+        m = importlib.import_module(mod)
+        assert m.__file__.startswith(PKG)
+        for fn in fns:
+            assert callable(getattr(m, fn)), f"{mod}.{fn}"
+    if os.path.isdir(os.path.join(REFERENCE, "aligned_vggt")):  # the frozen list is complete
+        for mod, fns in names.items():
+            tree = ast.parse(open(os.path.join(REFERENCE, *mod.split(".")) + ".py").read())
+            public = [n.name for n in tree.body if isinstance(n, ast.FunctionDef)]
+            missing = [n for n in public if not hasattr(importlib.import_module(mod), n)]
+            assert not missing, f"{mod} lacks {missing}"
+
+
+# ------------------------------------------------------------------------------------------------ host glue vs reference outputs
+def close(a, b, tol=1e-5):
+    as64 = lambda v: v.double() if torch.is_tensor(v) else torch.from_numpy(np.asarray(v, dtype=np.float64))
+    a, b = as64(a), as64(b)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = float((a - b).abs().max())
+    assert err <= tol * max(1.0, float(b.abs().max())), err
+
+
+def test_geometry_glue_matches_reference(golden):
+    from aligned_vggt.utils import geometry as G
+    g = golden("host_glue.npz")
+    close(G.compute_relative_poses(g["extr"]), g["rel_next"])
+    close(G.compute_relative_poses(g["extr"], 3, False), g["rel_prev3"])
+    with pytest.raises(Exception, match="To small sequence"):
+        G.compute_relative_poses(g["extr"], 5)
+    pix, valid = G.project_world_points_to_pixels(g["wp"], g["extr"], g["K"])
+    assert torch.equal(valid.float(), g["pix_valid"])
+    close(pix, g["pix"], 1e-5)
+    e = g["extr"].clone().requires_grad_(True)  # training/loss.py back-propagates through it
+    G.compute_relative_poses(e).square().sum().backward()
+    assert e.grad is not None and torch.isfinite(e.grad).all()
+
+
+def test_average_pose_encodings_matches_reference(golden):
+    from aligned_vggt.utils import geometry as G
+    g = golden("geometry.npz")
+    mine = G.averagePoseEncodings(g["enc"])
+    sgn = torch.sign((mine[..., 3:] * g["avg"][..., 3:]).sum(-1, keepdim=True))
+    close(mine[..., :3], g["avg"][..., :3], 1e-6)
+    close(mine[..., 3:] * sgn, g["avg"][..., 3:], 1e-5)
+
+
+def test_data_glue_matches_reference(golden):
+    from aligned_vggt.utils import data as D
+    g, gg = golden("host_glue.npz"), golden("geometry.npz")
+    close(D.pose_encoding_to_extri(gg["enc"]), gg["enc_extr"], 1e-6)
+    close(D.extri_to_pose_encoding(gg["enc_extr"]), gg["enc_back"], 1e-6)
+    masks = g["masks"] > 0.5
+    ne, nc, nw, nd = D.normalize_camera_extrinsics_and_points_batch(g["extr"], g["cam_pts"], g["wp"], g["depths"], True, masks)
+    close(ne, g["norm_extr"]), close(nc, g["norm_cam"]), close(nw, g["norm_world"]), close(nd, g["norm_depths"])
+    ne2, c2, nw2, d2 = D.normalize_camera_extrinsics_and_points_batch(g["extr"], g["cam_pts"], g["wp"], g["depths"], False, masks)
+    close(ne2, g["norm_extr_noscale"]), close(nw2, g["norm_world_noscale"])
+    assert c2 is g["cam_pts"] and d2 is g["depths"]
+    B = 2
+    batch = {"images": torch.zeros(B, 11, 3, 4, 4), "ids": torch.arange(B * 11).view(B, 11), "name": "not a tensor"}
+    cb = D.chunk_batch(batch, D.generate_chunks(11, "chunk_overlap", 5, 1))
+    assert sorted(cb.keys()) == ["ids", "images"] and len(cb["ids"]) == 3
+    assert torch.equal(cb["ids"][-1], g["chunk_ids_last"].long())
+    random.seed(7)  # same draws from the `random` module as the reference
+    tc = [D.generate_chunks(n, "two_chunks", 4, 1) for n in (2, 3, 9, 9)]
+    flat = np.array([i for chunks in tc for c in chunks for i in c + [-1]])
+    assert np.array_equal(flat, g["two_chunks_flat"].numpy())
+    with pytest.raises(ValueError, match="at least 2"):
+        D.generate_chunks(1, "two_chunks", 4, 1)
+    with pytest.raises(ValueError, match="Unknown sequence generation mode"):
+        D.generate_chunks(5, "nope", 4, 1)
+
+
+def test_alignment_solvers_match_reference(golden):
+    from aligned_vggt.utils import alignment as A
+    g = golden("host_glue.npz")
+    x, y = g["um_x"].numpy(), g["um_y"].numpy()
+    r, t, c = A.umeyama(x, y)
+    close(r, g["um_r"], 1e-9), close(t, g["um_t"], 1e-9), close(c, g["um_c"], 1e-9)
+    rh, th, sh = A.methodOfHorn(x, y)
+    close(rh, g["horn_r"], 1e-9), close(th, g["horn_t"], 1e-9), close(sh, g["horn_s"], 1e-9)
+    assert th.shape == (3,) and isinstance(sh, np.ndarray)
+    _, th1, sh1 = A.methodOfHorn(x, y, align_scale=False)
+    close(th1, g["horn_t_noscale"], 1e-9)
+    assert float(sh1) == 1.0
+    close(A.scale_lse_solver(x.T, y.T), g["lse"], 1e-12)
+
+
+def _preds(golden_rnd):
+    B, S, H, W = 2, 5, 6, 8
+    return {"pose_enc": torch.cat([golden_rnd(49, B, S, 3), golden_rnd(50, B, S, 4), torch.full((B, S, 2), 0.8)], -1),
+            "depth": golden_rnd(51, B, S, H, W, 1).abs() + 0.3, "world_points": golden_rnd(52, B, S, H, W, 3)}
+
+
+def test_ground_truth_scale_aligners_match_reference(golden):
+    from aligned_vggt.utils import alignment as A
+    from conftest import rnd
+    g = golden("host_glue.npz")
+    gtb = {"extrinsics": g["extr"]}
+    for name, fn in (("sfp", lambda p: A.scale_alignment_from_poses(p, gtb)), ("sfp3", lambda p: A.scale_alignment_from_poses(p, gtb, 3)),
+                     ("pfs", lambda p: A.per_frame_scale_alignment_from_poses(p, gtb))):
+        p = _preds(rnd)
+        fn(p)
+        close(p["pose_enc"], g[f"{name}_pose"]), close(p["depth"], g[f"{name}_depth"]), close(p["world_points"], g[f"{name}_points"])
+        close(np.array(p["alignment_scales"], dtype=np.float64), g[f"{name}_scales"], 1e-9)
+    pc = {k: [v[:, :3].clone(), v[:, 2:].clone()] for k, v in _preds(rnd).items()}
+    A.per_chunk_scale_alignment_from_poses(pc, {"extrinsics": [g["extr"][:, :3], g["extr"][:, 2:]]})
+    close(pc["pose_enc"][1], g["pcs_pose1"]), close(pc["depth"][0], g["pcs_depth0"])
+    close(torch.stack(pc["alignment_scales_per_chunk"]), g["pcs_scales"], 1e-9)
+    Tp, cp = A.umeyama_alignment_from_points(g["wp"][:, :3], g["ufp_conf"][:, :3], g["ufp_tgt"][:, :3], g["masks"][:, :3] > 0.5,
+                                             confidence_threshold=50.0)
+    close(Tp, g["ufp_T"], 2e-5), close(cp, g["ufp_c"], 2e-5)   # fp32 point inputs: the reference accumulates fp32 products
+
+
+def test_align_and_convert_outputs_dispatch():
+    """alignAndConvertOutputs (data.py:107-153): merge + dispatch on CPU-only alignment types; errors as in the reference."""
+    from aligned_vggt.utils import data as D
+    from conftest import rnd
+    B, S = 1, 4
+    def chunked():
+        pred = {"pose_enc": [torch.cat([rnd(60 + i, B, S, 3), rnd(70 + i, B, S, 4), torch.full((B, S, 2), 0.8)], -1) for i in range(2)]}
+        cb = {"extrinsics": [torch.cat([torch.eye(3).expand(B, S, 3, 3), rnd(80 + i, B, S, 3, 1)], -1) for i in range(2)]}
+        return pred, cb
+    pred, cb = chunked()
+    batch = {}
+    D.alignAndConvertOutputs(pred, batch, cb, "scale_from_poses", S, 1)
+    assert pred["pose_enc"].shape == (B, 2 * S - 1, 9) and batch["extrinsics"].shape == (B, 2 * S - 1, 3, 4) and len(pred["alignment_scales"]) == B
+    pred, cb = chunked()
+    D.alignAndConvertOutputs(pred, {}, cb, "per_chunk_scale_from_poses", S, 1)
+    assert len(pred["alignment_scales_per_chunk"]) == 2 and pred["pose_enc"].shape == (B, 2 * S - 1, 9)
+    pred, cb = chunked()
+    D.alignAndConvertOutputs(pred, {}, cb, "none", S, 0)
+    assert pred["pose_enc"].shape == (B, 2 * S, 9)
+    for kind, msg in (("scale_from_depths", "requires depth head"), ("sim3_from_points", "requires point head")):
+        pred, cb = chunked()
+        with pytest.raises(ValueError, match=msg):
+            D.alignAndConvertOutputs(pred, {}, cb, kind, S, 1)

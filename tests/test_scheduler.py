@@ -239,6 +239,55 @@ def test_peer_mailbox_protocol_on_host_memory(world, lag):
     _check_peer_mailboxes(world, lag, mock=True)
 
 
+def _lost_peer_worker(rank, world, port, q):
+    """Rank 1 owns chunks but never publishes them (a hung / dead producer).  Rank 0 must raise within a round of the timeout
+    instead of chaining on a stale mailbox, and what it sends back must be poison so that rank 1 fails fast as well."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mock_peer
+    tx = sch.PeerTransport(rank, world, (4, 5), torch.float32, (1, 1), 4, torch.device("cpu"), slots=3, timeout_s=0.5 if rank == 0 else 20.0,
+                           backend=mock_peer)   # rank 1 would wait 20 s: only the poison can wake it earlier
+    outcome = "no error"
+    try:
+        if rank == 0:
+            pipe = sch.ChunkPipeline(_encode, _align, _apply, rank, world, head_cost=0.6, transport=tx, lag=2)   # rank 0 only aligns
+            for j in range(3):
+                pipe.step(None)
+        else:
+            tx.recv_packet(0)       # the answer to a chunk this rank never sent
+            tx.poll()
+    except mock_peer.NativeError as e:
+        outcome = str(e)
+    status_after = int(tx.status[0])
+    q.put((rank, outcome, status_after))
+    dist.barrier()
+    tx.close()
+    dist.destroy_process_group()
+
+
+def test_lost_producer_raises_within_a_round_and_poisons_its_peers():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lost_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        got = {}
+        for _ in range(2):
+            rank, outcome, status_after = q.get(timeout=60)
+            got[rank] = (outcome, status_after)
+        for p in procs:
+            p.join(timeout=30)
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.terminate()
+    assert "did not publish its message" in got[0][0], got      # rank 0: its wait for the chunk timed out -> raised from step()
+    assert "reported a failure" in got[1][0], got               # rank 1: got poison instead of a packet built on stale tokens
+    assert got[0][1] == 0 and got[1][1] == 0                    # the status word is cleared once the error has been raised
+
+
 # ---- finite sequence with a short tail chunk (generate_chunks' last chunk, data.py:196-203): run_sequence ------------------
 FRAMES = [4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 2]     # 11 chunks; with 3 ranks the last round is cut to the chunks that remain
 

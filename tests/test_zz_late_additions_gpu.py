@@ -45,7 +45,7 @@ def test_peer_primitives_single_process():
     lib = native.lib()
     lib.lsvs_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
     lib.lsvs_peer_put.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
-    lib.lsvs_peer_signal.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p]
+    lib.lsvs_peer_signal.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p]
     lib.lsvs_peer_wait.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p]
     p = ctypes.c_void_p()
     native.check(lib.lsvs_peer_alloc(4096, ctypes.byref(p)), "alloc")
@@ -56,7 +56,7 @@ def test_peer_primitives_single_process():
         status = torch.zeros(1, dtype=torch.int32, device="cuda")
         st = native.stream_ptr()
         native.check(lib.lsvs_peer_put(base + 256, src.data_ptr(), 1024, st), "put")
-        native.check(lib.lsvs_peer_signal(base, 3, st), "signal")
+        native.check(lib.lsvs_peer_signal(base, 3, status.data_ptr(), st), "signal")
         native.check(lib.lsvs_peer_wait(base, 3, status.data_ptr(), 5.0, st), "wait")   # published: returns at once
         native.check(lib.lsvs_peer_wait(base, 2, status.data_ptr(), 5.0, st), "wait")   # an older message: satisfied too
         native.check(lib.lsvs_peer_put(out.data_ptr(), base + 256, 1024, st), "put")

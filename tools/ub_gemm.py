@@ -19,8 +19,8 @@ def timeit(fn, iters=10, warm=3):
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 13184
 from lsvs_b200 import native
-for mode in (1, 0):
-  native.lib().lsvs_debug_gemm_mode(mode)
+for mode in ((1, 0) if hasattr(native.lib(), 'lsvs_debug_gemm_mode') else (0,)):  # modes need a -DLSVS_MEASURE build
+  if mode: native.lib().lsvs_debug_gemm_mode(mode)
   print("--- gemm mode", mode, "(1 = single-CTA 128x256, 0 = CTA pairs 256x256)")
   for (N, K, kind, name) in [(3072, 1024, ops.EPI_BIAS_BF16, "qkv"), (3072, 1024, ops.EPI_HEADNORM64_BF16, "qkv+norm+rope"),
                              (1024, 1024, ops.EPI_RESID_F32, "proj+resid"), (4096, 1024, ops.EPI_BIAS_GELU_BF16, "fc1+gelu"),
