@@ -140,8 +140,9 @@ def test_geometry_glue_matches_reference(golden):
     pix, valid = G.project_world_points_to_pixels(g["wp"], g["extr"], g["K"])
     assert torch.equal(valid.float(), g["pix_valid"])
     close(pix, g["pix"], 1e-5)
-    e = g["extr"].clone().requires_grad_(True)  # training/loss.py back-propagates through it
-    G.compute_relative_poses(e).square().sum().backward()
+    with torch.enable_grad():  # training/loss.py back-propagates through it (other tests switch grad off process-wide)
+        e = g["extr"].clone().requires_grad_(True)
+        G.compute_relative_poses(e).square().sum().backward()
     assert e.grad is not None and torch.isfinite(e.grad).all()
 
 
