@@ -98,45 +98,88 @@ def oracle_state_dict(depth=24, dino_depth=24):
     return OW.fill_state_dict(spec, seed=0)
 
 
-def cpu_reference_run(steps, warmup, frames):
-    """The reference's CPU path (oracle port: reference-own code restated + restated upstream vggt), fp32, all host
-    cores, on a bounded sample: chunks of `frames` frames at 518x154, full depth, with context carry."""
-    from oracle import aligned as OA
-    torch.set_num_threads(os.cpu_count() or 1)
-    torch.set_grad_enabled(False)
-    sd = oracle_state_dict()
-    ov = 1
-    g = np.random.Generator(np.random.PCG64(0))
-    mk = lambda: torch.from_numpy(g.random((1, frames, 3, H, W), dtype=np.float32))
-    pts, dep = torch.randn(1, frames, H, W, 3), torch.rand(1, frames, H, W, 1)
-    ctx = None
-    times = []
-    for i in range(warmup + steps):
-        img = mk()
-        t0 = time.perf_counter()
-        o = OA.feature_aligned_forward(sd, img, ov, ctx, raw_points=pts, raw_depth=dep)
-        dt = time.perf_counter() - t0
-        ctx = {"overlap_tokens": o["overlap_tokens"], "memory_tokens": o["memory_tokens"], "pose_enc": o["pose_enc"]}
-        if i >= warmup:
-            times.append(dt)
-    new_frames = frames - ov
-    total = sum(times)
-    return {"value": new_frames * len(times) / total, "ms_per_step": 1e3 * total / len(times), "frames": frames, "overlap": ov,
-            "cores": torch.get_num_threads()}
+REF_SLICES = 10  # the CPU arm cuts one full-size chunk pass into this many steps of about equal work
+
+
+def workload_config(extra=None):
+    """`config` shared by both arms (the driver compares them): BASELINE configs[1]/[2] shape."""
+    cfg = {"workload": "feature-aligned VGGT chunk pipeline: 32-frame chunks, 8-frame overlap, 518x154 frames (BASELINE configs[1]/[2] shape), "
+                       "random-init VGGT-1B Aggregator + alignment head + camera head + Sim(3) apply on synthetic point/depth maps",
+           "frames_per_chunk": S_CHUNK, "overlap": OVERLAP, "image_hw": [H, W]}
+    cfg.update(extra or {})
+    return cfg
+
+
+class SlicedCpuReference:
+    """The reference's CPU path (oracle port: reference-own code restated + restated upstream vggt; fp32, all host cores) on the
+    SAME configuration as the B200 arm — 32-frame chunks of 518x154, 8-frame overlap, full depth, context carried from chunk to
+    chunk.  One chunk pass takes about a minute of CPU time, so a step is a bounded slice of it: the pass is cut into REF_SLICES
+    consecutive slices of about equal work (oracle.aligned.feature_aligned_forward_sliced yields after every block), one slice
+    per step; REF_SLICES consecutive steps are exactly one chunk pass, whatever slice the timed window starts at."""
+
+    def __init__(self):
+        from oracle import aligned as OA
+        self.OA = OA
+        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_grad_enabled(False)
+        self.sd = oracle_state_dict()
+        self.g = np.random.Generator(np.random.PCG64(0))
+        self.pts, self.dep = torch.randn(1, S_CHUNK, H, W, 3), torch.rand(1, S_CHUNK, H, W, 1)
+        self.ctx, self.gen, self.acc, self.k = None, None, 0.0, 0
+        # cost model of one pass (same weights as the generator yields): boundaries of the slices
+        probe = [1.0] * 24 + [1.0, 3.0] * 24
+        self.total = 0.3 + sum(probe) + 8.0
+        self.chunks_done = 0.0
+
+    def _start_chunk(self):
+        img = torch.from_numpy(self.g.random((1, S_CHUNK, 3, H, W), dtype=np.float32))
+        self.gen = self.OA.feature_aligned_forward_sliced(self.sd, img, OVERLAP, self.ctx, raw_points=self.pts, raw_depth=self.dep)
+        self.acc, self.k = 0.0, 0
+
+    def step(self):
+        """Advance by one slice (1/REF_SLICES of a chunk pass by the cost model); returns the fraction of a pass actually covered."""
+        if self.gen is None:
+            self._start_chunk()
+        target = self.total * (self.k + 1) / REF_SLICES
+        start = self.acc
+        while True:
+            try:
+                _, cost = next(self.gen)
+                self.acc += cost
+            except StopIteration as fin:
+                o = fin.value
+                self.ctx = {"overlap_tokens": o["overlap_tokens"], "memory_tokens": o["memory_tokens"], "pose_enc": o["pose_enc"]}
+                done = (self.total - start) / self.total
+                self.gen = None
+                return done
+            if self.acc >= target - 1e-9 and self.k < REF_SLICES - 1:
+                self.k += 1
+                return (self.acc - start) / self.total
+
+
+def cpu_reference_run(steps, warmup):
+    ref = SlicedCpuReference()
+    for _ in range(warmup):
+        ref.step()
+    t0 = time.perf_counter()
+    passes = 0.0
+    for _ in range(steps):
+        passes += ref.step()
+    total = time.perf_counter() - t0
+    return {"value": passes * (S_CHUNK - OVERLAP) / total, "ms_per_step": 1e3 * total / steps, "chunk_passes": passes,
+            "secs_per_chunk_pass": total / passes, "cores": torch.get_num_threads()}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    frames = 4 if (args.steps + args.warmup) <= 8 else 2
-    r = cpu_reference_run(args.steps, args.warmup, frames)
-    sample = f"{frames}-frame chunks ({r['overlap']} overlap) of 518x154, full depth, fp32 oracle port on {r['cores']} host threads"
+    r = cpu_reference_run(args.steps, args.warmup)
+    sample = (f"each step = 1/{REF_SLICES} of one full-size chunk pass ({S_CHUNK} frames of 518x154, {OVERLAP} overlap, full depth, context carried), "
+              f"fp32 oracle port on {r['cores']} host threads; {args.steps} steps = {r['chunk_passes']:.2f} chunk passes, {r['secs_per_chunk_pass']:.1f} s per pass")
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "feature-aligned VGGT chunk pipeline, 518x154 frames, random-init VGGT-1B weights (CPU sample: "
-                                   f"{frames}-frame chunks instead of {S_CHUNK})", "frames_per_chunk": frames, "overlap": r["overlap"]},
+            "dtype": "f32", "data": "synthetic", "config": workload_config(),
             "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port", "sample": sample},
             "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -426,9 +469,10 @@ def run_b200(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(1, 0, 4)
+        r = cpu_reference_run(REF_SLICES // 2, 0)
         cpu_baseline = {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": "port",
-                        "sample": "one 4-frame chunk (BASELINE config 1: 518x154, full depth, first chunk) through the fp32 oracle port"}
+                        "sample": f"first {REF_SLICES // 2} of the {REF_SLICES} slices of one full-size chunk pass ({S_CHUNK} frames of 518x154, full depth, first chunk) "
+                                  f"through the fp32 oracle port = {r['chunk_passes']:.2f} of a pass by the FLOP model; `--impl reference` times whole passes"}
 
     attention = None
     try:  # BASELINE.json's metric also names the attention tensor-pipe share of the bf16 peak: report it beside the roofline object

@@ -105,6 +105,25 @@ int lsvs_attention_bf16(const lsvs_bf16* q, int ldq, const lsvs_bf16* k, int ldk
                         lsvs_bf16* o, int ldo, int batches, int heads, int head_dim, int Lq, int Lk, float scale,
                         void* stream);
 
+/* ---- fp32-class operators behind lsvs_engine_config::precision (csrc/precise.cu), exported for parity tests ----------------
+ * An fp32 GEMM operand x is represented by two bf16 terms hi = bf16(x), lo = bf16(x - hi).  Activations are laid out as "split
+ * rows" [hi | lo | hi] (three sections of `cols` columns), weights as [hi | hi | lo]; lsvs_gemm_bf16 over the 3x longer K axis
+ * then returns A W^T to ~2^-16 relative with fp32 accumulation.
+ *   lsvs_layernorm_split   LayerNorm of (rows, D) fp32 (D in 512/1024/2048; w, b nullable) -> split rows, row stride ld_out >= 3D
+ *   lsvs_cast_split        (rows, cols) fp32 -> split rows; gelu != 0: through the exact-erf GELU first
+ *   lsvs_headnorm_rope_f32 per-head LayerNorm (+ 2-D / 1-D RoPE as in lsvs_gemm_epilogue) in place on the fp32 columns
+ *                          [col0, col0 + n_heads*head_dim) of buf (rows, ld)
+ *   lsvs_attention_f32     O = softmax(Q K^T scale) V with fp32 q/k/v (layout as lsvs_attention_bf16) on the CUDA cores; o: split
+ *                          rows with sections `section` elements apart (the A operand of the projection GEMM) */
+int lsvs_layernorm_split(const float* x, long long ld_in, const float* w, const float* b, float eps, lsvs_bf16* out, long long ld_out,
+                         long long rows, int D, void* stream);
+int lsvs_cast_split(const float* x, long long ld_in, lsvs_bf16* out, long long ld_out, long long rows, int cols, int gelu, void* stream);
+int lsvs_headnorm_rope_f32(float* buf, long long ld, long long rows, int col0, int n_heads, int head_dim, const float* w, const float* b,
+                           float eps, int rope_mode, const float* rope_tab, int tokens_per_frame, int n_special, int grid_w,
+                           const int* pos_ids, int pos_period, void* stream);
+int lsvs_attention_f32(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv, lsvs_bf16* o,
+                       long long ldo, long long section, int batches, int heads, int head_dim, int Lq, int Lk, float scale, void* stream);
+
 /* ---- engine: packed weights + kernel sequencing for the module forwards ---------------------------
  * One engine per process / GPU.  Parameters are pushed by state_dict name (the names are the reference's
  * checkpoint contract) from DEVICE fp32 pointers; the engine keeps its own copies (bf16 for the
@@ -116,6 +135,12 @@ typedef struct lsvs_engine_config {
   int head_depth_aa, num_memory_tokens;                      /* alignment head: 4, 8                       */
   int with_alignment_head, with_camera_head;
   float rope_base;                                           /* 100                                        */
+  int precision;  /* 0: bf16 operands / fp32 accumulate everywhere (the reference's bf16-mixed inference, run_model.py:472).
+                   * 1: the alignment-head blocks, project_in and the camera-head trunk run fp32-class (every GEMM operand split
+                   *    into two bf16 terms = 16 significant bits, fp32 LayerNorm / RoPE / attention): what the reference computes
+                   *    in fp32 (camera head with autocast disabled, featureAligned_vggt.py:103-104; decode alignment_head.py:340).
+                   * 2: every block of the path fp32-class (3x the GEMM work, attention on the CUDA cores): verification mode that
+                   *    shows the bf16 pipeline differs from the fp32 reference by rounding only.  Fixed at lsvs_engine_create. */
 } lsvs_engine_config;
 
 int lsvs_engine_create(const lsvs_engine_config* cfg, lsvs_engine** out);
@@ -136,7 +161,8 @@ int lsvs_aggregator_forward(lsvs_engine* e, const float* images, int B, int S, i
                             const int* tap_layers, int n_taps, void* stream);
 /* replaces AlignmentHead.forward  aligned_vggt/heads/alignment_head.py:224-345 (eval path).
  * tokens (B,S,P,2048) fp32; overlap_in (B,T,P+1,1024) fp32 or NULL (first chunk); memory_in (B,8,512) or NULL.
- * out: chunk_sim3 (B,1,8), frame_se3 (B,S-1,7), memory_out (B,8,512), overlap_out (B,1+next_overlap,P+1,1024). */
+ * out: chunk_sim3 (B,1,8), frame_se3 (B,S-1,7), memory_out (B,8,512), overlap_out (B,1+next_overlap,P+1,1024).
+ * An engine created with num_memory_tokens = 0 (alignment_head.py:211,468,504) ignores memory_in / memory_out (may be NULL). */
 int lsvs_alignment_head_forward(lsvs_engine* e, const float* tokens, int B, int S, int P, int H, int W, int next_overlap,
                                 const float* overlap_in, int T, const float* memory_in, float* chunk_sim3,
                                 float* frame_se3, float* memory_out, float* overlap_out, void* stream);

@@ -26,8 +26,9 @@ class AlignmentHead(_EngineBound):
                                  "is not runnable in the reference either)")
         if not (patch_size == 14 and in_dim == 2048 and embed_dim == 1024 and dec_dim == 512 and depth_decoder == 2
                 and num_heads == 8 and mlp_ratio == 4.0 and num_register_tokens == 4 and aa_block_size == 1 and qk_norm
-                and rope_freq > 0 and num_memory_tokens == 8 and list(aa_order) == ["frame", "temporal"]):
-            raise ValueError("only the reference's default AlignmentHead geometry is built on this path")
+                and rope_freq > 0 and num_memory_tokens in (0, 8) and list(aa_order) == ["frame", "temporal"]):
+            raise ValueError("only the reference's AlignmentHead geometry is built on this path (dim 1024, 8 heads, decoder dim 512, "
+                             "num_memory_tokens 8 or 0)")
         super().__init__(specs.alignment_head_spec(in_dim, embed_dim, dec_dim, depth_aa, depth_decoder, num_heads, num_memory_tokens))
         self.num_memory_tokens, self.temporal_attention = num_memory_tokens, temporal_attention
         self.depth_aa, self.patch_size, self.rope_freq = depth_aa, patch_size, float(rope_freq)

@@ -24,8 +24,11 @@ except Exception:  # pragma: no cover
 class FeatureAlignedVGGT(nn.Module, PyTorchModelHubMixin):
     def __init__(self, img_size=518, patch_size=14, embed_dim=1024, enable_camera=True, enable_point=True,
                  enable_depth=True, enable_track=True, num_memory_tokens=8, temporal_attention=True,
-                 depth=24, patch_embed_depth=24, intermediate_layer_indices=(4, 11, 17, 23)):
+                 depth=24, patch_embed_depth=24, intermediate_layer_indices=(4, 11, 17, 23), precision=None):
+        """precision (not a reference argument): None / 0 = bf16 tensor-core operands like the reference's bf16-mixed inference,
+        1 = fp32-class alignment head + camera-head trunk, 2 = fp32-class everywhere (include/lsvs_b200.h)."""
         super().__init__()
+        self.precision = precision
         self.embed_dim = embed_dim
         self.enable_memory = num_memory_tokens > 0
         self.intermediate_layer_indices = list(intermediate_layer_indices)
@@ -61,11 +64,27 @@ class FeatureAlignedVGGT(nn.Module, PyTorchModelHubMixin):
                                             temporal_attention=cfg.temporal_attention).to(dev)
         self._bind_children()
 
+    def set_precision(self, precision):
+        """Switch the arithmetic mode (0 / 1 / 2, see __init__); the native engine is rebuilt and re-packs the weights on the next forward."""
+        self.precision = precision
+        self.__dict__.pop("_native_engine", None)
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        from lsvs_b200.modules import load_state_dict_without_track_head
+        return load_state_dict_without_track_head(self, state_dict, strict, assign)
+
+    def __getstate__(self):
+        # copy.deepcopy / pickle (EMA copies, checkpoint cloning): the native engine handle is process-local and is rebuilt lazily
+        state = self.__dict__.copy()
+        state.pop("_native_engine", None)
+        return state
+
     def _engine(self) -> Engine:
         eng = self.__dict__.get("_native_engine")
         if eng is None:
             eng = Engine(self.aggregator.depth, self.aggregator.dino_depth, self.alignment_head.depth_aa,
-                         self.alignment_head.num_memory_tokens, True, self.camera_head is not None, self.aggregator.rope_freq)
+                         self.alignment_head.num_memory_tokens, True, self.camera_head is not None, self.aggregator.rope_freq,
+                         precision=self.precision)
             self.__dict__["_native_engine"] = eng
         eng.sync(self.named_parameters())
         return eng

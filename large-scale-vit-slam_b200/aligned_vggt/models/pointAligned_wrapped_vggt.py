@@ -89,6 +89,16 @@ class VGGT(nn.Module, PyTorchModelHubMixin):
         self.depth_head = self.depth_head if cfg.enable_depth else None
         self._bind_children()
 
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        from lsvs_b200.modules import load_state_dict_without_track_head
+        return load_state_dict_without_track_head(self, state_dict, strict, assign)
+
+    def __getstate__(self):
+        # copy.deepcopy / pickle (EMA copies, checkpoint cloning): the native engine handle is process-local and is rebuilt lazily
+        state = self.__dict__.copy()
+        state.pop("_native_engine", None)
+        return state
+
     def _engine(self) -> Engine:
         eng = self.__dict__.get("_native_engine")
         if eng is None:

@@ -45,6 +45,29 @@ extern "C" int lsvs_attention_bf16(const lsvs_bf16* q, int ldq, const lsvs_bf16*
   return lsvs::attention_fwd(a, (cudaStream_t)stream);
 }
 
+#include "precise.h"
+// ---- fp32-class operators (csrc/precise.cu), exported for parity tests of the precision modes
+extern "C" int lsvs_layernorm_split(const float* x, long long ld_in, const float* w, const float* b, float eps, lsvs_bf16* out,
+                                    long long ld_out, long long rows, int D, void* stream) {
+  return lsvs::layernorm_split(x, ld_in, w, b, eps, out, ld_out, rows, D, (cudaStream_t)stream);
+}
+extern "C" int lsvs_cast_split(const float* x, long long ld_in, lsvs_bf16* out, long long ld_out, long long rows, int cols, int gelu,
+                               void* stream) {
+  return lsvs::cast_split(x, ld_in, out, ld_out, rows, cols, gelu != 0, (cudaStream_t)stream);
+}
+extern "C" int lsvs_headnorm_rope_f32(float* buf, long long ld, long long rows, int col0, int n_heads, int head_dim, const float* w,
+                                      const float* b, float eps, int rope_mode, const float* rope_tab, int tokens_per_frame,
+                                      int n_special, int grid_w, const int* pos_ids, int pos_period, void* stream) {
+  return lsvs::headnorm_rope_f32(buf, ld, rows, col0, n_heads, head_dim, w, b, eps, rope_mode, reinterpret_cast<const float2*>(rope_tab),
+                                 tokens_per_frame, n_special, grid_w, pos_ids, pos_period, (cudaStream_t)stream);
+}
+extern "C" int lsvs_attention_f32(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
+                                  lsvs_bf16* o, long long ldo, long long section, int batches, int heads, int head_dim, int Lq, int Lk,
+                                  float scale, void* stream) {
+  lsvs::AttentionF32Args a{q, k, v, o, ldq, ldk, ldv, ldo, section, batches, heads, head_dim, Lq, Lk, scale};
+  return lsvs::attention_f32(a, (cudaStream_t)stream);
+}
+
 #ifdef LSVS_MEASURE   // measurement builds only: the product ABI has no switch that changes results
 namespace lsvs { extern int g_gemm_mode; }
 extern "C" int lsvs_debug_gemm_mode(int mode) {

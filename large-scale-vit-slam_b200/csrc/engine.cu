@@ -16,6 +16,7 @@
 #include "elementwise.h"
 #include "gemm.h"
 #include "host_common.h"
+#include "precise.h"
 #include "small_f32.h"
 
 namespace lsvs {
@@ -28,6 +29,7 @@ struct Param {
   __nv_bfloat16* bf16 = nullptr; // engine-owned bf16 copy of GEMM weights (K padded to a multiple of 64)
   long long numel = 0;
   int rows = 0, cols = 0, cols_padded = 0;
+  bool split = false;            // bf16 copy holds the fp32-class split [hi | hi | lo] (3 * cols_padded wide), csrc/precise.cu
 };
 
 struct DevBuf {
@@ -51,6 +53,7 @@ struct BlockW {  // UPSTREAM Block / reference CrossAttentionBlock parameters
   const float *qkv_b = nullptr, *q_b = nullptr, *kv_b = nullptr, *proj_b, *fc1_b, *fc2_b;
   const float *qn_w = nullptr, *qn_b = nullptr, *kn_w = nullptr, *kn_b = nullptr;
   const float *ls1 = nullptr, *ls2 = nullptr;
+  bool split = false;            // weights are split for the fp32-class path (engine precision mode)
 };
 
 struct BlockWF {  // fp32 block (camera trunk, decode cross blocks)
@@ -79,12 +82,14 @@ struct Engine {
   int rope_npos2d = 0, rope_npos1d = 0;
   // workspace
   DevBuf x, xn, qkv, att, h, tmp, im2col, yn, kvb, scratch, dpt_ws;
+  DevBuf p_xs, p_ys, p_qkv, p_kv, p_att, p_hf, p_hs;   // fp32-class path: split activations / fp32 GEMM outputs
   size_t scratch_off = 0;
 
   ~Engine() {
     for (auto& kv : params) { if (kv.second.f32) cudaFree(kv.second.f32); if (kv.second.bf16) cudaFree(kv.second.bf16); }
     for (auto& b : fused) b.release();
-    for (DevBuf* b : {&pos_embed, &rope2d_64, &rope2d_128, &rope1d_128, &ids_q, &ids_k, &x, &xn, &qkv, &att, &h, &tmp, &im2col, &yn, &kvb, &scratch, &dpt_ws}) b->release();
+    for (DevBuf* b : {&pos_embed, &rope2d_64, &rope2d_128, &rope1d_128, &ids_q, &ids_k, &x, &xn, &qkv, &att, &h, &tmp, &im2col, &yn, &kvb, &scratch, &dpt_ws,
+                       &p_xs, &p_ys, &p_qkv, &p_kv, &p_att, &p_hf, &p_hs}) b->release();
   }
 
   const Param* find(const std::string& n) const { auto it = params.find(n); return it == params.end() ? nullptr : &it->second; }
@@ -119,6 +124,14 @@ bool wants_bf16(const std::string& n) {
   return n == "alignment_head.project_in.weight";
 }
 
+// precision mode 1: alignment head (blocks + project_in) and camera-head trunk run fp32-class; mode 2: every block of the path.
+// (The DPT convolutions stay bf16 in every mode.)
+bool wants_split(const std::string& n, int precision) {
+  if (precision <= 0 || !wants_bf16(n) || contains(n, "depth_head.") || contains(n, "point_head.")) return false;
+  if (precision >= 2) return true;
+  return contains(n, "alignment_head.") || contains(n, "camera_head.trunk.");
+}
+
 int need(const Engine& e, const std::string& name, const Param** out) {
   const Param* p = e.find(name);
   if (!p) return fail(LSVS_EINVAL, "engine: parameter '%s' was never set (state_dict key missing)", name.c_str());
@@ -133,11 +146,13 @@ int need_f32(const Engine& e, const std::string& name, const float** out, long l
   *out = p->f32;
   return LSVS_OK;
 }
-int need_bf16(const Engine& e, const std::string& name, const __nv_bfloat16** out, int rows, int cols) {
+int need_bf16(const Engine& e, const std::string& name, const __nv_bfloat16** out, int rows, int cols, bool* split = nullptr) {
   const Param* p;
   TRY(need(e, name, &p));
   if (!p->bf16) return fail(LSVS_EINVAL, "engine: parameter '%s' has no bf16 copy", name.c_str());
   if (p->rows != rows || p->cols != cols) return fail(LSVS_EINVAL, "engine: parameter '%s' is %dx%d, expected %dx%d", name.c_str(), p->rows, p->cols, rows, cols);
+  if (split) *split = p->split;
+  else if (p->split) return fail(LSVS_EINVAL, "engine: parameter '%s' is stored split (precision mode) but its consumer has no fp32-class path", name.c_str());
   *out = p->bf16;
   return LSVS_OK;
 }
@@ -146,10 +161,12 @@ int load_block(const Engine& e, const std::string& pre, int D, bool qk_norm, boo
   const int hd_unused = 0; (void)hd_unused;
   TRY(need_f32(e, pre + "norm1.weight", &w->n1w, D)); TRY(need_f32(e, pre + "norm1.bias", &w->n1b, D));
   TRY(need_f32(e, pre + "norm2.weight", &w->n2w, D)); TRY(need_f32(e, pre + "norm2.bias", &w->n2b, D));
-  TRY(need_bf16(e, pre + "attn.qkv.weight", &w->qkv_w, 3 * D, D)); TRY(need_f32(e, pre + "attn.qkv.bias", &w->qkv_b, 3 * D));
-  TRY(need_bf16(e, pre + "attn.proj.weight", &w->proj_w, D, D)); TRY(need_f32(e, pre + "attn.proj.bias", &w->proj_b, D));
-  TRY(need_bf16(e, pre + "mlp.fc1.weight", &w->fc1_w, 4 * D, D)); TRY(need_f32(e, pre + "mlp.fc1.bias", &w->fc1_b, 4 * D));
-  TRY(need_bf16(e, pre + "mlp.fc2.weight", &w->fc2_w, D, 4 * D)); TRY(need_f32(e, pre + "mlp.fc2.bias", &w->fc2_b, D));
+  bool s1, s2, s3;
+  TRY(need_bf16(e, pre + "attn.qkv.weight", &w->qkv_w, 3 * D, D, &w->split)); TRY(need_f32(e, pre + "attn.qkv.bias", &w->qkv_b, 3 * D));
+  TRY(need_bf16(e, pre + "attn.proj.weight", &w->proj_w, D, D, &s1)); TRY(need_f32(e, pre + "attn.proj.bias", &w->proj_b, D));
+  TRY(need_bf16(e, pre + "mlp.fc1.weight", &w->fc1_w, 4 * D, D, &s2)); TRY(need_f32(e, pre + "mlp.fc1.bias", &w->fc1_b, 4 * D));
+  TRY(need_bf16(e, pre + "mlp.fc2.weight", &w->fc2_w, D, 4 * D, &s3)); TRY(need_f32(e, pre + "mlp.fc2.bias", &w->fc2_b, D));
+  if (s1 != w->split || s2 != w->split || s3 != w->split) return fail(LSVS_EINVAL, "engine: block '%s' mixes split and plain weights", pre.c_str());
   if (qk_norm) {
     TRY(need_f32(e, pre + "attn.q_norm.weight", &w->qn_w)); TRY(need_f32(e, pre + "attn.q_norm.bias", &w->qn_b));
     TRY(need_f32(e, pre + "attn.k_norm.weight", &w->kn_w)); TRY(need_f32(e, pre + "attn.k_norm.bias", &w->kn_b));
@@ -182,8 +199,40 @@ int load_block_f32(const Engine& e, const std::string& pre, int D, bool cross, b
 
 // ------------------------------------------------------------------------------------------------
 // bf16 transformer block on the fp32 residual stream x (M rows of D=1024).
+// fp32-class MLP half shared by the self- and cross-attention blocks: x += ls2 * fc2(gelu(fc1(LN(x))))  (csrc/precise.cu)
+int run_mlp_precise(Engine& e, float* x, long long M, const BlockW& w, float eps, int D, float* tap, int tap_ld, cudaStream_t st) {
+  TRY(e.p_xs.ensure((size_t)M * 3 * D * 2)); TRY(e.p_hf.ensure((size_t)M * 4 * D * 4)); TRY(e.p_hs.ensure((size_t)M * 12 * D * 2));
+  TRY(layernorm_split(x, D, w.n2w, w.n2b, eps, e.p_xs.p, 3 * D, M, D, st));
+  GemmEpilogue e1; e1.bias = w.fc1_b; e1.out = e.p_hf.p; e1.ldo = 4 * D;
+  TRY(gemm_bf16(e.p_xs.p, 3 * D, w.fc1_w, 3 * D, (int)M, 4 * D, 3 * D, EPI_BIAS_F32, e1, st));
+  TRY(cast_split(e.p_hf.as<float>(), 4 * D, e.p_hs.p, 12 * D, M, 4 * D, true, st));
+  GemmEpilogue e2; e2.bias = w.fc2_b; e2.gamma = w.ls2; e2.resid = x; e2.ldr = D; e2.out2 = tap; e2.ld2 = tap_ld;
+  return gemm_bf16(e.p_hs.p, 12 * D, w.fc2_w, 12 * D, (int)M, D, 12 * D, EPI_RESID_F32, e2, st);
+}
+
+// fp32-class transformer block: same structure as run_block below, GEMM operands split into bf16 pairs, attention in fp32
+int run_block_precise(Engine& e, float* x, long long M, const BlockW& w, float eps, int heads, int hd, int attn_batches, int L,
+                      const RopeCfg& rope, float* tap, int tap_ld, cudaStream_t st) {
+  const int D = heads * hd;
+  TRY(e.p_xs.ensure((size_t)M * 3 * D * 2)); TRY(e.p_qkv.ensure((size_t)M * 3 * D * 4)); TRY(e.p_att.ensure((size_t)M * 3 * D * 2));
+  float* qkv = e.p_qkv.as<float>();
+  TRY(layernorm_split(x, D, w.n1w, w.n1b, eps, e.p_xs.p, 3 * D, M, D, st));
+  GemmEpilogue ep; ep.bias = w.qkv_b; ep.out = qkv; ep.ldo = 3 * D;
+  TRY(gemm_bf16(e.p_xs.p, 3 * D, w.qkv_w, 3 * D, (int)M, 3 * D, 3 * D, EPI_BIAS_F32, ep, st));
+  if (w.qn_w) {
+    TRY(headnorm_rope_f32(qkv, 3 * D, M, 0, heads, hd, w.qn_w, w.qn_b, 1e-5f, rope.mode, rope.tab, rope.tpf, rope.nsp, rope.gw, rope.ids, rope.period, st));
+    TRY(headnorm_rope_f32(qkv, 3 * D, M, D, heads, hd, w.kn_w, w.kn_b, 1e-5f, rope.mode, rope.tab, rope.tpf, rope.nsp, rope.gw, rope.ids, rope.period, st));
+  }
+  AttentionF32Args aa{qkv, qkv + D, qkv + 2 * D, e.p_att.p, 3 * D, 3 * D, 3 * D, 3 * D, D, attn_batches, heads, hd, L, L, 1.0f / sqrtf((float)hd)};
+  TRY(attention_f32(aa, st));
+  GemmEpilogue er; er.bias = w.proj_b; er.gamma = w.ls1; er.resid = x; er.ldr = D;
+  TRY(gemm_bf16(e.p_att.p, 3 * D, w.proj_w, 3 * D, (int)M, D, 3 * D, EPI_RESID_F32, er, st));
+  return run_mlp_precise(e, x, M, w, eps, D, tap, tap_ld, st);
+}
+
 int run_block(Engine& e, float* x, long long M, const BlockW& w, float eps, int heads, int hd, int attn_batches, int L,
               const RopeCfg& rope, float* tap, int tap_ld, cudaStream_t st) {
+  if (w.split) return run_block_precise(e, x, M, w, eps, heads, hd, attn_batches, L, rope, tap, tap_ld, st);
   const int D = heads * hd;
   __nv_bfloat16 *xn = e.xn.as<__nv_bfloat16>(), *qkv = e.qkv.as<__nv_bfloat16>(), *att = e.att.as<__nv_bfloat16>(), *h = e.h.as<__nv_bfloat16>();
   TRY(layernorm(x, D, RowMap{}, w.n1w, w.n1b, eps, xn, D, RowMap{}, true, M, D, st));
@@ -266,10 +315,13 @@ extern "C" int lsvs_engine_set_param(lsvs_engine* h, const char* name, const flo
   if (as_bf16) {
     LSVS_CHECK_ARG(rows > 0 && cols > 0 && (long long)rows * cols == numel, "engine_set_param: '%s' needs a 2-D (rows, cols) view", name);
     const int kp = (cols + 63) / 64 * 64;
-    if (p.bf16 && ((long long)p.rows * p.cols_padded != (long long)rows * kp)) { cudaFree(p.bf16); p.bf16 = nullptr; }
-    if (!p.bf16) LSVS_CUDA(cudaMalloc(&p.bf16, (size_t)rows * kp * 2));
-    TRY(pack_weight_bf16(data, p.bf16, rows, cols, kp, st));
-    p.rows = rows; p.cols = cols; p.cols_padded = kp;
+    const bool split = wants_split(n, e.cfg.precision);
+    const int copies = split ? 3 : 1;
+    if (p.bf16 && ((long long)p.rows * p.cols_padded * (p.split ? 3 : 1) != (long long)rows * kp * copies)) { cudaFree(p.bf16); p.bf16 = nullptr; }
+    if (!p.bf16) LSVS_CUDA(cudaMalloc(&p.bf16, (size_t)rows * kp * 2 * copies));
+    if (split) TRY(pack_weight_split(data, p.bf16, rows, cols, kp, st));
+    else TRY(pack_weight_bf16(data, p.bf16, rows, cols, kp, st));
+    p.rows = rows; p.cols = cols; p.cols_padded = kp; p.split = split;
     if (p.f32) { cudaFree(p.f32); p.f32 = nullptr; }
   } else {
     if (p.f32 && p.numel != numel) { cudaFree(p.f32); p.f32 = nullptr; }
@@ -305,21 +357,25 @@ extern "C" int lsvs_engine_finalize(lsvs_engine* h, void* stream) {
       TRY(need_f32(e, pre + "norm1.weight", &w.n1w, D)); TRY(need_f32(e, pre + "norm1.bias", &w.n1b, D));
       TRY(need_f32(e, pre + "norm2.weight", &w.n2w, D)); TRY(need_f32(e, pre + "norm2.bias", &w.n2b, D));
       TRY(need_f32(e, pre + "norm3.weight", &w.n3w, D)); TRY(need_f32(e, pre + "norm3.bias", &w.n3b, D));
-      TRY(need_bf16(e, pre + "attn.q.weight", &w.q_w, D, D)); TRY(need_f32(e, pre + "attn.q.bias", &w.q_b, D));
+      bool sk, sv, sp, s1, s2;
+      TRY(need_bf16(e, pre + "attn.q.weight", &w.q_w, D, D, &w.split)); TRY(need_f32(e, pre + "attn.q.bias", &w.q_b, D));
       // k and v read the same input: fuse into one (2D, D) weight so one GEMM produces [k | v]
       const __nv_bfloat16 *kw, *vw; const float *kb, *vb;
-      TRY(need_bf16(e, pre + "attn.k.weight", &kw, D, D)); TRY(need_bf16(e, pre + "attn.v.weight", &vw, D, D));
+      TRY(need_bf16(e, pre + "attn.k.weight", &kw, D, D, &sk)); TRY(need_bf16(e, pre + "attn.v.weight", &vw, D, D, &sv));
       TRY(need_f32(e, pre + "attn.k.bias", &kb, D)); TRY(need_f32(e, pre + "attn.v.bias", &vb, D));
-      e.fused.emplace_back(); DevBuf& fw = e.fused.back(); TRY(fw.ensure((size_t)2 * D * D * 2));
+      const size_t wbytes = (size_t)D * D * 2 * (w.split ? 3 : 1);   // split weights: rows are 3*D wide
+      e.fused.emplace_back(); DevBuf& fw = e.fused.back(); TRY(fw.ensure(2 * wbytes));
       e.fused.emplace_back(); DevBuf& fb = e.fused.back(); TRY(fb.ensure((size_t)2 * D * 4));
-      LSVS_CUDA(cudaMemcpyAsync(fw.p, kw, (size_t)D * D * 2, cudaMemcpyDeviceToDevice, st));
-      LSVS_CUDA(cudaMemcpyAsync(fw.as<__nv_bfloat16>() + (size_t)D * D, vw, (size_t)D * D * 2, cudaMemcpyDeviceToDevice, st));
+      LSVS_CUDA(cudaMemcpyAsync(fw.p, kw, wbytes, cudaMemcpyDeviceToDevice, st));
+      LSVS_CUDA(cudaMemcpyAsync(fw.as<uint8_t>() + wbytes, vw, wbytes, cudaMemcpyDeviceToDevice, st));
       LSVS_CUDA(cudaMemcpyAsync(fb.p, kb, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
       LSVS_CUDA(cudaMemcpyAsync(fb.as<float>() + D, vb, (size_t)D * 4, cudaMemcpyDeviceToDevice, st));
       w.kv_w = fw.as<__nv_bfloat16>(); w.kv_b = fb.as<float>();
-      TRY(need_bf16(e, pre + "attn.proj.weight", &w.proj_w, D, D)); TRY(need_f32(e, pre + "attn.proj.bias", &w.proj_b, D));
-      TRY(need_bf16(e, pre + "mlp.fc1.weight", &w.fc1_w, 4 * D, D)); TRY(need_f32(e, pre + "mlp.fc1.bias", &w.fc1_b, 4 * D));
-      TRY(need_bf16(e, pre + "mlp.fc2.weight", &w.fc2_w, D, 4 * D)); TRY(need_f32(e, pre + "mlp.fc2.bias", &w.fc2_b, D));
+      TRY(need_bf16(e, pre + "attn.proj.weight", &w.proj_w, D, D, &sp)); TRY(need_f32(e, pre + "attn.proj.bias", &w.proj_b, D));
+      TRY(need_bf16(e, pre + "mlp.fc1.weight", &w.fc1_w, 4 * D, D, &s1)); TRY(need_f32(e, pre + "mlp.fc1.bias", &w.fc1_b, 4 * D));
+      TRY(need_bf16(e, pre + "mlp.fc2.weight", &w.fc2_w, D, 4 * D, &s2)); TRY(need_f32(e, pre + "mlp.fc2.bias", &w.fc2_b, D));
+      if (sk != w.split || sv != w.split || sp != w.split || s1 != w.split || s2 != w.split)
+        return fail(LSVS_EINVAL, "engine: block '%s' mixes split and plain weights", pre.c_str());
       TRY(need_f32(e, pre + "attn.q_norm.weight", &w.qn_w, 128)); TRY(need_f32(e, pre + "attn.q_norm.bias", &w.qn_b, 128));
       TRY(need_f32(e, pre + "attn.k_norm.weight", &w.kn_w, 128)); TRY(need_f32(e, pre + "attn.k_norm.bias", &w.kn_b, 128));
       TRY(need_f32(e, pre + "ls1.gamma", &w.ls1, D)); TRY(need_f32(e, pre + "ls2.gamma", &w.ls2, D));
@@ -363,9 +419,15 @@ extern "C" int lsvs_aggregator_forward(lsvs_engine* h, const float* images, int 
   TRY(ensure_tables(e, gh, gw, 0, st));
   float* x = e.x.as<float>();
   // --- DINOv2 ViT-L/14 patch embedding (A.2)
-  TRY(patch_unfold(images, e.im2col.p, frames, H, W, st));
   const Param* pw; const float *pb, *cls, *reg, *nw, *nb, *cam, *regtok;
   TRY(need(e, "aggregator.patch_embed.patch_embed.proj.weight", &pw));
+  if (pw->split) {  // fp32-class: fp32 im2col, split operands (K = 3 * 640)
+    TRY(e.p_hf.ensure((size_t)frames * Pp * 640 * 4)); TRY(e.p_xs.ensure((size_t)frames * Pp * 1920 * 2));
+    TRY(patch_unfold_f32(images, e.p_hf.as<float>(), frames, H, W, st));
+    TRY(cast_split(e.p_hf.as<float>(), 640, e.p_xs.p, 1920, (long long)frames * Pp, 640, false, st));
+  } else {
+    TRY(patch_unfold(images, e.im2col.p, frames, H, W, st));
+  }
   LSVS_CHECK_ARG(pw->bf16 && pw->rows == 1024 && pw->cols == 588, "aggregator: patch_embed.proj.weight must be (1024, 3*14*14)");
   TRY(need_f32(e, "aggregator.patch_embed.patch_embed.proj.bias", &pb, D));
   TRY(need_f32(e, "aggregator.patch_embed.cls_token", &cls, D)); TRY(need_f32(e, "aggregator.patch_embed.register_tokens", &reg, 4 * D));
@@ -373,7 +435,8 @@ extern "C" int lsvs_aggregator_forward(lsvs_engine* h, const float* images, int 
   TRY(need_f32(e, "aggregator.camera_token", &cam, 2 * D)); TRY(need_f32(e, "aggregator.register_token", &regtok, 8 * D));
   GemmEpilogue ep;
   ep.bias = pb; ep.out = e.tmp.p; ep.ldo = D;
-  TRY(gemm_bf16(e.im2col.p, 640, pw->bf16, 640, frames * Pp, D, 640, EPI_BIAS_F32, ep, st));
+  if (pw->split) TRY(gemm_bf16(e.p_xs.p, 1920, pw->bf16, 1920, frames * Pp, D, 1920, EPI_BIAS_F32, ep, st));
+  else TRY(gemm_bf16(e.im2col.p, 640, pw->bf16, 640, frames * Pp, D, 640, EPI_BIAS_F32, ep, st));
   TRY(dino_assemble(e.tmp.as<float>(), cls, reg, e.pos_embed.as<float>(), x, frames, Pp, 4, D, st));
   RopeCfg none;
   for (int i = 0; i < e.cfg.dino_depth; ++i) TRY(run_block(e, x, M, e.dino[i], 1e-6f, 16, 64, frames, P, none, nullptr, 0, st));
@@ -446,32 +509,37 @@ int decode_forward(Engine& e, const float* x, long long ld_tok, int B, int S, co
   const size_t need_scratch = (size_t)B * ((size_t)(S + NM) * DD * 16 + (size_t)S * DD * 24 + (size_t)NM * DD * 16 + 8192) + (1 << 16);
   TRY(e.scratch.ensure(need_scratch * 4));
   e.scratch_off = 0;
-  const float *pdw, *pdb, *dnw, *dnb, *memp, *alpha, *fpw, *fpb, *cnw, *cnb, *fnw, *fnb;
+  const float *pdw, *pdb, *dnw, *dnb, *memp = nullptr, *alpha = nullptr, *fpw = nullptr, *fpb = nullptr, *cnw, *cnb, *fnw, *fnb;
   TRY(need_f32(e, "alignment_head.project_dec.weight", &pdw, (long long)DD * D)); TRY(need_f32(e, "alignment_head.project_dec.bias", &pdb, DD));
   TRY(need_f32(e, "alignment_head.dec_norm.weight", &dnw, DD)); TRY(need_f32(e, "alignment_head.dec_norm.bias", &dnb, DD));
-  TRY(need_f32(e, "alignment_head.memory_token", &memp, (long long)NM * DD)); TRY(need_f32(e, "alignment_head.alpha", &alpha, 1));
-  TRY(need_f32(e, "alignment_head.frame_proj.weight", &fpw, (long long)NM * DD * DD)); TRY(need_f32(e, "alignment_head.frame_proj.bias", &fpb, NM * DD));
+  if (NM > 0) {  // num_memory_tokens = 0 (alignment_head.py:211,468,504): no memory parameters, keys = the frame tokens only
+    TRY(need_f32(e, "alignment_head.memory_token", &memp, (long long)NM * DD)); TRY(need_f32(e, "alignment_head.alpha", &alpha, 1));
+    TRY(need_f32(e, "alignment_head.frame_proj.weight", &fpw, (long long)NM * DD * DD)); TRY(need_f32(e, "alignment_head.frame_proj.bias", &fpb, NM * DD));
+  }
   TRY(need_f32(e, "alignment_head.chunk_norm.weight", &cnw, DD)); TRY(need_f32(e, "alignment_head.chunk_norm.bias", &cnb, DD));
   TRY(need_f32(e, "alignment_head.frame_norm.weight", &fnw, DD)); TRY(need_f32(e, "alignment_head.frame_norm.bias", &fnb, DD));
   float* t0 = e.scratch_f32((size_t)frames * DD); float* tok = e.scratch_f32((size_t)frames * DD);
   // per-frame alignment token = row 0 of every frame: stride P1*D
   TRY(linear_f32(x, ld_tok, pdw, pdb, t0, DD, frames, DD, D, ACT_NONE, ACT_NONE, nullptr, false, st));
   TRY(layernorm(t0, DD, RowMap{}, dnw, dnb, 1e-5f, tok, DD, RowMap{}, false, frames, DD, st));
-  float* mean_norm = e.scratch_f32(B);
-  TRY(mean_row_norm(tok, B, S, DD, mean_norm, st));
-  float* frame_init = nullptr;
-  if (!memory_in) {
-    frame_init = e.scratch_f32((size_t)B * NM * DD);
-    TRY(linear_f32(tok, (long long)S * DD, fpw, fpb, frame_init, (long long)NM * DD, B, NM * DD, DD, ACT_NONE, ACT_NONE, nullptr, false, st));
+  float* kvt = tok; float* directional = nullptr;
+  if (NM > 0) {
+    float* mean_norm = e.scratch_f32(B);
+    TRY(mean_row_norm(tok, B, S, DD, mean_norm, st));
+    float* frame_init = nullptr;
+    if (!memory_in) {
+      frame_init = e.scratch_f32((size_t)B * NM * DD);
+      TRY(linear_f32(tok, (long long)S * DD, fpw, fpb, frame_init, (long long)NM * DD, B, NM * DD, DD, ACT_NONE, ACT_NONE, nullptr, false, st));
+    }
+    kvt = e.scratch_f32((size_t)B * (S + NM) * DD); directional = e.scratch_f32((size_t)B * NM * DD);
+    TRY(memory_prepare(tok, memp, memory_in, frame_init, alpha, mean_norm, kvt, directional, B, S, NM, DD, st));
   }
-  float* kvt = e.scratch_f32((size_t)B * (S + NM) * DD); float* directional = e.scratch_f32((size_t)B * NM * DD);
-  TRY(memory_prepare(tok, memp, memory_in, frame_init, alpha, mean_norm, kvt, directional, B, S, NM, DD, st));
   // chunk token: frame-0 token attends over [all frame tokens ; scaled memory]
   float* chunk_tok = e.scratch_f32((size_t)B * DD);
   LSVS_CUDA(cudaMemcpy2DAsync(chunk_tok, DD * 4, tok, (size_t)S * DD * 4, DD * 4, B, cudaMemcpyDeviceToDevice, st));
   for (int i = 0; i < 2; ++i) TRY(run_cross_block_f32(e, chunk_tok, B, 1, kvt, S + NM, e.chunk_cross[i], DD, 8, d_dec /*[0]*/, d_dec, st));
   // gated memory update (gated_update.py:43-78)
-  {
+  if (NM > 0) {
     float* inp = e.scratch_f32((size_t)B * NM * 3 * DD); float* mem_scaled = e.scratch_f32((size_t)B * NM * DD);
     float* hid = e.scratch_f32((size_t)B * NM * DD); float* deltas = e.scratch_f32((size_t)B * NM * DD);
     float* gate_in = e.scratch_f32((size_t)B * NM * 2 * DD); float* ghid = e.scratch_f32((size_t)B * NM * DD); float* gate = e.scratch_f32((size_t)B * NM);
@@ -525,11 +593,12 @@ extern "C" int lsvs_alignment_head_forward(lsvs_engine* h, const float* tokens, 
   Engine& e = *reinterpret_cast<Engine*>(h);
   cudaStream_t st = (cudaStream_t)stream;
   LSVS_CHECK_ARG(e.finalized && e.cfg.with_alignment_head, "alignment_head_forward: engine has no alignment head / not finalized");
-  LSVS_CHECK_ARG(tokens && chunk_sim3 && memory_out && overlap_out && B > 0 && S > 0 && P > 5, "alignment_head_forward: bad arguments");
+  LSVS_CHECK_ARG(tokens && chunk_sim3 && overlap_out && B > 0 && S > 0 && P > 5, "alignment_head_forward: bad arguments");
+  LSVS_CHECK_ARG(memory_out || e.cfg.num_memory_tokens == 0, "alignment_head_forward: memory_out missing");
   LSVS_CHECK_ARG(S == 1 || frame_se3, "alignment_head_forward: frame_se3 output missing");
   const int gh = H / 14, gw = W / 14, D = 1024, DD = 512, NM = e.cfg.num_memory_tokens, P1 = P + 1, frames = B * S;
   LSVS_CHECK_ARG(gh * gw + 5 == P, "Size of tokens and image do not match (P=%d, grid %dx%d)", P, gh, gw);
-  LSVS_CHECK_ARG(NM == 8, "alignment_head_forward: num_memory_tokens must be 8");
+  LSVS_CHECK_ARG(NM == 8 || NM == 0, "alignment_head_forward: num_memory_tokens must be 8 or 0");
   LSVS_CHECK_ARG(!overlap_in || T >= 2, "Size of tokens and overlap tokens must match");
   LSVS_CHECK_ARG(next_overlap >= 0 && next_overlap <= S, "alignment_head_forward: next_num_overlap out of range");
   const bool first = overlap_in == nullptr;
@@ -561,9 +630,15 @@ extern "C" int lsvs_alignment_head_forward(lsvs_engine* h, const float* tokens, 
   TRY(need_f32(e, "alignment_head.token_norm.weight", &tnw, D)); TRY(need_f32(e, "alignment_head.token_norm.bias", &tnb, D));
   TRY(need_f32(e, "alignment_head.per_frame_alignment_token", &atok, 2 * D));
   // project_in + token_norm, written behind the per-frame alignment token (:242-270)
-  TRY(cast_rows_bf16(tokens, 2 * D, e.h.p, 2 * D, M, 2 * D, st));
   GemmEpilogue ep; ep.bias = pin_b; ep.out = e.tmp.p; ep.ldo = D;
-  TRY(gemm_bf16(e.h.p, 2 * D, pin->bf16, 2 * D, (int)M, D, 2 * D, EPI_BIAS_F32, ep, st));
+  if (pin->split) {
+    TRY(e.p_hs.ensure((size_t)M * 6 * D * 2));
+    TRY(cast_split(tokens, 2 * D, e.p_hs.p, 6 * D, M, 2 * D, false, st));
+    TRY(gemm_bf16(e.p_hs.p, 6 * D, pin->bf16, 6 * D, (int)M, D, 6 * D, EPI_BIAS_F32, ep, st));
+  } else {
+    TRY(cast_rows_bf16(tokens, 2 * D, e.h.p, 2 * D, M, 2 * D, st));
+    TRY(gemm_bf16(e.h.p, 2 * D, pin->bf16, 2 * D, (int)M, D, 2 * D, EPI_BIAS_F32, ep, st));
+  }
   TRY(layernorm(e.tmp.as<float>(), D, RowMap{}, tnw, tnb, 1e-5f, x, D, RowMap{P, P1, 1}, false, M, D, st));
   TRY(fill_special(atok, x, frames, S, P1, 0, 1, D, st));
 
@@ -572,6 +647,25 @@ extern "C" int lsvs_alignment_head_forward(lsvs_engine* h, const float* tokens, 
     TRY(run_block(e, x, Mh, e.h_frame[i], 1e-5f, 8, 128, frames, P1, r2, nullptr, 0, st));
     // temporal cross block on the RAW (B*P1, S, C) view: groups of S consecutive flat rows (:372-377)
     const BlockW& w = e.h_temporal[i];
+    if (w.split) {  // fp32-class cross block (csrc/precise.cu): split GEMM operands, fp32 q/k LayerNorm + 1-D RoPE + attention
+      TRY(e.p_xs.ensure((size_t)Mh * 3 * D * 2)); TRY(e.p_ys.ensure((size_t)My * 3 * D * 2)); TRY(e.p_qkv.ensure((size_t)Mh * D * 4));
+      TRY(e.p_kv.ensure((size_t)My * 2 * D * 4)); TRY(e.p_att.ensure((size_t)Mh * 3 * D * 2));
+      float *qf = e.p_qkv.as<float>(), *kvf = e.p_kv.as<float>();
+      TRY(layernorm_split(x, D, w.n1w, w.n1b, 1e-5f, e.p_xs.p, 3 * D, Mh, D, st));
+      TRY(layernorm_split(first ? x : overlap_in, D, w.n3w, w.n3b, 1e-5f, e.p_ys.p, 3 * D, My, D, st));
+      GemmEpilogue eq; eq.bias = w.q_b; eq.out = qf; eq.ldo = D;
+      TRY(gemm_bf16(e.p_xs.p, 3 * D, w.q_w, 3 * D, (int)Mh, D, 3 * D, EPI_BIAS_F32, eq, st));
+      GemmEpilogue ek; ek.bias = w.kv_b; ek.out = kvf; ek.ldo = 2 * D;
+      TRY(gemm_bf16(e.p_ys.p, 3 * D, w.kv_w, 3 * D, (int)My, 2 * D, 3 * D, EPI_BIAS_F32, ek, st));
+      TRY(headnorm_rope_f32(qf, D, Mh, 0, 8, 128, w.qn_w, w.qn_b, 1e-5f, ROPE_1D, e.rope1d_128.as<float2>(), 0, 0, 0, d_qi, S, st));
+      TRY(headnorm_rope_f32(kvf, 2 * D, My, 0, 8, 128, w.kn_w, w.kn_b, 1e-5f, ROPE_1D, e.rope1d_128.as<float2>(), 0, 0, 0, d_ki, T, st));
+      AttentionF32Args aa{qf, kvf, kvf + D, e.p_att.p, D, 2 * D, 2 * D, 3 * D, D, B * P1, 8, 128, S, T, 1.0f / sqrtf(128.f)};
+      TRY(attention_f32(aa, st));
+      GemmEpilogue er; er.bias = w.proj_b; er.gamma = w.ls1; er.resid = x; er.ldr = D;
+      TRY(gemm_bf16(e.p_att.p, 3 * D, w.proj_w, 3 * D, (int)Mh, D, 3 * D, EPI_RESID_F32, er, st));
+      TRY(run_mlp_precise(e, x, Mh, w, 1e-5f, D, nullptr, 0, st));
+      continue;
+    }
     __nv_bfloat16 *yn = e.yn.as<__nv_bfloat16>(), *q = e.qkv.as<__nv_bfloat16>(), *kv = e.kvb.as<__nv_bfloat16>(), *att = e.att.as<__nv_bfloat16>(), *hb = e.h.as<__nv_bfloat16>();
     TRY(layernorm(x, D, RowMap{}, w.n1w, w.n1b, 1e-5f, xn, D, RowMap{}, true, Mh, D, st));
     TRY(layernorm(first ? x : overlap_in, D, RowMap{}, w.n3w, w.n3b, 1e-5f, yn, D, RowMap{}, true, My, D, st));
@@ -829,9 +923,10 @@ extern "C" int lsvs_alignment_decode_forward(lsvs_engine* h, const float* align_
   Engine& e = *reinterpret_cast<Engine*>(h);
   cudaStream_t st = (cudaStream_t)stream;
   LSVS_CHECK_ARG(e.finalized && e.cfg.with_alignment_head, "alignment_decode_forward: engine has no alignment head / not finalized");
-  LSVS_CHECK_ARG(align_tokens && chunk_sim3 && memory_out && B > 0 && S > 0 && (S == 1 || frame_se3), "alignment_decode_forward: bad arguments");
-  LSVS_CHECK_ARG(e.cfg.num_memory_tokens == 8, "alignment_decode_forward: num_memory_tokens must be 8");
-  const int NM = 8;
+  LSVS_CHECK_ARG(align_tokens && chunk_sim3 && B > 0 && S > 0 && (S == 1 || frame_se3), "alignment_decode_forward: bad arguments");
+  const int NM = e.cfg.num_memory_tokens;
+  LSVS_CHECK_ARG(NM == 8 || NM == 0, "alignment_decode_forward: num_memory_tokens must be 8 or 0");
+  LSVS_CHECK_ARG(memory_out || NM == 0, "alignment_decode_forward: memory_out missing");
   std::vector<int> dec(S + NM);
   for (int j = 0; j < S; ++j) dec[j] = j;
   for (int j = 0; j < NM; ++j) dec[S + j] = 2 * S + j;

@@ -2,6 +2,7 @@
 Everything here is plumbing: device memory comes from torch, the work runs in liblsvs_b200.so."""
 import ctypes
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -16,7 +17,7 @@ class EngineConfig(ctypes.Structure):
     """mirror of `lsvs_engine_config` in include/lsvs_b200.h"""
     _fields_ = [("embed_dim", _i), ("num_heads", _i), ("patch_size", _i), ("num_register_tokens", _i), ("depth", _i),
                 ("dino_depth", _i), ("head_depth_aa", _i), ("num_memory_tokens", _i), ("with_alignment_head", _i),
-                ("with_camera_head", _i), ("rope_base", _f)]
+                ("with_camera_head", _i), ("rope_base", _f), ("precision", _i)]
 
 
 def interpolate_pos_embed(pos_embed: torch.Tensor, gh: int, gw: int) -> torch.Tensor:
@@ -51,9 +52,16 @@ class Engine:
     """One native engine per (model, device).  `sync(named_params)` pushes changed parameters."""
 
     def __init__(self, depth=24, dino_depth=24, head_depth_aa=4, num_memory_tokens=8, with_alignment_head=True,
-                 with_camera_head=True, rope_base=100.0):
+                 with_camera_head=True, rope_base=100.0, precision=None):
+        """precision (include/lsvs_b200.h lsvs_engine_config::precision): 0 bf16 tensor-core operands (default; env
+        LSVS_PRECISION overrides the default), 1 fp32-class alignment head + camera-head trunk, 2 fp32-class everywhere."""
+        if precision is None:
+            precision = int(os.environ.get("LSVS_PRECISION", "0"))
+        if precision not in (0, 1, 2):
+            raise ValueError(f"precision must be 0, 1 or 2, got {precision}")
+        self.precision = precision
         self.cfg = EngineConfig(1024, 16, 14, 4, depth, dino_depth, head_depth_aa, num_memory_tokens,
-                                int(with_alignment_head), int(with_camera_head), rope_base)
+                                int(with_alignment_head), int(with_camera_head), rope_base, precision)
         self._h = _vp()
         _n.check(_n.lib().lsvs_engine_create(ctypes.byref(self.cfg), ctypes.byref(self._h)), "engine_create")
         self._seen: Dict[str, Tuple[int, int]] = {}
@@ -145,11 +153,14 @@ class Engine:
             mem = memory_tokens.detach().to(dev, torch.float32).contiguous()
         sim3 = torch.empty(B, 1, 8, device=dev)
         se3 = torch.empty(B, max(S - 1, 0), 7, device=dev)
-        mem_out = torch.empty(B, 8, 512, device=dev)
+        nm = int(self.cfg.num_memory_tokens)
+        mem_out = torch.empty(B, nm, 512, device=dev) if nm > 0 else None
         ov_out = torch.empty(B, 1 + next_overlap, P + 1, 1024, device=dev)
         _n.check(_n.lib().lsvs_alignment_head_forward(self._h, _n.ptr(tok), _i(B), _i(S), _i(P), _i(H), _i(W), _i(next_overlap),
                                                       _n.ptr(ov), _i(T), _n.ptr(mem), _n.ptr(sim3), _n.ptr(se3), _n.ptr(mem_out),
                                                       _n.ptr(ov_out), _n.stream_ptr()), "alignment_head_forward")
+        if nm == 0:  # the reference hands the caller's memory_tokens argument back untouched (alignment_head.py:504-506)
+            mem_out = memory_tokens
         return sim3, se3, mem_out, ov_out
 
     def alignment_decode_forward(self, align_tokens: torch.Tensor, memory_tokens: Optional[torch.Tensor]):
@@ -159,10 +170,12 @@ class Engine:
         dev = align_tokens.device
         tok = align_tokens.detach().float().contiguous()
         mem = None if memory_tokens is None else memory_tokens.detach().to(dev, torch.float32).contiguous()
-        sim3, se3, mem_out = torch.empty(B, 1, 8, device=dev), torch.empty(B, max(S - 1, 0), 7, device=dev), torch.empty(B, 8, 512, device=dev)
+        nm = int(self.cfg.num_memory_tokens)
+        sim3, se3 = torch.empty(B, 1, 8, device=dev), torch.empty(B, max(S - 1, 0), 7, device=dev)
+        mem_out = torch.empty(B, nm, 512, device=dev) if nm > 0 else None
         _n.check(_n.lib().lsvs_alignment_decode_forward(self._h, _n.ptr(tok), _i(B), _i(S), _n.ptr(mem), _n.ptr(sim3), _n.ptr(se3),
                                                         _n.ptr(mem_out), _n.stream_ptr()), "alignment_decode_forward")
-        return sim3, se3, mem_out
+        return sim3, se3, (mem_out if nm > 0 else memory_tokens)
 
     def dpt_head_forward(self, prefix: str, taps: Sequence[torch.Tensor], image_hw, output_dim: int, activation: str,
                          frames_chunk: int = 8):

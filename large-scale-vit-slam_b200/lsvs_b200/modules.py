@@ -9,12 +9,26 @@ from . import specs
 from .engine import Engine
 
 
+def load_state_dict_without_track_head(self, state_dict, strict: bool = True, assign: bool = False):
+    """nn.Module.load_state_dict for the model mirrors: `track_head.*` entries of a facebook/VGGT-1B style checkpoint are skipped
+    while the model has no track head (the reference's forward never calls it), so strict loading keeps working."""
+    if getattr(self, "track_head", None) is None:
+        state_dict = {k: v for k, v in state_dict.items() if not k.startswith("track_head.")}
+    return nn.Module.load_state_dict(self, state_dict, strict=strict, assign=assign)
+
+
 class _EngineBound(specs.ParamTree):
     """A parameter tree bound to a (possibly shared) native engine under a name prefix."""
     _prefix = ""
 
     def _bind(self, owner):
         object.__setattr__(self, "_owner", owner)  # not a submodule: avoid a reference cycle in the module tree
+
+    def __getstate__(self):
+        # copy.deepcopy / pickle (EMA copies, checkpoint cloning): the native engine handle is process-local and is rebuilt lazily
+        state = self.__dict__.copy()
+        state.pop("_own_engine", None)
+        return state
 
     def _engine(self) -> Engine:
         owner = getattr(self, "_owner", None)

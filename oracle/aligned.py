@@ -144,11 +144,11 @@ def alignment_head_forward(p: Params, pre: str, tokens: torch.Tensor, image_size
     tokens (B,S,P,2048) -> chunk_sim3 (B,1,8), frame_se3 (B,S-1,7), memory (B,8,512), overlap (B,1+o,P+1,1024).
     amp=True emulates the reference's shipping precision (Lightning bf16-mixed, run_model.py:472): the token blocks
     run under bf16 autocast, the decode with autocast disabled (alignment_head.py:340)."""
-    with torch.autocast("cpu", dtype=torch.bfloat16, enabled=amp):
+    with torch.autocast(tokens.device.type, dtype=torch.bfloat16, enabled=amp):
         x, T, first_chunk, S, P1, C, B = _head_blocks(p, pre, tokens, image_size, overlap_tokens, patch_size, depth_aa, heads,
                                                       num_register_tokens, temporal_attention, rope_base)
     x = x.float()
-    with torch.autocast("cpu", enabled=False):
+    with torch.autocast(tokens.device.type, enabled=False):
         chunk_sim3, frame_se3, memory = decode_alignments(p, pre, x[:, :, 0], first_chunk, memory_tokens, heads,
                                                           num_memory_tokens=num_memory_tokens, rope_base=rope_base)
     new_overlap = torch.cat([x[:, :1], x[:, S - next_num_overlap:]], dim=1).contiguous()  # :343
@@ -419,9 +419,15 @@ def feature_aligned_forward(p: Params, images: torch.Tensor, num_overlap: int, c
     stand in for their outputs so the Sim(3) application can be checked.  Returns this chunk's tensors
     (not the accumulated lists) plus the context entries needed by the next chunk."""
     B, S, _, H, W = images.shape
-    with torch.autocast("cpu", dtype=torch.bfloat16, enabled=amp):  # amp: the reference's bf16-mixed inference precision
+    with torch.autocast(images.device.type, dtype=torch.bfloat16, enabled=amp):  # amp: the reference's bf16-mixed inference precision
         toks, _ = OF.aggregator_forward(p, "aggregator.", images, depth=depth, dino_depth=dino_depth, keep=taps)
     taps_t = [toks[i].float() for i in taps]
+    return _feature_aligned_tail(p, images, taps_t, num_overlap, context, raw_points, raw_depth, depth_aa, num_memory_tokens, amp, gt_poses)
+
+
+def _feature_aligned_tail(p, images, taps_t, num_overlap, context, raw_points, raw_depth, depth_aa, num_memory_tokens, amp, gt_poses):
+    """Everything of FeatureAlignedVGGT.forward after the Aggregator (featureAligned_vggt.py:84-225)."""
+    B, S, _, H, W = images.shape
     ctx_overlap = ctx_mem = prev_pose = None
     if context is not None:
         ctx_overlap = context["overlap_tokens"]
@@ -443,6 +449,51 @@ def feature_aligned_forward(p: Params, images: torch.Tensor, num_overlap: int, c
         Tp = point_transform(per_frame, pt_ident, context is not None)
         out["world_points"] = apply_sim3_points(raw_points, Tp, scale.view(B))  # :198-207
         out["point_transform"] = Tp
+    return out
+
+
+def feature_aligned_forward_sliced(p: Params, images: torch.Tensor, num_overlap: int, context: Optional[dict] = None, *,
+                                   raw_points: Optional[torch.Tensor] = None, raw_depth: Optional[torch.Tensor] = None,
+                                   depth: int = 24, dino_depth: int = 24, taps=(4, 11, 17, 23), depth_aa: int = 4,
+                                   num_memory_tokens: int = 8):
+    """The same computation as feature_aligned_forward (fp32), as a generator that yields (unit name, relative cost) after each
+    unit of work — patch embedding, every DINO block, every frame / global block, the tail (heads, pose chain, Sim(3) apply) —
+    and returns the output dict (StopIteration.value).  bench.py's CPU reference arm times a bounded slice of a full-size chunk
+    per step with it; tests/test_oracle_golden.py checks it against the monolithic function."""
+    B, S, _, H, W = images.shape
+    pre, n_reg, heads, patch = "aggregator.", 4, 16, 14
+    mean = torch.tensor(OF.RESNET_MEAN, dtype=images.dtype, device=images.device).view(1, 1, 3, 1, 1)
+    std = torch.tensor(OF.RESNET_STD, dtype=images.dtype, device=images.device).view(1, 1, 3, 1, 1)
+    x = ((images - mean) / std).view(B * S, 3, H, W)
+    dp = pre + "patch_embed."
+    gh, gw = H // patch, W // patch
+    x = torch.nn.functional.conv2d(x, p[dp + "patch_embed.proj.weight"], p[dp + "patch_embed.proj.bias"], stride=patch).flatten(2).transpose(1, 2)
+    x = torch.cat([p[dp + "cls_token"].expand(B * S, -1, -1), x], dim=1) + OF.interpolate_pos_embed(p[dp + "pos_embed"], gh, gw)
+    x = torch.cat([x[:, :1], p[dp + "register_tokens"].expand(B * S, -1, -1), x[:, 1:]], dim=1)
+    yield "patch_embed", 0.3
+    for i in range(dino_depth):
+        x = OF.block(p, f"{dp}blocks.{i}.", x, heads, ln_eps=1e-6)
+        yield f"dino.{i}", 1.0
+    patch_tok = OF.layer_norm(p, dp + "norm", x, 1e-6)[:, 1 + n_reg:]
+    C = patch_tok.shape[-1]
+    cam = OF.expand_special(p[pre + "camera_token"], B, S).reshape(B * S, 1, C)
+    reg = OF.expand_special(p[pre + "register_token"], B, S).reshape(B * S, n_reg, C)
+    tokens = torch.cat([cam, reg, patch_tok], dim=1)
+    pos = OF.token_positions(B * S, gh, gw, 1 + n_reg, images.device)
+    P = tokens.shape[1]
+    global_cost = 1.0 + 2.0 * (S * P) / 13184.0   # attention over all S*P tokens: twice the block's GEMM work at S*P = 13184
+    kept = {}
+    for i in range(depth):
+        tokens = OF.block(p, f"{pre}frame_blocks.{i}.", tokens.view(B * S, P, C), heads, pos, 100.0)
+        frame_out = tokens.view(B, S, P, C)
+        yield f"frame.{i}", 1.0
+        tokens = OF.block(p, f"{pre}global_blocks.{i}.", tokens.view(B, S * P, C), heads, pos.view(B, S * P, 2), 100.0)
+        if i in taps:
+            kept[i] = torch.cat([frame_out, tokens.view(B, S, P, C)], dim=-1)
+        yield f"global.{i}", global_cost
+    out = _feature_aligned_tail(p, images, [kept[i].float() for i in taps], num_overlap, context, raw_points, raw_depth, depth_aa,
+                                num_memory_tokens, False, None)
+    yield "tail", 8.0
     return out
 
 

@@ -604,6 +604,50 @@ def case_model_full():
     run_two_chunks(model, sd, 4, 154, 518, 1, (4, 11, 17, 23), 24, 24, "full", sample=8)
 
 
+def case_model_headline():
+    """The benchmarked configuration (BASELINE configs[1]/[2]): S=32 frames of 154x518, overlap 8, full depth, THREE chained chunks
+    (first chunk, context chunk, context + carried memory) through the reference's FeatureAlignedVGGT.  Token tensors are stored
+    column-subsampled (tap: every 64th of 2048 columns, overlap tokens: every 32nd of 1024)."""
+    print("[FeatureAlignedVGGT, full depth, headline config: S=32, 154x518, overlap 8, 3 chunks]")
+    model, sd = build_reference_model(None)
+    S, H, W, ov, taps, n = 32, 154, 518, 8, (4, 11, 17, 23), 3
+    imgs = [torch.from_numpy(np.random.Generator(np.random.PCG64(100 + i)).random((1, S, 3, H, W), dtype=np.float32)) for i in range(n)]
+    captured = []
+    hook = model.alignment_head.register_forward_pre_hook(lambda m, a: captured.append(a[0].detach().clone()))
+    snaps, secs, pred = [], [], None
+    with torch.no_grad():
+        for i in range(n):
+            t0 = time.time()
+            pred = model(imgs[i], ov, pred)
+            secs.append(time.time() - t0)
+            snap = {k: (v[-1] if isinstance(v, list) else v).clone() for k, v in pred.items() if k != "images"}
+            snap["chunk_sim3_alignment_enc"] = pred["chunk_sim3_alignment_enc"][:, -1:].clone()
+            snap["frame_se3_alignment_enc"] = pred["frame_se3_alignment_enc"][:, -(S - 1):].clone()
+            snaps.append(snap)
+            for k in ("images",):           # the reference keeps every chunk's images in the context: drop them (memory)
+                pred.pop(k, None)
+            print(f"  reference chunk {i + 1}: {secs[-1]:.1f}s ({torch.get_num_threads()} threads)", flush=True)
+    hook.remove()
+    ctx = None
+    with torch.no_grad():
+        for i in range(n):
+            o = OA.feature_aligned_forward(sd, imgs[i], ov, ctx, taps=taps)
+            ctx = {"overlap_tokens": o["overlap_tokens"], "memory_tokens": o["memory_tokens"], "pose_enc": o["pose_enc"]}
+            check(f"headline c{i + 1} last tap", o["taps"][-1], captured[i], 5e-4)
+            for k in ("chunk_sim3_alignment_enc", "frame_se3_alignment_enc", "memory_tokens", "overlap_tokens", "pose_enc"):
+                check(f"headline c{i + 1} {k}", o[k], snaps[i][k], 5e-4)
+    arrs = {"S": S, "H": H, "W": W, "ov": ov, "taps": np.array(taps), "n_chunks": n, "wsum": OW.checksum(sd), "tap_stride": 64,
+            "overlap_stride": 32, "secs_per_chunk": np.array(secs), "threads": torch.get_num_threads()}
+    for i in range(n):
+        c = f"c{i + 1}"
+        arrs[c + "_tap_last"] = captured[i][..., ::64].contiguous()
+        arrs[c + "_tap_last_norm"] = float(captured[i].norm())
+        arrs[c + "_overlap_tokens"] = snaps[i]["overlap_tokens"][..., ::32].contiguous()
+        for k in ("chunk_sim3_alignment_enc", "frame_se3_alignment_enc", "memory_tokens", "pose_enc"):
+            arrs[f"{c}_{k}"] = snaps[i][k]
+    save("model_headline.npz", **arrs)
+
+
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
     ap = argparse.ArgumentParser()
@@ -618,6 +662,7 @@ if __name__ == "__main__":
              "host_glue": case_host_glue}
     if args.full:
         cases["model_full"] = case_model_full
+        cases["model_headline"] = case_model_headline
     for name, fn in cases.items():
         if args.only and name != args.only:
             continue
