@@ -166,6 +166,11 @@ int lsvs_aggregator_forward(lsvs_engine* e, const float* images, int B, int S, i
 int lsvs_alignment_head_forward(lsvs_engine* e, const float* tokens, int B, int S, int P, int H, int W, int next_overlap,
                                 const float* overlap_in, int T, const float* memory_in, float* chunk_sim3,
                                 float* frame_se3, float* memory_out, float* overlap_out, void* stream);
+/* the same with the tokens already in bf16 — the form in which the chunk scheduler ships a chunk's last-layer tokens to the
+ * alignment rank (54 MB instead of 108 MB per 32-frame chunk); they are the first GEMM's operand as they stand (precision 0 only). */
+int lsvs_alignment_head_forward_bf16(lsvs_engine* e, const lsvs_bf16* tokens, int B, int S, int P, int H, int W, int next_overlap,
+                                     const float* overlap_in, int T, const float* memory_in, float* chunk_sim3,
+                                     float* frame_se3, float* memory_out, float* overlap_out, void* stream);
 /* the fp32 decode stage alone: AlignmentHead._decode_alignments alignment_head.py:427-540 (+ GatedUpdate,
  * gated_update.py:43-78).  align_tokens (B,S,1024) fp32 = the processed per-frame alignment tokens. */
 int lsvs_alignment_decode_forward(lsvs_engine* e, const float* align_tokens, int B, int S, const float* memory_in,

@@ -79,6 +79,8 @@ struct Engine {
   DevBuf pos_embed; int pos_gh = 0, pos_gw = 0;
   // tables
   DevBuf rope2d_64, rope2d_128, rope1d_128, ids_q, ids_k;
+  long long ids_q_key = -1, ids_k_key = -1;   // (S, T, first chunk) the position ids on the device were built for: uploaded once per
+                                               // configuration, so a steady-state forward issues no host-to-device copy (CUDA-graph capturable)
   int rope_npos2d = 0, rope_npos1d = 0;
   // workspace
   DevBuf x, xn, qkv, att, h, tmp, im2col, yn, kvb, scratch, dpt_ws;
@@ -587,13 +589,39 @@ int decode_forward(Engine& e, const float* x, long long ld_tok, int B, int S, co
 }  // namespace lsvs
 
 // ================================================================================================ AlignmentHead
+namespace lsvs {
+namespace {
+int alignment_head_forward_impl(lsvs_engine* h, const float* tokens, const __nv_bfloat16* tokens_bf16, int B, int S, int P, int H, int W,
+                                int next_overlap, const float* overlap_in, int T, const float* memory_in, float* chunk_sim3,
+                                float* frame_se3, float* memory_out, float* overlap_out, void* stream);
+}  // namespace
+}  // namespace lsvs
+
 extern "C" int lsvs_alignment_head_forward(lsvs_engine* h, const float* tokens, int B, int S, int P, int H, int W, int next_overlap,
                                            const float* overlap_in, int T, const float* memory_in, float* chunk_sim3,
                                            float* frame_se3, float* memory_out, float* overlap_out, void* stream) {
+  LSVS_CHECK_ARG(tokens, "alignment_head_forward: bad arguments");
+  return lsvs::alignment_head_forward_impl(h, tokens, nullptr, B, S, P, H, W, next_overlap, overlap_in, T, memory_in, chunk_sim3, frame_se3,
+                                           memory_out, overlap_out, stream);
+}
+
+extern "C" int lsvs_alignment_head_forward_bf16(lsvs_engine* h, const lsvs_bf16* tokens, int B, int S, int P, int H, int W, int next_overlap,
+                                                const float* overlap_in, int T, const float* memory_in, float* chunk_sim3,
+                                                float* frame_se3, float* memory_out, float* overlap_out, void* stream) {
+  LSVS_CHECK_ARG(tokens, "alignment_head_forward_bf16: bad arguments");
+  return lsvs::alignment_head_forward_impl(h, nullptr, reinterpret_cast<const __nv_bfloat16*>(tokens), B, S, P, H, W, next_overlap, overlap_in, T,
+                                           memory_in, chunk_sim3, frame_se3, memory_out, overlap_out, stream);
+}
+
+namespace lsvs {
+namespace {
+int alignment_head_forward_impl(lsvs_engine* h, const float* tokens, const __nv_bfloat16* tokens_bf16, int B, int S, int P, int H, int W,
+                                int next_overlap, const float* overlap_in, int T, const float* memory_in, float* chunk_sim3,
+                                float* frame_se3, float* memory_out, float* overlap_out, void* stream) {
   Engine& e = *reinterpret_cast<Engine*>(h);
   cudaStream_t st = (cudaStream_t)stream;
   LSVS_CHECK_ARG(e.finalized && e.cfg.with_alignment_head, "alignment_head_forward: engine has no alignment head / not finalized");
-  LSVS_CHECK_ARG(tokens && chunk_sim3 && overlap_out && B > 0 && S > 0 && P > 5, "alignment_head_forward: bad arguments");
+  LSVS_CHECK_ARG(chunk_sim3 && overlap_out && B > 0 && S > 0 && P > 5, "alignment_head_forward: bad arguments");
   LSVS_CHECK_ARG(memory_out || e.cfg.num_memory_tokens == 0, "alignment_head_forward: memory_out missing");
   LSVS_CHECK_ARG(S == 1 || frame_se3, "alignment_head_forward: frame_se3 output missing");
   const int gh = H / 14, gw = W / 14, D = 1024, DD = 512, NM = e.cfg.num_memory_tokens, P1 = P + 1, frames = B * S;
@@ -618,7 +646,12 @@ extern "C" int lsvs_alignment_head_forward(lsvs_engine* h, const float* tokens, 
   for (int j = 0; j < S; ++j) dec[j] = j;                        // [0,S): 0..S-1  (dec+1 = frame query ids; dec = chunk key ids)
   for (int j = 0; j < NM; ++j) dec[S + j] = 2 * S + j;           // memory keys
   std::vector<int> all(qi); all.insert(all.end(), ki.begin(), ki.end()); all.insert(all.end(), dec.begin(), dec.end());
-  TRY(upload_ids(e.ids_q, all, st));
+  const long long ids_key = (((long long)S * 4096 + T) * 2 + (first ? 1 : 0)) * 64 + NM;
+  if (e.ids_q_key != ids_key) {
+    e.ids_q_key = -1;
+    TRY(upload_ids(e.ids_q, all, st));
+    e.ids_q_key = ids_key;
+  }
   const int* d_qi = e.ids_q.as<int>(); const int* d_ki = d_qi + S; const int* d_dec = d_ki + T;
 
   float* x = e.x.as<float>();
@@ -631,7 +664,10 @@ extern "C" int lsvs_alignment_head_forward(lsvs_engine* h, const float* tokens, 
   TRY(need_f32(e, "alignment_head.per_frame_alignment_token", &atok, 2 * D));
   // project_in + token_norm, written behind the per-frame alignment token (:242-270)
   GemmEpilogue ep; ep.bias = pin_b; ep.out = e.tmp.p; ep.ldo = D;
-  if (pin->split) {
+  if (tokens_bf16) {  // tokens that already are bf16 (the chunk scheduler ships them that way): they are the GEMM operand as they stand
+    LSVS_CHECK_ARG(!pin->split, "alignment_head_forward_bf16: a precision-mode engine needs fp32 tokens");
+    TRY(gemm_bf16(tokens_bf16, 2 * D, pin->bf16, 2 * D, (int)M, D, 2 * D, EPI_BIAS_F32, ep, st));
+  } else if (pin->split) {
     TRY(e.p_hs.ensure((size_t)M * 6 * D * 2));
     TRY(cast_split(tokens, 2 * D, e.p_hs.p, 6 * D, M, 2 * D, false, st));
     TRY(gemm_bf16(e.p_hs.p, 6 * D, pin->bf16, 6 * D, (int)M, D, 6 * D, EPI_BIAS_F32, ep, st));
@@ -697,6 +733,8 @@ extern "C" int lsvs_alignment_head_forward(lsvs_engine* h, const float* tokens, 
 
   return decode_forward(e, x, (long long)P1 * D, B, S, d_dec, memory_in, chunk_sim3, frame_se3, memory_out, st);
 }
+}  // namespace
+}  // namespace lsvs
 
 // ================================================================================================ CameraHead
 extern "C" int lsvs_camera_head_forward(lsvs_engine* h, const float* tokens_last, int B, int S, int P, int num_iterations,
@@ -930,7 +968,11 @@ extern "C" int lsvs_alignment_decode_forward(lsvs_engine* h, const float* align_
   std::vector<int> dec(S + NM);
   for (int j = 0; j < S; ++j) dec[j] = j;
   for (int j = 0; j < NM; ++j) dec[S + j] = 2 * S + j;
-  TRY(upload_ids(e.ids_k, dec, st));
+  if (e.ids_k_key != (long long)S * 64 + NM) {
+    e.ids_k_key = -1;
+    TRY(upload_ids(e.ids_k, dec, st));
+    e.ids_k_key = (long long)S * 64 + NM;
+  }
   return decode_forward(e, align_tokens, 1024, B, S, e.ids_k.as<int>(), memory_in, chunk_sim3, frame_se3, memory_out, st);
 }
 

@@ -140,7 +140,8 @@ class Engine:
         B, S, P, C = tokens.shape
         H, W = image_size
         dev = tokens.device
-        tok = tokens.detach().float().contiguous()
+        as_bf16 = tokens.dtype == torch.bfloat16 and self.precision == 0   # shipped by the chunk scheduler: used as they are
+        tok = tokens.detach().contiguous() if as_bf16 else tokens.detach().float().contiguous()
         T = 0
         ov = mem = None
         if overlap_tokens is not None:
@@ -156,7 +157,8 @@ class Engine:
         nm = int(self.cfg.num_memory_tokens)
         mem_out = torch.empty(B, nm, 512, device=dev) if nm > 0 else None
         ov_out = torch.empty(B, 1 + next_overlap, P + 1, 1024, device=dev)
-        _n.check(_n.lib().lsvs_alignment_head_forward(self._h, _n.ptr(tok), _i(B), _i(S), _i(P), _i(H), _i(W), _i(next_overlap),
+        fn = _n.lib().lsvs_alignment_head_forward_bf16 if as_bf16 else _n.lib().lsvs_alignment_head_forward
+        _n.check(fn(self._h, _n.ptr(tok), _i(B), _i(S), _i(P), _i(H), _i(W), _i(next_overlap),
                                                       _n.ptr(ov), _i(T), _n.ptr(mem), _n.ptr(sim3), _n.ptr(se3), _n.ptr(mem_out),
                                                       _n.ptr(ov_out), _n.stream_ptr()), "alignment_head_forward")
         if nm == 0:  # the reference hands the caller's memory_tokens argument back untouched (alignment_head.py:504-506)

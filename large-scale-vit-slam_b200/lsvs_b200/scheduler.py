@@ -535,6 +535,9 @@ class ModelStages:
         self.model, self.ov, self.S, self.H, self.W, self.device = model, num_overlap, S, H, W, device
         self.P = 5 + (H // 14) * (W // 14)
         self.packet_numel = 1 + 16 + S * 9 + 8 + (S - 1) * 7
+        # the last-layer tokens travel as bf16 — exactly what the head's first GEMM consumes — unless the model runs a precision
+        # mode whose head takes fp32-class operands
+        self.tokens_dtype = torch.bfloat16 if not getattr(model, "precision", None) else torch.float32
         self._maps = {}   # id(inputs) -> DPT head outputs of a chunk whose packet has not arrived yet
 
     def shapes_of(self, frames: int):
@@ -542,7 +545,7 @@ class ModelStages:
         return (1, frames, self.P, 2048), (1, frames, 9), 1 + 16 + frames * 9 + 8 + (frames - 1) * 7
 
     def tokens_like(self):
-        return torch.empty(1, self.S, self.P, 2048, dtype=torch.bfloat16, device=self.device)
+        return torch.empty(1, self.S, self.P, 2048, dtype=self.tokens_dtype, device=self.device)
 
     def cam_like(self):
         return torch.empty(1, self.S, 9, dtype=torch.float32, device=self.device)
@@ -563,7 +566,7 @@ class ModelStages:
             maps["points"], maps["points_conf"] = m.point_head(taps, images=images, patch_start_idx=patch_start_idx)
         if maps:
             self._maps[id(inputs)] = maps
-        return last.to(torch.bfloat16), cam
+        return last.to(self.tokens_dtype), cam
 
     def align(self, tokens, cam, ctx):
         from .engine import pose_chain
@@ -573,7 +576,7 @@ class ModelStages:
         ov_in = mem_in = prev = None
         if ctx is not None:
             ov_in, mem_in, prev = ctx["overlap_tokens"], ctx["memory_tokens"], ctx["pose_enc"]
-        sim3, se3, mem, ov_out = m.alignment_head(tokens.float(), (self.H, self.W), overlap, overlap_tokens=ov_in, memory_tokens=mem_in)
+        sim3, se3, mem, ov_out = m.alignment_head(tokens, (self.H, self.W), overlap, overlap_tokens=ov_in, memory_tokens=mem_in)
         pose, point_T, scale = pose_chain(sim3, se3, cam, prev, overlap, (self.H, self.W))
         packet = torch.cat([scale.reshape(-1), point_T.reshape(-1), pose.reshape(-1), sim3.reshape(-1), se3.reshape(-1)])
         return packet, {"overlap_tokens": ov_out, "memory_tokens": mem, "pose_enc": pose}
@@ -607,7 +610,7 @@ def model_pipeline(model, num_overlap: int, S: int, H: int, W: int, rank: int, w
     tx = None
     if world > 1 and transport in ("auto", "peer"):
         try:
-            tx = PeerTransport(rank, world, (1, S, st.P, 2048), torch.bfloat16, (1, S, 9), st.packet_numel, device,
+            tx = PeerTransport(rank, world, (1, S, st.P, 2048), st.tokens_dtype, (1, S, 9), st.packet_numel, device,
                                group=handshake_group, slots=lag + 1)
         except Exception as e:  # noqa: BLE001  (raised on every rank together, see PeerTransport.__init__)
             if transport == "peer":

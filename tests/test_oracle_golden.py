@@ -273,3 +273,33 @@ def test_ragged_chunks_golden(golden):
         for k in ("pose_enc", "memory_tokens", "chunk_sim3_alignment_enc", "frame_se3_alignment_enc"):
             close(o[k], g[f"c{ci}_{k}"], 5e-4)
         close(o["overlap_tokens"][..., ::st], g[f"c{ci}_overlap_tokens"], 5e-4)
+
+
+def test_sliced_forward_equals_monolithic():
+    """oracle.aligned.feature_aligned_forward_sliced (what bench.py's CPU reference arm steps through) computes exactly what
+    feature_aligned_forward does, first chunk and chunk with context."""
+    import numpy as np
+    from lsvs_b200 import specs
+    from oracle import aligned as OA
+    from oracle import weights as OW
+    spec = [("aggregator." + n, s) for n, s in specs.aggregator_spec(2, 2)] + [("camera_head." + n, s) for n, s in specs.camera_head_spec()] \
+        + [("alignment_head." + n, s) for n, s in specs.alignment_head_spec()]
+    sd = OW.fill_state_dict(spec, seed=0)
+    img = torch.from_numpy(np.random.Generator(np.random.PCG64(0)).random((1, 3, 3, 28, 42), dtype=np.float32))
+    pts = torch.randn(1, 3, 28, 42, 3)
+    ctx = None
+    with torch.no_grad():
+        for _ in range(2):
+            a = OA.feature_aligned_forward(sd, img, 1, ctx, depth=2, dino_depth=2, taps=(0, 0, 1, 1), raw_points=pts)
+            gen = OA.feature_aligned_forward_sliced(sd, img, 1, ctx, depth=2, dino_depth=2, taps=(0, 0, 1, 1), raw_points=pts)
+            units = []
+            while True:
+                try:
+                    units.append(next(gen))
+                except StopIteration as fin:
+                    b = fin.value
+                    break
+            assert [u[0] for u in units] == ["patch_embed", "dino.0", "dino.1", "frame.0", "global.0", "frame.1", "global.1", "tail"]
+            for k in ("pose_enc", "overlap_tokens", "memory_tokens", "chunk_sim3_alignment_enc", "frame_se3_alignment_enc", "world_points"):
+                assert torch.equal(a[k], b[k]), k
+            ctx = {"overlap_tokens": a["overlap_tokens"], "memory_tokens": a["memory_tokens"], "pose_enc": a["pose_enc"]}

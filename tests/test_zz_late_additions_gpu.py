@@ -70,3 +70,31 @@ def test_peer_primitives_single_process():
         assert any(handle)
     finally:
         lib.lsvs_peer_free(ctypes.c_void_p(base))
+
+
+def test_graphed_chunk_chains_like_the_eager_loop():
+    """lsvs_b200.graphs.GraphedChunk: one CUDA-graph replay per chunk, context carried inside the graph — three chained chunks equal
+    the eager chunk loop (last-bit differences allowed: short chunks slice K of the residual GEMMs over L2 atomics)."""
+    from aligned_vggt.models.featureAligned_vggt import FeatureAlignedVGGT
+    from lsvs_b200.graphs import GraphedChunk
+    torch.manual_seed(0)
+    model = FeatureAlignedVGGT(enable_point=False, enable_depth=False, enable_track=False, depth=2, patch_embed_depth=2,
+                               intermediate_layer_indices=(0, 0, 1, 1)).cuda().eval()
+    S, ov, H, W = 4, 1, 56, 84
+    imgs = [torch.rand(1, S, 3, H, W, device="cuda") for _ in range(4)]
+    pts = torch.randn(1, S, H, W, 3, device="cuda")
+    with torch.no_grad():
+        first = model(imgs[0], ov, None, raw_points=pts)
+        g = GraphedChunk(model, ov, imgs[0], first, raw_points=pts)
+        ctx = {k: (list(v) if isinstance(v, list) else v) for k, v in first.items()}
+        for i in (1, 2, 3):
+            pred = model(imgs[i], ov, ctx, raw_points=pts)
+            out = g(imgs[i])
+            for key in ("pose_enc", "overlap_tokens", "memory_tokens", "world_points"):
+                ref = pred[key][-1] if isinstance(pred[key], list) else pred[key]
+                err = float((out[key] - ref).norm() / ref.norm())
+                assert err < 1e-4, (i, key, err)
+            assert float((out["chunk_sim3_alignment_enc"] - pred["chunk_sim3_alignment_enc"][:, -1:]).abs().max()) < 1e-4
+            ctx = pred
+    with pytest.raises(ValueError):
+        g(imgs[0][:, :2])
