@@ -24,6 +24,10 @@
 #include "ptx.cuh"
 #include "tensormap.h"
 
+#ifndef LSVS_ATTN_POLY_DEFAULT
+#define LSVS_ATTN_POLY_DEFAULT 0
+#endif
+
 namespace lsvs {
 namespace {
 
@@ -32,8 +36,12 @@ constexpr int QT = 128;            // query rows per tile (UMMA M)
 constexpr int KV_STAGES = 4;
 
 
-template <int HD, int NT_>
+// POLY_: of every 4 pairs of scores, POLY_ pairs are exponentiated on the FMA / ALU pipes (Cody-Waite range reduction + a degree-3
+// polynomial in packed fp32x2 arithmetic) instead of MUFU.EX2: at head dim 64 the softmax needs 2 x 128 x 128 exponentials per
+// 128-key block and SM at 16 per clock = 2048 cycles, twice the tensor-core time of the block, so the XU pipe is the bound.
+template <int HD, int NT_, int POLY_ = 0>
 struct Cfg {
+  static constexpr int POLY = POLY_;
   // NT_ = 2: two 128-row query tiles per CTA share every K/V block, one CTA per SM (long sequences).
   // NT_ = 1: one query tile, half the tensor memory and a 2-stage K/V ring so that TWO CTAs fit on an SM: for short
   //          sequences (frame attention, a few key blocks per CTA) the prologue / epilogue of one CTA hides behind the other.
@@ -134,12 +142,29 @@ __device__ int g_dbg_iter[64];
 #define DBG_ITER(i) do {} while (0)
 #endif
 
-template <int HD, int NT_>
-__global__ void __maxnreg__((Cfg<HD, NT_>::MAXNREG))
+// 2^x for x <= ~8 without the XU pipe: x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial
+// (max relative error 7.5e-5, far below the bf16 rounding of P); 2^n by adding n to the exponent field.  Inputs below -126
+// are clamped (their weight is < 2^-126).  Packed fp32x2: two scores per FADD2 / FFMA2.
+__device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& p0, float& p1) {
+  const float x0 = fmaxf(f2_lo(x2), -126.0f), x1 = fmaxf(f2_hi(x2), -126.0f);
+  const unsigned long long xc = f2_pack(x0, x1);
+  const unsigned long long magic = f2_pack(12582912.0f, 12582912.0f), nmagic = f2_pack(-12582912.0f, -12582912.0f);
+  const unsigned long long r = f2_add(xc, magic);                       // integer part in the low mantissa bits
+  const unsigned long long n = f2_add(r, nmagic);
+  const unsigned long long f = f2_fma(n, f2_pack(-1.0f, -1.0f), xc);    // x - n
+  unsigned long long p = f2_fma(f2_pack(0.05517167f, 0.05517167f), f, f2_pack(0.24261114f, 0.24261114f));
+  p = f2_fma(p, f, f2_pack(0.69326097f, 0.69326097f));
+  p = f2_fma(p, f, f2_pack(0.99992806f, 0.99992806f));
+  p0 = __uint_as_float(__float_as_uint(f2_lo(p)) + (__float_as_uint(f2_lo(r)) << 23));
+  p1 = __uint_as_float(__float_as_uint(f2_hi(p)) + (__float_as_uint(f2_hi(r)) << 23));
+}
+
+template <int HD, int NT_, int POLY_>
+__global__ void __maxnreg__((Cfg<HD, NT_, POLY_>::MAXNREG))
 attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int Lq, int Lk,
                       float scale_log2e) {
-  using C = Cfg<HD, NT_>;
+  using C = Cfg<HD, NT_, POLY_>;
   MS_ENTRY;
   extern __shared__ __align__(1024) uint8_t smem[];
   Bars* bars = reinterpret_cast<Bars*>(smem + C::OFF_BAR);
@@ -228,17 +253,23 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t sQ = ptx::smem_u32(smem + C::OFF_Q), sK = ptx::smem_u32(smem + C::OFF_K);
     const uint32_t sV = ptx::smem_u32(smem + C::OFF_V);
 
-    auto issue_S = [&](int t, int stage) {
+    // the last key block of a ragged sequence (412 = 3 x 128 + 28 keys) only spans n_last keys (a multiple of 32): a narrower
+    // S = Q K^T (UMMA N = n_last) and a shorter P V reduction, and the softmax warps touch n_last columns instead of BKV
+    const int n_last = min(C::BKV, ((Lk - (n_kv - 1) * C::BKV) + 31) & ~31);
+    const uint32_t idesc_s_last = ptx::umma_idesc_bf16(QT, n_last, 0, 0);
+    auto issue_S = [&](int t, int stage, bool last) {
+      const uint32_t id = last ? idesc_s_last : idesc_s;
 #pragma unroll
       for (int k = 0; k < HD / 16; ++k) {
         const uint64_t a = ptx::umma_desc_sw128(sQ + t * C::Q_TILE_BYTES + (k / 4) * (QT * 128) + (k % 4) * 32, 16, 1024);
         const uint64_t b = ptx::umma_desc_sw128(sK + stage * C::K_TILE_BYTES + (k / 4) * (C::BKV * 128) + (k % 4) * 32, 16, 1024);
-        ptx::umma_bf16_ss(tmem + C::S_COL + t * C::BKV, a, b, idesc_s, k != 0);
+        ptx::umma_bf16_ss(tmem + C::S_COL + t * C::BKV, a, b, id, k != 0);
       }
     };
-    auto issue_PV = [&](int t, int stage, bool accumulate) {
+    auto issue_PV = [&](int t, int stage, bool accumulate, int n_keys) {
 #pragma unroll
       for (int k = 0; k < C::BKV / 16; ++k) {
+        if (16 * k >= n_keys) break;
         // V block: rows = keys (K dim), 64-wide column blocks (N dim) C::BKV*128 bytes apart; 16 keys per step
         const uint64_t b = ptx::umma_desc_sw128(sV + stage * C::V_TILE_BYTES + k * (16 * 128), C::BKV * 128, 1024);
         // A = P from tensor memory: lane = query row, 8 columns (16 packed bf16) per step
@@ -250,7 +281,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     ptx::mbar_wait(&bars->k_full[0], 0);
     ptx::tc_fence_after();
     if (lane == 0) {
-      for (int t = 0; t < n_tiles; ++t) { issue_S(t, 0); ptx::umma_commit(&bars->s_full[t]); }
+      for (int t = 0; t < n_tiles; ++t) { issue_S(t, 0, n_kv == 1); ptx::umma_commit(&bars->s_full[t]); }
       ptx::umma_commit(&bars->k_empty[0]);  // K(0) free once S_A(0), S_B(0) retire
     }
     __syncwarp();
@@ -267,7 +298,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         for (int t = 0; t < n_tiles; ++t) {
           ptx::mbar_wait(&bars->s_free[t], i & 1);
           ptx::tc_fence_after();
-          if (lane == 0) { issue_S(t, nstage); ptx::umma_commit(&bars->s_full[t]); }
+          if (lane == 0) { issue_S(t, nstage, i + 2 == n_kv); ptx::umma_commit(&bars->s_full[t]); }
           __syncwarp();
         }
         if (lane == 0) ptx::umma_commit(&bars->k_empty[nstage]);  // K(i+1) free once both S MMAs retire
@@ -277,7 +308,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       for (int t = 0; t < n_tiles; ++t) {
         ptx::mbar_wait(&bars->p_ready[t][i & 1], (i >> 1) & 1);
         ptx::tc_fence_after();
-        if (lane == 0) { issue_PV(t, stage, i > 0); ptx::umma_commit(&bars->pv_done[t][i & 1]); }
+        if (lane == 0) { issue_PV(t, stage, i > 0, i + 1 == n_kv ? n_last : C::BKV); ptx::umma_commit(&bars->pv_done[t][i & 1]); }
         __syncwarp();
       }
       if (lane == 0) ptx::umma_commit(&bars->v_empty[stage]);
@@ -303,23 +334,31 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       // element exceeds it by more than 8 (log2 units), so P <= 2^8 and O / l stay exact after the final division,
       // while the TMEM rescale of O only happens on the rare block where a row's maximum jumps by more.
       float m_ref = -INFINITY, l_run = 0.f;
+      // a warp whose 32 query rows all lie past Lq (ragged last tile: 412 = 3 x 128 + 28 rows; 32-row temporal attention) only
+      // keeps the barrier protocol going: its rows of S / P / O are never stored, and rows of an MMA are independent
+      const bool warp_active = q0 + t * QT + quarter * 32 < Lq;
+      const int n_last = min(COLS, ((Lk - (n_kv - 1) * C::BKV) + 31) & ~31);
       PH_DECL;
       for (int i = 0; i < n_kv; ++i) {
         DBG_ITER(i);
+        const int n_cols = (i + 1 == n_kv) ? n_last : COLS;   // S columns of this key block (warp-uniform)
         ptx::mbar_wait(&bars->s_full[t], i & 1);
         ptx::tc_fence_after();
         PH(0);
         if (i == 0) MS(1);  // first S tile ready (Q, K(0) landed, first MMA retired)
         float s[COLS];
+        if (warp_active) {
 #pragma unroll
-        for (int c = 0; c < COLS; c += 32) ptx::tmem_ld_32x32b_x32(tS + c, reinterpret_cast<uint32_t*>(s + c));
-        ptx::tmem_ld_wait();
+          for (int c = 0; c < COLS; c += 32)
+            if (c < n_cols) ptx::tmem_ld_32x32b_x32(tS + c, reinterpret_cast<uint32_t*>(s + c));
+          ptx::tmem_ld_wait();
+        }
         PH(1);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->s_free[t]);
         const int kv_valid = Lk - i * C::BKV;  // keys of this block inside the sequence
-        if (kv_valid < COLS) {
+        if (warp_active && kv_valid < COLS) {
 #pragma unroll
           for (int c = 0; c < COLS; ++c) if (c >= kv_valid) s[c] = -INFINITY;
         }
@@ -332,12 +371,17 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < COLS / 8; ++j) {
+            if (8 * j >= n_cols) break;
             float p[8];
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
               const unsigned long long x = f2_fma(f2_pack(s[8 * j + e], s[8 * j + e + 1]), sc2, nmb2);
-              p[e] = ex2(f2_lo(x));
-              p[e + 1] = ex2(f2_hi(x));
+              if (e / 2 < C::POLY) {   // this pair on the FMA / ALU pipes
+                exp2_poly2(x, p[e], p[e + 1]);
+              } else {
+                p[e] = ex2(f2_lo(x));
+                p[e + 1] = ex2(f2_hi(x));
+              }
             }
             sum2[0] = f2_add(sum2[0], f2_add(f2_pack(p[0], p[1]), f2_pack(p[4], p[5])));
             sum2[1] = f2_add(sum2[1], f2_add(f2_pack(p[2], p[3]), f2_pack(p[6], p[7])));
@@ -352,6 +396,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
           for (int c = 0; c < COLS; c += 4) {
+            if (c >= n_cols) break;
             mx[0] = fmaxf(mx[0], s[c]); mx[1] = fmaxf(mx[1], s[c + 1]); mx[2] = fmaxf(mx[2], s[c + 2]); mx[3] = fmaxf(mx[3], s[c + 3]);
           }
           return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
@@ -360,8 +405,10 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (i >= 1) ptx::mbar_wait(&bars->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
         ptx::tc_fence_after();
         PH(2);
-        float blk_sum;
-        if (i == 0) {
+        float blk_sum = 0.f;
+        if (!warp_active) {
+          // nothing to compute for these rows
+        } else if (i == 0) {
           m_ref = block_max();
           blk_sum = emit_P(m_ref);
         } else {
@@ -438,15 +485,15 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   MS(5);
 }
 
-template <int HD, int NT_>
+template <int HD, int NT_, int POLY_ = 0>
 int launch(const AttentionArgs& a, cudaStream_t st) {
-  using C = Cfg<HD, NT_>;
+  using C = Cfg<HD, NT_, POLY_>;
   const size_t rows_q = (size_t)a.batches * a.Lq, rows_k = (size_t)a.batches * a.Lk;
   const CUtensorMap* tq = tmap_2d_bf16(a.q, (uint64_t)a.heads * HD, rows_q, (uint64_t)a.ldq * 2, 64, QT);
   const CUtensorMap* tk = tmap_2d_bf16(a.k, (uint64_t)a.heads * HD, rows_k, (uint64_t)a.ldk * 2, 64, C::BKV);
   const CUtensorMap* tv = tmap_2d_bf16(a.v, (uint64_t)a.heads * HD, rows_k, (uint64_t)a.ldv * 2, 64, C::BKV);
   if (!tq || !tk || !tv) return LSVS_ECUDA;
-  auto kern = attention_fwd_tcgen05<HD, NT_>;
+  auto kern = attention_fwd_tcgen05<HD, NT_, POLY_>;
   static bool configured = false;
   if (!configured) {
     LSVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -474,7 +521,10 @@ int attention_fwd(const AttentionArgs& a, cudaStream_t st) {
   static const int nt1_max_lk = [] { const char* e = getenv("LSVS_ATTN_NT1_MAX_LK"); return e ? atoi(e) : 1024; }();
   const bool one_tile = a.Lk <= nt1_max_lk;
   if (a.head_dim == 128) return one_tile ? launch<128, 1>(a, st) : launch<128, 2>(a, st);
-  return one_tile ? launch<64, 1>(a, st) : launch<64, 2>(a, st);
+  // head dim 64: share of the exponentials taken off the XU pipe (pairs out of 4; LSVS_ATTN_POLY overrides for A/B runs)
+  static const int poly = [] { const char* e = getenv("LSVS_ATTN_POLY"); return e ? atoi(e) : LSVS_ATTN_POLY_DEFAULT; }();
+  if (one_tile) return poly == 1 ? launch<64, 1, 1>(a, st) : poly == 2 ? launch<64, 1, 2>(a, st) : launch<64, 1, 0>(a, st);
+  return poly == 1 ? launch<64, 2, 1>(a, st) : poly == 2 ? launch<64, 2, 2>(a, st) : launch<64, 2, 0>(a, st);
 }
 
 }  // namespace lsvs
@@ -491,7 +541,7 @@ extern "C" int lsvs_debug_hang_read(int* out257, int* bar_base_offset) {
   cudaDeviceSynchronize();
   cudaMemcpyFromSymbol(out257, ptx::g_lsvs_hang, 257 * sizeof(int));
   cudaMemcpyFromSymbol(out257 + 257, lsvs::g_dbg_iter, 64 * sizeof(int));
-  *bar_base_offset = lsvs::Cfg<64, 2>::OFF_BAR;
+  *bar_base_offset = lsvs::Cfg<64, 2, 0>::OFF_BAR;
   static int zero[257] = {0};
   cudaMemcpyToSymbol(ptx::g_lsvs_hang, zero, sizeof(zero));
   return 0;
