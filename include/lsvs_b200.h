@@ -124,6 +124,18 @@ int lsvs_headnorm_rope_f32(float* buf, long long ld, long long rows, int col0, i
 int lsvs_attention_f32(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv, lsvs_bf16* o,
                        long long ldo, long long section, int batches, int heads, int head_dim, int Lq, int Lk, float scale, void* stream);
 
+/* ---- training of the alignment head (reference: only the head trains, its blocks run under
+ * torch.utils.checkpoint, alignment_head.py:361,385,498,527).  The autograd graph is torch's; its heavy nodes are these kernels
+ * (lsvs_b200/train.py): the tensor-core GEMM above for every Linear forward / input-gradient / weight-gradient product, and
+ *   lsvs_attention_f32_train     forward with fp32 output o (rows, ldo) and lse (batches, heads, Lq) = log2-sum-exp of the scaled scores
+ *   lsvs_attention_f32_backward  dq, dk, dv from q, k, v, o, d_o (o and d_o share ldo) and lse; d_buf: batches*heads*Lq floats scratch */
+int lsvs_attention_f32_train(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv, float* o,
+                             long long ldo, float* lse, int batches, int heads, int head_dim, int Lq, int Lk, float scale, void* stream);
+int lsvs_attention_f32_backward(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
+                                const float* o, const float* d_o, long long ldo, const float* lse, float* d_buf, float* dq,
+                                long long lddq, float* dk, long long lddk, float* dv, long long lddv, int batches, int heads,
+                                int head_dim, int Lq, int Lk, float scale, void* stream);
+
 /* ---- engine: packed weights + kernel sequencing for the module forwards ---------------------------
  * One engine per process / GPU.  Parameters are pushed by state_dict name (the names are the reference's
  * checkpoint contract) from DEVICE fp32 pointers; the engine keeps its own copies (bf16 for the

@@ -1,6 +1,8 @@
 """Drop-in for the reference's aligned_vggt/heads/alignment_head.py: same class name, constructor arguments,
-forward signature and state_dict keys (:52-221, :224-345); the forward runs in the native engine
-(csrc/engine.cu: lsvs_alignment_head_forward).  Inference path only (no autograd through the kernels)."""
+forward signature and state_dict keys (:52-221, :224-345).  Inference (eval(), torch.no_grad() or a frozen head) runs the fused
+native engine (csrc/engine.cu: lsvs_alignment_head_forward); in train() mode with gradients enabled the forward builds an autograd
+graph whose Linears and attention are this library's kernels (lsvs_b200/train.py) — the reference trains exactly this module
+(alignment_head.py:361,385,498,527) with everything else frozen."""
 from typing import Tuple
 
 import torch
@@ -42,6 +44,12 @@ class AlignmentHead(_EngineBound):
                 overlap_tokens: torch.Tensor = None, memory_tokens: torch.Tensor = None):
         """tokens (B,S,P,2048) -> chunk_sim3 (B,1,8), frame_se3 (B,S-1,7), memory (B,8,512),
         overlap tokens (B,1+next_num_overlap,P+1,1024) contiguous."""
+        from lsvs_b200 import train as _train
+        if _train.wants_training_path(self):
+            owner = getattr(self, "_owner", None)
+            precision = getattr(owner, "precision", None) or 0
+            return _train.alignment_head_forward_train(self, tokens, image_size, next_num_overlap, overlap_tokens, memory_tokens,
+                                                       precision=1 if precision else 0)
         return self._engine().alignment_head_forward(tokens, image_size, next_num_overlap, overlap_tokens, memory_tokens)
 
     def _decode_alignments(self, frame_alignment_tokens: torch.Tensor, num_overlap: int, is_first_chunk: bool,

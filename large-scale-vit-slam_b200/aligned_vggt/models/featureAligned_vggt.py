@@ -11,6 +11,7 @@ import torch.nn as nn
 
 from aligned_vggt.heads.alignment_head import AlignmentHead
 from aligned_vggt.utils import alignment as _al
+from lsvs_b200 import train as _train
 from lsvs_b200.engine import GT_MEAN, Engine, pose_chain
 from lsvs_b200.modules import Aggregator, CameraHead, DPTHead
 
@@ -104,6 +105,7 @@ class FeatureAlignedVGGT(nn.Module, PyTorchModelHubMixin):
             if self.enable_memory:
                 ctx_memory = context["memory_tokens"][-1]
         overlap = num_overlap if S > num_overlap else S - 1  # :93
+        train_path = _train.wants_training_path(self.alignment_head)   # train() + grad enabled + trainable head: autograd path
         chunk_sim3_enc, frame_se3_enc, memory_tokens, overlap_tokens = self.alignment_head(
             taps[-1], (H, W), overlap, overlap_tokens=ctx_overlap, memory_tokens=ctx_memory)
 
@@ -116,8 +118,12 @@ class FeatureAlignedVGGT(nn.Module, PyTorchModelHubMixin):
                 if tuple(gt_poses.shape[-2:]) != (4, 4):     # the reference's matmul with the (B,S,4,4) chain fails on (3,4) here
                     raise RuntimeError(f"gt_poses must be (B,S,4,4) homogeneous world-to-camera matrices, got {tuple(gt_poses.shape)}")
                 gt, gt_mode = gt_poses, GT_MEAN
-            aligned_pose_enc, point_T, chunk_scale = pose_chain(chunk_sim3_enc, frame_se3_enc, cam_enc, prev, overlap, (H, W),
-                                                                gt_poses=gt, gt_mode=gt_mode)
+            if train_path:  # differentiable twin of the kernel: the training losses on pose_enc reach the head through it
+                aligned_pose_enc, point_T, chunk_scale = _train.pose_chain_train(chunk_sim3_enc, frame_se3_enc, cam_enc, prev, overlap, (H, W),
+                                                                                 gt_mean=None if gt is None else gt[:, :1])
+            else:
+                aligned_pose_enc, point_T, chunk_scale = pose_chain(chunk_sim3_enc, frame_se3_enc, cam_enc, prev, overlap, (H, W),
+                                                                    gt_poses=gt, gt_mode=gt_mode)
             predictions["overlap_tokens"] = overlap_tokens
             if context is None:
                 predictions["pose_enc"] = [aligned_pose_enc]
@@ -142,12 +148,17 @@ class FeatureAlignedVGGT(nn.Module, PyTorchModelHubMixin):
         if raw_points is None and self.point_head is not None:  # :183-185
             raw_points, pts_conf = self.point_head(taps, images=images, patch_start_idx=patch_start_idx)
         if raw_depth is not None:  # :171 depth *= chunk_scale
-            depth = _al.scale_depth(raw_depth, chunk_scale)
+            depth = raw_depth * chunk_scale.view(B, 1, 1, 1, 1) if train_path else _al.scale_depth(raw_depth, chunk_scale)
             _append(predictions, context, "depth", depth)
             if depth_conf is not None:
                 _append(predictions, context, "depth_conf", depth_conf)
         if raw_points is not None:  # :187-207 scale, then the chunk's point transform
-            pts = _al.apply_sim3_alignment_on_point_maps(raw_points, point_T, chunk_scale) if point_T is not None else raw_points
+            if point_T is None:
+                pts = raw_points
+            elif train_path:
+                pts = _train.apply_sim3_points_train(raw_points, point_T, chunk_scale)
+            else:
+                pts = _al.apply_sim3_alignment_on_point_maps(raw_points, point_T, chunk_scale)
             _append(predictions, context, "world_points", pts)
             if pts_conf is not None:
                 _append(predictions, context, "world_points_conf", pts_conf)

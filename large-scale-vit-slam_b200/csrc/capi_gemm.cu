@@ -67,6 +67,21 @@ extern "C" int lsvs_attention_f32(const float* q, long long ldq, const float* k,
   lsvs::AttentionF32Args a{q, k, v, o, ldq, ldk, ldv, ldo, section, batches, heads, head_dim, Lq, Lk, scale};
   return lsvs::attention_f32(a, (cudaStream_t)stream);
 }
+extern "C" int lsvs_attention_f32_train(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv, float* o,
+                                        long long ldo, float* lse, int batches, int heads, int head_dim, int Lq, int Lk, float scale,
+                                        void* stream) {
+  LSVS_CHECK_ARG(o && lse, "attention_f32_train: null output");
+  lsvs::AttentionF32Args a{q, k, v, nullptr, ldq, ldk, ldv, 0, 0, batches, heads, head_dim, Lq, Lk, scale};
+  a.o32 = o; a.ldo32 = ldo; a.lse = lse;
+  return lsvs::attention_f32(a, (cudaStream_t)stream);
+}
+extern "C" int lsvs_attention_f32_backward(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
+                                           const float* o, const float* d_o, long long ldo, const float* lse, float* d_buf, float* dq,
+                                           long long lddq, float* dk, long long lddk, float* dv, long long lddv, int batches, int heads,
+                                           int head_dim, int Lq, int Lk, float scale, void* stream) {
+  lsvs::AttentionF32BwdArgs a{q, k, v, o, d_o, lse, d_buf, dq, dk, dv, ldq, ldk, ldv, ldo, lddq, lddk, lddv, batches, heads, head_dim, Lq, Lk, scale};
+  return lsvs::attention_f32_backward(a, (cudaStream_t)stream);
+}
 
 #ifdef LSVS_MEASURE   // measurement builds only: the product ABI has no switch that changes results
 namespace lsvs { extern int g_gemm_mode; }

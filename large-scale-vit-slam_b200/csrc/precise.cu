@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(256) headnorm_rope_f32_kernel(float* __restric
 template <int HD>
 __global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__ Q, long long ldq, const float* __restrict__ K, long long ldk,
                                                        const float* __restrict__ V, long long ldv, __nv_bfloat16* __restrict__ O,
-                                                       long long ldo, long long sec, int Lq, int Lk, float scale_log2e) {
+                                                       long long ldo, long long sec, int Lq, int Lk, float scale_log2e,
+                                                       float* __restrict__ O32, long long ldo32, float* __restrict__ LSE) {
   constexpr int KT = 32, NF = HD / 16;   // keys per tile, float4 per thread
   __shared__ float4 sK[KT][HD / 4], sV[KT][HD / 4];
   const int tid = threadIdx.x, part = tid & 3, qi = tid >> 2;
@@ -236,10 +237,168 @@ __global__ void __launch_bounds__(128) attn_f32_kernel(const float* __restrict__
   }
   if (q_ok) {
     const float inv = 1.0f / l_run;
-    __nv_bfloat16* row = O + ((long long)batch * Lq + q_idx) * ldo;
+    if (O) {
+      __nv_bfloat16* row = O + ((long long)batch * Lq + q_idx) * ldo;
 #pragma unroll
-    for (int i = 0; i < NF; ++i)
-      store_split4(row, sec, head * HD + 4 * (4 * i + part), make_float4(o[i].x * inv, o[i].y * inv, o[i].z * inv, o[i].w * inv));
+      for (int i = 0; i < NF; ++i)
+        store_split4(row, sec, head * HD + 4 * (4 * i + part), make_float4(o[i].x * inv, o[i].y * inv, o[i].z * inv, o[i].w * inv));
+    }
+    if (O32) {  // training forward: fp32 output and the row's log2-sum-exp of the scaled scores, for the backward kernels
+      float4* row = reinterpret_cast<float4*>(O32 + ((long long)batch * Lq + q_idx) * ldo32 + head * HD);
+#pragma unroll
+      for (int i = 0; i < NF; ++i) row[4 * i + part] = make_float4(o[i].x * inv, o[i].y * inv, o[i].z * inv, o[i].w * inv);
+    }
+    if (LSE && part == 0) LSE[((long long)batch * gridDim.y + head) * Lq + q_idx] = m_run + log2f(l_run);
+  }
+}
+
+// ---- backward of the fp32 attention (training of the alignment head, alignment_head.py:361,385: only the head trains).
+// With s_ij = scale * q_i . k_j (in log2 units), P_ij = 2^(s_ij - lse_i), D_i = dO_i . O_i:
+//   dV_j = sum_i P_ij dO_i     dS_ij = P_ij (dO_i . V_j - D_i)     dQ_i = scale sum_j dS_ij K_j     dK_j = scale sum_i dS_ij Q_i
+// Same thread layout as the forward: 32 rows x 4 threads, each thread owns every 4th float4 of the head dim.
+template <int HD>
+__global__ void __launch_bounds__(128) attn_f32_bwd_dq_kernel(const float* __restrict__ Q, long long ldq, const float* __restrict__ K, long long ldk,
+                                                              const float* __restrict__ V, long long ldv, const float* __restrict__ O,
+                                                              const float* __restrict__ dO, long long ldo, const float* __restrict__ LSE,
+                                                              float* __restrict__ Dbuf, float* __restrict__ dQ, long long lddq, int Lq, int Lk,
+                                                              float scale) {
+  constexpr int KT = 32, NF = HD / 16;
+  __shared__ float4 sK[KT][HD / 4], sV[KT][HD / 4];
+  const int tid = threadIdx.x, part = tid & 3, qi = tid >> 2;
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int q_idx = blockIdx.x * 32 + qi;
+  const bool q_ok = q_idx < Lq;
+  const long long qrow = (long long)batch * Lq + (q_ok ? q_idx : 0);
+  const float sl = scale * 1.4426950408889634f;
+  float4 q[NF], go[NF], dq[NF];
+  float Di = 0.f;
+  {
+    const float4* qp = reinterpret_cast<const float4*>(Q + qrow * ldq + head * HD);
+    const float4* op = reinterpret_cast<const float4*>(O + qrow * ldo + head * HD);
+    const float4* gp = reinterpret_cast<const float4*>(dO + qrow * ldo + head * HD);
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      const float4 t = qp[4 * i + part], oo = op[4 * i + part];
+      q[i] = make_float4(t.x * sl, t.y * sl, t.z * sl, t.w * sl);
+      go[i] = gp[4 * i + part];
+      dq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      Di += go[i].x * oo.x + go[i].y * oo.y + go[i].z * oo.z + go[i].w * oo.w;
+    }
+    Di += __shfl_xor_sync(0xffffffffu, Di, 1);
+    Di += __shfl_xor_sync(0xffffffffu, Di, 2);
+  }
+  const long long stat = ((long long)batch * gridDim.y + head) * Lq + (q_ok ? q_idx : 0);
+  const float lse = LSE[stat];
+  if (q_ok && part == 0) Dbuf[stat] = Di;
+  for (int k0 = 0; k0 < Lk; k0 += KT) {
+    __syncthreads();
+    for (int i = tid; i < KT * (HD / 4); i += 128) {
+      const int r = i / (HD / 4), c = i % (HD / 4);
+      const bool ok = k0 + r < Lk;
+      const long long row = (long long)batch * Lk + (ok ? k0 + r : 0);
+      sK[r][c] = ok ? reinterpret_cast<const float4*>(K + row * ldk + head * HD)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      sV[r][c] = ok ? reinterpret_cast<const float4*>(V + row * ldv + head * HD)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < KT; ++j) {
+      float a = 0.f, dp = 0.f;
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const float4 kk = sK[j][4 * i + part], vv = sV[j][4 * i + part];
+        a = fmaf(q[i].x, kk.x, a); a = fmaf(q[i].y, kk.y, a); a = fmaf(q[i].z, kk.z, a); a = fmaf(q[i].w, kk.w, a);
+        dp = fmaf(go[i].x, vv.x, dp); dp = fmaf(go[i].y, vv.y, dp); dp = fmaf(go[i].z, vv.z, dp); dp = fmaf(go[i].w, vv.w, dp);
+      }
+      a += __shfl_xor_sync(0xffffffffu, a, 1); dp += __shfl_xor_sync(0xffffffffu, dp, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2); dp += __shfl_xor_sync(0xffffffffu, dp, 2);
+      const float p = (k0 + j < Lk) ? exp2f(a - lse) : 0.f;
+      const float ds = p * (dp - Di);
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const float4 kk = sK[j][4 * i + part];
+        dq[i].x = fmaf(ds, kk.x, dq[i].x); dq[i].y = fmaf(ds, kk.y, dq[i].y); dq[i].z = fmaf(ds, kk.z, dq[i].z); dq[i].w = fmaf(ds, kk.w, dq[i].w);
+      }
+    }
+  }
+  if (q_ok) {
+    float4* row = reinterpret_cast<float4*>(dQ + ((long long)batch * Lq + q_idx) * lddq + head * HD);
+#pragma unroll
+    for (int i = 0; i < NF; ++i) row[4 * i + part] = make_float4(dq[i].x * scale, dq[i].y * scale, dq[i].z * scale, dq[i].w * scale);
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) attn_f32_bwd_dkv_kernel(const float* __restrict__ Q, long long ldq, const float* __restrict__ K, long long ldk,
+                                                               const float* __restrict__ V, long long ldv, const float* __restrict__ dO,
+                                                               long long ldo, const float* __restrict__ LSE, const float* __restrict__ Dbuf,
+                                                               float* __restrict__ dK, long long lddk, float* __restrict__ dV, long long lddv,
+                                                               int Lq, int Lk, float scale) {
+  constexpr int QTILE = 32, NF = HD / 16;
+  __shared__ float4 sQ[QTILE][HD / 4], sG[QTILE][HD / 4];
+  __shared__ float sL[QTILE], sD[QTILE];
+  const int tid = threadIdx.x, part = tid & 3, kj = tid >> 2;
+  const int head = blockIdx.y, batch = blockIdx.z;
+  const int k_idx = blockIdx.x * 32 + kj;
+  const bool k_ok = k_idx < Lk;
+  const long long krow = (long long)batch * Lk + (k_ok ? k_idx : 0);
+  const float sl = scale * 1.4426950408889634f;
+  float4 k[NF], v[NF], dk[NF], dv[NF];
+  {
+    const float4* kp = reinterpret_cast<const float4*>(K + krow * ldk + head * HD);
+    const float4* vp = reinterpret_cast<const float4*>(V + krow * ldv + head * HD);
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      k[i] = kp[4 * i + part]; v[i] = vp[4 * i + part];
+      dk[i] = make_float4(0.f, 0.f, 0.f, 0.f); dv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const long long stat0 = ((long long)batch * gridDim.y + head) * Lq;
+  for (int q0 = 0; q0 < Lq; q0 += QTILE) {
+    __syncthreads();
+    for (int i = tid; i < QTILE * (HD / 4); i += 128) {
+      const int r = i / (HD / 4), c = i % (HD / 4);
+      const bool ok = q0 + r < Lq;
+      const long long row = (long long)batch * Lq + (ok ? q0 + r : 0);
+      float4 t = ok ? reinterpret_cast<const float4*>(Q + row * ldq + head * HD)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      sQ[r][c] = make_float4(t.x * sl, t.y * sl, t.z * sl, t.w * sl);
+      sG[r][c] = ok ? reinterpret_cast<const float4*>(dO + row * ldo + head * HD)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tid < QTILE) {
+      const bool ok = q0 + tid < Lq;
+      sL[tid] = ok ? LSE[stat0 + q0 + tid] : INFINITY;   // 2^(s - inf) = 0 for rows past Lq
+      sD[tid] = ok ? Dbuf[stat0 + q0 + tid] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < QTILE; ++r) {
+      float a = 0.f, dp = 0.f;
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const float4 qq = sQ[r][4 * i + part], gg = sG[r][4 * i + part];
+        a = fmaf(qq.x, k[i].x, a); a = fmaf(qq.y, k[i].y, a); a = fmaf(qq.z, k[i].z, a); a = fmaf(qq.w, k[i].w, a);
+        dp = fmaf(gg.x, v[i].x, dp); dp = fmaf(gg.y, v[i].y, dp); dp = fmaf(gg.z, v[i].z, dp); dp = fmaf(gg.w, v[i].w, dp);
+      }
+      a += __shfl_xor_sync(0xffffffffu, a, 1); dp += __shfl_xor_sync(0xffffffffu, dp, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2); dp += __shfl_xor_sync(0xffffffffu, dp, 2);
+      const float p = exp2f(a - sL[r]);
+      const float ds = p * (dp - sD[r]);
+#pragma unroll
+      for (int i = 0; i < NF; ++i) {
+        const float4 qq = sQ[r][4 * i + part], gg = sG[r][4 * i + part];
+        dv[i].x = fmaf(p, gg.x, dv[i].x); dv[i].y = fmaf(p, gg.y, dv[i].y); dv[i].z = fmaf(p, gg.z, dv[i].z); dv[i].w = fmaf(p, gg.w, dv[i].w);
+        dk[i].x = fmaf(ds, qq.x, dk[i].x); dk[i].y = fmaf(ds, qq.y, dk[i].y); dk[i].z = fmaf(ds, qq.z, dk[i].z); dk[i].w = fmaf(ds, qq.w, dk[i].w);
+      }
+    }
+  }
+  if (k_ok) {
+    const float un = 1.0f / 1.4426950408889634f;   // the staged queries carry scale * log2(e); dK needs scale alone
+    float4* rk = reinterpret_cast<float4*>(dK + ((long long)batch * Lk + k_idx) * lddk + head * HD);
+    float4* rv = reinterpret_cast<float4*>(dV + ((long long)batch * Lk + k_idx) * lddv + head * HD);
+#pragma unroll
+    for (int i = 0; i < NF; ++i) {
+      rk[4 * i + part] = make_float4(dk[i].x * un, dk[i].y * un, dk[i].z * un, dk[i].w * un);
+      rv[4 * i + part] = dv[i];
+    }
   }
 }
 
@@ -306,7 +465,7 @@ int headnorm_rope_f32(float* buf, long long ld, long long rows, int col0, int n_
 }
 
 int attention_f32(const AttentionF32Args& a, cudaStream_t st) {
-  LSVS_CHECK_ARG(a.q && a.k && a.v && a.o, "attention_f32: null pointer");
+  LSVS_CHECK_ARG(a.q && a.k && a.v && (a.o || a.o32), "attention_f32: null pointer");
   LSVS_CHECK_ARG(a.batches > 0 && a.heads > 0 && a.Lq > 0 && a.Lk > 0 && a.batches <= 65535 && a.heads <= 65535, "attention_f32: bad shape");
   LSVS_CHECK_ARG(a.head_dim == 64 || a.head_dim == 128, "attention_f32: head_dim %d unsupported (64 or 128)", a.head_dim);
   LSVS_CHECK_ARG(a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0 && a.ldo % 4 == 0 && a.section % 4 == 0, "attention_f32: strides must be multiples of 4");
@@ -314,8 +473,29 @@ int attention_f32(const AttentionF32Args& a, cudaStream_t st) {
   dim3 grid((a.Lq + 31) / 32, a.heads, a.batches);
   const float sl = a.scale * 1.4426950408889634f;
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.o);
-  if (a.head_dim == 64) attn_f32_kernel<64><<<grid, 128, 0, st>>>(a.q, a.ldq, a.k, a.ldk, a.v, a.ldv, o, a.ldo, a.section, a.Lq, a.Lk, sl);
-  else attn_f32_kernel<128><<<grid, 128, 0, st>>>(a.q, a.ldq, a.k, a.ldk, a.v, a.ldv, o, a.ldo, a.section, a.Lq, a.Lk, sl);
+  if (a.head_dim == 64) attn_f32_kernel<64><<<grid, 128, 0, st>>>(a.q, a.ldq, a.k, a.ldk, a.v, a.ldv, o, a.ldo, a.section, a.Lq, a.Lk, sl, a.o32, a.ldo32, a.lse);
+  else attn_f32_kernel<128><<<grid, 128, 0, st>>>(a.q, a.ldq, a.k, a.ldk, a.v, a.ldv, o, a.ldo, a.section, a.Lq, a.Lk, sl, a.o32, a.ldo32, a.lse);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+
+int attention_f32_backward(const AttentionF32BwdArgs& a, cudaStream_t st) {
+  LSVS_CHECK_ARG(a.q && a.k && a.v && a.o && a.d_o && a.lse && a.d_buf && a.dq && a.dk && a.dv, "attention_f32_backward: null pointer");
+  LSVS_CHECK_ARG(a.batches > 0 && a.heads > 0 && a.Lq > 0 && a.Lk > 0 && a.batches <= 65535 && a.heads <= 65535, "attention_f32_backward: bad shape");
+  LSVS_CHECK_ARG(a.head_dim == 64 || a.head_dim == 128, "attention_f32_backward: head_dim %d unsupported (64 or 128)", a.head_dim);
+  LSVS_CHECK_ARG(a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0 && a.ldo % 4 == 0 && a.lddq % 4 == 0 && a.lddk % 4 == 0 && a.lddv % 4 == 0,
+                 "attention_f32_backward: strides must be multiples of 4");
+  ProfScope prof(PROF_ATTENTION, st, 10.0 * a.batches * (double)a.heads * a.Lq * (double)a.Lk * a.head_dim, 0);
+  dim3 gq((a.Lq + 31) / 32, a.heads, a.batches), gk((a.Lk + 31) / 32, a.heads, a.batches);
+  if (a.head_dim == 64) {
+    attn_f32_bwd_dq_kernel<64><<<gq, 128, 0, st>>>(a.q, a.ldq, a.k, a.ldk, a.v, a.ldv, a.o, a.d_o, a.ldo, a.lse, a.d_buf, a.dq, a.lddq, a.Lq, a.Lk, a.scale);
+    LSVS_LAUNCH_CHECK();
+    attn_f32_bwd_dkv_kernel<64><<<gk, 128, 0, st>>>(a.q, a.ldq, a.k, a.ldk, a.v, a.ldv, a.d_o, a.ldo, a.lse, a.d_buf, a.dk, a.lddk, a.dv, a.lddv, a.Lq, a.Lk, a.scale);
+  } else {
+    attn_f32_bwd_dq_kernel<128><<<gq, 128, 0, st>>>(a.q, a.ldq, a.k, a.ldk, a.v, a.ldv, a.o, a.d_o, a.ldo, a.lse, a.d_buf, a.dq, a.lddq, a.Lq, a.Lk, a.scale);
+    LSVS_LAUNCH_CHECK();
+    attn_f32_bwd_dkv_kernel<128><<<gk, 128, 0, st>>>(a.q, a.ldq, a.k, a.ldk, a.v, a.ldv, a.d_o, a.ldo, a.lse, a.d_buf, a.dk, a.lddk, a.dv, a.lddv, a.Lq, a.Lk, a.scale);
+  }
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }

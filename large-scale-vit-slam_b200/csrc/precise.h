@@ -23,6 +23,18 @@ struct AttentionF32Args {
   long long ldq, ldk, ldv, ldo, section;
   int batches, heads, head_dim, Lq, Lk;
   float scale;
+  // training forward (optional): fp32 output rows (stride ldo32) and per (batch, head, query) log2-sum-exp of the scaled scores
+  float* o32 = nullptr; long long ldo32 = 0; float* lse = nullptr;
 };
 int attention_f32(const AttentionF32Args& a, cudaStream_t st);
+// backward of attention_f32: q/k/v/o/d_o fp32 (o and d_o share the stride ldo), lse from the forward; d_buf: scratch of
+// batches*heads*Lq floats (dO . O per row); dq/dk/dv fp32 with their own strides
+struct AttentionF32BwdArgs {
+  const float* q; const float* k; const float* v; const float* o; const float* d_o; const float* lse;
+  float* d_buf; float* dq; float* dk; float* dv;
+  long long ldq, ldk, ldv, ldo, lddq, lddk, lddv;
+  int batches, heads, head_dim, Lq, Lk;
+  float scale;
+};
+int attention_f32_backward(const AttentionF32BwdArgs& a, cudaStream_t st);
 }  // namespace lsvs
