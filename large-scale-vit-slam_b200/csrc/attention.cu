@@ -111,6 +111,8 @@ __device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsig
   return r;
 }
 
+template <bool V> struct BoolTag { static constexpr bool value = V; };
+
 // register re-balancing between the service warpgroup and the softmax warpgroups (setmaxnreg, warpgroup-wide)
 template <class C> __device__ __forceinline__ void reg_dec() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::REG_SERVICE));
@@ -347,24 +349,96 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         PH(0);
         if (i == 0) MS(1);  // first S tile ready (Q, K(0) landed, first MMA retired)
         float s[COLS];
-        if (warp_active) {
-#pragma unroll
-          for (int c = 0; c < COLS; c += 32)
-            if (c < n_cols) ptx::tmem_ld_32x32b_x32(tS + c, reinterpret_cast<uint32_t*>(s + c));
-          ptx::tmem_ld_wait();
-        }
-        PH(1);
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bars->s_free[t]);
         const int kv_valid = Lk - i * C::BKV;  // keys of this block inside the sequence
-        if (warp_active && kv_valid < COLS) {
+        // steady-state block (not the first, all columns valid): only the first 32 columns of S are waited for here; the other
+        // tensor-memory loads stay in flight under the first exponentials, and so does the wait for P V(i-1) (emit_full's hooks)
+        const bool split = warp_active && i >= 1 && kv_valid >= COLS;
+        if (split) {
+          ptx::tmem_ld_32x32b_x32(tS, reinterpret_cast<uint32_t*>(s));
+          ptx::tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < COLS; ++c) if (c >= kv_valid) s[c] = -INFINITY;
+          for (int c = 32; c < COLS; c += 32) ptx::tmem_ld_32x32b_x32(tS + c, reinterpret_cast<uint32_t*>(s + c));
+        } else {
+          if (warp_active) {
+            if (n_cols == COLS) {
+#pragma unroll
+              for (int c = 0; c < COLS; c += 32) ptx::tmem_ld_32x32b_x32(tS + c, reinterpret_cast<uint32_t*>(s + c));
+            } else {
+#pragma unroll
+              for (int c = 0; c < COLS; c += 32)
+                if (c < n_cols) ptx::tmem_ld_32x32b_x32(tS + c, reinterpret_cast<uint32_t*>(s + c));
+            }
+            ptx::tmem_ld_wait();
+          }
+          PH(1);
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars->s_free[t]);
+          if (warp_active && kv_valid < COLS) {
+#pragma unroll
+            for (int c = 0; c < COLS; ++c) if (c >= kv_valid) s[c] = -INFINITY;
+          }
         }
+        auto rest_of_S = [&]() {   // before the first use of columns >= 32
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 32; c < COLS; ++c) asm volatile("" : "+f"(s[c]));   // no use of these registers may move above the wait
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars->s_free[t]);
+        };
+        auto p_free = [&]() {      // before the first tcgen05.st of P: P V(i-1) has consumed the previous P (and O is quiescent)
+          ptx::mbar_wait(&bars->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
+          ptx::tc_fence_after();
+        };
+        auto no_hook = []() {};
         // exp2 (packed fp32x2 scale-and-shift), row sum, and P packed to bf16 pairs and stored to its tensor-memory tile 32
         // keys at a time (measured alternative: keep all of P in registers and store after the wait for PV(i-1): 714 vs 730)
-        auto emit_P = [&](float m_use) -> float {
+        // FULL (compile-time): the block spans all COLS columns — every block but a ragged sequence's last one; the narrow variant
+        // carries the run-time column bound.  The row sums and the bf16 packing of a group of 8 exponentials are issued one group
+        // LATE, after the next group's MUFU.EX2 instructions: nothing in the stream then waits on the MUFU result latency (ncu
+        // source view, profiles/r2_ncu_attention_poly.md: the FADD2 / F2FP right behind their MUFUs cost 5.3 / 2.9 cycles each).
+        auto group_exp = [&](int j, float* p, unsigned long long sc2, unsigned long long nmb2) {
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const unsigned long long x = f2_fma(f2_pack(s[8 * j + e], s[8 * j + e + 1]), sc2, nmb2);
+            if (e / 2 < C::POLY) {   // this pair on the FMA / ALU pipes
+              exp2_poly2(x, p[e], p[e + 1]);
+            } else {
+              p[e] = ex2(f2_lo(x));
+              p[e + 1] = ex2(f2_hi(x));
+            }
+          }
+        };
+        auto group_out = [&](int j, const float* p, unsigned long long* sum2, uint32_t* pk) {
+          sum2[0] = f2_add(sum2[0], f2_add(f2_pack(p[0], p[1]), f2_pack(p[4], p[5])));
+          sum2[1] = f2_add(sum2[1], f2_add(f2_pack(p[2], p[3]), f2_pack(p[6], p[7])));
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pk[4 * (j & 3) + e] = ptx::pack_bf16(p[2 * e], p[2 * e + 1]);
+          if ((j & 3) == 3) ptx::tmem_st_32x32b_x16(tP + (j - 3) * 4, pk);   // 32 keys = 16 packed columns
+        };
+        // full block (every block but a ragged sequence's last one): all COLS columns, no run-time bounds
+        auto emit_full = [&](float m_use, auto&& need_rest, auto&& first_store) -> float {
+          const float nmb = -m_use * scale_log2e;
+          const unsigned long long sc2 = f2_pack(scale_log2e, scale_log2e), nmb2 = f2_pack(nmb, nmb);
+          unsigned long long sum2[2] = {0ull, 0ull};
+          uint32_t pk[16];
+          float pa[8], pb[8];
+          group_exp(0, pa, sc2, nmb2);
+#pragma unroll
+          for (int j = 1; j < COLS / 8; j += 2) {
+            group_exp(j, pb, sc2, nmb2);
+            group_out(j - 1, pa, sum2, pk);
+            if (j == 3) need_rest();          // group 4 is the first one in columns >= 32
+            if (j + 1 < COLS / 8) group_exp(j + 1, pa, sc2, nmb2);
+            if (j == 3) first_store();        // group_out(3) issues the first tcgen05.st of P
+            group_out(j, pb, sum2, pk);
+          }
+          const unsigned long long tot = f2_add(sum2[0], sum2[1]);
+          return f2_lo(tot) + f2_hi(tot);
+        };
+        // ragged last block: only the first n_cols columns
+        auto emit_part = [&](float m_use) -> float {
           const float nmb = -m_use * scale_log2e;
           const unsigned long long sc2 = f2_pack(scale_log2e, scale_log2e), nmb2 = f2_pack(nmb, nmb);
           unsigned long long sum2[2] = {0ull, 0ull};
@@ -373,53 +447,46 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           for (int j = 0; j < COLS / 8; ++j) {
             if (8 * j >= n_cols) break;
             float p[8];
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) {
-              const unsigned long long x = f2_fma(f2_pack(s[8 * j + e], s[8 * j + e + 1]), sc2, nmb2);
-              if (e / 2 < C::POLY) {   // this pair on the FMA / ALU pipes
-                exp2_poly2(x, p[e], p[e + 1]);
-              } else {
-                p[e] = ex2(f2_lo(x));
-                p[e + 1] = ex2(f2_hi(x));
-              }
-            }
-            sum2[0] = f2_add(sum2[0], f2_add(f2_pack(p[0], p[1]), f2_pack(p[4], p[5])));
-            sum2[1] = f2_add(sum2[1], f2_add(f2_pack(p[2], p[3]), f2_pack(p[6], p[7])));
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pk[4 * (j & 3) + e] = ptx::pack_bf16(p[2 * e], p[2 * e + 1]);
-            if ((j & 3) == 3) ptx::tmem_st_32x32b_x16(tP + (j - 3) * 4, pk);   // 32 keys = 16 packed columns
+            group_exp(j, p, sc2, nmb2);
+            group_out(j, p, sum2, pk);
           }
           const unsigned long long tot = f2_add(sum2[0], sum2[1]);
           return f2_lo(tot) + f2_hi(tot);
         };
-        auto block_max = [&]() -> float {
+        auto block_max = [&](auto full_tag) -> float {
+          constexpr bool FULL = decltype(full_tag)::value;
           float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
           for (int c = 0; c < COLS; c += 4) {
-            if (c >= n_cols) break;
+            if (!FULL && c >= n_cols) break;
             mx[0] = fmaxf(mx[0], s[c]); mx[1] = fmaxf(mx[1], s[c + 1]); mx[2] = fmaxf(mx[2], s[c + 2]); mx[3] = fmaxf(mx[3], s[c + 3]);
           }
           return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
         };
+        using FullT = BoolTag<true>;
+        using PartT = BoolTag<false>;
+        const bool full_block = n_cols == COLS;
+        auto emit = [&](float m_use) -> float { return full_block ? emit_full(m_use, no_hook, no_hook) : emit_part(m_use); };
+        auto bmax = [&]() -> float { return full_block ? block_max(FullT{}) : block_max(PartT{}); };
         // P is single-buffered in tensor memory: PV(i-1) must have consumed it (they retire in order, so O is quiescent too)
-        if (i >= 1) ptx::mbar_wait(&bars->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
+        if (i >= 1 && !split) ptx::mbar_wait(&bars->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
         ptx::tc_fence_after();
         PH(2);
         float blk_sum = 0.f;
         if (!warp_active) {
           // nothing to compute for these rows
         } else if (i == 0) {
-          m_ref = block_max();
-          blk_sum = emit_P(m_ref);
+          m_ref = bmax();
+          blk_sum = emit(m_ref);
         } else {
           // optimistic: exponentiate against the trailing reference maximum (no dependence on this block's maximum, so
           // the MUFU work starts as soon as S is in registers).  The block maximum itself is only needed when a row may have
           // exceeded the reference by more than 2^8: a row sum <= 2^8 proves that no element did (every p <= its row sum), so
           // the 128-element max pass is skipped on all other blocks.
-          blk_sum = emit_P(m_ref);
+          blk_sum = split ? emit_full(m_ref, rest_of_S, p_free) : emit(m_ref);
           const bool suspect = !(blk_sum <= 256.0f);
           if (__any_sync(0xffffffffu, suspect)) {
-            const float m_blk = block_max();
+            const float m_blk = bmax();
             const bool jump = (m_blk - m_ref) * scale_log2e > 8.0f;
             if (__any_sync(0xffffffffu, jump)) {
               // rescale O in TMEM, redo P against the new reference
@@ -435,7 +502,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
                 ptx::tmem_st_32x32b_x16(tO + c, o);
               }
-              blk_sum = emit_P(m_ref);
+              blk_sum = emit(m_ref);
             }
           }
         }
