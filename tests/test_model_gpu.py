@@ -21,6 +21,23 @@ pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
 
 
+# BASELINE config 1, bf16 pipeline vs the reference's fp32 outputs — (relative translation, rotation in degrees), 1.6x the values
+# measured on B200: Sim(3) 1.8e-3 / 0.16 deg, SE(3) 6.2e-3 / 0.49 deg, pose 8.8e-3 / 0.59 deg (profiles/r2_precision_report.json)
+CONFIG1_BOUNDS = {"chunk_sim3_alignment_enc": (3e-3, 0.26), "frame_se3_alignment_enc": (1e-2, 0.8), "pose_enc": (1.4e-2, 0.95)}
+
+
+def _report(key, value):
+    import json
+    import os
+    from conftest import ROOT
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        path = os.path.join(out, "precision_report.json")
+        old = json.load(open(path)) if os.path.exists(path) else {}
+        old[key] = value
+        json.dump(old, open(path, "w"), indent=1, sort_keys=True)
+
+
 def within(mine, ref_amp, north_star, slack=3.0):
     return mine <= max(slack * ref_amp, north_star)
 
@@ -131,11 +148,11 @@ def test_aggregator_vs_oracle(S, H, W):
 
 
 # ------------------------------------------------------------------------------------------------ full model
-def _run_model_case(golden, tag, depth, dino, taps):
+def _run_model_case(golden, tag, depth, dino, taps, precision=None):
     from aligned_vggt.models.featureAligned_vggt import FeatureAlignedVGGT
     g = golden(f"model_{tag}.npz")
     model = FeatureAlignedVGGT(enable_point=False, enable_depth=False, enable_track=False, depth=depth, patch_embed_depth=dino,
-                               intermediate_layer_indices=taps)
+                               intermediate_layer_indices=taps, precision=precision)
     sd = load_synth_weights(model, seed=0)
     assert abs(OW.checksum(sd) - g["wsum"]) < 1e-6 * abs(g["wsum"]), "synthetic weights differ from the golden run"
     model = model.cuda().eval()
@@ -189,10 +206,30 @@ def test_model_full_golden(golden):
     """BASELINE config 1 (4 frames of 518x154, full 24+24+24 depth, two chained chunks) vs the reference run."""
     g, sd, out, imgs, pts, dep, (S, H, W, ov, st) = _run_model_case(golden, "full", 24, 24, (4, 11, 17, 23))
     _check_tokens(g, out, st)
+    measured = {}
     for c, snap in (("c1", out[0]), ("c2", out[1])):
-        for key, tr, rd in (("chunk_sim3_alignment_enc", 1e-2, 1.0), ("frame_se3_alignment_enc", 2e-2, 2.0), ("pose_enc", 5e-2, 3.0)):
-            m = pose_metrics(snap[key], g[f"{c}_{key}"])  # loose sanity bounds; the calibrated check is the small case
-            assert m["trans_rel"] < tr and m["rot_deg"] < rd, (c, key, m)
+        for key in ("chunk_sim3_alignment_enc", "frame_se3_alignment_enc", "pose_enc"):
+            measured[f"{c}_{key}"] = pose_metrics(snap[key], g[f"{c}_{key}"])
+    _report("model_full_config1_precision0", measured)
+    # bf16 pipeline vs the reference's fp32 outputs: bounds calibrated on the measured deviation (B200: see DESIGN.md section 3;
+    # the fp32-class pipeline meets 1e-3 / 0.05 deg on the benchmarked configuration, tests/test_precision_gpu.py)
+    for name, m in measured.items():
+        tr, rd = CONFIG1_BOUNDS[name.split("_", 1)[1]]
+        assert m["trans_rel"] < tr and m["rot_deg"] < rd, (name, m)
+
+
+def test_model_full_golden_fp32_class(golden):
+    """BASELINE config 1 with every block fp32-class (engine precision 2): the north_star Sim(3) / SE(3) / pose numbers hold against
+    the reference's fp32 outputs, both chained chunks."""
+    g, sd, out, imgs, pts, dep, (S, H, W, ov, st) = _run_model_case(golden, "full", 24, 24, (4, 11, 17, 23), precision=2)
+    measured = {}
+    for c, snap in (("c1", out[0]), ("c2", out[1])):
+        assert rel_l2(snap["tap_last"][..., ::st], g[c + "_tap_last"]) < 1e-3
+        assert rel_l2(snap["overlap_tokens"][..., ::st], g[c + "_overlap_tokens"]) < 1e-3
+        for key in ("chunk_sim3_alignment_enc", "frame_se3_alignment_enc", "pose_enc"):
+            m = measured[f"{c}_{key}"] = pose_metrics(snap[key], g[f"{c}_{key}"])
+            assert m["trans_rel"] < TRANS_REL and m["rot_deg"] < ROT_DEG, (c, key, m)
+    _report("model_full_config1_precision2", measured)
 
 
 def test_model_state_and_errors():
