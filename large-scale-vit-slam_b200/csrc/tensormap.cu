@@ -22,7 +22,14 @@ struct KeyHash {
   }
 };
 std::mutex g_mu;
-std::unordered_map<Key, std::unique_ptr<CUtensorMap>, KeyHash> g_cache;
+// Two generations bound the cache: caller-owned tensors (tapped layers, per-forward outputs) bring a new address — a new key —
+// on every call, so entries accumulate over long runs.  When the young generation reaches kGenLimit entries the old one is
+// dropped and the young one takes its place; a hit in the old generation is promoted.  A pointer handed out stays valid for at
+// least kGenLimit further insertions — a call encodes at most a handful of maps and passes them to its kernels by value.
+using Map = std::unordered_map<Key, std::unique_ptr<CUtensorMap>, KeyHash>;
+constexpr size_t kGenLimit = 2048;
+Map g_young, g_old;
+int g_device = -1;   // the library keeps per-process state (this cache, kernel attributes, SM count): one GPU per process
 PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 }  // namespace
 
@@ -44,8 +51,27 @@ const CUtensorMap* tmap_2d(const void* base, uint64_t inner, uint64_t outer, uin
   std::memset(&key, 0, sizeof(key));
   key.base = base; key.inner = inner; key.outer = outer; key.pitch = pitch_bytes; key.bi = box_inner; key.bo = box_outer; key.kind = (uint64_t)dtype;
   std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_cache.find(key);
-  if (it != g_cache.end()) return it->second.get();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (g_device < 0) g_device = dev;
+  if (dev != g_device) {
+    fail(LSVS_EUNSUPPORTED, "liblsvs_b200 was first used on CUDA device %d and is now called on device %d: one process per GPU "
+         "(per-process tensor-map cache, kernel attributes and SM count)", g_device, dev);
+    return nullptr;
+  }
+  auto it = g_young.find(key);
+  if (it != g_young.end()) return it->second.get();
+  it = g_old.find(key);
+  if (it != g_old.end()) {   // promote
+    const CUtensorMap* hit = it->second.get();
+    g_young.emplace(key, std::move(it->second));
+    g_old.erase(it);
+    return hit;
+  }
+  if (g_young.size() >= kGenLimit) {
+    g_old.swap(g_young);
+    g_young.clear();
+  }
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -75,7 +101,7 @@ const CUtensorMap* tmap_2d(const void* base, uint64_t inner, uint64_t outer, uin
     return nullptr;
   }
   const CUtensorMap* out = tm.get();
-  g_cache.emplace(key, std::move(tm));
+  g_young.emplace(key, std::move(tm));
   return out;
 }
 }  // namespace
