@@ -531,9 +531,12 @@ struct Smem2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int PARAM_OFFSET = BAR_OFFSET + 256;
-  static constexpr int TILE_OFFSET = (PARAM_OFFSET + 2048 + 1023) / 1024 * 1024;  // 128B-swizzled tiles: 1024-byte aligned
-  static constexpr int TILE_BYTES = 32 * 32 * 4;       // per epilogue warp: one 32 x 32 fp32 block
-  static constexpr int TOTAL = TILE_OFFSET + (TILES ? 8 * TILE_BYTES : 0) + 1024;
+  static constexpr int PARAM_BYTES = TRANSPOSE ? 0 : 2048;   // q/k LayerNorm parameters (head-norm epilogues only)
+  static constexpr int TILE_OFFSET = (PARAM_OFFSET + PARAM_BYTES + 1023) / 1024 * 1024;  // 128B-swizzled tiles: 1024-byte aligned
+  static constexpr int TILE_BYTES = 32 * 32 * 4;       // one 32 x 32 fp32 block (or 32 x 64 bf16)
+  static constexpr int TILE_BUFS = TRANSPOSE ? 2 : 1;  // the residual epilogue keeps two tiles per warp (load / store double buffer)
+  static constexpr int TOTAL = TILE_OFFSET + (TILES ? 8 * TILE_BUFS * TILE_BYTES : 0) + 1024;
+  static_assert(TOTAL <= 232448, "shared memory budget");
 };
 
 // resid[m, n] += gamma[n] * (acc[m, n] + bias[n]) without reading the residual in the SM: each warp scales its 32 x 32
@@ -586,6 +589,8 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* tmem_full = empty_bar + STAGES2;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* resid_bar = tmem_empty + 3;   // 2 per epilogue warp: residual tiles landed (load-add-store epilogue)
+  static_assert(!L::TRANSPOSE || (STAGES2 * 2 + 4 + 1 + 2 * EW) * 8 <= 256, "barrier area");
   EpiSmem* sp = reinterpret_cast<EpiSmem*>(smem + L::PARAM_OFFSET);
   if constexpr (EPI == EPI_HEADNORM64_BF16 || EPI == EPI_HEADNORM128_BF16) stage_epi_params(sp, epi, EPI == EPI_HEADNORM64_BF16 ? 64 : 128);
 
@@ -607,6 +612,10 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int i = 0; i < STAGES2; ++i) { ptx::mbar_init(full_bar + i, 2); ptx::mbar_init(empty_bar + i, 1); }
 #pragma unroll
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(tmem_full + i, 1); ptx::mbar_init(tmem_empty + i, 2 * EW); }
+    if constexpr (L::TRANSPOSE) {
+#pragma unroll
+      for (int i = 0; i < 2 * EW; ++i) ptx::mbar_init(resid_bar + i, 1);
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -687,6 +696,74 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
     constexpr int COLS = BN2 / (EW / 4);
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (L::TRANSPOSE && (use_tma_reduce & 16)) {
+      // ---- residual epilogue without L2 atomics: resid tile -> shared memory (TMA load, issued one 32-column chunk ahead), add
+      // gamma * (acc + bias) in place, TMA store back.  The reduce-add form moves 54 MB of fp32 through the L2 atomic units per
+      // projection GEMM (~2.2 TB/s measured: as long as the whole K = 1024 main loop); plain loads and stores run at L2 speed.
+      // One split only (every element is written once per GEMM, so the prefetched tile of the NEXT output tile is never stale).
+      uint8_t* tiles = smem + L::TILE_OFFSET + (warp - 2) * 2 * L::TILE_BYTES;
+      uint64_t* lbar = resid_bar + 2 * (warp - 2);
+      constexpr int NCH = COLS / 32;
+      auto chunk_coords = [&](int item, int c, int& n, int& mb) {
+        mb = (item / n_tiles_n) * (2 * BM) + (int)cta * BM + quarter * 32;
+        n = (item % n_tiles_n) * BN2 + part * COLS + 32 * c;
+      };
+      uint32_t g = 0;   // chunks processed by this warp: buffer g & 1, barrier phase (g >> 1) & 1
+      if (pair < n_tiles && lane == 0) {
+        int n, mb;
+        chunk_coords(pair, 0, n, mb);
+        ptx::mbar_expect_tx(lbar, L::TILE_BYTES);
+        ptx::tma_load_2d(tiles, &tmR, lbar, n, mb);
+      }
+      for (int item = pair; item < n_tiles; item += n_pairs) {
+        ptx::mbar_wait(tmem_full + acc, acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2;
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c, ++g) {
+          int n, mb;
+          chunk_coords(item, c, n, mb);
+          if (lane == 0) {   // prefetch the next chunk's residual tile into the other buffer once its last store has read it
+            const bool next_here = c + 1 < NCH, next_item = item + n_pairs < n_tiles;
+            if (next_here || next_item) {
+              int nn, nmb;
+              chunk_coords(next_here ? item : item + n_pairs, next_here ? c + 1 : 0, nn, nmb);
+              ptx::tma_store_wait_read<0>();
+              ptx::mbar_expect_tx(lbar + ((g + 1) & 1), L::TILE_BYTES);
+              ptx::tma_load_2d(tiles + ((g + 1) & 1) * L::TILE_BYTES, &tmR, lbar + ((g + 1) & 1), nn, nmb);
+            }
+          }
+          float v[32];
+          __syncwarp();
+          load_acc<32>(taddr + part * COLS + 32 * c, v);
+          ptx::mbar_wait(lbar + (g & 1), (g >> 1) & 1);
+          uint8_t* tile = tiles + (g & 1) * L::TILE_BYTES;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4* slot = reinterpret_cast<float4*>(tile + lane * 128 + ((i ^ (lane & 7)) << 4));
+            float4 r = *slot;
+            const float4 gm = epi.gamma ? __ldg(reinterpret_cast<const float4*>(epi.gamma + n) + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 bb = epi.bias ? __ldg(reinterpret_cast<const float4*>(epi.bias + n) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            r.x += gm.x * (v[4 * i + 0] + bb.x); r.y += gm.y * (v[4 * i + 1] + bb.y);
+            r.z += gm.z * (v[4 * i + 2] + bb.z); r.w += gm.w * (v[4 * i + 3] + bb.w);
+            *slot = r;
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&tmR, tile, n, mb);
+            ptx::tma_store_commit();
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (cta == 0) ptx::mbar_arrive(tmem_empty + acc);
+          else ptx::mbar_arrive_remote(tmem_empty + acc, 0);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else
     for (int item = pair; item < n_tiles; item += n_pairs) {
       const int tile = item / splits, slice = item - tile * splits;
       const int m0 = (tile / n_tiles_n) * (2 * BM) + (int)cta * BM;
@@ -696,7 +773,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int m = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2;
       if (L::TRANSPOSE && (use_tma_reduce & 1)) {
-        epilogue_resid_tma(epi, &tmR, smem + L::TILE_OFFSET + (warp - 2) * L::TILE_BYTES, taddr, m0 + quarter * 32, n0, part * COLS, (part + 1) * COLS, slice == 0);
+        epilogue_resid_tma(epi, &tmR, smem + L::TILE_OFFSET + (warp - 2) * L::TILE_BUFS * L::TILE_BYTES, taddr, m0 + quarter * 32, n0, part * COLS, (part + 1) * COLS, slice == 0);
       } else if (L::TMA_BF16 && (use_tma_reduce & 4)) {
         const TmaOut to{&tmR, smem + L::TILE_OFFSET + (warp - 2) * L::TILE_BYTES, m0 + quarter * 32};
         epilogue_row<BN2, EPI, L::TMA_BF16>(epi, sp, taddr, m, n0, m < M, part * COLS, (part + 1) * COLS, &to);
@@ -750,6 +827,9 @@ int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K,
     const int n_kb = K / BK;
     while (splits < 8 && tiles * splits * 2 <= max_pairs && n_kb % (2 * splits) == 0 && n_kb / (2 * splits) >= 4) splits *= 2;
   }
+  // one split: load-add-store epilogue instead of reduce-add (LSVS_GEMM_RESID_ATOMIC=1 keeps the reduce-add form for A/B runs)
+  static const bool resid_atomic = [] { const char* v = getenv("LSVS_GEMM_RESID_ATOMIC"); return v && atoi(v) != 0; }();
+  if ((use_red & 1) && splits == 1 && !resid_atomic) use_red |= 16;
   use_red |= splits << 8;
   const int items = tiles * splits;
   const int pairs = items < max_pairs ? items : max_pairs;

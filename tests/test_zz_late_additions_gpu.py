@@ -98,3 +98,56 @@ def test_graphed_chunk_chains_like_the_eager_loop():
             ctx = pred
     with pytest.raises(ValueError):
         g(imgs[0][:, :2])
+
+
+def test_alignment_head_without_memory_tokens():
+    """num_memory_tokens = 0 (alignment_head.py:211,468,504): no memory parameters, the chunk token attends over the frame tokens
+    only, `memory_tokens` is handed back untouched; two chained chunks vs the oracle."""
+    from aligned_vggt.heads.alignment_head import AlignmentHead
+    from oracle import aligned as OA
+    head = AlignmentHead(num_memory_tokens=0)
+    assert not any("memory" in k or "gated_update" in k or k in ("alpha", "frame_proj.weight") for k in head.state_dict())
+    sd = load_synth_weights(head, seed=5, ls_gamma=0.2)
+    head = head.cuda().eval()
+    S, gh, gw, ov = 5, 2, 3, 2
+    P = 5 + gh * gw
+    from conftest import rnd
+    toks = [rnd(70 + i, 1, S, P, 2048) for i in range(2)]
+    with torch.no_grad():
+        r1 = OA.alignment_head_forward(sd, "", toks[0], (gh * 14, gw * 14), ov, num_memory_tokens=0)
+        g1 = head(toks[0].cuda(), (gh * 14, gw * 14), ov)
+        r2 = OA.alignment_head_forward(sd, "", toks[1], (gh * 14, gw * 14), ov, r1[3], None, num_memory_tokens=0)
+        g2 = head(toks[1].cuda(), (gh * 14, gw * 14), ov, overlap_tokens=g1[3], memory_tokens=None)
+    for r, g in ((r1, g1), (r2, g2)):
+        assert g[2] is None and r[2] is None
+        assert rel_l2(g[3], r[3]) < TOK_REL_L2
+        assert rel_l2(g[0], r[0]) < 5e-2 and rel_l2(g[1], r[1]) < 5e-2
+
+
+def test_bf16_tokens_entry_and_model_copies():
+    """(i) The head fed with bf16 tokens (what the chunk scheduler ships) equals the head fed with the same values in fp32, bit for bit;
+    (ii) a model can be deep-copied / pickled after its first forward (the native engine handle is rebuilt lazily) and strict
+    load_state_dict tolerates `track_head.*` keys."""
+    import copy
+    import pickle
+    from aligned_vggt.models.featureAligned_vggt import FeatureAlignedVGGT
+    torch.manual_seed(0)
+    model = FeatureAlignedVGGT(enable_point=False, enable_depth=False, enable_track=False, depth=1, patch_embed_depth=1,
+                               intermediate_layer_indices=(0, 0, 0, 0)).cuda().eval()
+    S, H, W = 3, 28, 42
+    img = torch.rand(1, S, 3, H, W, device="cuda")
+    with torch.no_grad():
+        tap = model.aggregator(img)[0][0]
+        a = model.alignment_head(tap.bfloat16(), (H, W), 1)
+        b = model.alignment_head(tap.bfloat16().float(), (H, W), 1)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+        p = model(img, 1)
+        clone = copy.deepcopy(model)
+        q = clone(img, 1)
+        assert torch.equal(p["pose_enc"][-1], q["pose_enc"][-1]) and torch.equal(p["overlap_tokens"], q["overlap_tokens"])
+        again = pickle.loads(pickle.dumps(model))
+        assert torch.equal(again(img, 1)["pose_enc"][-1], p["pose_enc"][-1])
+        sd = dict(model.state_dict())
+        sd["track_head.feature_extractor.norm.weight"] = torch.zeros(3)
+        model.load_state_dict(sd, strict=True)
