@@ -697,9 +697,9 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     if (L::TRANSPOSE && (use_tma_reduce & 16)) {
-      // ---- residual epilogue without L2 atomics: resid tile -> shared memory (TMA load, issued one 32-column chunk ahead), add
-      // gamma * (acc + bias) in place, TMA store back.  The reduce-add form moves 54 MB of fp32 through the L2 atomic units per
-      // projection GEMM (~2.2 TB/s measured: as long as the whole K = 1024 main loop); plain loads and stores run at L2 speed.
+      // ---- alternative residual epilogue without L2 reductions (LSVS_GEMM_RESID_LOADSTORE=1): resid tile -> shared memory (TMA
+      // load, issued one 32-column chunk ahead), add gamma * (acc + bias) in place, TMA store back.  Measured slower than the
+      // reduce-add form on B200 (see launch2); kept for A/B runs.
       // One split only (every element is written once per GEMM, so the prefetched tile of the NEXT output tile is never stale).
       uint8_t* tiles = smem + L::TILE_OFFSET + (warp - 2) * 2 * L::TILE_BYTES;
       uint64_t* lbar = resid_bar + 2 * (warp - 2);
@@ -827,9 +827,11 @@ int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K,
     const int n_kb = K / BK;
     while (splits < 8 && tiles * splits * 2 <= max_pairs && n_kb % (2 * splits) == 0 && n_kb / (2 * splits) >= 4) splits *= 2;
   }
-  // one split: load-add-store epilogue instead of reduce-add (LSVS_GEMM_RESID_ATOMIC=1 keeps the reduce-add form for A/B runs)
-  static const bool resid_atomic = [] { const char* v = getenv("LSVS_GEMM_RESID_ATOMIC"); return v && atoi(v) != 0; }();
-  if ((use_red & 1) && splits == 1 && !resid_atomic) use_red |= 16;
+  // LSVS_GEMM_RESID_LOADSTORE=1 (A/B runs): load-add-store epilogue instead of the TMA reduce-add.  Measured on B200: slower
+  // (projection 34.3 vs 33.1 us, fc2 89.5 vs 85.5 us, 398 vs 404 frames/s in the pipeline — profiles/r2_gemm_resid_ab.md), so the
+  // L2 reduction units are not what holds the residual epilogue back; the reduce-add stays the default.
+  static const bool resid_loadstore = [] { const char* v = getenv("LSVS_GEMM_RESID_LOADSTORE"); return v && atoi(v) != 0; }();
+  if ((use_red & 1) && splits == 1 && resid_loadstore) use_red |= 16;
   use_red |= splits << 8;
   const int items = tiles * splits;
   const int pairs = items < max_pairs ? items : max_pairs;
