@@ -395,7 +395,7 @@ def run_b200(args):
 
     if world > 1:
         from lsvs_b200.scheduler import model_pipeline
-        kw = dict(head_cost=args.head_cost, lag=args.lag, defer_chain=not args.no_defer)
+        kw = dict(head_cost=args.head_cost, lag=args.lag, defer_chain=not args.no_defer, head_prefix_on_owner=not args.no_head_prefix)
         pipe = None
         if args.transport in ("auto", "peer"):
             try:  # a failure here is raised on every rank together (PeerTransport.__init__), so all ranks take the same branch
@@ -596,7 +596,8 @@ def run_b200(args):
     sequence = None
     if args.sequence_frames > 0:
         try:
-            sequence = sequence_leg(model, world, rank, dev, args, dict(head_cost=args.head_cost, lag=args.lag, defer_chain=not args.no_defer))
+            sequence = sequence_leg(model, world, rank, dev, args, dict(head_cost=args.head_cost, lag=args.lag, defer_chain=not args.no_defer,
+                                                                        head_prefix_on_owner=not args.no_head_prefix))
         except Exception as e:  # noqa: BLE001
             if world > 1:
                 raise   # a rank that left the collective protocol cannot be papered over
@@ -742,7 +743,9 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--with-dpt", action="store_true", help="also run the DPT depth / point heads inside every step (not the headline configuration)")
-    ap.add_argument("--head-cost", type=float, default=0.085, help="alignment-head time / aggregator time (rank-0 load balancing; measured 0.081)")
+    ap.add_argument("--head-cost", type=float, default=0.075, help="alignment-rank time per chunk / aggregator time (rank-0 load balancing; 0.081 measured with the "
+                    "whole head on rank 0, the context-free prefix now runs on the owners)")
+    ap.add_argument("--no-head-prefix", action="store_true", help="N>1: keep the whole alignment head on rank 0 (A/B)")
     ap.add_argument("--transport", default="auto", choices=["auto", "peer", "dist"], help="N>1: CUDA-IPC peer mailboxes or torch.distributed p2p")
     ap.add_argument("--lag", type=int, default=2, help="N>1: chunks an owner keeps in flight before it needs a Sim(3) packet")
     ap.add_argument("--no-defer", action="store_true", help="N>1: rank 0 chains a round's heads in the same round (A/B)")

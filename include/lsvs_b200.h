@@ -183,6 +183,14 @@ int lsvs_alignment_head_forward(lsvs_engine* e, const float* tokens, int B, int 
 int lsvs_alignment_head_forward_bf16(lsvs_engine* e, const lsvs_bf16* tokens, int B, int S, int P, int H, int W, int next_overlap,
                                      const float* overlap_in, int T, const float* memory_in, float* chunk_sim3,
                                      float* frame_se3, float* memory_out, float* overlap_out, void* stream);
+/* The head split at its only context-free boundary (project_in + token_norm + the first frame block need neither the
+ * previous chunk's overlap tokens nor its memory).  lsvs_alignment_head_prefix runs that part — on the rank that encoded the chunk —
+ * and writes the fp32 token stream prefix_out (B,S,P+1,1024); lsvs_alignment_head_resume continues from it on the alignment rank
+ * (first temporal block ... decode).  prefix + resume produce bit for bit what lsvs_alignment_head_forward does. */
+int lsvs_alignment_head_prefix(lsvs_engine* e, const float* tokens, int B, int S, int P, int H, int W, float* prefix_out, void* stream);
+int lsvs_alignment_head_resume(lsvs_engine* e, const float* prefix, int B, int S, int P, int H, int W, int next_overlap,
+                               const float* overlap_in, int T, const float* memory_in, float* chunk_sim3, float* frame_se3,
+                               float* memory_out, float* overlap_out, void* stream);
 /* the fp32 decode stage alone: AlignmentHead._decode_alignments alignment_head.py:427-540 (+ GatedUpdate,
  * gated_update.py:43-78).  align_tokens (B,S,1024) fp32 = the processed per-frame alignment tokens. */
 int lsvs_alignment_decode_forward(lsvs_engine* e, const float* align_tokens, int B, int S, const float* memory_in,

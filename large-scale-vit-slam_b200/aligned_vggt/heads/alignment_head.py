@@ -52,6 +52,17 @@ class AlignmentHead(_EngineBound):
                                                        precision=1 if precision else 0)
         return self._engine().alignment_head_forward(tokens, image_size, next_num_overlap, overlap_tokens, memory_tokens)
 
+    def forward_prefix(self, tokens: torch.Tensor, image_size: Tuple[int, int]) -> torch.Tensor:
+        """The part of forward() that needs no context of the previous chunk (project_in, token_norm, alignment token, first frame
+        block): (B,S,P,2048) -> fp32 token stream (B,S,P+1,1024).  The chunk scheduler runs it on the rank that encoded
+        the chunk and ships the stream instead of the tapped tokens."""
+        return self._engine().alignment_head_prefix(tokens, image_size)
+
+    def forward_from_prefix(self, prefix: torch.Tensor, image_size: Tuple[int, int], next_num_overlap: int,
+                            overlap_tokens: torch.Tensor = None, memory_tokens: torch.Tensor = None):
+        """forward() continued from forward_prefix()'s stream: identical outputs, bit for bit."""
+        return self._engine().alignment_head_resume(prefix, image_size, next_num_overlap, overlap_tokens, memory_tokens)
+
     def _decode_alignments(self, frame_alignment_tokens: torch.Tensor, num_overlap: int, is_first_chunk: bool,
                            memory_tokens: torch.Tensor = None):
         """reference :427-540 (eval path): (B,S,1024) -> chunk_sim3 (B,1,8), frame_se3 (B,S-1,7), memory (B,8,512).

@@ -591,9 +591,12 @@ int decode_forward(Engine& e, const float* x, long long ld_tok, int B, int S, co
 // ================================================================================================ AlignmentHead
 namespace lsvs {
 namespace {
+// prefix_out != NULL: stop after the context-free prefix (project_in, token_norm, alignment token, first frame block) and copy the
+// fp32 token stream (B,S,P+1,1024) there.  prefix_in != NULL: start from such a stream instead of `tokens`.
 int alignment_head_forward_impl(lsvs_engine* h, const float* tokens, const __nv_bfloat16* tokens_bf16, int B, int S, int P, int H, int W,
                                 int next_overlap, const float* overlap_in, int T, const float* memory_in, float* chunk_sim3,
-                                float* frame_se3, float* memory_out, float* overlap_out, void* stream);
+                                float* frame_se3, float* memory_out, float* overlap_out, void* stream, float* prefix_out = nullptr,
+                                const float* prefix_in = nullptr);
 }  // namespace
 }  // namespace lsvs
 
@@ -613,17 +616,37 @@ extern "C" int lsvs_alignment_head_forward_bf16(lsvs_engine* h, const lsvs_bf16*
                                            memory_in, chunk_sim3, frame_se3, memory_out, overlap_out, stream);
 }
 
+extern "C" int lsvs_alignment_head_prefix(lsvs_engine* h, const float* tokens, int B, int S, int P, int H, int W, float* prefix_out,
+                                          void* stream) {
+  LSVS_CHECK_ARG(tokens && prefix_out, "alignment_head_prefix: bad arguments");
+  return lsvs::alignment_head_forward_impl(h, tokens, nullptr, B, S, P, H, W, 0, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, stream,
+                                           prefix_out, nullptr);
+}
+
+extern "C" int lsvs_alignment_head_resume(lsvs_engine* h, const float* prefix, int B, int S, int P, int H, int W, int next_overlap,
+                                          const float* overlap_in, int T, const float* memory_in, float* chunk_sim3, float* frame_se3,
+                                          float* memory_out, float* overlap_out, void* stream) {
+  LSVS_CHECK_ARG(prefix, "alignment_head_resume: bad arguments");
+  return lsvs::alignment_head_forward_impl(h, nullptr, nullptr, B, S, P, H, W, next_overlap, overlap_in, T, memory_in, chunk_sim3, frame_se3,
+                                           memory_out, overlap_out, stream, nullptr, prefix);
+}
+
 namespace lsvs {
 namespace {
 int alignment_head_forward_impl(lsvs_engine* h, const float* tokens, const __nv_bfloat16* tokens_bf16, int B, int S, int P, int H, int W,
                                 int next_overlap, const float* overlap_in, int T, const float* memory_in, float* chunk_sim3,
-                                float* frame_se3, float* memory_out, float* overlap_out, void* stream) {
+                                float* frame_se3, float* memory_out, float* overlap_out, void* stream, float* prefix_out,
+                                const float* prefix_in) {
   Engine& e = *reinterpret_cast<Engine*>(h);
   cudaStream_t st = (cudaStream_t)stream;
   LSVS_CHECK_ARG(e.finalized && e.cfg.with_alignment_head, "alignment_head_forward: engine has no alignment head / not finalized");
-  LSVS_CHECK_ARG(chunk_sim3 && overlap_out && B > 0 && S > 0 && P > 5, "alignment_head_forward: bad arguments");
-  LSVS_CHECK_ARG(memory_out || e.cfg.num_memory_tokens == 0, "alignment_head_forward: memory_out missing");
-  LSVS_CHECK_ARG(S == 1 || frame_se3, "alignment_head_forward: frame_se3 output missing");
+  LSVS_CHECK_ARG(B > 0 && S > 0 && P > 5, "alignment_head_forward: bad arguments");
+  if (!prefix_out) {
+    LSVS_CHECK_ARG(chunk_sim3 && overlap_out, "alignment_head_forward: bad arguments");
+    LSVS_CHECK_ARG(memory_out || e.cfg.num_memory_tokens == 0, "alignment_head_forward: memory_out missing");
+    LSVS_CHECK_ARG(S == 1 || frame_se3, "alignment_head_forward: frame_se3 output missing");
+  }
+  LSVS_CHECK_ARG(e.cfg.head_depth_aa >= 1, "alignment_head_forward: head has no blocks");
   const int gh = H / 14, gw = W / 14, D = 1024, DD = 512, NM = e.cfg.num_memory_tokens, P1 = P + 1, frames = B * S;
   LSVS_CHECK_ARG(gh * gw + 5 == P, "Size of tokens and image do not match (P=%d, grid %dx%d)", P, gh, gw);
   LSVS_CHECK_ARG(NM == 8 || NM == 0, "alignment_head_forward: num_memory_tokens must be 8 or 0");
@@ -664,7 +687,9 @@ int alignment_head_forward_impl(lsvs_engine* h, const float* tokens, const __nv_
   TRY(need_f32(e, "alignment_head.per_frame_alignment_token", &atok, 2 * D));
   // project_in + token_norm, written behind the per-frame alignment token (:242-270)
   GemmEpilogue ep; ep.bias = pin_b; ep.out = e.tmp.p; ep.ldo = D;
-  if (tokens_bf16) {  // tokens that already are bf16 (the chunk scheduler ships them that way): they are the GEMM operand as they stand
+  if (prefix_in) {   // the owner of the chunk already ran the context-free prefix: its token stream is the starting point
+    LSVS_CUDA(cudaMemcpyAsync(x, prefix_in, (size_t)Mh * D * 4, cudaMemcpyDeviceToDevice, st));
+  } else if (tokens_bf16) {  // tokens that already are bf16 (the chunk scheduler ships them that way): they are the GEMM operand as they stand
     LSVS_CHECK_ARG(!pin->split, "alignment_head_forward_bf16: a precision-mode engine needs fp32 tokens");
     TRY(gemm_bf16(tokens_bf16, 2 * D, pin->bf16, 2 * D, (int)M, D, 2 * D, EPI_BIAS_F32, ep, st));
   } else if (pin->split) {
@@ -675,12 +700,18 @@ int alignment_head_forward_impl(lsvs_engine* h, const float* tokens, const __nv_
     TRY(cast_rows_bf16(tokens, 2 * D, e.h.p, 2 * D, M, 2 * D, st));
     TRY(gemm_bf16(e.h.p, 2 * D, pin->bf16, 2 * D, (int)M, D, 2 * D, EPI_BIAS_F32, ep, st));
   }
-  TRY(layernorm(e.tmp.as<float>(), D, RowMap{}, tnw, tnb, 1e-5f, x, D, RowMap{P, P1, 1}, false, M, D, st));
-  TRY(fill_special(atok, x, frames, S, P1, 0, 1, D, st));
+  if (!prefix_in) {
+    TRY(layernorm(e.tmp.as<float>(), D, RowMap{}, tnw, tnb, 1e-5f, x, D, RowMap{P, P1, 1}, false, M, D, st));
+    TRY(fill_special(atok, x, frames, S, P1, 0, 1, D, st));
+  }
 
   RopeCfg r2; r2.mode = ROPE_2D; r2.tab = e.rope2d_128.as<float2>(); r2.tpf = P1; r2.nsp = 6; r2.gw = gw;
   for (int i = 0; i < e.cfg.head_depth_aa; ++i) {
-    TRY(run_block(e, x, Mh, e.h_frame[i], 1e-5f, 8, 128, frames, P1, r2, nullptr, 0, st));
+    if (!(prefix_in && i == 0)) TRY(run_block(e, x, Mh, e.h_frame[i], 1e-5f, 8, 128, frames, P1, r2, nullptr, 0, st));
+    if (prefix_out && i == 0) {   // everything up to here needs no context: it can run on the rank that encoded the chunk
+      LSVS_CUDA(cudaMemcpyAsync(prefix_out, x, (size_t)Mh * D * 4, cudaMemcpyDeviceToDevice, st));
+      return LSVS_OK;
+    }
     // temporal cross block on the RAW (B*P1, S, C) view: groups of S consecutive flat rows (:372-377)
     const BlockW& w = e.h_temporal[i];
     if (w.split) {  // fp32-class cross block (csrc/precise.cu): split GEMM operands, fp32 q/k LayerNorm + 1-D RoPE + attention

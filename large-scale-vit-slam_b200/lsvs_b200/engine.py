@@ -165,6 +165,45 @@ class Engine:
             mem_out = memory_tokens
         return sim3, se3, mem_out, ov_out
 
+    def alignment_head_prefix(self, tokens: torch.Tensor, image_size) -> torch.Tensor:
+        """The context-free part of the head (project_in, token_norm, alignment token, first frame block): tokens (B,S,P,2048) ->
+        fp32 token stream (B,S,P+1,1024).  Runs on the rank that encoded the chunk (lsvs_alignment_head_prefix)."""
+        B, S, P, C = tokens.shape
+        H, W = image_size
+        tok = tokens.detach().float().contiguous()
+        out = torch.empty(B, S, P + 1, 1024, dtype=torch.float32, device=tok.device)
+        _n.check(_n.lib().lsvs_alignment_head_prefix(self._h, _n.ptr(tok), _i(B), _i(S), _i(P), _i(H), _i(W), _n.ptr(out), _n.stream_ptr()),
+                 "alignment_head_prefix")
+        return out
+
+    def alignment_head_resume(self, prefix: torch.Tensor, image_size, next_overlap: int, overlap_tokens: Optional[torch.Tensor],
+                              memory_tokens: Optional[torch.Tensor]):
+        """The rest of the head from a prefix stream (B,S,P+1,1024): same outputs as alignment_head_forward, bit for bit."""
+        B, S, P1, C = prefix.shape
+        assert C == 1024
+        P = P1 - 1
+        H, W = image_size
+        dev = prefix.device
+        x0 = prefix.detach().float().contiguous()
+        T = 0
+        ov = mem = None
+        if overlap_tokens is not None:
+            assert overlap_tokens.shape[0] == B and overlap_tokens.shape[2] == P1 and overlap_tokens.shape[3] == 1024, \
+                "Size of tokens and overlap tokens must match"
+            T = overlap_tokens.shape[1]
+            ov = overlap_tokens.detach().to(dev, torch.float32).contiguous()
+        if memory_tokens is not None:
+            mem = memory_tokens.detach().to(dev, torch.float32).contiguous()
+        nm = int(self.cfg.num_memory_tokens)
+        sim3 = torch.empty(B, 1, 8, device=dev)
+        se3 = torch.empty(B, max(S - 1, 0), 7, device=dev)
+        mem_out = torch.empty(B, nm, 512, device=dev) if nm > 0 else None
+        ov_out = torch.empty(B, 1 + next_overlap, P1, 1024, device=dev)
+        _n.check(_n.lib().lsvs_alignment_head_resume(self._h, _n.ptr(x0), _i(B), _i(S), _i(P), _i(H), _i(W), _i(next_overlap), _n.ptr(ov),
+                                                     _i(T), _n.ptr(mem), _n.ptr(sim3), _n.ptr(se3), _n.ptr(mem_out), _n.ptr(ov_out),
+                                                     _n.stream_ptr()), "alignment_head_resume")
+        return sim3, se3, (mem_out if nm > 0 else memory_tokens), ov_out
+
     def alignment_decode_forward(self, align_tokens: torch.Tensor, memory_tokens: Optional[torch.Tensor]):
         """fp32 decode stage alone (alignment_head.py:427-540): (B,S,1024) -> sim3 (B,1,8), se3 (B,S-1,7), memory (B,8,512)."""
         B, S, C = align_tokens.shape

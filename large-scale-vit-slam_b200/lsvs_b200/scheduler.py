@@ -531,21 +531,31 @@ class ModelStages:
     inputs = (images (1,S,3,H,W), raw_points (1,S,H,W,3) | None, raw_depth (1,S,H,W,1) | None); with None and a model that has its
     DPT heads, the owner computes the maps itself (results then also carry world_points_conf / depth_conf)."""
 
-    def __init__(self, model, num_overlap: int, S: int, H: int, W: int, device):
+    def __init__(self, model, num_overlap: int, S: int, H: int, W: int, device, head_prefix_on_owner: bool = True):
+        """head_prefix_on_owner: the owner of a chunk also runs the context-free prefix of the alignment head (project_in,
+        token_norm, first frame block: 0.45 of the 4.2 ms the head costs the alignment rank per chunk) and ships the fp32 token
+        stream (1,S,P+1,1024) — the same 54 MB as the bf16 tapped tokens it replaces; rank 0 resumes from it."""
         self.model, self.ov, self.S, self.H, self.W, self.device = model, num_overlap, S, H, W, device
+        self.prefix = bool(head_prefix_on_owner)
         self.P = 5 + (H // 14) * (W // 14)
         self.packet_numel = 1 + 16 + S * 9 + 8 + (S - 1) * 7
         # the last-layer tokens travel as bf16 — exactly what the head's first GEMM consumes — unless the model runs a precision
         # mode whose head takes fp32-class operands
         self.tokens_dtype = torch.bfloat16 if not getattr(model, "precision", None) else torch.float32
+        if self.prefix:
+            self.tokens_dtype = torch.float32
         self._maps = {}   # id(inputs) -> DPT head outputs of a chunk whose packet has not arrived yet
 
     def shapes_of(self, frames: int):
         """(tokens shape, camera-encoding shape, packet numel) of a chunk of `frames` frames."""
-        return (1, frames, self.P, 2048), (1, frames, 9), 1 + 16 + frames * 9 + 8 + (frames - 1) * 7
+        return self.tokens_shape(frames), (1, frames, 9), 1 + 16 + frames * 9 + 8 + (frames - 1) * 7
+
+    def tokens_shape(self, frames: int):
+        """what travels owner -> alignment rank: the head's prefix stream, or the last tapped Aggregator layer"""
+        return (1, frames, self.P + 1, 1024) if self.prefix else (1, frames, self.P, 2048)
 
     def tokens_like(self):
-        return torch.empty(1, self.S, self.P, 2048, dtype=self.tokens_dtype, device=self.device)
+        return torch.empty(self.tokens_shape(self.S), dtype=self.tokens_dtype, device=self.device)
 
     def cam_like(self):
         return torch.empty(1, self.S, 9, dtype=torch.float32, device=self.device)
@@ -566,6 +576,8 @@ class ModelStages:
             maps["points"], maps["points_conf"] = m.point_head(taps, images=images, patch_start_idx=patch_start_idx)
         if maps:
             self._maps[id(inputs)] = maps
+        if self.prefix:
+            return m.alignment_head.forward_prefix(last, (self.H, self.W)), cam
         return last.to(self.tokens_dtype), cam
 
     def align(self, tokens, cam, ctx):
@@ -576,7 +588,8 @@ class ModelStages:
         ov_in = mem_in = prev = None
         if ctx is not None:
             ov_in, mem_in, prev = ctx["overlap_tokens"], ctx["memory_tokens"], ctx["pose_enc"]
-        sim3, se3, mem, ov_out = m.alignment_head(tokens, (self.H, self.W), overlap, overlap_tokens=ov_in, memory_tokens=mem_in)
+        head = m.alignment_head.forward_from_prefix if self.prefix else m.alignment_head
+        sim3, se3, mem, ov_out = head(tokens, (self.H, self.W), overlap, overlap_tokens=ov_in, memory_tokens=mem_in)
         pose, point_T, scale = pose_chain(sim3, se3, cam, prev, overlap, (self.H, self.W))
         packet = torch.cat([scale.reshape(-1), point_T.reshape(-1), pose.reshape(-1), sim3.reshape(-1), se3.reshape(-1)])
         return packet, {"overlap_tokens": ov_out, "memory_tokens": mem, "pose_enc": pose}
@@ -600,17 +613,17 @@ class ModelStages:
         return out
 
 
-def model_pipeline(model, num_overlap: int, S: int, H: int, W: int, rank: int, world: int, device, head_cost: float = 0.085,
+def model_pipeline(model, num_overlap: int, S: int, H: int, W: int, rank: int, world: int, device, head_cost: float = 0.075,
                    fwd_group=None, bwd_group=None, transport: str = "auto", lag: int = 2, defer_chain: bool = True,
-                   handshake_group=None, chunk_frames: Optional[Sequence[int]] = None) -> ChunkPipeline:
+                   handshake_group=None, chunk_frames: Optional[Sequence[int]] = None, head_prefix_on_owner: bool = True) -> ChunkPipeline:
     """transport: "peer" (CUDA-IPC mailboxes, one box), "dist" (torch.distributed isend/irecv) or "auto" (peer, and
     torch.distributed only if every rank agrees that the mailboxes could not be set up).  S = frames of the largest chunk;
     chunk_frames = per-chunk frame counts of a finite sequence (see run_sequence), None = endless rounds of S-frame chunks."""
-    st = ModelStages(model, num_overlap, S, H, W, device)
+    st = ModelStages(model, num_overlap, S, H, W, device, head_prefix_on_owner=head_prefix_on_owner)
     tx = None
     if world > 1 and transport in ("auto", "peer"):
         try:
-            tx = PeerTransport(rank, world, (1, S, st.P, 2048), st.tokens_dtype, (1, S, 9), st.packet_numel, device,
+            tx = PeerTransport(rank, world, st.tokens_shape(S), st.tokens_dtype, (1, S, 9), st.packet_numel, device,
                                group=handshake_group, slots=lag + 1)
         except Exception as e:  # noqa: BLE001  (raised on every rank together, see PeerTransport.__init__)
             if transport == "peer":

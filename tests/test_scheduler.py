@@ -455,7 +455,10 @@ def test_model_stages_run_dpt_heads_on_the_owner(monkeypatch):
         def camera_head(self, toks):
             return [torch.zeros(1, S, 9)]
 
-    st = sch.ModelStages(Model(), 1, S, H, W, "cpu")
+    # with the head prefix on the owner what travels is the head's token stream (alignment token + P tokens, 1024 wide, fp32)
+    assert sch.ModelStages(Model(), 1, S, H, W, "cpu").shapes_of(2) == ((1, 2, 12, 1024), (1, 2, 9), 1 + 16 + 18 + 8 + 7)
+    assert sch.ModelStages(Model(), 1, S, H, W, "cpu").tokens_like().shape == (1, S, 12, 1024)
+    st = sch.ModelStages(Model(), 1, S, H, W, "cpu", head_prefix_on_owner=False)
     assert st.shapes_of(2) == ((1, 2, 11, 2048), (1, 2, 9), 1 + 16 + 18 + 8 + 7)
     packet = torch.zeros(st.packet_numel)
     packet[0] = 2.0                                      # scale

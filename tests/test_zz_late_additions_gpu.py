@@ -151,3 +151,40 @@ def test_bf16_tokens_entry_and_model_copies():
         sd = dict(model.state_dict())
         sd["track_head.feature_extractor.norm.weight"] = torch.zeros(3)
         model.load_state_dict(sd, strict=True)
+
+
+@pytest.mark.parametrize("precision", [0, 2])
+def test_head_prefix_on_the_owner_equals_the_whole_head(precision):
+    """lsvs_alignment_head_prefix (project_in, token_norm, alignment token, first frame block: what the chunk's owner runs) followed
+    by lsvs_alignment_head_resume (the alignment rank) gives bit for bit what lsvs_alignment_head_forward gives, first chunk and chained
+    chunk, also for a shorter tail chunk; and the single-process ChunkPipeline built either way produces identical outputs."""
+    from aligned_vggt.models.featureAligned_vggt import FeatureAlignedVGGT
+    from lsvs_b200 import scheduler as sch
+    torch.manual_seed(0)
+    model = FeatureAlignedVGGT(enable_point=False, enable_depth=False, enable_track=False, depth=1, patch_embed_depth=1,
+                               intermediate_layer_indices=(0, 0, 0, 0), precision=precision).cuda().eval()
+    S, H, W, ov = 5, 28, 42, 2
+    P = 5 + (H // 14) * (W // 14)
+    head = model.alignment_head
+    with torch.no_grad():
+        taps = [model.aggregator(torch.rand(1, s, 3, H, W, device="cuda"))[0][0] for s in (S, S, 3)]
+        ctx_ov = ctx_mem = None
+        for tap in taps:
+            whole = head(tap, (H, W), ov, overlap_tokens=ctx_ov, memory_tokens=ctx_mem)
+            stream = head.forward_prefix(tap, (H, W))
+            assert stream.shape == (1, tap.shape[1], P + 1, 1024) and stream.dtype == torch.float32
+            split = head.forward_from_prefix(stream, (H, W), ov, overlap_tokens=ctx_ov, memory_tokens=ctx_mem)
+            for a, b in zip(whole, split):
+                assert torch.equal(a, b)
+            ctx_ov, ctx_mem = whole[3], whole[2]
+        # the scheduler's stages, with and without the prefix on the owner
+        imgs = [torch.rand(1, S, 3, H, W, device="cuda") for _ in range(3)]
+        outs = []
+        for on_owner in (True, False):
+            pipe = sch.model_pipeline(model, ov, S, H, W, 0, 1, torch.device("cuda"), head_prefix_on_owner=on_owner,
+                                      chunk_frames=[S] * len(imgs))
+            outs.append(sch.run_sequence(pipe, lambda k: (imgs[k], torch.zeros(1, S, H, W, 3, device="cuda"),
+                                                          torch.zeros(1, S, H, W, 1, device="cuda"))))
+        assert [k for k, _ in outs[0]] == [k for k, _ in outs[1]] == [0, 1, 2]
+        for (_, a), (_, b) in zip(*outs):
+            assert torch.equal(a["pose_enc"], b["pose_enc"])
