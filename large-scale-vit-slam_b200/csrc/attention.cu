@@ -1,7 +1,8 @@
 // Fused flash-style attention  O = softmax(Q K^T * scale) V  on tcgen05 / TMEM / TMA (no mask; ragged tails).
 //
-// One CTA owns two 128-row query tiles (A, B) of one (batch, head) and streams the K/V blocks once for both (long
-// sequences), or one tile with two CTAs per SM (Lk <= 1024).  Everything the tensor core touches besides Q/K/V lives in
+// One CTA owns one 128-row query tile of one (batch, head), two CTAs per SM (NT = 1, the default at every sequence length since
+// round 2: two independent CTAs fill each other's waits); the NT = 2 variant — two tiles (A, B) per CTA sharing every K/V block,
+// one CTA per SM — is kept behind LSVS_ATTN_NT1_MAX_LK for comparison.  Everything the tensor core touches besides Q/K/V lives in
 // tensor memory: S_t (fp32), O_t (fp32) and P_t (bf16 pairs, the A operand of the PV product).  Warp roles, NT = 2:
 //   warps 0-3   softmax for tile A, warps 4-7 for tile B (registers moved to them with setmaxnreg): one thread per query row
 //               (TMEM lane), so row sums need no shuffles.  exp2 with the softmax scale folded in, against a trailing
@@ -584,8 +585,13 @@ int attention_fwd(const AttentionArgs& a, cudaStream_t st) {
   LSVS_CHECK_ARG(a.ldq >= D && a.ldk >= D && a.ldv >= D && a.ldo >= D, "attention: leading dimension smaller than heads*head_dim");
   LSVS_CHECK_ARG(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: leading dimensions must be multiples of 8");
   ProfScope prof(a.Lk >= 2048 ? PROF_ATTENTION_GLOBAL : PROF_ATTENTION, st, 4.0 * a.batches * (double)a.heads * a.Lq * (double)a.Lk * a.head_dim, 0);
-  // short sequences: one query tile per CTA, two CTAs per SM (fixed per-CTA cost ~10 us vs ~1 us per key block)
-  static const int nt1_max_lk = [] { const char* e = getenv("LSVS_ATTN_NT1_MAX_LK"); return e ? atoi(e) : 1024; }();
+  // One query tile per CTA and two CTAs per SM at every sequence length.  Short sequences: the prologue / epilogue of one CTA
+  // hides behind the other.  Long sequences (measured, profiles/r2b_attention_experiments.md): two independent CTAs beat one
+  // CTA whose two tiles share each K/V block — 746-752 vs 695-700 TFLOP/s at 13 184 tokens, 824 vs 732 at 21 984 — although
+  // every K/V block is then fetched twice per SM: the two tiles of one CTA run in lock-step (their softmax warps wait for
+  // their barriers and tensor-memory loads at the same time, leaving the XU pipe idle), two CTAs drift apart and fill
+  // each other's waits.  LSVS_ATTN_NT1_MAX_LK=<n> restores the two-tile kernel for Lk > n (A/B runs).
+  static const int nt1_max_lk = [] { const char* e = getenv("LSVS_ATTN_NT1_MAX_LK"); return e ? atoi(e) : 0x7fffffff; }();
   const bool one_tile = a.Lk <= nt1_max_lk;
   if (a.head_dim == 128) return one_tile ? launch<128, 1>(a, st) : launch<128, 2>(a, st);
   // head dim 64: share of the exponentials taken off the XU pipe (pairs out of 4; LSVS_ATTN_POLY overrides for A/B runs)
