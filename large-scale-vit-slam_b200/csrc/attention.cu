@@ -19,6 +19,8 @@
 // alignment-head frame blocks alignment_head.py:363, camera-head trunk); q_norm/k_norm/RoPE are already applied
 // by the QKV GEMM epilogue (csrc/gemm.cu).
 #include <cstdlib>
+#include <map>
+#include <mutex>
 
 #include "attention.h"
 #include "host_common.h"
@@ -126,10 +128,10 @@ template <class C> __device__ __forceinline__ void reg_inc() {
 __device__ unsigned long long g_attn_phase[8 * 8];  // [warp][phase] cycle sums for CTA (0,0,0)
 #define PH_DECL unsigned ph_t = clock(); unsigned long long ph_acc[6] = {0, 0, 0, 0, 0, 0}
 #define PH(k) do { const unsigned now_ = clock(); ph_acc[k] += now_ - ph_t; ph_t = now_; } while (0)
-#define PH_FLUSH() do { if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) for (int k_ = 0; k_ < 6; ++k_) g_attn_phase[warp * 8 + k_] = ph_acc[k_]; } while (0)
+#define PH_FLUSH() do { if (lane == 0 && blockIdx.x == 0) for (int k_ = 0; k_ < 6; ++k_) g_attn_phase[warp * 8 + k_] = ph_acc[k_]; } while (0)
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define MS_ENTRY const unsigned long long ms_t0 = gtime()
-#define MS(k) do { if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == gridDim.z - 1) g_attn_phase[48 + (k)] = gtime() - ms_t0; } while (0)
+#define MS(k) do { if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) g_attn_phase[48 + (k)] = gtime() - ms_t0; } while (0)
 #else
 #define MS_ENTRY do {} while (0)
 #define MS(k) do {} while (0)
@@ -162,11 +164,55 @@ __device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& p0, flo
   p1 = __uint_as_float(__float_as_uint(f2_hi(p)) + (__float_as_uint(f2_hi(r)) << 23));
 }
 
+// How the grid maps to work (see the decode at the top of the kernel).
+struct WorkSplit {
+  int n_qt, heads;      // query-tile groups per sequence, heads: unit = (batch * heads + head) * n_qt + tile group
+  int n_full;           // units [0, n_full) run their whole key range in one CTA
+  int parts;            // every later unit is cut into `parts` key ranges (CTAs n_full + (unit - n_full) * parts + part)
+  float* partial;       // [(unit - n_full) * parts + part][NT * QT rows][HD + 2]: unnormalised O, reference maximum, row sum
+};
+
+// Merges the key-range partials of the split units:  O = sum_p w_p O_p / sum_p w_p l_p,  w_p = 2^((m_p - max_p m_p) * scale).
+// One warp per query row, HD / 32 columns per lane.
+template <int HD, int ROWS>
+__global__ void attention_combine_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ O, int ldo, int Lq,
+                                         float scale_log2e, int n_qt, int heads, int n_full, int parts) {
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int su = blockIdx.x / (ROWS / 4);                     // split unit
+  const int row = (blockIdx.x % (ROWS / 4)) * 4 + warp;       // row within the unit
+  const int unit = n_full + su;
+  const int q_local = (unit % n_qt) * ROWS + row;
+  if (q_local >= Lq) return;
+  const int head = (unit / n_qt) % heads, batch = unit / (n_qt * heads);
+  const float* base = partial + ((size_t)su * parts * ROWS + row) * (HD + 2);
+  const size_t pstride = (size_t)ROWS * (HD + 2);
+  float m = -INFINITY;
+  for (int p = 0; p < parts; ++p) m = fmaxf(m, base[p * pstride + HD]);
+  constexpr int CPL = HD / 32;
+  float acc[CPL] = {}, l = 0.f;
+  for (int p = 0; p < parts; ++p) {
+    const float* src = base + p * pstride;
+    const float w = exp2f((src[HD] - m) * scale_log2e);
+    l += w * src[HD + 1];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) acc[c] += w * src[lane * CPL + c];
+  }
+  const float inv = 1.0f / l;
+  __nv_bfloat16* dst = O + (size_t)(batch * (size_t)Lq + q_local) * ldo + head * HD + lane * CPL;
+  if constexpr (CPL == 2) {
+    *reinterpret_cast<uint32_t*>(dst) = ptx::pack_bf16(acc[0] * inv, acc[1] * inv);
+  } else {
+    uint2 u; u.x = ptx::pack_bf16(acc[0] * inv, acc[1] * inv); u.y = ptx::pack_bf16(acc[2] * inv, acc[3] * inv);
+    *reinterpret_cast<uint2*>(dst) = u;
+  }
+}
+
 template <int HD, int NT_, int POLY_>
 __global__ void __maxnreg__((Cfg<HD, NT_, POLY_>::MAXNREG))
 attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int Lq, int Lk,
-                      float scale_log2e) {
+                      float scale_log2e, WorkSplit ws) {
   using C = Cfg<HD, NT_, POLY_>;
   MS_ENTRY;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -175,12 +221,20 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NT = C::NT;
   constexpr int W_TMA = 4 * C::NWG, W_MMA = 4 * C::NWG + 1, W_TMA_V = 4 * C::NWG + 2;  // warp ids of the two service warps
-  const int q0 = blockIdx.x * (NT * QT);      // first query row (within the sequence) of this CTA
-  const int head = blockIdx.y, batch = blockIdx.z;
+  // work decode (WorkSplit): CTAs [0, n_full) own a whole unit = (batch, head, NT query tiles) over every key block; the units of
+  // the last, partial round of CTAs are cut into `parts` key ranges each, written as unnormalised partials and merged by
+  // attention_combine_kernel — the tail of the grid then lasts 1/parts of a unit instead of a whole one.
+  int unit = blockIdx.x, part = 0, n_parts = 1;
+  if (unit >= ws.n_full) { const int idx = unit - ws.n_full; unit = ws.n_full + idx / ws.parts; part = idx % ws.parts; n_parts = ws.parts; }
+  const int q0 = (unit % ws.n_qt) * (NT * QT);   // first query row (within the sequence) of this CTA
+  const int head = (unit / ws.n_qt) % ws.heads, batch = unit / (ws.n_qt * ws.heads);
   const int n_tiles = min(NT, (Lq - q0 + QT - 1) / QT);  // only tiles with at least one valid row
-  const int n_kv = (Lk + C::BKV - 1) / C::BKV;
+  const int n_kv_seq = (Lk + C::BKV - 1) / C::BKV;
+  const int kb0 = (int)((long long)part * n_kv_seq / n_parts);   // key blocks [kb0, kb0 + n_kv) of the sequence
+  const int n_kv = (int)((long long)(part + 1) * n_kv_seq / n_parts) - kb0;
+  const int Lkp = min(Lk - kb0 * C::BKV, n_kv * C::BKV);         // valid keys of this CTA's range (ragged only at the sequence end)
   const int q_row0 = batch * Lq + q0;          // global row of tile A's first query
-  const int kv_row0 = batch * Lk;
+  const int kv_row0 = batch * Lk + kb0 * C::BKV;
   const int col0 = head * HD;
 
   if (warp == W_TMA && lane == 0) {
@@ -258,7 +312,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
     // the last key block of a ragged sequence (412 = 3 x 128 + 28 keys) only spans n_last keys (a multiple of 32): a narrower
     // S = Q K^T (UMMA N = n_last) and a shorter P V reduction, and the softmax warps touch n_last columns instead of BKV
-    const int n_last = min(C::BKV, ((Lk - (n_kv - 1) * C::BKV) + 31) & ~31);
+    const int n_last = min(C::BKV, ((Lkp - (n_kv - 1) * C::BKV) + 31) & ~31);
     const uint32_t idesc_s_last = ptx::umma_idesc_bf16(QT, n_last, 0, 0);
     auto issue_S = [&](int t, int stage, bool last) {
       const uint32_t id = last ? idesc_s_last : idesc_s;
@@ -340,7 +394,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       // a warp whose 32 query rows all lie past Lq (ragged last tile: 412 = 3 x 128 + 28 rows; 32-row temporal attention) only
       // keeps the barrier protocol going: its rows of S / P / O are never stored, and rows of an MMA are independent
       const bool warp_active = q0 + t * QT + quarter * 32 < Lq;
-      const int n_last = min(COLS, ((Lk - (n_kv - 1) * C::BKV) + 31) & ~31);
+      const int n_last = min(COLS, ((Lkp - (n_kv - 1) * C::BKV) + 31) & ~31);
       PH_DECL;
       for (int i = 0; i < n_kv; ++i) {
         DBG_ITER(i);
@@ -350,7 +404,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         PH(0);
         if (i == 0) MS(1);  // first S tile ready (Q, K(0) landed, first MMA retired)
         float s[COLS];
-        const int kv_valid = Lk - i * C::BKV;  // keys of this block inside the sequence
+        const int kv_valid = Lkp - i * C::BKV;  // keys of this block inside the sequence
         // steady-state block (not the first, all columns valid): only the first 32 columns of S are waited for here; the other
         // tensor-memory loads stay in flight under the first exponentials, and so does the wait for P V(i-1) (emit_full's hooks)
         const bool split = warp_active && i >= 1 && kv_valid >= COLS;
@@ -525,12 +579,24 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const float inv_l = 1.0f / l_run;
       const int q_local = q0 + t * QT + r;
       __nv_bfloat16* dst = O + (size_t)(batch * (size_t)Lq + q_local) * ldo + col0;
+      // split unit: this CTA saw only its key range — unnormalised O (fp32), reference maximum and row sum go to the workspace
+      float* pdst = nullptr;
+      if (n_parts > 1) {
+        const size_t prow = ((size_t)(unit - ws.n_full) * ws.parts + part) * (NT * QT) + t * QT + r;
+        pdst = ws.partial + prow * (HD + 2);
+        if (q_local < Lq) { pdst[HD] = m_ref; pdst[HD + 1] = l_run; }
+      }
 #pragma unroll
       for (int c = 0; c < OCOLS; c += 32) {
         uint32_t o[32];
         ptx::tmem_ld_32x32b_x32(tO + c, o);
         ptx::tmem_ld_wait();
-        if (q_local < Lq) {
+        if (pdst != nullptr) {
+          if (q_local < Lq) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) *reinterpret_cast<float2*>(pdst + c + 2 * j) = make_float2(__uint_as_float(o[2 * j]), __uint_as_float(o[2 * j + 1]));
+          }
+        } else if (q_local < Lq) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
@@ -553,6 +619,25 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   MS(5);
 }
 
+// Workspace of the split units' partials: one buffer per stream (launches on one stream are ordered, so a buffer is reused by
+// the next launch only after the previous merge has read it), grown on demand; never allocated while the stream is being
+// captured into a CUDA graph (the launch then simply does not split).
+float* split_workspace(cudaStream_t st, size_t bytes) {
+  struct Buf { float* p = nullptr; size_t cap = 0; };
+  static std::mutex mu;
+  static std::map<cudaStream_t, Buf> bufs;
+  std::lock_guard<std::mutex> lock(mu);
+  Buf& b = bufs[st];
+  if (b.cap >= bytes) return b.p;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
+  if (b.p) { cudaStreamSynchronize(st); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+  const size_t cap = bytes + bytes / 4;
+  if (cudaMalloc(&b.p, cap) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return nullptr; }
+  b.cap = cap;
+  return b.p;
+}
+
 template <int HD, int NT_, int POLY_ = 0>
 int launch(const AttentionArgs& a, cudaStream_t st) {
   using C = Cfg<HD, NT_, POLY_>;
@@ -567,10 +652,41 @@ int launch(const AttentionArgs& a, cudaStream_t st) {
     LSVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
-  dim3 grid((a.Lq + C::NT * QT - 1) / (C::NT * QT), a.heads, a.batches);
   const float scale_log2e = a.scale * 1.4426950408889634f;
-  LSVS_CUDA(launch_pdl(kern, grid, dim3(C::NTHREADS), C::SMEM, st, *tq, *tk, *tv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, a.Lk, scale_log2e));
+  WorkSplit ws;
+  ws.n_qt = (a.Lq + C::NT * QT - 1) / (C::NT * QT);
+  ws.heads = a.heads;
+  const long long n_units = (long long)ws.n_qt * a.heads * a.batches;
+  LSVS_CHECK_ARG(n_units < (1ll << 30), "attention: too many (batch, head, query tile) units");
+  ws.n_full = (int)n_units; ws.parts = 1; ws.partial = nullptr;
+  // Tail balancing: CTAs are dispatched in rounds of `slots`; a last round that fills only part of the SMs still lasts a whole
+  // unit.  Cutting its units into p key ranges makes it last ceil(leftover * p / slots) / p of a unit (+ the merge).
+  static const int split_max = [] { const char* e = getenv("LSVS_ATTN_SPLIT_MAX"); return e ? atoi(e) : 4; }();
+  const int slots = num_sms() * (NT_ == 1 ? 2 : 1);
+  const int n_kv_seq = (a.Lk + C::BKV - 1) / C::BKV;
+  const int leftover = (int)(n_units % slots);
+  if (n_units > slots && leftover > 0 && split_max > 1) {
+    int best_p = 1; double best = 1.0;
+    for (int p = 2; p <= split_max && n_kv_seq / p >= 8; ++p) {
+      const double cost = (double)(((long long)leftover * p + slots - 1) / slots) / p + 0.03 * p;
+      if (cost < best - 0.05) { best = cost; best_p = p; }
+    }
+    if (best_p > 1) {
+      const size_t need = (size_t)leftover * best_p * (C::NT * QT) * (HD + 2) * sizeof(float);
+      float* buf = split_workspace(st, need);
+      if (buf) { ws.n_full = (int)(n_units - leftover); ws.parts = best_p; ws.partial = buf; }
+    }
+  }
+  const unsigned grid = (unsigned)(ws.n_full + (n_units - ws.n_full) * ws.parts);
+  LSVS_CUDA(launch_pdl(kern, dim3(grid), dim3(C::NTHREADS), C::SMEM, st, *tq, *tk, *tv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, a.Lk, scale_log2e, ws));
   LSVS_LAUNCH_CHECK();
+  if (ws.parts > 1) {
+    constexpr int ROWS = C::NT * QT;
+    auto ck = attention_combine_kernel<HD, ROWS>;
+    LSVS_CUDA(launch_pdl(ck, dim3((unsigned)((n_units - ws.n_full) * (ROWS / 4))), dim3(128), 0, st, (const float*)ws.partial,
+                         reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, scale_log2e, ws.n_qt, ws.heads, ws.n_full, ws.parts));
+    LSVS_LAUNCH_CHECK();
+  }
   return LSVS_OK;
 }
 
@@ -579,7 +695,6 @@ int launch(const AttentionArgs& a, cudaStream_t st) {
 int attention_fwd(const AttentionArgs& a, cudaStream_t st) {
   LSVS_CHECK_ARG(a.q && a.k && a.v && a.o, "attention: null pointer");
   LSVS_CHECK_ARG(a.batches > 0 && a.heads > 0 && a.Lq > 0 && a.Lk > 0, "attention: empty shape");
-  LSVS_CHECK_ARG(a.batches <= 65535 && a.heads <= 65535, "attention: batch/head count exceeds the grid limit");
   LSVS_CHECK_ARG(a.head_dim == 64 || a.head_dim == 128, "attention: head_dim %d unsupported (64 or 128)", a.head_dim);
   const int D = a.heads * a.head_dim;
   LSVS_CHECK_ARG(a.ldq >= D && a.ldk >= D && a.ldv >= D && a.ldo >= D, "attention: leading dimension smaller than heads*head_dim");

@@ -95,3 +95,31 @@ def test_rising_and_plateau_scores(Lk):
         out = ops.attention(q.cuda(), k.cuda(), v.cuda(), 1, H, hd, Lq, Lk).cpu()
         assert torch.isfinite(out.float()).all()
         assert rel_l2(out, ref) < 8e-3, rel_l2(out, ref)
+
+
+@pytest.mark.parametrize("L,rising", [(2560, False), (2500, True), (2500, False)])
+def test_split_key_ranges_are_merged(L, rising):
+    """320 (head, query tile) units on 296 CTA slots: the 24 units of the partial last round are cut into key ranges, written as
+    unnormalised partials and merged (attention_combine_kernel).  With scores that rise along the keys every range has its own
+    reference maximum and the last range carries almost all of the weight."""
+    from lsvs_b200 import ops
+    H, hd = 16, 64
+    D = H * hd
+    g = torch.Generator().manual_seed(L + rising)
+    if rising:
+        u = torch.nn.functional.normalize(torch.randn(H, hd, generator=g), dim=-1) * 8.0
+        q = (u[None] + 0.05 * torch.randn(L, H, hd, generator=g)).reshape(L, D).bfloat16()
+        ramp = (torch.arange(L).float() * 0.02).view(L, 1, 1)
+        k = (u[None] / 8.0 * ramp + 0.05 * torch.randn(L, H, hd, generator=g)).reshape(L, D).bfloat16()
+    else:
+        q = (1.5 * torch.randn(L, D, generator=g)).bfloat16()
+        k = (1.5 * torch.randn(L, D, generator=g)).bfloat16()
+    v = torch.randn(L, D, generator=g).bfloat16()
+    qf, kf, vf = (t.float().reshape(1, L, H, hd).transpose(1, 2) for t in (q, k, v))
+    ref = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(L, D)
+    out = ops.attention(q.cuda(), k.cuda(), v.cuda(), 1, H, hd, L, L).cpu()
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < 8e-3, rel_l2(out, ref)
+    # the units of the last round (head 15, query tiles 16..19 at least) on their own
+    tail = slice(16 * 128, L)
+    assert rel_l2(out[tail, 15 * hd:], ref[tail, 15 * hd:]) < 8e-3

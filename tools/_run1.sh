@@ -1,12 +1,8 @@
+timeout 600 python -m pytest tests/test_attention_gpu.py -x -q -m gpu > gpurun_out/r2b_test_attn_split.log 2>&1; tail -5 gpurun_out/r2b_test_attn_split.log
 for rep in 1 2; do
-LSVS_B200_LIB=variants/base0/liblsvs_b200.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-incumbent --sequence-frames 0 > gpurun_out/r2b_bench_ab_base_$rep.json 2> gpurun_out/r2b_bench_ab_base_$rep.err
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-incumbent --sequence-frames 0 > gpurun_out/r2b_bench_ab_nt1_$rep.json 2> gpurun_out/r2b_bench_ab_nt1_$rep.err
-done
-python - <<'PY'
-import json,glob
-for f in sorted(glob.glob('gpurun_out/r2b_bench_ab_*.json')):
-    try:
-        d=json.loads(open(f).read().strip().splitlines()[-1]); kc=d['kernel_classes']
-        print(f, round(d['value'],1), round(d['ms_per_step'],2), {k:round(v['ms_per_step'],2) for k,v in kc.items()}, d['attention']['tflops'])
-    except Exception as e: print(f, 'ERR', e)
-PY
+python tools/ub_attn.py 2>&1 | grep "global\|frame S" | sed "s/^/split rep$rep /"
+LSVS_ATTN_SPLIT_MAX=1 python tools/ub_attn.py 2>&1 | grep "global\|frame S" | sed "s/^/nosplit rep$rep /"
+done > gpurun_out/r2b_ab_split.log 2>&1
+LSVS_ATTN_SPLIT_MAX=3 python tools/ub_attn.py 2>&1 | grep "global" | sed "s/^/split3 /" >> gpurun_out/r2b_ab_split.log
+LSVS_ATTN_SPLIT_MAX=6 python tools/ub_attn.py 2>&1 | grep "global" | sed "s/^/split6 /" >> gpurun_out/r2b_ab_split.log
+cut -c1-200 gpurun_out/r2b_ab_split.log | sed 's/"poly": "default", "rel_l2_vs_sdpa"/err/; s/"B": 1, "H": 16, "hd": 64, //'
