@@ -123,3 +123,19 @@ def test_split_key_ranges_are_merged(L, rising):
     # the units of the last round (head 15, query tiles 16..19 at least) on their own
     tail = slice(16 * 128, L)
     assert rel_l2(out[tail, 15 * hd:], ref[tail, 15 * hd:]) < 8e-3
+
+
+@pytest.mark.parametrize("B,H,hd,Lq,Lk", [(413, 8, 128, 32, 9), (40, 8, 128, 32, 32), (7, 8, 128, 5, 2), (9, 8, 128, 64, 17), (3, 16, 64, 33, 64)])
+def test_temporal_cross_attention_shapes(B, H, hd, Lq, Lk):
+    """The alignment head's temporal cross attention (cross_attention.py:65-73): many (group, head) pairs of a few queries against
+    a few keys (mostly padding on the 128-row tile: inactive warps, narrow last key block)."""
+    from lsvs_b200 import ops
+    D = H * hd
+    q = rnd(11 * Lq + Lk, B * Lq, D, scale=1.5).to(torch.bfloat16)
+    kv = rnd(13 * Lq + Lk, B * Lk, 2 * D, scale=1.5).to(torch.bfloat16)
+    sh = lambda t, L: t.float().reshape(B, L, H, hd).transpose(1, 2)
+    ref = torch.nn.functional.scaled_dot_product_attention(sh(q, Lq), sh(kv[:, :D], Lk), sh(kv[:, D:], Lk)).transpose(1, 2).reshape(B * Lq, D)
+    kvd = kv.cuda()
+    out = ops.attention(q.cuda(), kvd[:, :D], kvd[:, D:], B, H, hd, Lq, Lk).cpu()
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < 4e-3, rel_l2(out, ref)
