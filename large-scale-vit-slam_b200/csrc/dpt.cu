@@ -22,6 +22,26 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return make_uint4(ptx::pack_bf16(f[0], f[1]), ptx::pack_bf16(f[2], f[3]), ptx::pack_bf16(f[4], f[5]), ptx::pack_bf16(f[6], f[7]));
 }
 
+// Eight consecutive channels of one pixel: 16 bytes of bf16 (the benchmarked path) or 32 bytes of fp32 (precision modes,
+// where the DPT heads keep fp32 activations like the reference: featureAligned_vggt.py:103, autocast disabled).
+template <class T> struct V8;
+template <> struct V8<__nv_bfloat16> {
+  uint4 u;
+  __device__ static V8 zero() { V8 v; v.u = make_uint4(0u, 0u, 0u, 0u); return v; }
+  __device__ static V8 load(const __nv_bfloat16* p) { V8 v; v.u = *reinterpret_cast<const uint4*>(p); return v; }
+  __device__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = u; }
+  __device__ void to_float(float* f) const { unpack8(u, f); }
+  __device__ static V8 from_float(const float* f) { V8 v; v.u = pack8(f); return v; }
+};
+template <> struct V8<float> {
+  float4 a, b;
+  __device__ static V8 zero() { V8 v; v.a = v.b = make_float4(0.f, 0.f, 0.f, 0.f); return v; }
+  __device__ static V8 load(const float* p) { V8 v; v.a = *reinterpret_cast<const float4*>(p); v.b = *reinterpret_cast<const float4*>(p + 4); return v; }
+  __device__ void store(float* p) const { *reinterpret_cast<float4*>(p) = a; *reinterpret_cast<float4*>(p + 4) = b; }
+  __device__ void to_float(float* f) const { f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w; }
+  __device__ static V8 from_float(const float* f) { V8 v; v.a = make_float4(f[0], f[1], f[2], f[3]); v.b = make_float4(f[4], f[5], f[6], f[7]); return v; }
+};
+
 // torch.linspace(-span*(n-1)/n, +span*(n-1)/n, n)[i] (symmetric evaluation like ATen)
 __device__ __forceinline__ float uv_coord(int i, int n, float span) {
   const float end = span * (float)(n - 1) / (float)n, start = -end;
@@ -80,72 +100,77 @@ __global__ void uv_table_kernel(float* U, float* V, int h, int w, int C, float a
   }
 }
 
-__global__ void pos_embed_kernel(uint4* x, int h, int w, int C8, float aspect, float ratio, const float* U, const float* V) {
+template <class T>
+__global__ void pos_embed_kernel(T* x, int h, int w, int C8, float aspect, float ratio, const float* U, const float* V) {
   const int idx = blockIdx.y * TPB + threadIdx.x;
   if (idx >= w * C8) return;
   const int xx = idx / C8, c8 = idx - xx * C8;
   const int yy = blockIdx.x % h;
-  uint4* p = x + (size_t)blockIdx.x * w * C8 + idx;
+  T* p = x + ((size_t)blockIdx.x * w * C8 + idx) * 8;
   float f[8];
-  unpack8(*p, f);
+  V8<T>::load(p).to_float(f);
   add_embed8(f, c8, C8 * 8, xx, yy, w, h, aspect, ratio, U, V);
-  *p = pack8(f);
+  V8<T>::from_float(f).store(p);
 }
 
-__global__ void pad_kernel(const uint4* in, uint4* out, int h, int w, int C8) {
+template <class T>
+__global__ void pad_kernel(const T* in, T* out, int h, int w, int C8) {
   const int wp = w + 2, hp = h + 2;
   const int idx = blockIdx.y * TPB + threadIdx.x;
   if (idx >= wp * C8) return;
   const int xp = idx / C8, c8 = idx - xp * C8;
   const int f = blockIdx.x / hp, yp = blockIdx.x - f * hp;
-  uint4 v = make_uint4(0u, 0u, 0u, 0u);
-  if (xp >= 1 && xp <= w && yp >= 1 && yp <= h) v = in[(((size_t)f * h + (yp - 1)) * w + (xp - 1)) * C8 + c8];
-  out[(size_t)blockIdx.x * wp * C8 + idx] = v;
+  V8<T> v = V8<T>::zero();
+  if (xp >= 1 && xp <= w && yp >= 1 && yp <= h) v = V8<T>::load(in + ((((size_t)f * h + (yp - 1)) * w + (xp - 1)) * C8 + c8) * 8);
+  v.store(out + ((size_t)blockIdx.x * wp * C8 + idx) * 8);
 }
 
-__global__ void convt_shuffle_kernel(const uint4* in, const float* bias, uint4* out, int h, int w, int C8, int k) {
+template <class T>
+__global__ void convt_shuffle_kernel(const T* in, const float* bias, T* out, int h, int w, int C8, int k) {
   const int wp = k * w + 2, hp = k * h + 2;
   const int idx = blockIdx.y * TPB + threadIdx.x;
   if (idx >= wp * C8) return;
   const int xp = idx / C8, c8 = idx - xp * C8;
   const int f = blockIdx.x / hp, yp = blockIdx.x - f * hp;
-  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  V8<T> v = V8<T>::zero();
   if (xp >= 1 && xp <= k * w && yp >= 1 && yp <= k * h) {
     const int oy = yp - 1, ox = xp - 1;
     const int y = oy / k, ii = oy - y * k, x = ox / k, jj = ox - x * k;
-    v = in[((((size_t)f * h + y) * w + x) * (k * k) + ii * k + jj) * C8 + c8];
+    v = V8<T>::load(in + (((((size_t)f * h + y) * w + x) * (k * k) + ii * k + jj) * C8 + c8) * 8);
     if (bias) {
       float t[8];
-      unpack8(v, t);
+      v.to_float(t);
 #pragma unroll
       for (int j = 0; j < 8; ++j) t[j] += bias[c8 * 8 + j];
-      v = pack8(t);
+      v = V8<T>::from_float(t);
     }
   }
-  out[(size_t)blockIdx.x * wp * C8 + idx] = v;
+  v.store(out + ((size_t)blockIdx.x * wp * C8 + idx) * 8);
 }
 
 // blockIdx.x = output pixel row (f, oy), idx = (ox, tap, c8)
-__global__ void im2col_s2_kernel(const uint4* in, uint4* out, int h, int w, int ho, int wo, int C8) {
+template <class T>
+__global__ void im2col_s2_kernel(const T* in, T* out, int h, int w, int ho, int wo, int C8) {
   const int idx = blockIdx.y * TPB + threadIdx.x;
   if (idx >= wo * 9 * C8) return;
   const int c8 = idx % C8, r = idx / C8, tap = r % 9, ox = r / 9;
   const int f = blockIdx.x / ho, oy = blockIdx.x - f * ho;
   const int y = 2 * oy - 1 + tap / 3, x = 2 * ox - 1 + tap % 3;
-  uint4 v = make_uint4(0u, 0u, 0u, 0u);
-  if (y >= 0 && y < h && x >= 0 && x < w) v = in[(((size_t)f * h + y) * w + x) * C8 + c8];
-  out[(size_t)blockIdx.x * wo * 9 * C8 + idx] = v;
+  V8<T> v = V8<T>::zero();
+  if (y >= 0 && y < h && x >= 0 && x < w) v = V8<T>::load(in + ((((size_t)f * h + y) * w + x) * C8 + c8) * 8);
+  v.store(out + ((size_t)blockIdx.x * wo * 9 * C8 + idx) * 8);
 }
 
-__global__ void bilinear_kernel(const uint4* in, uint4* out, int hi, int wi, int ho, int wo, int C8, float aspect, float ratio,
+template <class T>
+__global__ void bilinear_kernel(const T* in, T* out, int hi, int wi, int ho, int wo, int C8, float aspect, float ratio,
                                 const float* U, const float* V) {
   const int wpo = wo + 2, hpo = ho + 2, wpi = wi + 2, hpi = hi + 2;
   const int idx = blockIdx.y * TPB + threadIdx.x;
   if (idx >= wpo * C8) return;
   const int xp = idx / C8, c8 = idx - xp * C8;
   const int f = blockIdx.x / hpo, yp = blockIdx.x - f * hpo;
-  uint4* dst = out + (size_t)blockIdx.x * wpo * C8 + idx;
-  if (xp < 1 || xp > wo || yp < 1 || yp > ho) { *dst = make_uint4(0u, 0u, 0u, 0u); return; }
+  T* dst = out + ((size_t)blockIdx.x * wpo * C8 + idx) * 8;
+  if (xp < 1 || xp > wo || yp < 1 || yp > ho) { V8<T>::zero().store(dst); return; }
   const int oy = yp - 1, ox = xp - 1;
   // align_corners=True (ATen area_pixel_compute_scale / source index)
   const float sy = ho > 1 ? (float)(hi - 1) / (float)(ho - 1) * (float)oy : 0.f;
@@ -154,21 +179,22 @@ __global__ void bilinear_kernel(const uint4* in, uint4* out, int hi, int wi, int
   const int y1 = y0 + (y0 < hi - 1 ? 1 : 0), x1 = x0 + (x0 < wi - 1 ? 1 : 0);
   const float ly = sy - (float)y0, lx = sx - (float)x0;
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-  const uint4* r0 = in + ((size_t)f * hpi + y0 + 1) * wpi * C8 + c8;
-  const uint4* r1 = in + ((size_t)f * hpi + y1 + 1) * wpi * C8 + c8;
+  const T* r0 = in + (((size_t)f * hpi + y0 + 1) * wpi * C8 + c8) * 8;
+  const T* r1 = in + (((size_t)f * hpi + y1 + 1) * wpi * C8 + c8) * 8;
   float a[8], b[8], c[8], d[8], o[8];
-  unpack8(r0[(size_t)(x0 + 1) * C8], a);
-  unpack8(r0[(size_t)(x1 + 1) * C8], b);
-  unpack8(r1[(size_t)(x0 + 1) * C8], c);
-  unpack8(r1[(size_t)(x1 + 1) * C8], d);
+  V8<T>::load(r0 + (size_t)(x0 + 1) * C8 * 8).to_float(a);
+  V8<T>::load(r0 + (size_t)(x1 + 1) * C8 * 8).to_float(b);
+  V8<T>::load(r1 + (size_t)(x0 + 1) * C8 * 8).to_float(c);
+  V8<T>::load(r1 + (size_t)(x1 + 1) * C8 * 8).to_float(d);
 #pragma unroll
   for (int j = 0; j < 8; ++j) o[j] = w00 * a[j] + w01 * b[j] + w10 * c[j] + w11 * d[j];
   if (ratio > 0.f) add_embed8(o, c8, C8 * 8, ox, oy, wo, ho, aspect, ratio, U, V);
-  *dst = pack8(o);
+  V8<T>::from_float(o).store(dst);
 }
 
-// one thread per pixel: 32 input channels (post-ReLU, bf16) x od fp32 weights, then activate_head
-__global__ void final_kernel(const __nv_bfloat16* in, int ldc, const float* w, const float* b, int od, int activation, float* pred,
+// one thread per pixel: 32 input channels (post-ReLU) x od fp32 weights, then activate_head
+template <class T>
+__global__ void final_kernel(const T* in, int ldc, const float* w, const float* b, int od, int activation, float* pred,
                              float* conf, long long total, int H, int W) {
   __shared__ float sw[4 * 32 + 4];
   if (threadIdx.x < od * 32) sw[threadIdx.x] = w[threadIdx.x];
@@ -178,12 +204,12 @@ __global__ void final_kernel(const __nv_bfloat16* in, int ldc, const float* w, c
   if (i >= total) return;
   const int x = (int)(i % W), y = (int)((i / W) % H);
   const long long f = i / ((long long)W * H);
-  const uint4* src = reinterpret_cast<const uint4*>(in + ((f * (H + 2) + y + 1) * (long long)(W + 2) + x + 1) * ldc);
+  const T* src = in + ((f * (H + 2) + y + 1) * (long long)(W + 2) + x + 1) * ldc;
   float acc[4] = {sw[128], sw[129], sw[130], sw[131]};
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float v[8];
-    unpack8(src[q], v);
+    V8<T>::load(src + 8 * q).to_float(v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -197,6 +223,51 @@ __global__ void final_kernel(const __nv_bfloat16* in, int ldc, const float* w, c
   conf[i] = 1.0f + expf(acc[od - 1]);
 }
 
+// fp32-class 3x3 convolution operand: row q of the padded grid -> [hi(tap 0..8) | lo(tap 0..8) | hi(tap 0..8)], 27 C bf16 wide,
+// against weights [hi | hi | lo] (pack_weight_split of the [oc][(ky,kx,ic)] matrix): x = hi + lo to 16 bits, and
+// hi w_hi + lo w_hi + hi w_lo drops only lo w_lo (2^-16 relative).  blockIdx.x = row of the padded grid, idx = (tap, c8).
+__global__ void split_im2col3_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long rows, int wp, int C8) {
+  const int idx = blockIdx.y * TPB + threadIdx.x;
+  if (idx >= 9 * C8) return;
+  const int tap = idx / C8, c8 = idx - tap * C8;
+  const long long q = blockIdx.x;
+  const long long src = q + (long long)(tap / 3 - 1) * wp + (tap % 3 - 1);
+  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (src >= 0 && src < rows) V8<float>::load(in + ((size_t)src * C8 + c8) * 8).to_float(f);
+  float hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { hi[j] = __bfloat162float(__float2bfloat16_rn(f[j])); lo[j] = f[j] - hi[j]; }
+  const size_t K9 = (size_t)9 * C8 * 8;
+  __nv_bfloat16* o = out + (size_t)q * 3 * K9 + (size_t)idx * 8;
+  const V8<__nv_bfloat16> vh = V8<__nv_bfloat16>::from_float(hi);
+  vh.store(o);
+  V8<__nv_bfloat16>::from_float(lo).store(o + K9);
+  vh.store(o + 2 * K9);
+}
+
+// y = mask(relu?(y + r1 + r2)) on the padded grid (rows, OC) fp32: the tail of EPI_CONV_BF16 for the fp32-class path
+__global__ void post_f32_kernel(float* y, const float* r1, const float* r2, int relu, int hp, int wp, int OC8) {
+  const int idx = blockIdx.y * TPB + threadIdx.x;
+  if (idx >= wp * OC8) return;
+  const int xp = idx / OC8;
+  const int yp = blockIdx.x % hp;
+  float* p = y + ((size_t)blockIdx.x * wp * OC8 + idx) * 8;
+  if (xp < 1 || xp > wp - 2 || yp < 1 || yp > hp - 2) { V8<float>::zero().store(p); return; }
+  float f[8], t[8];
+  V8<float>::load(p).to_float(f);
+  if (r1) { V8<float>::load(r1 + (p - y)).to_float(t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += t[j]; }
+  if (r2) { V8<float>::load(r2 + (p - y)).to_float(t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] += t[j]; }
+  if (relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  V8<float>::from_float(f).store(p);
+}
+
 int blocks_for(long long total) { return (int)((total + TPB - 1) / TPB); }
 dim3 row_grid(long long rows, int per_row) { return dim3((unsigned)rows, (unsigned)((per_row + TPB - 1) / TPB)); }
 
@@ -208,47 +279,74 @@ int dpt_uv_tables(float* U, float* V, int h, int w, int C, float aspect, float r
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
-int dpt_add_pos_embed(void* x, int frames, int h, int w, int C, float aspect, float ratio, const float* U, const float* V, cudaStream_t st) {
+// `f32`: the activations are fp32 instead of bf16 (precision modes)
+template <class T> const T* in_as(const void* p) { return reinterpret_cast<const T*>(p); }
+
+int dpt_add_pos_embed(void* x, int frames, int h, int w, int C, float aspect, float ratio, const float* U, const float* V, cudaStream_t st, bool f32) {
   LSVS_CHECK_ARG(x && C % 16 == 0, "dpt_add_pos_embed: bad arguments");
   ProfScope prof(PROF_ELEMENTWISE, st, 0, 4.0 * frames * h * (double)w * C);
-  pos_embed_kernel<<<row_grid((long long)frames * h, w * (C / 8)), TPB, 0, st>>>(reinterpret_cast<uint4*>(x), h, w, C / 8, aspect, ratio, U, V);
+  const dim3 grid = row_grid((long long)frames * h, w * (C / 8));
+  if (f32) pos_embed_kernel<float><<<grid, TPB, 0, st>>>(reinterpret_cast<float*>(x), h, w, C / 8, aspect, ratio, U, V);
+  else pos_embed_kernel<__nv_bfloat16><<<grid, TPB, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(x), h, w, C / 8, aspect, ratio, U, V);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
-int dpt_pad(const void* in, void* out, int frames, int h, int w, int C, cudaStream_t st) {
+int dpt_pad(const void* in, void* out, int frames, int h, int w, int C, cudaStream_t st, bool f32) {
   ProfScope prof(PROF_ELEMENTWISE, st, 0, 2.0 * frames * ((double)h * w + (double)(h + 2) * (w + 2)) * C);
-  pad_kernel<<<row_grid((long long)frames * (h + 2), (w + 2) * (C / 8)), TPB, 0, st>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), h, w, C / 8);
+  const dim3 grid = row_grid((long long)frames * (h + 2), (w + 2) * (C / 8));
+  if (f32) pad_kernel<float><<<grid, TPB, 0, st>>>(in_as<float>(in), reinterpret_cast<float*>(out), h, w, C / 8);
+  else pad_kernel<__nv_bfloat16><<<grid, TPB, 0, st>>>(in_as<__nv_bfloat16>(in), reinterpret_cast<__nv_bfloat16*>(out), h, w, C / 8);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
-int dpt_convt_shuffle(const void* in, const float* bias, void* out, int frames, int h, int w, int C, int k, cudaStream_t st) {
+int dpt_convt_shuffle(const void* in, const float* bias, void* out, int frames, int h, int w, int C, int k, cudaStream_t st, bool f32) {
   ProfScope prof(PROF_ELEMENTWISE, st, 0, 2.0 * frames * ((double)k * k * h * w + (double)(k * h + 2) * (k * w + 2)) * C);
-  convt_shuffle_kernel<<<row_grid((long long)frames * (k * h + 2), (k * w + 2) * (C / 8)), TPB, 0, st>>>(
-      reinterpret_cast<const uint4*>(in), bias, reinterpret_cast<uint4*>(out), h, w, C / 8, k);
+  const dim3 grid = row_grid((long long)frames * (k * h + 2), (k * w + 2) * (C / 8));
+  if (f32) convt_shuffle_kernel<float><<<grid, TPB, 0, st>>>(in_as<float>(in), bias, reinterpret_cast<float*>(out), h, w, C / 8, k);
+  else convt_shuffle_kernel<__nv_bfloat16><<<grid, TPB, 0, st>>>(in_as<__nv_bfloat16>(in), bias, reinterpret_cast<__nv_bfloat16*>(out), h, w, C / 8, k);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
-int dpt_im2col_s2(const void* in, void* out, int frames, int h, int w, int C, cudaStream_t st) {
+int dpt_im2col_s2(const void* in, void* out, int frames, int h, int w, int C, cudaStream_t st, bool f32) {
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
   ProfScope prof(PROF_ELEMENTWISE, st, 0, 2.0 * frames * ((double)h * w + 9.0 * ho * wo) * C);
-  im2col_s2_kernel<<<row_grid((long long)frames * ho, wo * 9 * (C / 8)), TPB, 0, st>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), h, w, ho, wo, C / 8);
+  const dim3 grid = row_grid((long long)frames * ho, wo * 9 * (C / 8));
+  if (f32) im2col_s2_kernel<float><<<grid, TPB, 0, st>>>(in_as<float>(in), reinterpret_cast<float*>(out), h, w, ho, wo, C / 8);
+  else im2col_s2_kernel<__nv_bfloat16><<<grid, TPB, 0, st>>>(in_as<__nv_bfloat16>(in), reinterpret_cast<__nv_bfloat16*>(out), h, w, ho, wo, C / 8);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
 int dpt_bilinear(const void* in, void* out, int frames, int hi, int wi, int ho, int wo, int C, float aspect, float ratio, const float* U,
-                 const float* V, cudaStream_t st) {
+                 const float* V, cudaStream_t st, bool f32) {
   ProfScope prof(PROF_ELEMENTWISE, st, 0, 2.0 * frames * ((double)(hi + 2) * (wi + 2) + (double)(ho + 2) * (wo + 2)) * C);
-  bilinear_kernel<<<row_grid((long long)frames * (ho + 2), (wo + 2) * (C / 8)), TPB, 0, st>>>(
-      reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), hi, wi, ho, wo, C / 8, aspect, ratio, U, V);
+  const dim3 grid = row_grid((long long)frames * (ho + 2), (wo + 2) * (C / 8));
+  if (f32) bilinear_kernel<float><<<grid, TPB, 0, st>>>(in_as<float>(in), reinterpret_cast<float*>(out), hi, wi, ho, wo, C / 8, aspect, ratio, U, V);
+  else bilinear_kernel<__nv_bfloat16><<<grid, TPB, 0, st>>>(in_as<__nv_bfloat16>(in), reinterpret_cast<__nv_bfloat16*>(out), hi, wi, ho, wo, C / 8, aspect, ratio, U, V);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
 int dpt_final(const void* in, int ldc, const float* w, const float* b, int od, int activation, float* pred, float* conf, int frames,
-              int H, int W, cudaStream_t st) {
+              int H, int W, cudaStream_t st, bool f32) {
   ProfScope prof(PROF_ELEMENTWISE, st, 0, (double)frames * H * W * (64.0 + 4.0 * od));
   LSVS_CHECK_ARG(od >= 2 && od <= 4 && ldc >= 32 && ldc % 8 == 0, "dpt_final: output_dim must be 2..4");
   const long long total = (long long)frames * H * W;
-  final_kernel<<<blocks_for(total), TPB, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), ldc, w, b, od, activation, pred, conf, total, H, W);
+  if (f32) final_kernel<float><<<blocks_for(total), TPB, 0, st>>>(in_as<float>(in), ldc, w, b, od, activation, pred, conf, total, H, W);
+  else final_kernel<__nv_bfloat16><<<blocks_for(total), TPB, 0, st>>>(in_as<__nv_bfloat16>(in), ldc, w, b, od, activation, pred, conf, total, H, W);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+int dpt_split_im2col3(const float* in, void* out, int frames, int hp, int wp, int C, cudaStream_t st) {
+  LSVS_CHECK_ARG(in && out && C % 8 == 0, "dpt_split_im2col3: bad arguments");
+  const long long rows = (long long)frames * hp * wp;
+  ProfScope prof(PROF_ELEMENTWISE, st, 0, (double)rows * C * (9.0 * 4 + 27.0 * 2));
+  split_im2col3_kernel<<<row_grid(rows, 9 * (C / 8)), TPB, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out), rows, wp, C / 8);
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+int dpt_post_f32(float* y, const float* r1, const float* r2, int relu, int frames, int hp, int wp, int OC, cudaStream_t st) {
+  LSVS_CHECK_ARG(y && OC % 8 == 0, "dpt_post_f32: bad arguments");
+  ProfScope prof(PROF_ELEMENTWISE, st, 0, (double)frames * hp * wp * OC * 4.0 * (2 + (r1 != nullptr) + (r2 != nullptr)));
+  post_f32_kernel<<<row_grid((long long)frames * hp, wp * (OC / 8)), TPB, 0, st>>>(y, r1, r2, relu, hp, wp, OC / 8);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }

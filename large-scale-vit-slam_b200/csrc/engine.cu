@@ -126,12 +126,13 @@ bool wants_bf16(const std::string& n) {
   return n == "alignment_head.project_in.weight";
 }
 
-// precision mode 1: alignment head (blocks + project_in) and camera-head trunk run fp32-class; mode 2: every block of the path.
-// (The DPT convolutions stay bf16 in every mode.)
+// precision mode 1: what the reference itself computes in fp32 (autocast disabled, featureAligned_vggt.py:103-104) runs fp32-class —
+// the camera-head trunk and the DPT heads' convolutions — and so do the alignment head's blocks + project_in; mode 2: every
+// block of the path.
 bool wants_split(const std::string& n, int precision) {
-  if (precision <= 0 || !wants_bf16(n) || contains(n, "depth_head.") || contains(n, "point_head.")) return false;
+  if (precision <= 0 || !wants_bf16(n)) return false;
   if (precision >= 2) return true;
-  return contains(n, "alignment_head.") || contains(n, "camera_head.trunk.");
+  return contains(n, "alignment_head.") || contains(n, "camera_head.trunk.") || contains(n, "depth_head.") || contains(n, "point_head.");
 }
 
 int need(const Engine& e, const std::string& name, const Param** out) {
@@ -848,21 +849,30 @@ extern "C" int lsvs_dpt_head_forward(lsvs_engine* h, const char* prefix, const f
     F0 = fit < 1 ? 1 : fit;
   }
   if (F0 > frames) F0 = frames;
+  const int F0_plain = F0;
   // ---- weights
   const float *nw, *nb;
   TRY(need_f32(e, pre + "norm.weight", &nw, C)); TRY(need_f32(e, pre + "norm.bias", &nb, C));
   const __nv_bfloat16 *pw_[4], *rnw[4], *ct0w, *ct1w, *c3w, *oc1w, *oc2w;
   const float *pb_[4], *ct0b, *ct1b, *c3b, *oc1b, *oc2b, *finw, *finb;
+  // fp32-class mode (precision >= 1): every weight below is stored split [hi | hi | lo]; the flags must agree
+  int n_w = 0, n_split = 0;
+  auto need_w = [&](const std::string& name, const __nv_bfloat16** out, int rows, int cols) -> int {
+    bool sp = false;
+    TRY(need_bf16(e, name, out, rows, cols, &sp));
+    ++n_w; n_split += sp ? 1 : 0;
+    return LSVS_OK;
+  };
   for (int l = 0; l < 4; ++l) {
-    TRY(need_bf16(e, pre + "projects." + std::to_string(l) + ".weight", &pw_[l], oc[l], C));
+    TRY(need_w(pre + "projects." + std::to_string(l) + ".weight", &pw_[l], oc[l], C));
     TRY(need_f32(e, pre + "projects." + std::to_string(l) + ".bias", &pb_[l], oc[l]));
-    TRY(need_bf16(e, pre + "scratch.layer" + std::to_string(l + 1) + "_rn.weight", &rnw[l], 256, 9 * oc[l]));
+    TRY(need_w(pre + "scratch.layer" + std::to_string(l + 1) + "_rn.weight", &rnw[l], 256, 9 * oc[l]));
   }
-  TRY(need_bf16(e, pre + "resize_layers.0.weight", &ct0w, 16 * 256, 256)); TRY(need_f32(e, pre + "resize_layers.0.bias", &ct0b, 256));
-  TRY(need_bf16(e, pre + "resize_layers.1.weight", &ct1w, 4 * 512, 512)); TRY(need_f32(e, pre + "resize_layers.1.bias", &ct1b, 512));
-  TRY(need_bf16(e, pre + "resize_layers.3.weight", &c3w, 1024, 9 * 1024)); TRY(need_f32(e, pre + "resize_layers.3.bias", &c3b, 1024));
-  TRY(need_bf16(e, pre + "scratch.output_conv1.weight", &oc1w, 128, 9 * 256)); TRY(need_f32(e, pre + "scratch.output_conv1.bias", &oc1b, 128));
-  TRY(need_bf16(e, pre + "scratch.output_conv2.0.weight", &oc2w, 64, 9 * 128)); TRY(need_f32(e, pre + "scratch.output_conv2.0.bias", &oc2b, 64));
+  TRY(need_w(pre + "resize_layers.0.weight", &ct0w, 16 * 256, 256)); TRY(need_f32(e, pre + "resize_layers.0.bias", &ct0b, 256));
+  TRY(need_w(pre + "resize_layers.1.weight", &ct1w, 4 * 512, 512)); TRY(need_f32(e, pre + "resize_layers.1.bias", &ct1b, 512));
+  TRY(need_w(pre + "resize_layers.3.weight", &c3w, 1024, 9 * 1024)); TRY(need_f32(e, pre + "resize_layers.3.bias", &c3b, 1024));
+  TRY(need_w(pre + "scratch.output_conv1.weight", &oc1w, 128, 9 * 256)); TRY(need_f32(e, pre + "scratch.output_conv1.bias", &oc1b, 128));
+  TRY(need_w(pre + "scratch.output_conv2.0.weight", &oc2w, 64, 9 * 128)); TRY(need_f32(e, pre + "scratch.output_conv2.0.bias", &oc2b, 64));
   TRY(need_f32(e, pre + "scratch.output_conv2.2.weight", &finw, 32LL * output_dim)); TRY(need_f32(e, pre + "scratch.output_conv2.2.bias", &finb, output_dim));
   struct Rcu { const __nv_bfloat16 *w1, *w2; const float *b1, *b2; };
   struct Fuse { Rcu u1, u2; const __nv_bfloat16* ow; const float* ob; };
@@ -872,15 +882,24 @@ extern "C" int lsvs_dpt_head_forward(lsvs_engine* h, const char* prefix, const f
     for (int u = (r == 3 ? 2 : 1); u <= 2; ++u) {
       Rcu& q = u == 1 ? fu[r].u1 : fu[r].u2;
       const std::string c = b + "resConfUnit" + std::to_string(u) + ".";
-      TRY(need_bf16(e, c + "conv1.weight", &q.w1, 256, 9 * 256)); TRY(need_f32(e, c + "conv1.bias", &q.b1, 256));
-      TRY(need_bf16(e, c + "conv2.weight", &q.w2, 256, 9 * 256)); TRY(need_f32(e, c + "conv2.bias", &q.b2, 256));
+      TRY(need_w(c + "conv1.weight", &q.w1, 256, 9 * 256)); TRY(need_f32(e, c + "conv1.bias", &q.b1, 256));
+      TRY(need_w(c + "conv2.weight", &q.w2, 256, 9 * 256)); TRY(need_f32(e, c + "conv2.bias", &q.b2, 256));
     }
-    TRY(need_bf16(e, b + "out_conv.weight", &fu[r].ow, 256, 256)); TRY(need_f32(e, b + "out_conv.bias", &fu[r].ob, 256));
+    TRY(need_w(b + "out_conv.weight", &fu[r].ow, 256, 256)); TRY(need_f32(e, b + "out_conv.bias", &fu[r].ob, 256));
   }
-  // ---- workspace (bf16 elements), bump-allocated
+  LSVS_CHECK_ARG(n_split == 0 || n_split == n_w, "dpt_head_forward: '%s' mixes split and plain weights", prefix);
+  const bool precise = n_split > 0;   // fp32 activations, split-bf16 GEMM operands (3x the reduction length)
+  // ---- workspace (bf16 elements; fp32 in the fp32-class mode), bump-allocated
+  if (precise && frames_chunk <= 0) {   // the split patch rows of the full-resolution convolution are 27 * 128 * 2 bytes per pixel
+    const double per_frame = (double)(gF.h + 2) * (gF.w + 2) * (27.0 * 128 * 2 + 4.0 * 192) + (double)(g5.h + 2) * (g5.w + 2) * 4.0 * 384 +
+                             (double)(g1.h + 2) * (g1.w + 2) * 4.0 * 2304 + (double)Pp * 4.0 * 16384;
+    const int fit = (int)(6.0e9 / per_frame);
+    F0 = fit < 1 ? 1 : (fit < F0_plain ? fit : F0_plain);
+  }
+  const size_t esz = precise ? 4 : 2;
   const long long rows0 = (long long)F0 * Pp, rows4 = (long long)F0 * g4.h * g4.w;
   size_t off = 0;
-  auto take = [&](long long elems) { const size_t o = off; off += ((size_t)elems * 2 + 255) & ~size_t(255); return o; };
+  auto take = [&](long long elems) { const size_t o = off; off += ((size_t)elems * esz + 255) & ~size_t(255); return o; };
   const size_t o_tok = take(rows0 * C), o_proj = take(rows0 * 1024), o_ct = take(rows0 * 4096 > rows4 * 1024 ? rows0 * 4096 : rows4 * 1024),
                o_col = take(rows4 * 9 * 1024);
   size_t o_x[4], o_rn[4];
@@ -893,6 +912,14 @@ extern "C" int lsvs_dpt_head_forward(lsvs_engine* h, const char* prefix, const f
   size_t o_tab[5];
   for (int l = 0; l < 4; ++l) o_tab[l] = take((long long)(ph + pw) * oc[l]);          // (w + h) * C/2 floats = (w + h) * C bf16-sized slots
   o_tab[4] = take((long long)(gF.h + gF.w) * 128);
+  size_t o_split = 0;   // fp32-class mode: split-bf16 GEMM operand of the largest convolution / projection
+  if (precise) {
+    long long mx = rows0 * 3 * C;
+    auto upd = [&](long long v) { if (v > mx) mx = v; };
+    for (int l = 0; l < 4; ++l) upd(lvl[l].rows(F0) * 27 * oc[l]);
+    upd(g1.rows(F0) * 27 * 256); upd(g5.rows(F0) * 27 * 256); upd(gF.rows(F0) * 27 * 128); upd(rows4 * 27 * 1024); upd(rows0 * 3 * 1024);
+    o_split = off; off += ((size_t)mx * 2 + 255) & ~size_t(255);
+  }
   LSVS_CHECK_ARG(gF.rows(F0) < (1ll << 31), "dpt_head_forward: frame chunk too large");
   TRY(e.dpt_ws.ensure(off));
   uint8_t* ws = e.dpt_ws.as<uint8_t>();
@@ -920,6 +947,73 @@ extern "C" int lsvs_dpt_head_forward(lsvs_engine* h, const char* prefix, const f
     TRY(conv(a, g, F, 256, q.w1, q.b1, 256, 9, true, nullptr, nullptr, B16(o_t)));
     return conv(B16(o_t), g, F, 256, q.w2, q.b2, 256, 9, relu_out, a, extra, out);
   };
+
+  if (precise) {
+    // ---- fp32-class flow: the same graph with fp32 activations (the reference runs these heads with autocast disabled,
+    // featureAligned_vggt.py:103).  A convolution = split patch rows (dpt_split_im2col3 / cast_split) x split weights on the
+    // tcgen05 GEMM (fp32 out) + its tail (residuals, ReLU, border mask) as one element-wise pass.
+    void* S = ws + o_split;
+    auto gemm_f32 = [&](long long rows, int K3, const __nv_bfloat16* w, const float* b, int OC, float* out) -> int {
+      GemmEpilogue ep;
+      ep.bias = b; ep.out = out; ep.ldo = OC;
+      return gemm_bf16(S, K3, w, K3, (int)rows, OC, K3, EPI_BIAS_F32, ep, st);
+    };
+    auto convp = [&](const float* x, const Grid& g, int F, int Cin, const __nv_bfloat16* w, const float* b, int OC, int taps_, bool relu,
+                     const float* r1, const float* r2, float* out) -> int {
+      const long long rows = g.rows(F);
+      if (taps_ == 9) TRY(dpt_split_im2col3(x, S, F, g.h + 2, g.w + 2, Cin, st));
+      else TRY(cast_split(x, Cin, S, 3LL * Cin, rows, Cin, false, st));
+      TRY(gemm_f32(rows, 3 * taps_ * Cin, w, b, OC, out));
+      return dpt_post_f32(out, r1, r2, relu ? 1 : 0, F, g.h + 2, g.w + 2, OC, st);
+    };
+    auto rcup = [&](const Rcu& q, const float* a, const Grid& g, int F, const float* extra, bool relu_out, float* out) -> int {
+      TRY(convp(a, g, F, 256, q.w1, q.b1, 256, 9, true, nullptr, nullptr, F32(o_t)));
+      return convp(F32(o_t), g, F, 256, q.w2, q.b2, 256, 9, relu_out, a, extra, out);
+    };
+    for (int f0 = 0; f0 < frames; f0 += F0) {
+      const int F = frames - f0 < F0 ? frames - f0 : F0;
+      const long long r0 = (long long)F * Pp;
+      for (int l = 0; l < 4; ++l) {
+        for (int f = 0; f < F; ++f)   // patch tokens of one frame (the 5 special tokens are skipped)
+          TRY(layernorm_split(taps[l] + ((size_t)(f0 + f) * P + 5) * C, C, nw, nb, 1e-5f, reinterpret_cast<__nv_bfloat16*>(S) + (size_t)f * Pp * 3 * C, 3LL * C, Pp, C, st));
+        TRY(gemm_f32(r0, 3 * C, pw_[l], pb_[l], oc[l], F32(o_proj)));
+        TRY(dpt_add_pos_embed(F32(o_proj), F, ph, pw, oc[l], aspect, 0.1f, tabU[l], tabV[l], st, true));
+        if (l == 0 || l == 1) {
+          const int k = l == 0 ? 4 : 2;
+          TRY(cast_split(F32(o_proj), oc[l], S, 3LL * oc[l], r0, oc[l], false, st));
+          TRY(gemm_f32(r0, 3 * oc[l], l == 0 ? ct0w : ct1w, nullptr, k * k * oc[l], F32(o_ct)));
+          TRY(dpt_convt_shuffle(F32(o_ct), l == 0 ? ct0b : ct1b, F32(o_x[l]), F, ph, pw, oc[l], k, st, true));
+        } else if (l == 2) {
+          TRY(dpt_pad(F32(o_proj), F32(o_x[l]), F, ph, pw, oc[l], st, true));
+        } else {
+          TRY(dpt_im2col_s2(F32(o_proj), F32(o_col), F, ph, pw, oc[l], st, true));
+          const long long r4 = (long long)F * g4.h * g4.w;
+          TRY(cast_split(F32(o_col), 9 * 1024, S, 27LL * 1024, r4, 9 * 1024, false, st));
+          TRY(gemm_f32(r4, 27 * 1024, c3w, c3b, 1024, F32(o_ct)));
+          TRY(dpt_pad(F32(o_ct), F32(o_x[l]), F, g4.h, g4.w, 1024, st, true));
+        }
+        TRY(convp(F32(o_x[l]), lvl[l], F, oc[l], rnw[l], nullptr, 256, 9, true, nullptr, nullptr, F32(o_rn[l])));
+      }
+      TRY(rcup(fu[3].u2, F32(o_rn[3]), g4, F, nullptr, false, F32(o_o)));
+      TRY(convp(F32(o_o), g4, F, 256, fu[3].ow, fu[3].ob, 256, 1, false, nullptr, nullptr, F32(o_oc)));
+      TRY(dpt_bilinear(F32(o_oc), F32(o_u3), F, g4.h, g4.w, g3.h, g3.w, 256, aspect, 0.f, nullptr, nullptr, st, true));
+      const size_t o_upp[4] = {o_u1, o_u2, o_u3, 0};
+      for (int r = 2; r >= 0; --r) {
+        const Grid& g = lvl[r];
+        TRY(rcup(fu[r].u1, F32(o_rn[r]), g, F, F32(o_upp[r]), true, F32(o_a2)));
+        TRY(rcup(fu[r].u2, F32(o_a2), g, F, nullptr, false, F32(o_o)));
+        TRY(convp(F32(o_o), g, F, 256, fu[r].ow, fu[r].ob, 256, 1, false, nullptr, nullptr, F32(o_oc)));
+        const Grid& gn = r == 0 ? g5 : lvl[r - 1];
+        TRY(dpt_bilinear(F32(o_oc), F32(r == 0 ? o_u5 : o_upp[r - 1]), F, g.h, g.w, gn.h, gn.w, 256, aspect, 0.f, nullptr, nullptr, st, true));
+      }
+      TRY(convp(F32(o_u5), g5, F, 256, oc1w, oc1b, 128, 9, false, nullptr, nullptr, F32(o_o1)));
+      TRY(dpt_bilinear(F32(o_o1), F32(o_uf), F, g5.h, g5.w, gF.h, gF.w, 128, aspect, 0.1f, tabU[4], tabV[4], st, true));
+      TRY(convp(F32(o_uf), gF, F, 128, oc2w, oc2b, 64, 9, true, nullptr, nullptr, F32(o_o2)));
+      TRY(dpt_final(F32(o_o2), 64, finw, finb, output_dim, activation, pred + (size_t)f0 * gF.h * gF.w * (output_dim - 1),
+                    conf + (size_t)f0 * gF.h * gF.w, F, gF.h, gF.w, st, true));
+    }
+    return LSVS_OK;
+  }
 
   for (int f0 = 0; f0 < frames; f0 += F0) {
     const int F = frames - f0 < F0 ? frames - f0 : F0;

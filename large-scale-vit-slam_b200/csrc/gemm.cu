@@ -875,7 +875,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   }
   LSVS_CHECK_ARG(lda >= a_cols && ldw >= K && lda % 8 == 0 && ldw % 8 == 0, "gemm: leading dimensions must be >= K and 16-byte aligned");
   const bool bn256 = (N % 256 == 0);
-  const bool bn64 = conv && N == 64;   // full-resolution DPT output convolution (32 channels padded to 64)
+  const bool bn64 = (conv || epi_kind == EPI_BIAS_F32) && N == 64;   // full-resolution DPT output convolution (32 channels padded to 64)
   LSVS_CHECK_ARG(bn256 || bn64 || N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
   bool pair = bn256 && M > 2 * BM && g_gemm_mode != 1;  // CTA pairs (256x256 tiles) once there are enough rows
   bool wide = bn256;                                     // single-CTA kernel: 128x256 tiles, else 128x128
@@ -916,6 +916,11 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
       case EPI_RESID_F32: return launch<64, EPI_RESID_F32>(tmA, tmB64, M, N, K, e, st);
       default: break;
     }
+  }
+  if (bn64 && epi_kind == EPI_BIAS_F32) {   // the same convolution in the fp32-class mode (split operands, fp32 out)
+    const CUtensorMap* tmB64 = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, 64);
+    if (!tmB64) return LSVS_ECUDA;
+    return launch<64, EPI_BIAS_F32>(tmA, tmB64, M, N, K, e, st);
   }
   switch (epi_kind) {
     LSVS_GEMM_CASE(EPI_BIAS_BF16)

@@ -131,12 +131,45 @@ def test_dpt_head_matches_oracle(H, W, frames, od, activation, prefix):
     assert torch.isfinite(pred).all() and torch.isfinite(conf).all()
     la, lb = _logits(pred[:, :n_ref], conf[:, :n_ref], activation), _logits(ref_pred, ref_conf, activation)
     err = rel_l2(la, lb)
+    from test_precision_gpu import report
+    report(f"dpt_{prefix}{H}x{W}x{frames}_precision0_logits_rel_l2", err)
     assert err < 3e-2, err
     assert rel_l2(pred[:, :n_ref], ref_pred) < 3e-2 and rel_l2(conf[:, :n_ref], ref_conf) < 3e-2
     if frames > 8:  # frames beyond the first chunk of 8 go through the second pass of the frame-chunk loop
         with torch.no_grad():
             p2, c2 = head([t[:, 8:].cuda() for t in taps], images=images[:, 8:].cuda(), patch_start_idx=5)
         assert torch.equal(p2, pred[:, 8:]) and torch.equal(c2, conf[:, 8:])
+
+
+@pytest.mark.parametrize("H,W,frames,od,activation,prefix", [(56, 84, 3, 2, "exp", "depth_head."), (154, 518, 2, 4, "inv_log", "point_head.")])
+def test_dpt_head_fp32_class_matches_oracle(H, W, frames, od, activation, prefix, monkeypatch):
+    """precision >= 1: the DPT heads run like the reference runs them — fp32 activations (autocast disabled,
+    featureAligned_vggt.py:103) — with split-bf16 GEMM operands on the tensor cores: logits within 2e-4 of the fp32 oracle
+    (bf16 activations: 3e-2 above)."""
+    from lsvs_b200.modules import DPTHead
+    from oracle import functional as OF
+    from oracle import weights as OW
+    monkeypatch.setenv("LSVS_PRECISION", "1")
+    head = DPTHead(dim_in=2048, output_dim=od, activation=activation, conf_activation="expp1", prefix=prefix)
+    sd = OW.fill_state_dict([(k, tuple(v.shape)) for k, v in head.state_dict().items()], seed=3)
+    head.load_state_dict(sd, strict=True)
+    head = head.cuda().eval()
+    P = 5 + (H // 14) * (W // 14)
+    g = torch.Generator().manual_seed(11)
+    taps = [torch.randn(1, frames, P, 2048, generator=g) for _ in range(4)]
+    images = torch.zeros(1, frames, 3, H, W)
+    with torch.no_grad():
+        pred, conf = head([t.cuda() for t in taps], images=images.cuda(), patch_start_idx=5)
+        pred1, conf1 = head([t.cuda() for t in taps], images=images.cuda(), patch_start_idx=5, frames_chunk_size=1)
+    torch.cuda.synchronize()
+    assert torch.equal(pred, pred1) and torch.equal(conf, conf1)   # per-frame computation: independent of the frames per pass
+    ref_pred, ref_conf = OF.dpt_head_forward(sd, "", taps, (H, W), activation=activation)
+    la, lb = _logits(pred, conf, activation), _logits(ref_pred, ref_conf, activation)
+    err = rel_l2(la, lb)
+    from test_precision_gpu import report
+    report(f"dpt_{prefix}{H}x{W}_precision1_logits_rel_l2", err)
+    assert err < 2e-4, err
+    assert rel_l2(pred, ref_pred) < 2e-4 and rel_l2(conf, ref_conf) < 2e-4
 
 
 def test_model_depth_and_points_match_oracle():
