@@ -128,10 +128,10 @@ template <class C> __device__ __forceinline__ void reg_inc() {
 __device__ unsigned long long g_attn_phase[8 * 8];  // [warp][phase] cycle sums for CTA (0,0,0)
 #define PH_DECL unsigned ph_t = clock(); unsigned long long ph_acc[6] = {0, 0, 0, 0, 0, 0}
 #define PH(k) do { const unsigned now_ = clock(); ph_acc[k] += now_ - ph_t; ph_t = now_; } while (0)
-#define PH_FLUSH() do { if (lane == 0 && blockIdx.x == 0) for (int k_ = 0; k_ < 6; ++k_) g_attn_phase[warp * 8 + k_] = ph_acc[k_]; } while (0)
+#define PH_FLUSH() do { if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) for (int k_ = 0; k_ < 6; ++k_) g_attn_phase[warp * 8 + k_] = ph_acc[k_]; } while (0)
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define MS_ENTRY const unsigned long long ms_t0 = gtime()
-#define MS(k) do { if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) g_attn_phase[48 + (k)] = gtime() - ms_t0; } while (0)
+#define MS(k) do { if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && blockIdx.y == 0 && blockIdx.z == gridDim.z - 1) g_attn_phase[48 + (k)] = gtime() - ms_t0; } while (0)
 #else
 #define MS_ENTRY do {} while (0)
 #define MS(k) do {} while (0)
@@ -208,7 +208,7 @@ __global__ void attention_combine_kernel(const float* __restrict__ partial, __nv
   }
 }
 
-template <int HD, int NT_, int POLY_>
+template <int HD, int NT_, int POLY_, bool SPLIT>
 __global__ void __maxnreg__((Cfg<HD, NT_, POLY_>::MAXNREG))
 attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ O, int ldo, int Lq, int Lk,
@@ -224,10 +224,14 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   // work decode (WorkSplit): CTAs [0, n_full) own a whole unit = (batch, head, NT query tiles) over every key block; the units of
   // the last, partial round of CTAs are cut into `parts` key ranges each, written as unnormalised partials and merged by
   // attention_combine_kernel — the tail of the grid then lasts 1/parts of a unit instead of a whole one.
-  int unit = blockIdx.x, part = 0, n_parts = 1;
-  if (unit >= ws.n_full) { const int idx = unit - ws.n_full; unit = ws.n_full + idx / ws.parts; part = idx % ws.parts; n_parts = ws.parts; }
-  const int q0 = (unit % ws.n_qt) * (NT * QT);   // first query row (within the sequence) of this CTA
-  const int head = (unit / ws.n_qt) % ws.heads, batch = unit / (ws.n_qt * ws.heads);
+  // (Launches that split nothing keep the 3-D grid (tile group, head, batch): no integer divisions in the short-sequence CTAs.)
+  int unit = 0, part = 0, n_parts = 1, qt = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+  if (SPLIT) {   // (compile-time: the short-sequence instantiations carry none of this)
+    unit = blockIdx.x;
+    if (unit >= ws.n_full) { const int idx = unit - ws.n_full; unit = ws.n_full + idx / ws.parts; part = idx % ws.parts; n_parts = ws.parts; }
+    qt = unit % ws.n_qt; head = (unit / ws.n_qt) % ws.heads; batch = unit / (ws.n_qt * ws.heads);
+  }
+  const int q0 = qt * (NT * QT);   // first query row (within the sequence) of this CTA
   const int n_tiles = min(NT, (Lq - q0 + QT - 1) / QT);  // only tiles with at least one valid row
   const int n_kv_seq = (Lk + C::BKV - 1) / C::BKV;
   const int kb0 = (int)((long long)part * n_kv_seq / n_parts);   // key blocks [kb0, kb0 + n_kv) of the sequence
@@ -581,7 +585,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       __nv_bfloat16* dst = O + (size_t)(batch * (size_t)Lq + q_local) * ldo + col0;
       // split unit: this CTA saw only its key range — unnormalised O (fp32), reference maximum and row sum go to the workspace
       float* pdst = nullptr;
-      if (n_parts > 1) {
+      if (SPLIT && n_parts > 1) {
         const size_t prow = ((size_t)(unit - ws.n_full) * ws.parts + part) * (NT * QT) + t * QT + r;
         pdst = ws.partial + prow * (HD + 2);
         if (q_local < Lq) { pdst[HD] = m_ref; pdst[HD + 1] = l_run; }
@@ -591,7 +595,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         uint32_t o[32];
         ptx::tmem_ld_32x32b_x32(tO + c, o);
         ptx::tmem_ld_wait();
-        if (pdst != nullptr) {
+        if (SPLIT && pdst != nullptr) {
           if (q_local < Lq) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) *reinterpret_cast<float2*>(pdst + c + 2 * j) = make_float2(__uint_as_float(o[2 * j]), __uint_as_float(o[2 * j + 1]));
@@ -646,10 +650,11 @@ int launch(const AttentionArgs& a, cudaStream_t st) {
   const CUtensorMap* tk = tmap_2d_bf16(a.k, (uint64_t)a.heads * HD, rows_k, (uint64_t)a.ldk * 2, 64, C::BKV);
   const CUtensorMap* tv = tmap_2d_bf16(a.v, (uint64_t)a.heads * HD, rows_k, (uint64_t)a.ldv * 2, 64, C::BKV);
   if (!tq || !tk || !tv) return LSVS_ECUDA;
-  auto kern = attention_fwd_tcgen05<HD, NT_, POLY_>;
+  constexpr bool CAN_SPLIT = (HD == 64 && NT_ == 1);   // the key-range split is built for the long head-dim-64 passes only
   static bool configured = false;
   if (!configured) {
-    LSVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    LSVS_CUDA(cudaFuncSetAttribute(attention_fwd_tcgen05<HD, NT_, POLY_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    if (CAN_SPLIT) LSVS_CUDA(cudaFuncSetAttribute(attention_fwd_tcgen05<HD, NT_, POLY_, CAN_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
   const float scale_log2e = a.scale * 1.4426950408889634f;
@@ -665,7 +670,7 @@ int launch(const AttentionArgs& a, cudaStream_t st) {
   const int slots = num_sms() * (NT_ == 1 ? 2 : 1);
   const int n_kv_seq = (a.Lk + C::BKV - 1) / C::BKV;
   const int leftover = (int)(n_units % slots);
-  if (n_units > slots && leftover > 0 && split_max > 1) {
+  if (CAN_SPLIT && n_units > slots && leftover > 0 && split_max > 1) {
     int best_p = 1; double best = 1.0;
     for (int p = 2; p <= split_max && n_kv_seq / p >= 8; ++p) {
       const double cost = (double)(((long long)leftover * p + slots - 1) / slots) / p + 0.03 * p;
@@ -677,8 +682,10 @@ int launch(const AttentionArgs& a, cudaStream_t st) {
       if (buf) { ws.n_full = (int)(n_units - leftover); ws.parts = best_p; ws.partial = buf; }
     }
   }
-  const unsigned grid = (unsigned)(ws.n_full + (n_units - ws.n_full) * ws.parts);
-  LSVS_CUDA(launch_pdl(kern, dim3(grid), dim3(C::NTHREADS), C::SMEM, st, *tq, *tk, *tv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, a.Lk, scale_log2e, ws));
+  LSVS_CHECK_ARG(ws.parts > 1 || (a.batches <= 65535 && a.heads <= 65535), "attention: batch/head count exceeds the grid limit");
+  const dim3 grid = ws.parts > 1 ? dim3((unsigned)(ws.n_full + (n_units - ws.n_full) * ws.parts)) : dim3(ws.n_qt, a.heads, a.batches);
+  auto kern = ws.parts > 1 ? attention_fwd_tcgen05<HD, NT_, POLY_, CAN_SPLIT> : attention_fwd_tcgen05<HD, NT_, POLY_, false>;
+  LSVS_CUDA(launch_pdl(kern, grid, dim3(C::NTHREADS), C::SMEM, st, *tq, *tk, *tv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, a.Lk, scale_log2e, ws));
   LSVS_LAUNCH_CHECK();
   if (ws.parts > 1) {
     constexpr int ROWS = C::NT * QT;
@@ -709,8 +716,11 @@ int attention_fwd(const AttentionArgs& a, cudaStream_t st) {
   static const int nt1_max_lk = [] { const char* e = getenv("LSVS_ATTN_NT1_MAX_LK"); return e ? atoi(e) : 0x7fffffff; }();
   const bool one_tile = a.Lk <= nt1_max_lk;
   if (a.head_dim == 128) return one_tile ? launch<128, 1>(a, st) : launch<128, 2>(a, st);
-  // head dim 64: share of the exponentials taken off the XU pipe (pairs out of 4; LSVS_ATTN_POLY overrides for A/B runs)
-  static const int poly = [] { const char* e = getenv("LSVS_ATTN_POLY"); return e ? atoi(e) : LSVS_ATTN_POLY_DEFAULT; }();
+  // head dim 64: share of the exponentials taken off the XU pipe (pairs out of 4; LSVS_ATTN_POLY overrides for A/B runs).  With two
+  // independent CTAs per SM the XU pipe is the contended resource on long sequences (one pair of four on the FMA / ALU pipes:
+  // 787 -> 850 TFLOP/s at 13 184 tokens, 842 -> 915 at 21 984; two pairs: slower); on 412-token sequences it costs 3 %.
+  static const int poly_env = [] { const char* e = getenv("LSVS_ATTN_POLY"); return e ? atoi(e) : -1; }();
+  const int poly = poly_env >= 0 ? poly_env : (a.Lk > 1024 ? 1 : LSVS_ATTN_POLY_DEFAULT);
   if (one_tile) return poly == 1 ? launch<64, 1, 1>(a, st) : poly == 2 ? launch<64, 1, 2>(a, st) : launch<64, 1, 0>(a, st);
   return poly == 1 ? launch<64, 2, 1>(a, st) : poly == 2 ? launch<64, 2, 2>(a, st) : launch<64, 2, 0>(a, st);
 }

@@ -55,3 +55,19 @@ def load_synth_weights(model, seed=0, ls_gamma=None):
     sd = OW.fill_state_dict(spec, seed=seed, ls_gamma=ls_gamma)
     model.load_state_dict(sd, strict=True)
     return sd
+
+
+REPORT = {}
+
+
+def report(key, value):
+    """Collect measured deviations; written to gpurun_out/precision_report.json when the directory exists (GPU box runs)."""
+    import json
+    import os
+    REPORT[key] = value
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        path = os.path.join(out, "precision_report.json")
+        old = json.load(open(path)) if os.path.exists(path) else {}
+        old.update(REPORT)
+        json.dump(old, open(path, "w"), indent=1, sort_keys=True)

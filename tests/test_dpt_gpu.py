@@ -131,7 +131,7 @@ def test_dpt_head_matches_oracle(H, W, frames, od, activation, prefix):
     assert torch.isfinite(pred).all() and torch.isfinite(conf).all()
     la, lb = _logits(pred[:, :n_ref], conf[:, :n_ref], activation), _logits(ref_pred, ref_conf, activation)
     err = rel_l2(la, lb)
-    from test_precision_gpu import report
+    from parity_util import report
     report(f"dpt_{prefix}{H}x{W}x{frames}_precision0_logits_rel_l2", err)
     assert err < 3e-2, err
     assert rel_l2(pred[:, :n_ref], ref_pred) < 3e-2 and rel_l2(conf[:, :n_ref], ref_conf) < 3e-2
@@ -166,7 +166,7 @@ def test_dpt_head_fp32_class_matches_oracle(H, W, frames, od, activation, prefix
     ref_pred, ref_conf = OF.dpt_head_forward(sd, "", taps, (H, W), activation=activation)
     la, lb = _logits(pred, conf, activation), _logits(ref_pred, ref_conf, activation)
     err = rel_l2(la, lb)
-    from test_precision_gpu import report
+    from parity_util import report
     report(f"dpt_{prefix}{H}x{W}_precision1_logits_rel_l2", err)
     assert err < 2e-4, err
     assert rel_l2(pred, ref_pred) < 2e-4 and rel_l2(conf, ref_conf) < 2e-4

@@ -27,18 +27,7 @@ from parity_util import ROT_DEG, TOK_REL_L2, TRANS_REL, load_synth_weights, pose
 pytestmark = pytest.mark.gpu
 torch.set_grad_enabled(False)
 
-REPORT = {}
-
-
-def report(key, value):
-    """Collect measured deviations; written to gpurun_out/precision_report.json when the directory exists (GPU box runs)."""
-    REPORT[key] = value
-    out = os.path.join(ROOT, "gpurun_out")
-    if os.path.isdir(out):
-        path = os.path.join(out, "precision_report.json")
-        old = json.load(open(path)) if os.path.exists(path) else {}
-        old.update(REPORT)
-        json.dump(old, open(path, "w"), indent=1, sort_keys=True)
+from parity_util import report  # noqa: E402  (measured deviations -> gpurun_out/precision_report.json)
 
 
 def unsplit(t, cols):
