@@ -83,7 +83,7 @@ struct Cfg {
 };
 
 struct Bars {
-  uint64_t q_full;
+  uint64_t q_full, q_empty;
   uint64_t k_full[KV_STAGES], k_empty[KV_STAGES], v_full[KV_STAGES], v_empty[KV_STAGES];
   uint64_t s_full[4], s_free[4], p_ready[4][2], pv_done[4][2];  // [tile][P buffer = iteration parity]
   uint32_t tmem_slot;
@@ -128,10 +128,10 @@ template <class C> __device__ __forceinline__ void reg_inc() {
 __device__ unsigned long long g_attn_phase[8 * 8];  // [warp][phase] cycle sums for CTA (0,0,0)
 #define PH_DECL unsigned ph_t = clock(); unsigned long long ph_acc[6] = {0, 0, 0, 0, 0, 0}
 #define PH(k) do { const unsigned now_ = clock(); ph_acc[k] += now_ - ph_t; ph_t = now_; } while (0)
-#define PH_FLUSH() do { if (lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) for (int k_ = 0; k_ < 6; ++k_) g_attn_phase[warp * 8 + k_] = ph_acc[k_]; } while (0)
+#define PH_FLUSH() do { if (lane == 0 && blockIdx.x == 0) for (int k_ = 0; k_ < 6; ++k_) g_attn_phase[warp * 8 + k_] = ph_acc[k_]; } while (0)
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define MS_ENTRY const unsigned long long ms_t0 = gtime()
-#define MS(k) do { if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && blockIdx.y == 0 && blockIdx.z == gridDim.z - 1) g_attn_phase[48 + (k)] = gtime() - ms_t0; } while (0)
+#define MS(k) do { if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) g_attn_phase[48 + (k)] = gtime() - ms_t0; } while (0)
 #else
 #define MS_ENTRY do {} while (0)
 #define MS(k) do {} while (0)
@@ -167,6 +167,7 @@ __device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& p0, flo
 // How the grid maps to work (see the decode at the top of the kernel).
 struct WorkSplit {
   int n_qt, heads;      // query-tile groups per sequence, heads: unit = (batch * heads + head) * n_qt + tile group
+  int n_items;          // work items in all: n_full whole units + (units - n_full) * parts key ranges
   int n_full;           // units [0, n_full) run their whole key range in one CTA
   int parts;            // every later unit is cut into `parts` key ranges (CTAs n_full + (unit - n_full) * parts + part)
   float* partial;       // [(unit - n_full) * parts + part][NT * QT rows][HD + 2]: unnormalised O, reference maximum, row sum
@@ -221,29 +222,41 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int NT = C::NT;
   constexpr int W_TMA = 4 * C::NWG, W_MMA = 4 * C::NWG + 1, W_TMA_V = 4 * C::NWG + 2;  // warp ids of the two service warps
-  // work decode (WorkSplit): CTAs [0, n_full) own a whole unit = (batch, head, NT query tiles) over every key block; the units of
-  // the last, partial round of CTAs are cut into `parts` key ranges each, written as unnormalised partials and merged by
+  // Work items (WorkSplit): item < n_full is a whole unit = (batch, head, NT query tiles) over every key block; the units of the
+  // last, partial round of CTAs are cut into `parts` key ranges each, written as unnormalised partials and merged by
   // attention_combine_kernel — the tail of the grid then lasts 1/parts of a unit instead of a whole one.
-  // (Launches that split nothing keep the 3-D grid (tile group, head, batch): no integer divisions in the short-sequence CTAs.)
-  int unit = 0, part = 0, n_parts = 1, qt = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
-  if (SPLIT) {   // (compile-time: the short-sequence instantiations carry none of this)
-    unit = blockIdx.x;
-    if (unit >= ws.n_full) { const int idx = unit - ws.n_full; unit = ws.n_full + idx / ws.parts; part = idx % ws.parts; n_parts = ws.parts; }
-    qt = unit % ws.n_qt; head = (unit / ws.n_qt) % ws.heads; batch = unit / (ws.n_qt * ws.heads);
-  }
-  const int q0 = qt * (NT * QT);   // first query row (within the sequence) of this CTA
-  const int n_tiles = min(NT, (Lq - q0 + QT - 1) / QT);  // only tiles with at least one valid row
+  // PERSISTENT CTAs (NT = 1): CTA c runs items c, c + gridDim.x, ...  Barriers, the K / V rings and tensor memory are set up once;
+  // every role walks the concatenated block sequence of its items, so the loads of item n+1 (Q once the last S of item n has
+  // retired, K / V through their rings) and its first S MMA are in flight while the softmax warps finish item n and store its
+  // rows — the ~2 us of set-up, first loads and tear-down that a 412-token CTA spent per 8 us of life are paid once.
   const int n_kv_seq = (Lk + C::BKV - 1) / C::BKV;
-  const int kb0 = (int)((long long)part * n_kv_seq / n_parts);   // key blocks [kb0, kb0 + n_kv) of the sequence
-  const int n_kv = (int)((long long)(part + 1) * n_kv_seq / n_parts) - kb0;
-  const int Lkp = min(Lk - kb0 * C::BKV, n_kv * C::BKV);         // valid keys of this CTA's range (ragged only at the sequence end)
-  const int q_row0 = batch * Lq + q0;          // global row of tile A's first query
-  const int kv_row0 = batch * Lk + kb0 * C::BKV;
-  const int col0 = head * HD;
+  struct Item { int q0, n_tiles, n_kv, Lkp, q_row0, kv_row0, col0, batch; bool partial; long long prow0; };
+  auto decode = [&](int item) -> Item {
+    int unit = item, part = 0, n_parts = 1;
+    if (SPLIT && unit >= ws.n_full) { const int idx = unit - ws.n_full; unit = ws.n_full + idx / ws.parts; part = idx % ws.parts; n_parts = ws.parts; }
+    const int qt = unit % ws.n_qt, head = (unit / ws.n_qt) % ws.heads;
+    Item it;
+    it.batch = unit / (ws.n_qt * ws.heads);
+    it.q0 = qt * (NT * QT);                                   // first query row (within the sequence)
+    it.n_tiles = min(NT, (Lq - it.q0 + QT - 1) / QT);         // only tiles with at least one valid row
+    const int kb0 = (int)((long long)part * n_kv_seq / n_parts);   // key blocks [kb0, kb0 + n_kv) of the sequence
+    it.n_kv = (int)((long long)(part + 1) * n_kv_seq / n_parts) - kb0;
+    it.Lkp = min(Lk - kb0 * C::BKV, it.n_kv * C::BKV);        // valid keys of the range (ragged only at the sequence end)
+    it.q_row0 = it.batch * Lq + it.q0;                        // global row of tile A's first query
+    it.kv_row0 = it.batch * Lk + kb0 * C::BKV;
+    it.col0 = head * HD;
+    it.partial = SPLIT && n_parts > 1;
+    it.prow0 = it.partial ? ((long long)(unit - ws.n_full) * ws.parts + part) * (NT * QT) : 0;
+    return it;
+  };
+  // the last key block of a ragged sequence (412 = 3 x 128 + 28 keys) only spans n_last keys (a multiple of 32): a narrower
+  // S = Q K^T (UMMA N = n_last) and a shorter P V reduction, and the softmax warps touch n_last columns instead of BKV
+  auto last_cols = [](const Item& it) { return min(C::BKV, ((it.Lkp - (it.n_kv - 1) * C::BKV) + 31) & ~31); };
+  const int item0 = blockIdx.x, item_step = gridDim.x;
 
   if (warp == W_TMA && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
-    ptx::mbar_init(&bars->q_full, 1);
+    ptx::mbar_init(&bars->q_full, 1); ptx::mbar_init(&bars->q_empty, 1);
     for (int i = 0; i < C::KVS; ++i) {
       ptx::mbar_init(&bars->k_full[i], 1); ptx::mbar_init(&bars->k_empty[i], 1);
       ptx::mbar_init(&bars->v_full[i], 1); ptx::mbar_init(&bars->v_empty[i], 1);
@@ -265,61 +278,63 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   MS(0);  // setup done (barriers, TMEM allocation, CTA sync)
 
   if (warp == W_TMA) {
-    // ============================================================ TMA producer
+    // ============================================================ TMA producer (Q tiles, K blocks)
     reg_dec<C>();
-    if (lane == 0) {
-      ptx::mbar_expect_tx(&bars->q_full, n_tiles * C::Q_TILE_BYTES);
-      for (int t = 0; t < n_tiles; ++t)
-        for (int kb = 0; kb < C::KB; ++kb)
-          ptx::tma_load_2d(smem + C::OFF_Q + t * C::Q_TILE_BYTES + kb * (QT * 128), &tmQ, &bars->q_full, col0 + kb * 64,
-                           q_row0 + t * QT);
-    }
     // K blocks only: V has its own producer warp so that a V slot that frees late (after PV(i-1)) never holds back the
     // request for K(i+2) — each ring then runs a full two key blocks ahead of its consumer
     int stage = 0;
     uint32_t phase = 0;
-    for (int i = 0; i < n_kv; ++i) {
-      DBG_ITER(i);
-      ptx::mbar_wait(&bars->k_empty[stage], phase ^ 1);
+    int n = 0;
+    for (int item = item0; item < ws.n_items; item += item_step, ++n) {
+      const Item it = decode(item);
+      if (n > 0) ptx::mbar_wait(&bars->q_empty, (n - 1) & 1);   // every S MMA of the previous item has read its Q tiles
       if (lane == 0) {
-        ptx::mbar_expect_tx(&bars->k_full[stage], C::K_TILE_BYTES);
-        for (int kb = 0; kb < C::KB; ++kb)
-          ptx::tma_load_2d(smem + C::OFF_K + stage * C::K_TILE_BYTES + kb * (C::BKV * 128), &tmK, &bars->k_full[stage],
-                           col0 + kb * 64, kv_row0 + i * C::BKV);
+        ptx::mbar_expect_tx(&bars->q_full, it.n_tiles * C::Q_TILE_BYTES);
+        for (int t = 0; t < it.n_tiles; ++t)
+          for (int kb = 0; kb < C::KB; ++kb)
+            ptx::tma_load_2d(smem + C::OFF_Q + t * C::Q_TILE_BYTES + kb * (QT * 128), &tmQ, &bars->q_full, it.col0 + kb * 64,
+                             it.q_row0 + t * QT);
       }
-      __syncwarp();
-      if (++stage == C::KVS) { stage = 0; phase ^= 1; }
+      for (int i = 0; i < it.n_kv; ++i) {
+        DBG_ITER(i);
+        ptx::mbar_wait(&bars->k_empty[stage], phase ^ 1);
+        if (lane == 0) {
+          ptx::mbar_expect_tx(&bars->k_full[stage], C::K_TILE_BYTES);
+          for (int kb = 0; kb < C::KB; ++kb)
+            ptx::tma_load_2d(smem + C::OFF_K + stage * C::K_TILE_BYTES + kb * (C::BKV * 128), &tmK, &bars->k_full[stage],
+                             it.col0 + kb * 64, it.kv_row0 + i * C::BKV);
+        }
+        __syncwarp();
+        if (++stage == C::KVS) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp == W_TMA_V) {
     // ============================================================ TMA producer (V blocks)
     reg_dec<C>();
     int stage = 0;
     uint32_t phase = 0;
-    for (int i = 0; i < n_kv; ++i) {
-      ptx::mbar_wait(&bars->v_empty[stage], phase ^ 1);
-      if (lane == 0) {
-        ptx::mbar_expect_tx(&bars->v_full[stage], C::V_TILE_BYTES);
-        for (int kb = 0; kb < C::KB; ++kb)
-          ptx::tma_load_2d(smem + C::OFF_V + stage * C::V_TILE_BYTES + kb * (C::BKV * 128), &tmV, &bars->v_full[stage],
-                           col0 + kb * 64, kv_row0 + i * C::BKV);
+    for (int item = item0; item < ws.n_items; item += item_step) {
+      const Item it = decode(item);
+      for (int i = 0; i < it.n_kv; ++i) {
+        ptx::mbar_wait(&bars->v_empty[stage], phase ^ 1);
+        if (lane == 0) {
+          ptx::mbar_expect_tx(&bars->v_full[stage], C::V_TILE_BYTES);
+          for (int kb = 0; kb < C::KB; ++kb)
+            ptx::tma_load_2d(smem + C::OFF_V + stage * C::V_TILE_BYTES + kb * (C::BKV * 128), &tmV, &bars->v_full[stage],
+                             it.col0 + kb * 64, it.kv_row0 + i * C::BKV);
+        }
+        __syncwarp();
+        if (++stage == C::KVS) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == C::KVS) { stage = 0; phase ^= 1; }
     }
   } else if (warp == W_MMA) {
     // ============================================================ MMA issuer
     reg_dec<C>();
-    constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(QT, C::BKV, 0, 0);  // S = Q K^T : both K-major
     constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(QT, HD, 0, 1);      // O = P V   : A K-major, B (V) MN-major
     const uint32_t sQ = ptx::smem_u32(smem + C::OFF_Q), sK = ptx::smem_u32(smem + C::OFF_K);
     const uint32_t sV = ptx::smem_u32(smem + C::OFF_V);
-
-    // the last key block of a ragged sequence (412 = 3 x 128 + 28 keys) only spans n_last keys (a multiple of 32): a narrower
-    // S = Q K^T (UMMA N = n_last) and a shorter P V reduction, and the softmax warps touch n_last columns instead of BKV
-    const int n_last = min(C::BKV, ((Lkp - (n_kv - 1) * C::BKV) + 31) & ~31);
-    const uint32_t idesc_s_last = ptx::umma_idesc_bf16(QT, n_last, 0, 0);
-    auto issue_S = [&](int t, int stage, bool last) {
-      const uint32_t id = last ? idesc_s_last : idesc_s;
+    auto issue_S = [&](int t, int stage, int n_cols) {                    // S = Q K^T : both K-major, UMMA N = n_cols
+      const uint32_t id = ptx::umma_idesc_bf16(QT, n_cols, 0, 0);
 #pragma unroll
       for (int k = 0; k < HD / 16; ++k) {
         const uint64_t a = ptx::umma_desc_sw128(sQ + t * C::Q_TILE_BYTES + (k / 4) * (QT * 128) + (k % 4) * 32, 16, 1024);
@@ -338,44 +353,67 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     };
 
-    ptx::mbar_wait(&bars->q_full, 0);
-    ptx::mbar_wait(&bars->k_full[0], 0);
-    ptx::tc_fence_after();
-    if (lane == 0) {
-      for (int t = 0; t < n_tiles; ++t) { issue_S(t, 0, n_kv == 1); ptx::umma_commit(&bars->s_full[t]); }
-      ptx::umma_commit(&bars->k_empty[0]);  // K(0) free once S_A(0), S_B(0) retire
-    }
-    __syncwarp();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int i = 0; i < n_kv; ++i) {
-      DBG_ITER(i);
-      int nstage = stage + 1;
-      uint32_t nphase = phase;
-      if (nstage == C::KVS) { nstage = 0; nphase ^= 1; }
-      if (i + 1 < n_kv) {
-        // S_t(i+1) as soon as the softmax warps hold S_t(i) in registers
-        ptx::mbar_wait(&bars->k_full[nstage], nphase);
-        for (int t = 0; t < n_tiles; ++t) {
-          ptx::mbar_wait(&bars->s_free[t], i & 1);
-          ptx::tc_fence_after();
-          if (lane == 0) { issue_S(t, nstage, i + 2 == n_kv); ptx::umma_commit(&bars->s_full[t]); }
-          __syncwarp();
-        }
-        if (lane == 0) ptx::umma_commit(&bars->k_empty[nstage]);  // K(i+1) free once both S MMAs retire
-        __syncwarp();
+    if (item0 < ws.n_items) {
+      Item cur = decode(item0);
+      int cur_last = last_cols(cur);
+      ptx::mbar_wait(&bars->q_full, 0);
+      ptx::mbar_wait(&bars->k_full[0], 0);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        for (int t = 0; t < cur.n_tiles; ++t) { issue_S(t, 0, cur.n_kv == 1 ? cur_last : C::BKV); ptx::umma_commit(&bars->s_full[t]); }
+        ptx::umma_commit(&bars->k_empty[0]);  // K(0) free once S_A(0), S_B(0) retire
+        if (cur.n_kv == 1) ptx::umma_commit(&bars->q_empty);
       }
-      ptx::mbar_wait(&bars->v_full[stage], phase);
-      for (int t = 0; t < n_tiles; ++t) {
-        ptx::mbar_wait(&bars->p_ready[t][i & 1], (i >> 1) & 1);
-        ptx::tc_fence_after();
-        if (lane == 0) { issue_PV(t, stage, i > 0, i + 1 == n_kv ? n_last : C::BKV); ptx::umma_commit(&bars->pv_done[t][i & 1]); }
-        __syncwarp();
-      }
-      if (lane == 0) ptx::umma_commit(&bars->v_empty[stage]);
       __syncwarp();
-      stage = nstage;
-      phase = nphase;
+      int stage = 0;
+      uint32_t phase = 0, g = 0;   // g: blocks issued so far by this CTA (barrier parities run across items)
+      int n = 0;
+      for (int item = item0; item < ws.n_items; item += item_step, ++n) {
+        const bool more_items = item + item_step < ws.n_items;
+        Item nxt = cur;
+        int nxt_last = cur_last;
+        if (more_items) { nxt = decode(item + item_step); nxt_last = last_cols(nxt); }
+        for (int i = 0; i < cur.n_kv; ++i, ++g) {
+          DBG_ITER(i);
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == C::KVS) { nstage = 0; nphase ^= 1; }
+          const bool in_item = i + 1 < cur.n_kv;
+          if (in_item || more_items) {
+            // the next block's S_t as soon as the softmax warps hold this block's S_t in registers; across an item boundary the
+            // next item's Q tiles must have landed as well
+            const Item& ni = in_item ? cur : nxt;
+            const int bi = in_item ? i + 1 : 0;                       // its index within its item
+            const bool ni_last = bi + 1 == ni.n_kv;
+            if (!in_item) ptx::mbar_wait(&bars->q_full, (n + 1) & 1);
+            ptx::mbar_wait(&bars->k_full[nstage], nphase);
+            for (int t = 0; t < ni.n_tiles; ++t) {
+              ptx::mbar_wait(&bars->s_free[t], g & 1);
+              ptx::tc_fence_after();
+              if (lane == 0) { issue_S(t, nstage, ni_last ? (in_item ? cur_last : nxt_last) : C::BKV); ptx::umma_commit(&bars->s_full[t]); }
+              __syncwarp();
+            }
+            if (lane == 0) {
+              ptx::umma_commit(&bars->k_empty[nstage]);               // that K block is free once its S MMAs retire
+              if (ni_last) ptx::umma_commit(&bars->q_empty);          // and so are the item's Q tiles after its last S
+            }
+            __syncwarp();
+          }
+          ptx::mbar_wait(&bars->v_full[stage], phase);
+          for (int t = 0; t < cur.n_tiles; ++t) {
+            ptx::mbar_wait(&bars->p_ready[t][g & 1], (g >> 1) & 1);
+            ptx::tc_fence_after();
+            if (lane == 0) { issue_PV(t, stage, i > 0, i + 1 == cur.n_kv ? cur_last : C::BKV); ptx::umma_commit(&bars->pv_done[t][g & 1]); }
+            __syncwarp();
+          }
+          if (lane == 0) ptx::umma_commit(&bars->v_empty[stage]);
+          __syncwarp();
+          stage = nstage;
+          phase = nphase;
+        }
+        cur = nxt;
+        cur_last = nxt_last;
+      }
     }
   } else if (warp > W_TMA_V) {
     reg_dec<C>();  // idle warp of the service warpgroup (setmaxnreg is warpgroup-wide)
@@ -386,7 +424,11 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int t = warp >> 2;                   // query tile of this softmax warpgroup
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;         // query row within the tile == TMEM lane
-    if (t < n_tiles) {
+    uint32_t g0 = 0;                           // blocks of the items before the current one (barrier parities run across items)
+    for (int item = item0; item < ws.n_items; item += item_step) {
+    const Item it = decode(item);
+    const int n_kv = it.n_kv, Lkp = it.Lkp, q0 = it.q0;
+    if (t < it.n_tiles) {
       const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
       const uint32_t tS = tmem + lane_addr + C::S_COL + t * C::BKV;
       const uint32_t tO = tmem + lane_addr + C::O_COL + t * HD;
@@ -398,12 +440,13 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       // a warp whose 32 query rows all lie past Lq (ragged last tile: 412 = 3 x 128 + 28 rows; 32-row temporal attention) only
       // keeps the barrier protocol going: its rows of S / P / O are never stored, and rows of an MMA are independent
       const bool warp_active = q0 + t * QT + quarter * 32 < Lq;
-      const int n_last = min(COLS, ((Lkp - (n_kv - 1) * C::BKV) + 31) & ~31);
+      const int n_last = last_cols(it);
       PH_DECL;
       for (int i = 0; i < n_kv; ++i) {
         DBG_ITER(i);
+        const uint32_t g = g0 + i;                            // block index within this CTA's whole run
         const int n_cols = (i + 1 == n_kv) ? n_last : COLS;   // S columns of this key block (warp-uniform)
-        ptx::mbar_wait(&bars->s_full[t], i & 1);
+        ptx::mbar_wait(&bars->s_full[t], g & 1);
         ptx::tc_fence_after();
         PH(0);
         if (i == 0) MS(1);  // first S tile ready (Q, K(0) landed, first MMA retired)
@@ -447,7 +490,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           if (lane == 0) ptx::mbar_arrive(&bars->s_free[t]);
         };
         auto p_free = [&]() {      // before the first tcgen05.st of P: P V(i-1) has consumed the previous P (and O is quiescent)
-          ptx::mbar_wait(&bars->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
+          ptx::mbar_wait(&bars->pv_done[t][(g - 1) & 1], ((g - 1) >> 1) & 1);
           ptx::tc_fence_after();
         };
         auto no_hook = []() {};
@@ -528,7 +571,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         auto emit = [&](float m_use) -> float { return full_block ? emit_full(m_use, no_hook, no_hook) : emit_part(m_use); };
         auto bmax = [&]() -> float { return full_block ? block_max(FullT{}) : block_max(PartT{}); };
         // P is single-buffered in tensor memory: PV(i-1) must have consumed it (they retire in order, so O is quiescent too)
-        if (i >= 1 && !split) ptx::mbar_wait(&bars->pv_done[t][(i - 1) & 1], ((i - 1) >> 1) & 1);
+        if (i >= 1 && !split) ptx::mbar_wait(&bars->pv_done[t][(g - 1) & 1], ((g - 1) >> 1) & 1);
         ptx::tc_fence_after();
         PH(2);
         float blk_sum = 0.f;
@@ -572,21 +615,21 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bars->p_ready[t][i & 1]);
+        if (lane == 0) ptx::mbar_arrive(&bars->p_ready[t][g & 1]);
         PH(4);
       }
       PH_FLUSH();
       MS(2);  // key loop done
       // ---- epilogue: O / l -> bf16 -> global
-      ptx::mbar_wait(&bars->pv_done[t][(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1);
+      ptx::mbar_wait(&bars->pv_done[t][(g0 + n_kv - 1) & 1], ((g0 + n_kv - 1) >> 1) & 1);
       ptx::tc_fence_after();
       const float inv_l = 1.0f / l_run;
       const int q_local = q0 + t * QT + r;
-      __nv_bfloat16* dst = O + (size_t)(batch * (size_t)Lq + q_local) * ldo + col0;
+      __nv_bfloat16* dst = O + (size_t)(it.batch * (size_t)Lq + q_local) * ldo + it.col0;
       // split unit: this CTA saw only its key range — unnormalised O (fp32), reference maximum and row sum go to the workspace
       float* pdst = nullptr;
-      if (SPLIT && n_parts > 1) {
-        const size_t prow = ((size_t)(unit - ws.n_full) * ws.parts + part) * (NT * QT) + t * QT + r;
+      if (SPLIT && it.partial) {
+        const size_t prow = (size_t)it.prow0 + t * QT + r;
         pdst = ws.partial + prow * (HD + 2);
         if (q_local < Lq) { pdst[HD] = m_ref; pdst[HD + 1] = l_run; }
       }
@@ -614,6 +657,8 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         __syncwarp();
       }
     }
+    g0 += (uint32_t)n_kv;
+    }  // items of this CTA
   }
   MS(3);  // epilogue stores issued
   ptx::tc_fence_before();
@@ -682,8 +727,14 @@ int launch(const AttentionArgs& a, cudaStream_t st) {
       if (buf) { ws.n_full = (int)(n_units - leftover); ws.parts = best_p; ws.partial = buf; }
     }
   }
-  LSVS_CHECK_ARG(ws.parts > 1 || (a.batches <= 65535 && a.heads <= 65535), "attention: batch/head count exceeds the grid limit");
-  const dim3 grid = ws.parts > 1 ? dim3((unsigned)(ws.n_full + (n_units - ws.n_full) * ws.parts)) : dim3(ws.n_qt, a.heads, a.batches);
+  ws.n_items = (int)(ws.n_full + (n_units - ws.n_full) * ws.parts);
+  // persistent CTAs (one-tile kernel, short sequences): one per slot, each walking its items.  Measured in the step
+  // (profiles/r2b_attention_experiments.md): 412-token passes 4.45 -> 4.17 ms; on the long global pass the static round-robin
+  // loses to the hardware's dynamic CTA dispatch (21.5 -> 22.2 ms), so long sequences keep one CTA per item.
+  // LSVS_ATTN_PERSIST=0 / 2: never / always (A/B runs).
+  static const int persist = [] { const char* e = getenv("LSVS_ATTN_PERSIST"); return e ? atoi(e) : 1; }();
+  const bool persistent = NT_ == 1 && ws.n_items > slots && (persist == 2 || (persist == 1 && n_kv_seq <= 16));
+  const dim3 grid((unsigned)(persistent ? slots : ws.n_items));
   auto kern = ws.parts > 1 ? attention_fwd_tcgen05<HD, NT_, POLY_, CAN_SPLIT> : attention_fwd_tcgen05<HD, NT_, POLY_, false>;
   LSVS_CUDA(launch_pdl(kern, grid, dim3(C::NTHREADS), C::SMEM, st, *tq, *tk, *tv, reinterpret_cast<__nv_bfloat16*>(a.o), a.ldo, a.Lq, a.Lk, scale_log2e, ws));
   LSVS_LAUNCH_CHECK();

@@ -1,8 +1,10 @@
-timeout 600 python -m pytest tests/test_attention_gpu.py -x -q -m gpu 2>&1 | tail -2
 for rep in 1 2; do
-LSVS_ATTN_POLY=0 python tools/ub_attn.py 2>&1 | grep "global S=32\|cfg5" | sed "s/^/p0.000 /"
-LSVS_ATTN_POLY=0 LSVS_B200_LIB=variants/polyx/liblsvs_b200.so python tools/ub_attn.py 2>&1 | grep "global S=32\|cfg5" | sed "s/^/p0.125 /"
-LSVS_ATTN_POLY=1 python tools/ub_attn.py 2>&1 | grep "global S=32\|cfg5" | sed "s/^/p0.250 /"
-LSVS_ATTN_POLY=1 LSVS_B200_LIB=variants/polyx/liblsvs_b200.so python tools/ub_attn.py 2>&1 | grep "global S=32\|cfg5" | sed "s/^/p0.375 /"
-done 2>&1 | cut -c1-230 | sed 's/"rel_l2_vs_sdpa"/err/; s/"B": 1, "H": 16, "hd": 64, //; s/"poly": "[01]", //' | tee gpurun_out/r2b_ab_poly_share.log
-python tools/ub_attn.py 2>&1 | grep "frame S" | cut -c1-200
+for p in 0 1; do
+LSVS_ATTN_PERSIST=$p python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-incumbent --sequence-frames 0 > gpurun_out/r2b_bench_persist_${p}_$rep.json 2> gpurun_out/r2b_bench_persist_${p}_$rep.err
+done; done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r2b_bench_persist_*.json')):
+    d=json.loads(open(f).read().strip().splitlines()[-1]); kc=d['kernel_classes']
+    print(f, round(d['value'],1), round(d['ms_per_step'],2), {k:round(v['ms_per_step'],2) for k,v in kc.items()}, round(d['attention']['tflops'],1), d['clocks']['sm_mhz'])
+PY
