@@ -113,9 +113,17 @@ bool ends_with(const std::string& s, const char* suf) {
 }
 bool contains(const std::string& s, const char* sub) { return s.find(sub) != std::string::npos; }
 
+// The two large Linears of the camera head's fp32 vector path (adaLN modulation 2048 -> 6144, pose branch fc1 2048 -> 1024, 32 rows):
+// as CUDA-core fp32 GEMVs they were latency-bound weight streams (130 us / 35 us per launch, 0.4 TB/s); they now run fp32-class on
+// the tensor cores in EVERY precision mode — split weights [hi | hi | lo] against split activations, 2^-16 relative.
+bool camera_vector_gemm(const std::string& n) {
+  return n == "camera_head.poseLN_modulation.1.weight" || n == "camera_head.pose_branch.fc1.weight";
+}
+
 // GEMM weights that run on the tensor cores in bf16 (everything the reference runs under bf16 autocast at scale).
 bool wants_bf16(const std::string& n) {
   if (!ends_with(n, ".weight")) return false;
+  if (camera_vector_gemm(n)) return true;
   if (contains(n, "camera_head.") && !contains(n, "camera_head.trunk.")) return false;
   const bool big_block = contains(n, "camera_head.trunk.") || contains(n, "aggregator.") || contains(n, "alignment_head.frame_blocks.") || contains(n, "alignment_head.temporal_blocks.");
   if (big_block && (contains(n, "attn.qkv.") || contains(n, "attn.proj.") || contains(n, "attn.q.") || contains(n, "attn.k.") ||
@@ -130,6 +138,7 @@ bool wants_bf16(const std::string& n) {
 // the camera-head trunk and the DPT heads' convolutions — and so do the alignment head's blocks + project_in; mode 2: every
 // block of the path.
 bool wants_split(const std::string& n, int precision) {
+  if (camera_vector_gemm(n)) return true;
   if (precision <= 0 || !wants_bf16(n)) return false;
   if (precision >= 2) return true;
   return contains(n, "alignment_head.") || contains(n, "camera_head.trunk.") || contains(n, "depth_head.") || contains(n, "point_head.");
@@ -780,13 +789,18 @@ extern "C" int lsvs_camera_head_forward(lsvs_engine* h, const float* tokens_last
   const size_t need_scratch = (size_t)frames * (size_t)(C * 8 + 3 * C + 3 * C + 4 * C + 4096) + (1 << 14);
   TRY(e.scratch.ensure(need_scratch * 4));
   e.scratch_off = 0;
-  const float *tnw, *tnb, *trw, *trb, *empty, *epw, *epb, *mw, *mb, *b1w, *b1b, *b2w, *b2b;
+  const float *tnw, *tnb, *trw, *trb, *empty, *epw, *epb, *mb, *b1b, *b2w, *b2b;
   TRY(need_f32(e, "camera_head.token_norm.weight", &tnw, C)); TRY(need_f32(e, "camera_head.token_norm.bias", &tnb, C));
   TRY(need_f32(e, "camera_head.trunk_norm.weight", &trw, C)); TRY(need_f32(e, "camera_head.trunk_norm.bias", &trb, C));
   TRY(need_f32(e, "camera_head.empty_pose_tokens", &empty, 9));
   TRY(need_f32(e, "camera_head.embed_pose.weight", &epw, 9LL * C)); TRY(need_f32(e, "camera_head.embed_pose.bias", &epb, C));
-  TRY(need_f32(e, "camera_head.poseLN_modulation.1.weight", &mw, 3LL * C * C)); TRY(need_f32(e, "camera_head.poseLN_modulation.1.bias", &mb, 3 * C));
-  TRY(need_f32(e, "camera_head.pose_branch.fc1.weight", &b1w, (long long)(C / 2) * C)); TRY(need_f32(e, "camera_head.pose_branch.fc1.bias", &b1b, C / 2));
+  const __nv_bfloat16 *mws, *b1ws;   // split [hi | hi | lo] (camera_vector_gemm)
+  bool sp1 = false, sp2 = false;
+  TRY(need_bf16(e, "camera_head.poseLN_modulation.1.weight", &mws, 3 * C, C, &sp1)); TRY(need_f32(e, "camera_head.poseLN_modulation.1.bias", &mb, 3 * C));
+  TRY(need_bf16(e, "camera_head.pose_branch.fc1.weight", &b1ws, C / 2, C, &sp2)); TRY(need_f32(e, "camera_head.pose_branch.fc1.bias", &b1b, C / 2));
+  LSVS_CHECK_ARG(sp1 && sp2, "camera_head_forward: vector-path weights are not stored split");
+  TRY(e.p_xs.ensure((size_t)frames * 3 * C * 2));
+  void* xs = e.p_xs.p;
   TRY(need_f32(e, "camera_head.pose_branch.fc2.weight", &b2w, 9LL * (C / 2))); TRY(need_f32(e, "camera_head.pose_branch.fc2.bias", &b2b, 9));
   float* tok = e.scratch_f32((size_t)frames * C); float* normed = e.scratch_f32((size_t)frames * C);
   float* emb = e.scratch_f32((size_t)frames * C); float* mod = e.scratch_f32((size_t)frames * 3 * C);
@@ -801,13 +815,21 @@ extern "C" int lsvs_camera_head_forward(lsvs_engine* h, const float* tokens_last
     if (it == 0) TRY(combine_rows(empty, 0, nullptr, 0, pin, 9, frames, 9, -1, -1, st));  // broadcast the empty pose token
     else TRY(combine_rows(pred, 9, nullptr, 0, pin, 9, frames, 9, -1, -1, st));
     TRY(linear_f32(pin, 9, epw, epb, emb, C, frames, C, 9, ACT_NONE, ACT_NONE, nullptr, false, st));
-    TRY(linear_f32(emb, C, mw, mb, mod, 3 * C, frames, 3 * C, C, ACT_SILU, ACT_NONE, nullptr, false, st));
+    {   // mod = Linear(SiLU(emb)): fp32-class on the tensor cores (weight stream 75 MB)
+      TRY(cast_split_act(emb, C, xs, 3LL * C, frames, C, 2, st));
+      GemmEpilogue em; em.bias = mb; em.out = mod; em.ldo = 3 * C;
+      TRY(gemm_bf16(xs, 3 * C, mws, 3 * C, frames, 3 * C, 3 * C, EPI_BIAS_F32, em, st));
+    }
     TRY(modulate(normed, tok, mod, xx, frames, C, st));
     // trunk: bf16 tensor-core blocks on the fp32 residual stream (16 heads x 128, sequence = the S frames of a chunk)
     for (int i = 0; i < 4; ++i) TRY(run_block(e, xx, frames, e.cam_trunk[i], 1e-5f, 16, 128, B, S, RopeCfg{}, nullptr, 0, st));
     TRY(layernorm(xx, C, RowMap{}, trw, trb, 1e-5f, xn, C, RowMap{}, false, frames, C, st));
-    TRY(linear_f32(xn, C, b1w, b1b, bh, C / 2, frames, C / 2, C, ACT_NONE, ACT_GELU, nullptr, false, st));
-    TRY(linear_f32(bh, C / 2, b2w, b2b, delta, 9, frames, 9, C / 2, ACT_NONE, ACT_NONE, nullptr, false, st));
+    {   // pose branch: fc1 fp32-class on the tensor cores, its GELU applied on the way into fc2
+      TRY(cast_split_act(xn, C, xs, 3LL * C, frames, C, 0, st));
+      GemmEpilogue e1; e1.bias = b1b; e1.out = bh; e1.ldo = C / 2;
+      TRY(gemm_bf16(xs, 3 * C, b1ws, 3 * C, frames, C / 2, 3 * C, EPI_BIAS_F32, e1, st));
+    }
+    TRY(linear_f32(bh, C / 2, b2w, b2b, delta, 9, frames, 9, C / 2, ACT_GELU, ACT_NONE, nullptr, false, st));
     if (it == 0) TRY(combine_rows(delta, 9, nullptr, 0, pred, 9, frames, 9, -1, -1, st));
     else TRY(combine_rows(pred, 9, delta, 9, pred, 9, frames, 9, -1, -1, st));
     // UPSTREAM returns the activated encoding of every refinement iteration (the reference only reads the last, :109)

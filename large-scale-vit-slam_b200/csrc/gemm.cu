@@ -906,7 +906,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
     if (pair) return launch2<KIND>(tmA, tmB, M, N, K, e, st);                           \
     return wide ? launch<256, KIND>(tmA, tmB, M, N, K, e, st) : launch<128, KIND>(tmA, tmB, M, N, K, e, st);
   // few rows (camera-head trunk, M = frames of one chunk): the job is weight streaming, so spread N over many CTAs
-  if (M <= BM && N % 64 == 0 && N / 64 >= 32) {
+  if (M <= BM && N % 64 == 0 && N / 64 >= 16) {
     const CUtensorMap* tmB64 = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, 64);
     if (!tmB64) return LSVS_ECUDA;
     switch (epi_kind) {

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) layernorm_split_kernel(const float* __res
   }
 }
 
-// (rows, cols) fp32 -> split (rows, 3*cols) bf16, optionally through the exact GELU
+// (rows, cols) fp32 -> split (rows, 3*cols) bf16, optionally through the exact GELU (act 1) or SiLU (act 2)
 __global__ void __launch_bounds__(256) cast_split_kernel(const float* __restrict__ x, long long ld_in, __nv_bfloat16* __restrict__ out,
                                                          long long ld_out, long long rows, int cols, int gelu) {
   const int c4 = cols / 4;
@@ -79,9 +79,11 @@ __global__ void __launch_bounds__(256) cast_split_kernel(const float* __restrict
     const long long r = i / c4;
     const int c = (int)(i % c4);
     float4 v = reinterpret_cast<const float4*>(x + r * ld_in)[c];
-    if (gelu) {
+    if (gelu == 1) {
       v.x = 0.5f * v.x * (1.f + erff(v.x * 0.70710678118654752f)); v.y = 0.5f * v.y * (1.f + erff(v.y * 0.70710678118654752f));
       v.z = 0.5f * v.z * (1.f + erff(v.z * 0.70710678118654752f)); v.w = 0.5f * v.w * (1.f + erff(v.w * 0.70710678118654752f));
+    } else if (gelu == 2) {
+      v.x = v.x / (1.f + expf(-v.x)); v.y = v.y / (1.f + expf(-v.y)); v.z = v.z / (1.f + expf(-v.z)); v.w = v.w / (1.f + expf(-v.w));
     }
     store_split4(out + r * ld_out, cols, 4 * c, v);
   }
@@ -425,13 +427,16 @@ int layernorm_split(const float* x, long long ld_in, const float* w, const float
   return LSVS_OK;
 }
 
-int cast_split(const float* x, long long ld_in, void* out, long long ld_out, long long rows, int cols, bool gelu, cudaStream_t st) {
+int cast_split_act(const float* x, long long ld_in, void* out, long long ld_out, long long rows, int cols, int act, cudaStream_t st) {
   LSVS_CHECK_ARG(x && out && cols % 4 == 0 && ld_in % 4 == 0 && ld_out >= 3LL * cols && ld_out % 4 == 0, "cast_split: bad arguments");
   if (rows == 0) return LSVS_OK;
   ProfScope prof(PROF_ELEMENTWISE, st, 0, (double)rows * cols * 10);
-  cast_split_kernel<<<blocks_for(rows * (cols / 4)), 256, 0, st>>>(x, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out, rows, cols, gelu ? 1 : 0);
+  cast_split_kernel<<<blocks_for(rows * (cols / 4)), 256, 0, st>>>(x, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out, rows, cols, act);
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
+}
+int cast_split(const float* x, long long ld_in, void* out, long long ld_out, long long rows, int cols, bool gelu, cudaStream_t st) {
+  return cast_split_act(x, ld_in, out, ld_out, rows, cols, gelu ? 1 : 0, st);
 }
 
 int pack_weight_split(const float* w, void* out, long long rows, int k_in, int k_pad, cudaStream_t st) {

@@ -10,6 +10,8 @@ int layernorm_split(const float* x, long long ld_in, const float* w, const float
                     long long rows, int D, cudaStream_t st);
 // (rows, cols) fp32 -> split bf16 (rows, 3*cols); gelu: through the exact-erf GELU first
 int cast_split(const float* x, long long ld_in, void* out, long long ld_out, long long rows, int cols, bool gelu, cudaStream_t st);
+// act: 0 none, 1 GELU, 2 SiLU
+int cast_split_act(const float* x, long long ld_in, void* out, long long ld_out, long long rows, int cols, int act, cudaStream_t st);
 // weights (rows, k_in) fp32 -> (rows, 3*k_pad) bf16 = [hi | hi | lo]
 int pack_weight_split(const float* w, void* out, long long rows, int k_in, int k_pad, cudaStream_t st);
 // images -> fp32 im2col of the patch convolution: (frames*gh*gw, 640)

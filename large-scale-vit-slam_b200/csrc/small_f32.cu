@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
         if (m < mt) {
           float4 x4 = *reinterpret_cast<const float4*>(x + (size_t)(m0 + m) * ldx + k0);
           if (in_act == ACT_SILU) { x4.x = silu(x4.x); x4.y = silu(x4.y); x4.z = silu(x4.z); x4.w = silu(x4.w); }
+          else if (in_act == ACT_GELU) { x4.x = gelu_erf(x4.x); x4.y = gelu_erf(x4.y); x4.z = gelu_erf(x4.z); x4.w = gelu_erf(x4.w); }
 #pragma unroll
           for (int j = 0; j < LIN_NW; ++j)
             acc[m][j] = fmaf(w4[j].x, x4.x, fmaf(w4[j].y, x4.y, fmaf(w4[j].z, x4.z, fmaf(w4[j].w, x4.w, acc[m][j]))));
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
         if (m < mt) {
           float xv = x[(size_t)(m0 + m) * ldx + k];
           if (in_act == ACT_SILU) xv = silu(xv);
+          else if (in_act == ACT_GELU) xv = gelu_erf(xv);
 #pragma unroll
           for (int j = 0; j < LIN_NW; ++j) acc[m][j] = fmaf(w[j], xv, acc[m][j]);
         }
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(256) linear_f32_tiled_kernel(const float* __re
       if (m0 + r < M) {
         float4 x4 = *reinterpret_cast<const float4*>(x + (size_t)(m0 + r) * ldx + k);
         if (in_act == ACT_SILU) { x4.x = silu(x4.x); x4.y = silu(x4.y); x4.z = silu(x4.z); x4.w = silu(x4.w); }
+        else if (in_act == ACT_GELU) { x4.x = gelu_erf(x4.x); x4.y = gelu_erf(x4.y); x4.z = gelu_erf(x4.z); x4.w = gelu_erf(x4.w); }
 #pragma unroll
         for (int c = 0; c < NC; ++c)
           acc[r][c] = fmaf(w4[c].x, x4.x, fmaf(w4[c].y, x4.y, fmaf(w4[c].z, x4.z, fmaf(w4[c].w, x4.w, acc[r][c]))));
