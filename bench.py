@@ -571,9 +571,12 @@ def run_b200(args):
         # `traffic` is null: the reported kernel is a CLASS of launches of several shapes, no single ncu capture measures it.  The
         # offline `ncu --set full` capture of its most frequent shape is quoted beside it (profiles/, not measured by this run).
         traffic, traffic_sample = None, None
-        tpath = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-        if os.path.exists(tpath) and names[dom] in json.load(open(tpath)):
-            traffic_sample = dict(json.load(open(tpath))[names[dom]], source="profiles/r1_ncu_traffic.json (offline ncu --set full, one launch of one shape)")
+        for tname in ("r2c_ncu_traffic.json", "r1_ncu_traffic.json"):   # newest offline capture first
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath) and names[dom] in json.load(open(tpath)):
+                traffic_sample = dict(json.load(open(tpath))[names[dom]])
+                traffic_sample["source"] = f"profiles/{tname} (offline ncu --set full, one launch of one shape): " + traffic_sample.get("source", "")
+                break
         roofline = {"kernel": names[dom], "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic, "traffic_sample": traffic_sample, "peak_source": pk["src"] + " (sustained, kernel timed inside a long step)",
                     "avg_launch_ms": pms[dom] / max(1, pln[dom]), "share_of_step": (pms[dom] / n_prof) / ms_per_step,
