@@ -181,7 +181,9 @@ __device__ __forceinline__ void pos2d(const GemmEpilogue& e, int m, int& py, int
 
 // Rotate pairs (j, j+R/2) of the R-wide region v[0..R) by angle table row `tab` (cos,sin per frequency).
 // q/k LayerNorm parameters staged once per CTA in shared memory (broadcast LDS.128 instead of one LDG per element)
+constexpr int ROPE_SP = 64;   // positions per frequency in the shared-memory copy of the 2-D RoPE table
 struct EpiSmem { float qn_w[128], qn_b[128], kn_w[128], kn_b[128]; };
+struct EpiSmemRope { EpiSmem p; float2 rope[32 * 64]; };   // + the 2-D RoPE table, transposed: [frequency (<= 32)][position (<= 64)]
 
 __device__ __forceinline__ void stage_epi_params(EpiSmem* sp, const GemmEpilogue& e, int hd) {
   const int t = threadIdx.x;
@@ -189,6 +191,23 @@ __device__ __forceinline__ void stage_epi_params(EpiSmem* sp, const GemmEpilogue
     sp->qn_w[t] = e.qn_w ? __ldg(e.qn_w + t) : 1.f; sp->qn_b[t] = e.qn_b ? __ldg(e.qn_b + t) : 0.f;
     sp->kn_w[t] = e.kn_w ? __ldg(e.kn_w + t) : 1.f; sp->kn_b[t] = e.kn_b ? __ldg(e.kn_b + t) : 0.f;
   }
+}
+// positions a 2-D RoPE launch can ask for: rows 0 .. max(last grid row, grid width) of the table
+__device__ __forceinline__ int rope2d_positions(const GemmEpilogue& e) {
+  const int rows = (e.tokens_per_frame - e.n_special + e.grid_w - 1) / e.grid_w;
+  return (rows > e.grid_w ? rows : e.grid_w) + 1;
+}
+// returns the shared-memory table, or nullptr when the launch has no 2-D RoPE / more positions than the copy holds.
+// (The table is engine set-up data written long before this launch: reading it ahead of griddepcontrol.wait is safe.)
+__device__ __forceinline__ const float2* stage_rope_table(EpiSmemRope* sp, const GemmEpilogue& e, int hd) {
+  if (e.rope_mode != ROPE_2D) return nullptr;
+  const int npos = rope2d_positions(e), nf = hd / 4;
+  if (npos > ROPE_SP) return nullptr;
+  for (int i = threadIdx.x; i < npos * nf; i += blockDim.x) {
+    const int pos = i / nf, f = i - pos * nf;
+    sp->rope[f * ROPE_SP + pos] = __ldg(e.rope_tab + i);
+  }
+  return sp->rope;
 }
 
 // Rotate pairs (j, j+R/2) of the R-wide region v[0..R) by the angle table row `tab4` ((cos,sin) per frequency, two
@@ -206,39 +225,60 @@ __device__ __forceinline__ void rope_region(float* v, const float4* __restrict__
   }
 }
 
+// The same rotation from the TRANSPOSED shared-memory copy of the table ([frequency][position], ROPE_SP positions per frequency):
+// the 32 rows of a warp are consecutive tokens, i.e. consecutive x positions, so a lane-per-row read of the global
+// [position][frequency] table touches 32 different 128-byte lines per instruction — measured: 10.8 of the 81 us of the
+// qkv + LayerNorm + RoPE GEMM (tools/ub_gemm_epi4.py) — while the transposed copy is read 8 consecutive bytes per lane.
+template <int R>
+__device__ __forceinline__ void rope_region_s(float* v, const float2* tab_t, int pos) {
+#pragma unroll
+  for (int j = 0; j < R / 2; ++j) {
+    const float2 cs = tab_t[j * ROPE_SP + pos];
+    const float a0 = v[j], b0 = v[j + R / 2];
+    v[j] = a0 * cs.x - b0 * cs.y;
+    v[j + R / 2] = b0 * cs.x + a0 * cs.y;
+  }
+}
+
 // bias + LayerNorm over one head (HD columns, all in this thread) + RoPE, in place.  bias: global (16-byte loads),
-// w / b: shared-memory copies of the head LayerNorm parameters.
+// w / b: shared-memory copies of the head LayerNorm parameters.  The epilogue warps are latency-bound (two per SM
+// sub-partition, ncu: 22 % issue slots, half of the arithmetic stalled on the long scoreboard), so the reductions run on four
+// independent accumulators and the token position (three integer divisions) is computed once per row by the caller.
 template <int HD>
 __device__ __forceinline__ void head_norm_rope(float* v, const float* __restrict__ bias, const float* w, const float* b,
-                                               const GemmEpilogue& e, int m) {
-  float s = 0.f;
+                                               const GemmEpilogue& e, int py, int px, const float2* rope_s = nullptr) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int i = 0; i < HD; i += 4) {
     const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + i));
     v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
-    s += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
+    s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3];
   }
-  const float mean = s * (1.0f / HD);
-  float q = 0.f;
+  const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / HD);
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-  for (int i = 0; i < HD; ++i) { const float d = v[i] - mean; q += d * d; }
-  const float rstd = rsqrtf(q * (1.0f / HD) + e.ln_eps);
+  for (int i = 0; i < HD; i += 4) {
+    const float d0 = v[i] - mean, d1 = v[i + 1] - mean, d2 = v[i + 2] - mean, d3 = v[i + 3] - mean;
+    q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+  }
+  const float rstd = rsqrtf(((q0 + q1) + (q2 + q3)) * (1.0f / HD) + e.ln_eps);
+  const float nmr = -mean * rstd;
 #pragma unroll
   for (int i = 0; i < HD; i += 4) {
     const float4 ww = *reinterpret_cast<const float4*>(w + i), bb = *reinterpret_cast<const float4*>(b + i);
-    v[i] = (v[i] - mean) * rstd * ww.x + bb.x;
-    v[i + 1] = (v[i + 1] - mean) * rstd * ww.y + bb.y;
-    v[i + 2] = (v[i + 2] - mean) * rstd * ww.z + bb.z;
-    v[i + 3] = (v[i + 3] - mean) * rstd * ww.w + bb.w;
+    v[i] = fmaf(fmaf(v[i], rstd, nmr), ww.x, bb.x);
+    v[i + 1] = fmaf(fmaf(v[i + 1], rstd, nmr), ww.y, bb.y);
+    v[i + 2] = fmaf(fmaf(v[i + 2], rstd, nmr), ww.z, bb.z);
+    v[i + 3] = fmaf(fmaf(v[i + 3], rstd, nmr), ww.w, bb.w);
   }
-  if (e.rope_mode == ROPE_2D) {
-    int py, px;
-    pos2d(e, m, py, px);
+  if (e.rope_mode == ROPE_2D && rope_s != nullptr) {
+    rope_region_s<HD / 2>(v, rope_s, py);
+    rope_region_s<HD / 2>(v + HD / 2, rope_s, px);
+  } else if (e.rope_mode == ROPE_2D) {
     rope_region<HD / 2>(v, reinterpret_cast<const float4*>(e.rope_tab + (size_t)py * (HD / 4)));
     rope_region<HD / 2>(v + HD / 2, reinterpret_cast<const float4*>(e.rope_tab + (size_t)px * (HD / 4)));
   } else if (e.rope_mode == ROPE_1D) {
-    const int p = __ldg(e.pos_ids + (m % e.pos_period));
-    rope_region<HD>(v, reinterpret_cast<const float4*>(e.rope_tab + (size_t)p * (HD / 2)));
+    rope_region<HD>(v, reinterpret_cast<const float4*>(e.rope_tab + (size_t)py * (HD / 2)));   // py carries the 1-D position
   }
 }
 
@@ -253,7 +293,7 @@ __device__ __forceinline__ void conv_tap_coords(const GemmEpilogue& e, int& a_k,
 
 template <int BN, int EPI, bool TMA = false>
 __device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, const EpiSmem* sp, uint32_t taddr, int m, int n0, bool row_ok, int c_begin = 0, int c_end = BN,
-                                             const TmaOut* to = nullptr) {
+                                             const TmaOut* to = nullptr, const float2* rope_s = nullptr) {
   if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_F32) {
     constexpr int CH = TMA ? 64 : 32;
 #pragma unroll 1
@@ -370,6 +410,9 @@ __device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, const EpiSme
     }
   } else {  // EPI_QKV_NORM_ROPE_64 / _128 : columns [0,n_q) q heads, [n_q, n_q+n_k) k heads, remainder plain (+bias)
     constexpr int HD = (EPI == EPI_HEADNORM64_BF16) ? 64 : 128;
+    int py = 0, px = 0;   // RoPE position of this row: once per tile, not once per head
+    if (e.rope_mode == ROPE_2D) pos2d(e, m, py, px);
+    else if (e.rope_mode == ROPE_1D) py = __ldg(e.pos_ids + (m % e.pos_period));
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += HD) {
       float v[HD];
@@ -378,9 +421,9 @@ __device__ __forceinline__ void epilogue_row(const GemmEpilogue& e, const EpiSme
       if (!row_ok && !TMA) continue;  // reconverges at the __syncwarp above / after the loop (TMA: computed and clipped)
       const int n = n0 + c;
       if (n < e.n_q_cols) {
-        head_norm_rope<HD>(v, e.bias + n, sp->qn_w, sp->qn_b, e, m);
+        head_norm_rope<HD>(v, e.bias + n, sp->qn_w, sp->qn_b, e, py, px, rope_s);
       } else if (n < e.n_q_cols + e.n_k_cols) {
-        head_norm_rope<HD>(v, e.bias + n, sp->kn_w, sp->kn_b, e, m);
+        head_norm_rope<HD>(v, e.bias + n, sp->kn_w, sp->kn_b, e, py, px, rope_s);
       } else {
 #pragma unroll
         for (int i = 0; i < HD; i += 4) {
@@ -531,7 +574,8 @@ struct Smem2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int PARAM_OFFSET = BAR_OFFSET + 256;
-  static constexpr int PARAM_BYTES = TRANSPOSE ? 0 : 2048;   // q/k LayerNorm parameters (head-norm epilogues only)
+  static constexpr bool HEADNORM = (EPI == EPI_HEADNORM64_BF16 || EPI == EPI_HEADNORM128_BF16);
+  static constexpr int PARAM_BYTES = TRANSPOSE ? 0 : (HEADNORM ? (int)sizeof(EpiSmemRope) : 2048);   // q/k LayerNorm parameters + transposed RoPE table (head-norm epilogues only)
   static constexpr int TILE_OFFSET = (PARAM_OFFSET + PARAM_BYTES + 1023) / 1024 * 1024;  // 128B-swizzled tiles: 1024-byte aligned
   static constexpr int TILE_BYTES = 32 * 32 * 4;       // one 32 x 32 fp32 block (or 32 x 64 bf16)
   static constexpr int TILE_BUFS = TRANSPOSE ? 2 : 1;  // the residual epilogue keeps two tiles per warp (load / store double buffer)
@@ -592,7 +636,11 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* resid_bar = tmem_empty + 3;   // 2 per epilogue warp: residual tiles landed (load-add-store epilogue)
   static_assert(!L::TRANSPOSE || (STAGES2 * 2 + 4 + 1 + 2 * EW) * 8 <= 256, "barrier area");
   EpiSmem* sp = reinterpret_cast<EpiSmem*>(smem + L::PARAM_OFFSET);
-  if constexpr (EPI == EPI_HEADNORM64_BF16 || EPI == EPI_HEADNORM128_BF16) stage_epi_params(sp, epi, EPI == EPI_HEADNORM64_BF16 ? 64 : 128);
+  const float2* rope_s = nullptr;
+  if constexpr (EPI == EPI_HEADNORM64_BF16 || EPI == EPI_HEADNORM128_BF16) {
+    stage_epi_params(sp, epi, EPI == EPI_HEADNORM64_BF16 ? 64 : 128);
+    rope_s = stage_rope_table(reinterpret_cast<EpiSmemRope*>(sp), epi, EPI == EPI_HEADNORM64_BF16 ? 64 : 128);
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta = ptx::cluster_ctarank();  // 0 = leader
@@ -776,9 +824,9 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
         epilogue_resid_tma(epi, &tmR, smem + L::TILE_OFFSET + (warp - 2) * L::TILE_BUFS * L::TILE_BYTES, taddr, m0 + quarter * 32, n0, part * COLS, (part + 1) * COLS, slice == 0);
       } else if (L::TMA_BF16 && (use_tma_reduce & 4)) {
         const TmaOut to{&tmR, smem + L::TILE_OFFSET + (warp - 2) * L::TILE_BYTES, m0 + quarter * 32};
-        epilogue_row<BN2, EPI, L::TMA_BF16>(epi, sp, taddr, m, n0, m < M, part * COLS, (part + 1) * COLS, &to);
+        epilogue_row<BN2, EPI, L::TMA_BF16>(epi, sp, taddr, m, n0, m < M, part * COLS, (part + 1) * COLS, &to, rope_s);
       } else {
-        epilogue_row<BN2, EPI>(epi, sp, taddr, m, n0, m < M, part * COLS, (part + 1) * COLS);
+        epilogue_row<BN2, EPI>(epi, sp, taddr, m, n0, m < M, part * COLS, (part + 1) * COLS, nullptr, rope_s);
       }
       ptx::tc_fence_before();
       __syncwarp();
