@@ -130,9 +130,12 @@ __device__ unsigned long long g_attn_phase[8 * 8];  // [warp][phase] cycle sums 
 #define PH(k) do { const unsigned now_ = clock(); ph_acc[k] += now_ - ph_t; ph_t = now_; } while (0)
 #define PH_FLUSH() do { if (lane == 0 && blockIdx.x == 0) for (int k_ = 0; k_ < 6; ++k_) g_attn_phase[warp * 8 + k_] = ph_acc[k_]; } while (0)
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ unsigned long long g_attn_tl[8 * 8];   // timeline of CTA 0, softmax warp 0: [item ordinal][0: start, 1..6: after block 0..5, 7: rows stored]
+#define TL(n_, k_) do { if (lane == 0 && warp == 0 && blockIdx.x == 0 && (n_) < 8 && (k_) < 8) g_attn_tl[(n_) * 8 + (k_)] = gtime(); } while (0)
 #define MS_ENTRY const unsigned long long ms_t0 = gtime()
 #define MS(k) do { if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) g_attn_phase[48 + (k)] = gtime() - ms_t0; } while (0)
 #else
+#define TL(n_, k_) do {} while (0)
 #define MS_ENTRY do {} while (0)
 #define MS(k) do {} while (0)
 #define PH_DECL do {} while (0)
@@ -425,8 +428,10 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int r = quarter * 32 + lane;         // query row within the tile == TMEM lane
     uint32_t g0 = 0;                           // blocks of the items before the current one (barrier parities run across items)
-    for (int item = item0; item < ws.n_items; item += item_step) {
+    int n_ord = 0;
+    for (int item = item0; item < ws.n_items; item += item_step, ++n_ord) {
     const Item it = decode(item);
+    TL(n_ord, 0);
     const int n_kv = it.n_kv, Lkp = it.Lkp, q0 = it.q0;
     if (t < it.n_tiles) {
       const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -617,6 +622,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->p_ready[t][g & 1]);
         PH(4);
+        TL(n_ord, 1 + i);
       }
       PH_FLUSH();
       MS(2);  // key loop done
@@ -657,6 +663,7 @@ attention_fwd_tcgen05(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         __syncwarp();
       }
     }
+    TL(n_ord, 7);
     g0 += (uint32_t)n_kv;
     }  // items of this CTA
   }
@@ -779,6 +786,10 @@ int attention_fwd(const AttentionArgs& a, cudaStream_t st) {
 }  // namespace lsvs
 
 #ifdef LSVS_ATTN_PHASES
+extern "C" int lsvs_debug_attn_timeline(unsigned long long* out64) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out64, lsvs::g_attn_tl, 64 * sizeof(unsigned long long));
+}
 extern "C" int lsvs_debug_attn_phases(unsigned long long* out64) {
   cudaDeviceSynchronize();
   return (int)cudaMemcpyFromSymbol(out64, lsvs::g_attn_phase, 64 * sizeof(unsigned long long));
