@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <vector>
 
 #include "attention.h"
 #include "host_common.h"
@@ -687,7 +688,9 @@ float* split_workspace(cudaStream_t st, size_t bytes) {
   if (b.cap >= bytes) return b.p;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
-  if (b.p) { cudaStreamSynchronize(st); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+  // a buffer that is outgrown is retired, not freed: a CUDA graph captured earlier on this stream may hold its address
+  static std::vector<float*> retired;
+  if (b.p) { retired.push_back(b.p); b.p = nullptr; b.cap = 0; }
   const size_t cap = bytes + bytes / 4;
   if (cudaMalloc(&b.p, cap) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return nullptr; }
   b.cap = cap;
