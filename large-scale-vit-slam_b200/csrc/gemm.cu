@@ -888,6 +888,224 @@ int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K,
   return LSVS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Few rows (M <= 128; the camera-head trunk runs on the S frames of a chunk: 32 rows, D = 2048): the GEMM is WEIGHT STREAMING —
+// 2 bytes of W per 2 M flops — and bounded by HBM, not by the tensor cores (UPSTREAM CameraHead trunk: 4 iterations x 4 blocks
+// = 1.6 GB of bf16 weights per chunk).  The operands are swapped so that W is the 128-row side of the MMA,
+//     D^T[128 weight rows, MT rows of A] (+)= W_tile[128, 64] . A_tile[MT, 64]^T          (MT = 32 / 64 / 128 >= M)
+// so every byte staged for the tensor core is payload (the 128 x 64 tiles of the kernel above pad the A side to 128 rows — two
+// thirds of the shared-memory fill are zeros — and N / 64 tiles keep only 32..128 SMs loading).  Work item = (128 weight rows,
+// K slice); the slices of one tile form a thread-block CLUSTER (up to 16 CTAs, two CTAs per SM): each CTA streams its K range
+// through a 5-stage TMA ring, leaves its fp32 partial tile in its own shared memory, and after one cluster barrier CTA r sums
+// rows [r, r+1) * MT / slices of all partials over distributed shared memory IN SLICE ORDER (bit-reproducible: no atomics, no
+// workspace) and runs the fused epilogue on them; the transposed tile makes those global stores coalesced (lanes = consecutive n).
+// The W loads of the first ring stages are issued BEFORE griddepcontrol.wait: weights never depend on the previous kernel.
+template <int MT>
+struct SmemFewRows {
+  static constexpr int STAGES = MT == 32 ? 5 : (MT == 64 ? 4 : 3);
+  static constexpr int W_BYTES = 128 * BK * 2;          // 16 KB of weights per k-block
+  static constexpr int X_BYTES = MT * BK * 2;
+  static constexpr int STAGE_BYTES = W_BYTES + X_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+  static_assert(STAGES * STAGE_BYTES >= MT * 128 * 4, "the partial tile reuses the ring");
+  static_assert(2 * TOTAL <= 232448, "two CTAs per SM");
+};
+
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t cta) {
+  float v;
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %1, %2;\n\tld.shared::cluster.f32 %0, [ra];\n\t}" : "=f"(v) : "r"(local_addr), "r"(cta) : "memory");
+  return v;
+}
+
+template <int MT, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 2)
+gemm_fewrows_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
+                     GemmEpilogue epi) {
+  using L = SmemFewRows<MT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + L::STAGES;
+  uint64_t* acc_bar = empty_bar + L::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x, slices = gridDim.x;   // cluster = the K slices of one tile: cluster rank == blockIdx.x
+  const int n0 = blockIdx.y * 128;
+  const int n_kb_all = K / BK;
+  const int kb0 = (int)((long long)slice * n_kb_all / slices);
+  const int n_kb = (int)((long long)(slice + 1) * n_kb_all / slices) - kb0;   // >= 1 (host: slices <= K / BK)
+  const int pre = n_kb < L::STAGES ? n_kb : L::STAGES;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmW);
+    ptx::prefetch_tmap(&tmX);
+#pragma unroll
+    for (int i = 0; i < L::STAGES; ++i) { ptx::mbar_init(full_bar + i, 1); ptx::mbar_init(empty_bar + i, 1); }
+    ptx::mbar_init(acc_bar, 1);
+    ptx::fence_mbar_init();
+    for (int i = 0; i < pre; ++i) {   // weights first: they do not depend on the predecessor in the stream
+      ptx::mbar_expect_tx(full_bar + i, L::STAGE_BYTES);
+      ptx::tma_load_2d(smem + i * L::STAGE_BYTES, &tmW, full_bar + i, (kb0 + i) * BK, n0);
+    }
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, MT);
+    ptx::tmem_relinquish();
+  }
+  pdl_launch_dependents();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0)
+      for (int i = 0; i < pre; ++i) ptx::tma_load_2d(smem + i * L::STAGE_BYTES + L::W_BYTES, &tmX, full_bar + i, (kb0 + i) * BK, 0);
+    for (int i = pre; i < n_kb; ++i) {
+      const int stage = i % L::STAGES;
+      ptx::mbar_wait(empty_bar + stage, ((i / L::STAGES) & 1) ^ 1);
+      if (lane == 0) {
+        uint8_t* s = smem + stage * L::STAGE_BYTES;
+        ptx::mbar_expect_tx(full_bar + stage, L::STAGE_BYTES);
+        ptx::tma_load_2d(s, &tmW, full_bar + stage, (kb0 + i) * BK, n0);
+        ptx::tma_load_2d(s + L::W_BYTES, &tmX, full_bar + stage, (kb0 + i) * BK, 0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, MT, 0, 0);
+    for (int i = 0; i < n_kb; ++i) {
+      const int stage = i % L::STAGES;
+      ptx::mbar_wait(full_bar + stage, (i / L::STAGES) & 1);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t s = ptx::smem_u32(smem + stage * L::STAGE_BYTES);
+        const uint64_t adesc = ptx::umma_desc_sw128(s, 16, 1024);
+        const uint64_t bdesc = ptx::umma_desc_sw128(s + L::W_BYTES, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) ptx::umma_bf16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
+        ptx::umma_commit(empty_bar + stage);
+        if (i == n_kb - 1) ptx::umma_commit(acc_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------ partial tile -> shared memory (ring storage: every MMA has retired)
+    const int quarter = warp & 3;
+    ptx::mbar_wait(acc_bar, 0);
+    ptx::tc_fence_after();
+    float* part = reinterpret_cast<float*>(smem) + quarter * 32 + lane;   // [MT][128]: lanes = consecutive weight rows
+#pragma unroll
+    for (int c = 0; c < MT; c += 32) {
+      float v[32];
+      load_acc<32>(tmem_base + ((uint32_t)(quarter * 32) << 16) + c, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) part[(c + j) * 128] = v[j];
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();   // every slice's partial is in its CTA's shared memory
+  if (warp >= 2) {
+    // ------------------------------------------------------------ slice-ordered sum over the cluster + fused epilogue
+    const int nl = (warp & 3) * 32 + lane, n = n0 + nl;
+    const int m_begin = (int)((long long)slice * MT / slices), m_end_t = (int)((long long)(slice + 1) * MT / slices);
+    const int m_end = m_end_t < M ? m_end_t : M;
+    const float bias = epi.bias ? __ldg(epi.bias + n) : 0.f;
+    const float gamma = (EPI == EPI_RESID_F32 && epi.gamma) ? __ldg(epi.gamma + n) : 1.f;
+    const uint32_t base = ptx::smem_u32(reinterpret_cast<float*>(smem) + nl);
+    constexpr int MAXS = 16, RG = 4;   // four rows at a time: up to 64 distributed-shared-memory loads in flight per thread
+    for (int m = m_begin; m < m_end; m += RG) {
+      float rv[RG], p[RG][MAXS];
+      if constexpr (EPI == EPI_RESID_F32) {
+#pragma unroll
+        for (int j = 0; j < RG; ++j) rv[j] = (m + j < m_end) ? epi.resid[(size_t)(m + j) * epi.ldr + n] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < RG; ++j)
+#pragma unroll
+        for (int s = 0; s < MAXS; ++s) p[j][s] = (m + j < m_end && s < slices) ? ld_dsmem_f32(base + (uint32_t)(m + j) * 512u, (uint32_t)s) : 0.f;
+#pragma unroll
+      for (int j = 0; j < RG; ++j) {
+        if (m + j >= m_end) break;
+        float acc = p[j][0];
+#pragma unroll
+        for (int s = 1; s < MAXS; ++s) acc += p[j][s];   // slice order; absent slices add +0
+        float x = acc + bias;
+        if constexpr (EPI == EPI_BIAS_GELU_BF16) x = gelu_erf(x);
+        const size_t row = (size_t)(m + j);
+        if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16) {
+          reinterpret_cast<__nv_bfloat16*>(epi.out)[row * epi.ldo + n] = __float2bfloat16_rn(x);
+        } else if constexpr (EPI == EPI_BIAS_F32) {
+          reinterpret_cast<float*>(epi.out)[row * epi.ldo + n] = x;
+        } else {
+          const float y = rv[j] + gamma * x;
+          epi.resid[row * epi.ldr + n] = y;
+          if (epi.out2) epi.out2[row * epi.ld2 + n] = y;
+        }
+      }
+    }
+  }
+  ptx::cluster_sync();   // no CTA leaves while a peer still reads its partial
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, MT);
+}
+
+template <int MT, int EPI>
+int launch_fewrows(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmEpilogue& e, cudaStream_t st) {
+  using L = SmemFewRows<MT>;
+  const CUtensorMap* tmW = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, 128);
+  const CUtensorMap* tmX = tmap_2d_bf16(A, K, M, (uint64_t)lda * 2, BK, MT);
+  if (!tmW || !tmX) return LSVS_ECUDA;
+  auto kern = gemm_fewrows_tcgen05<MT, EPI>;
+  // K slices (= cluster size, a power of two <= 16; 16 is a non-portable cluster size, used only if the occupancy query accepts it):
+  // as many as keep every CTA resident at two per SM with at least 4 k-blocks (64 KB of W) each
+  static int max_slices = 0;
+  if (!max_slices) {
+    LSVS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    const char* v = getenv("LSVS_GEMM_FEWROWS_SLICES");
+    int want = v ? atoi(v) : 8;   // measured: clusters of 16 run the K = 8192 shape at 17.3 us instead of 11.1 (few clusters of that size are co-resident)
+    want = want < 1 ? 1 : (want > 16 ? 16 : want);
+    if (want > 8) {
+      int n_clusters = 0;
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(16, 1); q.blockDim = dim3(NUM_THREADS); q.dynamicSmemBytes = L::TOTAL;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 16; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess ||
+          cudaOccupancyMaxActiveClusters(&n_clusters, kern, &q) != cudaSuccess || n_clusters < 1) {
+        cudaGetLastError();
+        want = 8;
+      }
+    }
+    max_slices = want;
+  }
+  const int tiles = N / 128, n_kb = K / BK, slots = 2 * num_sms();
+  int slices = 1;
+  while (2 * slices <= max_slices && tiles * 2 * slices <= slots && n_kb / (2 * slices) >= 4) slices *= 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)slices, (unsigned)tiles); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = (unsigned)slices; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 2;
+  LSVS_CUDA(cudaLaunchKernelEx(&cfg, kern, *tmW, *tmX, M, N, K, e));
+  LSVS_LAUNCH_CHECK();
+  return LSVS_OK;
+}
+
+template <int EPI>
+int launch_fewrows_mt(const void* A, int lda, const void* W, int ldw, int M, int N, int K, const GemmEpilogue& e, cudaStream_t st) {
+  if (M <= 32) return launch_fewrows<32, EPI>(A, lda, W, ldw, M, N, K, e, st);
+  if (M <= 64) return launch_fewrows<64, EPI>(A, lda, W, ldw, M, N, K, e, st);
+  return launch_fewrows<128, EPI>(A, lda, W, ldw, M, N, K, e, st);
+}
+
 template <int BN, int EPI>
 int launch(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K, const GemmEpilogue& e, cudaStream_t st) {
   using L = SmemLayout<BN>;
@@ -937,6 +1155,18 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
     const long long rounds_pair = (tiles_pair + sms / 2 - 1) / (sms / 2), rounds_128 = (tiles_128 + sms - 1) / sms;
     if ((double)rounds_128 * 0.5 * penalty < (double)rounds_pair) { pair = false; wide = false; }
   }
+  // few rows (camera-head trunk, M = frames of one chunk): weight streaming with swapped operands, K slices over a cluster
+  static const bool fewrows = [] { const char* v = getenv("LSVS_GEMM_FEWROWS"); return !(v && v[0] == '0'); }();
+  if (fewrows && M <= BM && N % 128 == 0 && (epi_kind == EPI_BIAS_BF16 || epi_kind == EPI_BIAS_GELU_BF16 || epi_kind == EPI_BIAS_F32 || epi_kind == EPI_RESID_F32)) {
+    LSVS_CHECK_ARG(epi_kind == EPI_RESID_F32 ? (e.resid != nullptr && e.ldr >= N) : (e.out != nullptr && e.ldo >= N), "gemm: missing output / residual");
+    ProfScope prof(PROF_GEMM, st, 2.0 * M * (double)N * K, 0);
+    switch (epi_kind) {
+      case EPI_BIAS_BF16: return launch_fewrows_mt<EPI_BIAS_BF16>(A, lda, W, ldw, M, N, K, e, st);
+      case EPI_BIAS_GELU_BF16: return launch_fewrows_mt<EPI_BIAS_GELU_BF16>(A, lda, W, ldw, M, N, K, e, st);
+      case EPI_BIAS_F32: return launch_fewrows_mt<EPI_BIAS_F32>(A, lda, W, ldw, M, N, K, e, st);
+      default: return launch_fewrows_mt<EPI_RESID_F32>(A, lda, W, ldw, M, N, K, e, st);
+    }
+  }
   const int BN = wide ? 256 : 128;
   const CUtensorMap* tmA = tmap_2d_bf16(A, a_cols, M, (uint64_t)lda * 2, BK, BM);
   const CUtensorMap* tmB = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, pair ? BN2 / 2 : BN);
@@ -953,7 +1183,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   case KIND:                                                                            \
     if (pair) return launch2<KIND>(tmA, tmB, M, N, K, e, st);                           \
     return wide ? launch<256, KIND>(tmA, tmB, M, N, K, e, st) : launch<128, KIND>(tmA, tmB, M, N, K, e, st);
-  // few rows (camera-head trunk, M = frames of one chunk): the job is weight streaming, so spread N over many CTAs
+  // few rows, N / 64 tiles (the round-2 path; LSVS_GEMM_FEWROWS=0 for A/B runs against gemm_fewrows_tcgen05)
   if (M <= BM && N % 64 == 0 && N / 64 >= 16) {
     const CUtensorMap* tmB64 = tmap_2d_bf16(W, K, N, (uint64_t)ldw * 2, BK, 64);
     if (!tmB64) return LSVS_ECUDA;

@@ -150,3 +150,31 @@ def test_gemm_residual_tma_reduce_and_split_k(M, N, K):
     assert rel_l2(r_dev.cpu().double(), ref) < 1e-5
     # the update itself (not hidden behind the residual's magnitude)
     assert rel_l2(r_dev.cpu().double() - resid.double(), ref - resid.double()) < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 2048, 2048), (32, 6144, 2048), (32, 8192, 2048), (32, 2048, 8192), (5, 2048, 2048), (1, 1024, 6144),
+                                   (64, 1024, 512), (100, 256, 1024), (128, 384, 192), (33, 128, 64)])
+def test_gemm_few_rows_weight_streaming(M, N, K):
+    """M <= 128 (camera-head trunk: the S frames of a chunk x 2048 channels): gemm_fewrows_tcgen05 — swapped operands, the K slices
+    of a 128-row weight tile summed over a thread-block cluster in slice order.  Every epilogue of that path vs the fp32 oracle,
+    rows past M untouched, and two launches bit-identical (no atomics)."""
+    from lsvs_b200 import ops
+    a, w, bias = mk(M, N, K, seed=M + N)
+    lin = a.float() @ w.float().T + bias
+    ad, wd, bd = a.cuda(), w.cuda(), bias.cuda()
+    guard = torch.full((M + 3, N), 7.0, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(ad, wd, ops.EPI_BIAS_BF16, bias=bd, out=guard[:M])
+    assert rel_l2(guard[:M].cpu(), lin) < 4e-3 and float((guard[M:].float() - 7.0).abs().max()) == 0.0
+    o2 = ops.gemm(ad, wd, ops.EPI_BIAS_BF16, bias=bd)
+    assert torch.equal(o2, guard[:M])
+    out = ops.gemm(ad, wd, ops.EPI_BIAS_F32, bias=bd).cpu()
+    assert rel_l2(out, lin) < 1e-4
+    out = ops.gemm(ad, wd, ops.EPI_BIAS_GELU_BF16, bias=bd).cpu()
+    assert rel_l2(out, torch.nn.functional.gelu(lin)) < 4e-3
+    resid, gamma = rnd(9, M, N), 0.1 * (1 + 0.1 * rnd(10, N))
+    r1, r2 = resid.cuda(), resid.cuda()
+    tap = torch.zeros(M, 2 * N, device="cuda")
+    ops.gemm(ad, wd, ops.EPI_RESID_F32, bias=bd, gamma=gamma.cuda(), resid=r1, out2=tap[:, N:])
+    ops.gemm(ad, wd, ops.EPI_RESID_F32, bias=bd, gamma=gamma.cuda(), resid=r2)
+    assert rel_l2(r1.cpu(), resid + gamma * lin) < 1e-4
+    assert torch.equal(r1, r2) and torch.equal(tap[:, N:], r1) and float(tap[:, :N].abs().max()) == 0.0
