@@ -758,102 +758,6 @@ int launch(const AttentionArgs& a, cudaStream_t st) {
   return LSVS_OK;
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Few queries against few keys: the camera-head trunk (UPSTREAM CameraHead: one sequence of the chunk's S = 32 frame tokens, 16
-// heads x 128) and the alignment head's temporal cross attention (cross_attention.py:65-73: 413 groups x 8 heads, 32 queries
-// against T = 9 keys).  On the 128-row tcgen05 tile those are almost empty tiles behind a ~17 us (one item) / ~45 us latency
-// chain.  Here one WARP owns one (batch, head, query): the head dimension lies across the lanes (2 or 4 elements each), scores
-// are warp-reduced four keys at a time, softmax and the P V sum stay in fp32 registers.  Chosen by work (queries x keys), see
-// attention_fwd.
-template <int E>
-__device__ __forceinline__ void ld_bf16_vec(const __nv_bfloat16* p, float* f) {
-  if constexpr (E == 4) {
-    const uint2 u = *reinterpret_cast<const uint2*>(p);
-    f[0] = ptx::bf16_lo(u.x); f[1] = ptx::bf16_hi(u.x); f[2] = ptx::bf16_lo(u.y); f[3] = ptx::bf16_hi(u.y);
-  } else {
-    const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
-    f[0] = ptx::bf16_lo(u); f[1] = ptx::bf16_hi(u);
-  }
-}
-
-template <int HD>
-__global__ void __launch_bounds__(256) attention_warp_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ Kp,
-                                                             const __nv_bfloat16* __restrict__ V, __nv_bfloat16* __restrict__ O, int ldq,
-                                                             int ldk, int ldv, int ldo, int heads, int Lq, int Lk, float scale_log2e,
-                                                             long long n_queries) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);   // consecutive warps: queries of one (batch, head) -> its K / V stay in L1
-  if (w >= n_queries) return;
-  const int i = (int)(w % Lq);
-  const long long bh = w / Lq;
-  const int head = (int)(bh % heads);
-  const long long batch = bh / heads;
-  constexpr int E = HD / 32;
-  const int col = head * HD + lane * E;
-  float qf[E], acc[E];
-  ld_bf16_vec<E>(Q + (batch * Lq + i) * ldq + col, qf);
-#pragma unroll
-  for (int e = 0; e < E; ++e) { qf[e] *= scale_log2e; acc[e] = 0.f; }
-  const __nv_bfloat16* kb = Kp + batch * Lk * ldk + col;
-  const __nv_bfloat16* vb = V + batch * Lk * ldv + col;
-  float m = -INFINITY, l = 0.f;
-  for (int j0 = 0; j0 < Lk; j0 += 4) {
-    float d[4], vf[4][E];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      d[t] = 0.f;
-      if (j0 + t < Lk) {
-        float kf[E];
-        ld_bf16_vec<E>(kb + (size_t)(j0 + t) * ldk, kf);
-        ld_bf16_vec<E>(vb + (size_t)(j0 + t) * ldv, vf[t]);
-#pragma unroll
-        for (int e = 0; e < E; ++e) d[t] = fmaf(qf[e], kf[e], d[t]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < E; ++e) vf[t][e] = 0.f;
-      }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-      for (int t = 0; t < 4; ++t) d[t] += __shfl_xor_sync(0xffffffffu, d[t], off);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) if (j0 + t >= Lk) d[t] = -INFINITY;
-    const float m_new = fmaxf(fmaxf(m, fmaxf(d[0], d[1])), fmaxf(d[2], d[3]));   // finite: key j0 exists
-    const float corr = ex2(m - m_new);
-    l *= corr;
-#pragma unroll
-    for (int e = 0; e < E; ++e) acc[e] *= corr;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float pt = ex2(d[t] - m_new);
-      l += pt;
-#pragma unroll
-      for (int e = 0; e < E; ++e) acc[e] = fmaf(pt, vf[t][e], acc[e]);
-    }
-    m = m_new;
-  }
-  const float inv = 1.0f / l;
-  __nv_bfloat16* dst = O + (batch * Lq + i) * ldo + col;
-  if constexpr (E == 4) {
-    *reinterpret_cast<uint2*>(dst) = make_uint2(ptx::pack_bf16(acc[0] * inv, acc[1] * inv), ptx::pack_bf16(acc[2] * inv, acc[3] * inv));
-  } else {
-    *reinterpret_cast<uint32_t*>(dst) = ptx::pack_bf16(acc[0] * inv, acc[1] * inv);
-  }
-}
-
-template <int HD>
-int launch_warp(const AttentionArgs& a, cudaStream_t st) {
-  const long long nq = (long long)a.batches * a.heads * a.Lq;
-  LSVS_CUDA(launch_pdl(attention_warp_kernel<HD>, dim3((unsigned)((nq + 7) / 8)), dim3(256), 0, st, reinterpret_cast<const __nv_bfloat16*>(a.q),
-                       reinterpret_cast<const __nv_bfloat16*>(a.k), reinterpret_cast<const __nv_bfloat16*>(a.v), reinterpret_cast<__nv_bfloat16*>(a.o),
-                       a.ldq, a.ldk, a.ldv, a.ldo, a.heads, a.Lq, a.Lk, a.scale * 1.4426950408889634f, nq));
-  LSVS_LAUNCH_CHECK();
-  return LSVS_OK;
-}
-
 }  // namespace
 
 int attention_fwd(const AttentionArgs& a, cudaStream_t st) {
@@ -864,13 +768,6 @@ int attention_fwd(const AttentionArgs& a, cudaStream_t st) {
   LSVS_CHECK_ARG(a.ldq >= D && a.ldk >= D && a.ldv >= D && a.ldo >= D, "attention: leading dimension smaller than heads*head_dim");
   LSVS_CHECK_ARG(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention: leading dimensions must be multiples of 8");
   ProfScope prof(a.Lk >= 2048 ? PROF_ATTENTION_GLOBAL : PROF_ATTENTION, st, 4.0 * a.batches * (double)a.heads * a.Lq * (double)a.Lk * a.head_dim, 0);
-  // Few queries x few keys (camera-head trunk, temporal cross attention): one warp per query on the CUDA cores.  Work bound in
-  // queries x keys (LSVS_ATTN_WARP_MAX_WORK; 0 = never): the warp kernel costs ~2.3 ns per 1000 of them, the tcgen05 kernel 17-50 us
-  // at these shapes whatever the key count (tools/ub_attn_small.py).
-  static const long long warp_max_work = [] { const char* e = getenv("LSVS_ATTN_WARP_MAX_WORK"); return e ? atoll(e) : 1600000ll; }();
-  if (a.Lk <= 64 && (long long)a.batches * a.heads * a.Lq * a.Lk <= warp_max_work && ((uintptr_t)a.q % 8 == 0) && ((uintptr_t)a.k % 8 == 0) &&
-      ((uintptr_t)a.v % 8 == 0) && ((uintptr_t)a.o % 8 == 0))
-    return a.head_dim == 128 ? launch_warp<128>(a, st) : launch_warp<64>(a, st);
   // One query tile per CTA and two CTAs per SM at every sequence length.  Short sequences: the prologue / epilogue of one CTA
   // hides behind the other.  Long sequences (measured, profiles/r2b_attention_experiments.md): two independent CTAs beat one
   // CTA whose two tiles share each K/V block — 746-752 vs 695-700 TFLOP/s at 13 184 tokens, 824 vs 732 at 21 984 — although

@@ -3,16 +3,9 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 250 python -m pytest tests/test_attention_gpu.py tests/test_gemm_gpu.py -x -q -m gpu 2>&1 | tail -3
-timeout 60 python tools/ub_attn_small.py > gpurun_out/r2d_ub_attn_small_warp.log 2>&1
-LSVS_ATTN_WARP_MAX_WORK=0 timeout 60 python tools/ub_attn_small.py > gpurun_out/r2d_ub_attn_small_tcgen05.log 2>&1
-cat gpurun_out/r2d_ub_attn_small_warp.log gpurun_out/r2d_ub_attn_small_tcgen05.log
 timeout 60 python tools/ub_gemm_fewrows.py > gpurun_out/r2d_ub_fewrows_new.log 2>&1; cat gpurun_out/r2d_ub_fewrows_new.log
 B="python bench.py --no-cpu-baseline --no-incumbent --sequence-frames 0"
-timeout 150 $B > gpurun_out/r2d_bench_ab_new_3.json 2> gpurun_out/r2d_bench_ab_new_3.err
-LSVS_ATTN_WARP_MAX_WORK=0 timeout 150 $B > gpurun_out/r2d_bench_ab_nowarp_3.json 2>/dev/null
-LSVS_ATTN_WARP_MAX_WORK=0 LSVS_GEMM_FEWROWS=0 timeout 150 $B > gpurun_out/r2d_bench_ab_r2c_3.json 2>/dev/null
 timeout 150 $B --workload short > gpurun_out/r2d_bench_short_new2.json 2>/dev/null
-LSVS_ATTN_WARP_MAX_WORK=0 LSVS_GEMM_FEWROWS=0 timeout 150 $B --workload short > gpurun_out/r2d_bench_short_r2c.json 2>/dev/null
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2d_launches_short.csv $B --workload short --steps 1 --warmup 1 > gpurun_out/r2d_ncu_short.log 2>&1
 python tools/summarize_launches.py gpurun_out/r2d_launches_short.csv > gpurun_out/r2d_launches_short_summary.txt 2>&1; head -40 gpurun_out/r2d_launches_short_summary.txt
 python - <<PY

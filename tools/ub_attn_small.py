@@ -1,6 +1,5 @@
 """Short-sequence attention shapes of the alignment / camera heads, 50 back-to-back launches between two events (a single
-launch is shorter than the host-side launch path), replayed from one CUDA graph.  LSVS_ATTN_WARP_MAX_WORK=0 routes them to the
-tcgen05 kernel (the product default sends queries x keys <= 1.6 M to the warp-per-query kernel)."""
+launch is shorter than the host-side launch path).  LSVS_ATTN_WARP=0 routes them to the tcgen05 kernel."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "large-scale-vit-slam_b200")]
@@ -15,16 +14,10 @@ for (name, B, H, hd, Lq, Lk) in [("head temporal 32x9", 413, 8, 128, 32, 9), ("h
     fn = lambda: ops.attention(q, kv[:, :D], kv[:, D:], B, H, hd, Lq, Lk, out=out)
     for _ in range(5): fn()
     torch.cuda.synchronize()
-    g, st = torch.cuda.CUDAGraph(), torch.cuda.Stream()
-    with torch.cuda.stream(st):
-        fn(); torch.cuda.synchronize()
-        with torch.cuda.graph(g, stream=st):
-            for _ in range(50): fn()
-    g.replay(); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(4): g.replay()
+    for _ in range(50): fn()
     b.record(); torch.cuda.synchronize()
-    us = a.elapsed_time(b) * 1000 / 200
+    us = a.elapsed_time(b) * 1000 / 50
     mb = (q.numel() + kv.numel() + out.numel()) * 2 / 1e6
-    print(json.dumps({"attn": name, "warp_max_work": os.environ.get("LSVS_ATTN_WARP_MAX_WORK", "default"), "us": round(us, 2), "MB": round(mb, 1), "GBps": round(mb / us * 1e3, 0)}))
+    print(json.dumps({"attn": name, "warp_path": os.environ.get("LSVS_ATTN_WARP", "1"), "us": round(us, 2), "MB": round(mb, 1), "GBps": round(mb / us * 1e3, 0)}))
