@@ -1147,8 +1147,8 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   bool wide = bn256;                                     // single-CTA kernel: 128x256 tiles, else 128x128
   if (pair && g_gemm_mode == 0 && !(epi_kind == EPI_RESID_F32 && e.out2 == nullptr)) {  // (residual GEMMs: pair kernel + split-K instead)
     // few rows (short chunks: S = 4..8 frames): the 256x256 pair tiles leave SMs idle or waste a whole round; 128x128 single-CTA
-    // tiles do a quarter of the work on half the SMs at ~0.8x the per-tile efficiency
-    static const double penalty = [] { const char* v = getenv("LSVS_GEMM_NARROW_PENALTY"); return v ? atof(v) : 1.25; }();
+    // tiles do a quarter of the work on half the SMs at ~0.6x the per-tile efficiency
+    static const double penalty = [] { const char* v = getenv("LSVS_GEMM_NARROW_PENALTY"); return v ? atof(v) : 1.6; }();   // 1.25 / 1.6 / 2.0 measured at 4- and 5-frame chunks: 10.33 / 9.97 / 10.14 and 10.85 / 10.49 / 10.65 ms (profiles/r2d_narrow_penalty.log)
     const int sms = num_sms();
     const long long tiles_pair = (long long)((M + 2 * BM - 1) / (2 * BM)) * (N / BN2);
     const long long tiles_128 = (long long)((M + BM - 1) / BM) * (N / 128);
