@@ -852,6 +852,7 @@ extern "C" int lsvs_dpt_head_forward(lsvs_engine* h, const char* prefix, const f
   Engine& e = *reinterpret_cast<Engine*>(h);
   cudaStream_t st = (cudaStream_t)stream;
   LSVS_CHECK_ARG(prefix && taps && pred && conf && frames > 0, "dpt_head_forward: bad arguments");
+  FewRowsKernel no_fewrows(false);   // per-frame results must not depend on the frames per pass (coarse levels cross M = 128)
   LSVS_CHECK_ARG(output_dim >= 2 && output_dim <= 4 && (activation == 0 || activation == 1), "dpt_head_forward: output_dim 2..4, activation 0 (exp) or 1 (inv_log)");
   const int ph = H / 14, pw = W / 14, Pp = ph * pw, C = 2048;
   LSVS_CHECK_ARG(ph > 0 && pw > 0 && P == Pp + 5, "dpt_head_forward: token count %d does not match the %dx%d patch grid (+5)", P, ph, pw);

@@ -38,6 +38,9 @@ static bool deterministic() {
   static const bool on = [] { const char* v = getenv("LSVS_DETERMINISTIC"); return v && atoi(v) != 0; }();
   return on;
 }
+static thread_local bool g_fewrows_kernel = true;
+FewRowsKernel::FewRowsKernel(bool on) : prev(g_fewrows_kernel) { g_fewrows_kernel = on; }
+FewRowsKernel::~FewRowsKernel() { g_fewrows_kernel = prev; }
 namespace {
 
 constexpr int BM = 128;
@@ -1157,7 +1160,7 @@ int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int 
   }
   // few rows (camera-head trunk, M = frames of one chunk): weight streaming with swapped operands, K slices over a cluster
   static const bool fewrows = [] { const char* v = getenv("LSVS_GEMM_FEWROWS"); return !(v && v[0] == '0'); }();
-  if (fewrows && M <= BM && N % 128 == 0 && (epi_kind == EPI_BIAS_BF16 || epi_kind == EPI_BIAS_GELU_BF16 || epi_kind == EPI_BIAS_F32 || epi_kind == EPI_RESID_F32)) {
+  if (fewrows && g_fewrows_kernel && M <= BM && N % 128 == 0 && (epi_kind == EPI_BIAS_BF16 || epi_kind == EPI_BIAS_GELU_BF16 || epi_kind == EPI_BIAS_F32 || epi_kind == EPI_RESID_F32)) {
     LSVS_CHECK_ARG(epi_kind == EPI_RESID_F32 ? (e.resid != nullptr && e.ldr >= N) : (e.out != nullptr && e.ldo >= N), "gemm: missing output / residual");
     ProfScope prof(PROF_GEMM, st, 2.0 * M * (double)N * K, 0);
     switch (epi_kind) {

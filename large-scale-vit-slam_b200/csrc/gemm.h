@@ -38,6 +38,15 @@ struct GemmEpilogue {
   const void* res1 = nullptr; const void* res2 = nullptr;   // optional bf16 residual inputs, same layout / stride as out
 };
 
+// The few-row kernel (M <= 128, gemm_fewrows_tcgen05) slices K over a cluster: bit-reproducible, but a different summation order
+// than the other kernels.  A caller whose results must not depend on WHICH kernel its row count selects (the DPT heads: a pass over
+// 1 or 8 frames crosses M = 128 on the coarse levels) switches that kernel off for its scope; the default is on.
+struct FewRowsKernel {
+  bool prev;
+  explicit FewRowsKernel(bool on);
+  ~FewRowsKernel();
+};
+
 int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epi_kind, const GemmEpilogue& e,
               cudaStream_t st);
 
