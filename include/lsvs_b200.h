@@ -90,7 +90,9 @@ int lsvs_gemm_bf16(const lsvs_bf16* A, int lda, const lsvs_bf16* W, int ldw, int
                    const lsvs_gemm_epilogue* epilogue, void* stream);
 /* Determinism: results are bit-reproducible from run to run except for the residual GEMMs (LSVS_EPI_RESID_F32) of SHORT chunks
  * (fewer than 37 output tiles, i.e. about 4-8 frames of 518x154), where K is sliced over idle CTA pairs and the slices are added
- * into the fp32 residual by L2 atomics in arrival order.  LSVS_DETERMINISTIC=1 in the environment disables the slicing. */
+ * into the fp32 residual by L2 atomics in arrival order.  LSVS_DETERMINISTIC=1 in the environment disables the slicing.
+ * M <= 128 rows (UPSTREAM CameraHead trunk on the S frame tokens of a chunk): a weight-streaming kernel with swapped operands
+ * whose K slices are summed in slice order over a thread-block cluster — bit-reproducible, HBM-bound (N*K*2 bytes per call). */
 /* cos/sin table used by the RoPE epilogues: tab[p][j] = (cos, sin)(p * base^(-2j/(2*n_freq))), p < n_pos.
  * (rope.py:46-58; fp32 angles)  `tab` holds n_pos*n_freq*2 floats. */
 int lsvs_rope_table(float* tab, int n_pos, int n_freq, float base, void* stream);
