@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) mean_row_norm_kernel(const float* __restr
 // first chunk: frame_init (B, NM*D) = frame_proj(tokens[:,0]); directional = (1-s)*mem + s*normalize(frame_init), s = sigmoid(alpha)
 //              effective = mem * mean_norm (the un-blended parameter)      (alignment_head.py:471-479)
 // later      : directional = memory_in; effective = memory_in * mean_norm    (:484-485)
-// One block per (batch, memory token); also copies the S token rows (block y == NM).
+// One block per (batch, memory token), plus one block per copied token row (block y >= NM).
 __global__ void __launch_bounds__(128) memory_prepare_kernel(const float* __restrict__ tokens, const float* __restrict__ mem_param,
                                                              const float* __restrict__ mem_in, const float* __restrict__ frame_init,
                                                              const float* __restrict__ alpha, const float* __restrict__ mean_norm,
@@ -275,8 +275,9 @@ __global__ void __launch_bounds__(128) memory_prepare_kernel(const float* __rest
   pdl_wait();  // programmatic dependent launch (host_common.h)
   __shared__ float red[4];
   const int b = blockIdx.x, j = blockIdx.y;
-  if (j == NM) {  // copy tokens
-    for (int i = threadIdx.x; i < S * D; i += blockDim.x) kv[((size_t)b * (S + NM)) * D + i] = tokens[(size_t)b * S * D + i];
+  if (j >= NM) {  // blocks NM .. NM + S - 1: one token row each (one block copying all S rows was a 59 us latency chain)
+    const int r = j - NM;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) kv[((size_t)b * (S + NM) + r) * D + i] = tokens[((size_t)b * S + r) * D + i];
     return;
   }
   const float mn = mean_norm[b];
@@ -450,7 +451,7 @@ int mean_row_norm(const float* x, int B, int S, int D, float* out, cudaStream_t 
 
 int memory_prepare(const float* tokens, const float* mem_param, const float* mem_in, const float* frame_init, const float* alpha,
                    const float* mean_norm, float* kv, float* directional, int B, int S, int NM, int D, cudaStream_t st) {
-  LSVS_CUDA(launch_pdl(memory_prepare_kernel, dim3(dim3(B, NM + 1)), dim3(128), 0, st, tokens, mem_param, mem_in, frame_init, alpha, mean_norm, kv, directional, S, NM, D));
+  LSVS_CUDA(launch_pdl(memory_prepare_kernel, dim3(dim3(B, NM + S)), dim3(128), 0, st, tokens, mem_param, mem_in, frame_init, alpha, mean_norm, kv, directional, S, NM, D));
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }
