@@ -784,6 +784,7 @@ extern "C" int lsvs_camera_head_forward(lsvs_engine* h, const float* tokens_last
   cudaStream_t st = (cudaStream_t)stream;
   LSVS_CHECK_ARG(e.finalized && e.cfg.with_camera_head, "camera_head_forward: engine has no camera head / not finalized");
   LSVS_CHECK_ARG(tokens_last && pose_enc && B > 0 && S > 0 && P > 0 && num_iterations > 0, "camera_head_forward: bad arguments");
+  ConstWeights const_w(true);   // every W below is an engine-owned weight: the few-row GEMMs prefetch it under their predecessor
   const int C = 2048, frames = B * S;
   TRY(ensure_workspace(e, 2 * (long long)frames + 256, 0));
   const size_t need_scratch = (size_t)frames * (size_t)(C * 8 + 3 * C + 3 * C + 4 * C + 4096) + (1 << 14);

@@ -38,6 +38,9 @@ static bool deterministic() {
   static const bool on = [] { const char* v = getenv("LSVS_DETERMINISTIC"); return v && atoi(v) != 0; }();
   return on;
 }
+static thread_local bool g_const_weights = false;
+ConstWeights::ConstWeights(bool on) : prev(g_const_weights) { g_const_weights = on; }
+ConstWeights::~ConstWeights() { g_const_weights = prev; }
 static thread_local bool g_fewrows_kernel = true;
 FewRowsKernel::FewRowsKernel(bool on) : prev(g_fewrows_kernel) { g_fewrows_kernel = on; }
 FewRowsKernel::~FewRowsKernel() { g_fewrows_kernel = prev; }
@@ -902,7 +905,9 @@ int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K,
 // through a 5-stage TMA ring, leaves its fp32 partial tile in its own shared memory, and after one cluster barrier CTA r sums
 // rows [r, r+1) * MT / slices of all partials over distributed shared memory IN SLICE ORDER (bit-reproducible: no atomics, no
 // workspace) and runs the fused epilogue on them; the transposed tile makes those global stores coalesced (lanes = consecutive n).
-// The W loads of the first ring stages are issued BEFORE griddepcontrol.wait: weights never depend on the previous kernel.
+// Inside a ConstWeights scope (the engine's forward passes: W are model weights packed at load time) the W loads of the first ring
+// stages are issued BEFORE griddepcontrol.wait; a caller of the bare C ABI may have produced W with the previous kernel, so there
+// they wait like every other load.
 template <int MT>
 struct SmemFewRows {
   static constexpr int STAGES = MT == 32 ? 5 : (MT == 64 ? 4 : 3);
@@ -924,7 +929,7 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t cta)
 template <int MT, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 gemm_fewrows_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
-                     GemmEpilogue epi) {
+                     GemmEpilogue epi, int w_is_constant) {
   using L = SmemFewRows<MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -947,9 +952,11 @@ gemm_fewrows_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_const
     for (int i = 0; i < L::STAGES; ++i) { ptx::mbar_init(full_bar + i, 1); ptx::mbar_init(empty_bar + i, 1); }
     ptx::mbar_init(acc_bar, 1);
     ptx::fence_mbar_init();
-    for (int i = 0; i < pre; ++i) {   // weights first: they do not depend on the predecessor in the stream
-      ptx::mbar_expect_tx(full_bar + i, L::STAGE_BYTES);
-      ptx::tma_load_2d(smem + i * L::STAGE_BYTES, &tmW, full_bar + i, (kb0 + i) * BK, n0);
+    if (w_is_constant) {
+      for (int i = 0; i < pre; ++i) {   // weights first: they do not depend on the predecessor in the stream
+        ptx::mbar_expect_tx(full_bar + i, L::STAGE_BYTES);
+        ptx::tma_load_2d(smem + i * L::STAGE_BYTES, &tmW, full_bar + i, (kb0 + i) * BK, n0);
+      }
     }
   }
   if (warp == 1) {
@@ -965,8 +972,16 @@ gemm_fewrows_tcgen05(const __grid_constant__ CUtensorMap tmW, const __grid_const
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0)
-      for (int i = 0; i < pre; ++i) ptx::tma_load_2d(smem + i * L::STAGE_BYTES + L::W_BYTES, &tmX, full_bar + i, (kb0 + i) * BK, 0);
+    if (lane == 0) {
+      for (int i = 0; i < pre; ++i) {
+        if (!w_is_constant) {
+          ptx::mbar_expect_tx(full_bar + i, L::STAGE_BYTES);
+          ptx::tma_load_2d(smem + i * L::STAGE_BYTES, &tmW, full_bar + i, (kb0 + i) * BK, n0);
+        }
+        ptx::tma_load_2d(smem + i * L::STAGE_BYTES + L::W_BYTES, &tmX, full_bar + i, (kb0 + i) * BK, 0);
+      }
+    }
+    __syncwarp();
     for (int i = pre; i < n_kb; ++i) {
       const int stage = i % L::STAGES;
       ptx::mbar_wait(empty_bar + stage, ((i / L::STAGES) & 1) ^ 1);
@@ -1097,7 +1112,7 @@ int launch_fewrows(const void* A, int lda, const void* W, int ldw, int M, int N,
   at[1].id = cudaLaunchAttributeClusterDimension;
   at[1].val.clusterDim.x = (unsigned)slices; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 2;
-  LSVS_CUDA(cudaLaunchKernelEx(&cfg, kern, *tmW, *tmX, M, N, K, e));
+  LSVS_CUDA(cudaLaunchKernelEx(&cfg, kern, *tmW, *tmX, M, N, K, e, g_const_weights ? 1 : 0));
   LSVS_LAUNCH_CHECK();
   return LSVS_OK;
 }

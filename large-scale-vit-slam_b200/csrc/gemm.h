@@ -47,6 +47,15 @@ struct FewRowsKernel {
   ~FewRowsKernel();
 };
 
+// Promise that the W operands of the GEMMs launched in this scope are constants (model weights packed at load time): the few-row
+// kernel then streams its first W tiles before griddepcontrol.wait, under the tail of the preceding kernel.  Off by default: through
+// the bare C ABI W may be the output of the previous kernel on the stream.
+struct ConstWeights {
+  bool prev;
+  explicit ConstWeights(bool on);
+  ~ConstWeights();
+};
+
 int gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int N, int K, int epi_kind, const GemmEpilogue& e,
               cudaStream_t st);
 
