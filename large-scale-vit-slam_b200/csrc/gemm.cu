@@ -626,6 +626,44 @@ __device__ __forceinline__ void epilogue_resid_tma(const GemmEpilogue& e, const 
   }
 }
 
+// The same update without shared memory (LSVS_GEMM_RESID_RED=1, A/B): the warp transposes its 32 x 32 accumulator block in registers
+// (5 butterfly stages of 16 shuffles) so that a lane owns one COLUMN, and issues one red.global.add.f32 per row — 128 contiguous
+// bytes per warp instruction, added in L2 like the TMA reduction, but the 2 x 128 KB per tile of staging traffic (st.shared + the
+// TMA engine's read) never touch the shared-memory pipe that the main loop saturates.
+__device__ __forceinline__ void epilogue_resid_red(const GemmEpilogue& e, uint32_t taddr, int m_base, int M, int n0, int c_begin, int c_end,
+                                                   bool with_bias = true) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; c += 32) {
+    float v[32];
+    __syncwarp();
+    load_acc<32>(taddr + c, v);
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if ((j & s) == 0) {
+          const float send = (lane & s) ? v[j] : v[j | s];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+          if (lane & s) v[j] = recv; else v[j | s] = recv;
+        }
+      }
+    }
+    // now v[j] = element (row j, column lane) of the block
+    const int n = n0 + c + lane;
+    const float g = e.gamma ? __ldg(e.gamma + n) : 1.f;
+    const float bb = (e.bias && with_bias) ? __ldg(e.bias + n) : 0.f;
+    float* dst = e.resid + (size_t)m_base * e.ldr + n;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (m_base + j < M) {
+        const float x = g * (v[j] + bb);
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (size_t)j * e.ldr), "f"(x) : "memory");
+      }
+    }
+  }
+}
+
 template <int EPI, int EW>  // EW epilogue warps per CTA (4 or 8)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -826,7 +864,9 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       ptx::tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN2;
-      if (L::TRANSPOSE && (use_tma_reduce & 1)) {
+      if (L::TRANSPOSE && (use_tma_reduce & 32)) {
+        epilogue_resid_red(epi, taddr, m0 + quarter * 32, M, n0, part * COLS, (part + 1) * COLS, slice == 0);
+      } else if (L::TRANSPOSE && (use_tma_reduce & 1)) {
         epilogue_resid_tma(epi, &tmR, smem + L::TILE_OFFSET + (warp - 2) * L::TILE_BUFS * L::TILE_BYTES, taddr, m0 + quarter * 32, n0, part * COLS, (part + 1) * COLS, slice == 0);
       } else if (L::TMA_BF16 && (use_tma_reduce & 4)) {
         const TmaOut to{&tmR, smem + L::TILE_OFFSET + (warp - 2) * L::TILE_BYTES, m0 + quarter * 32};
@@ -843,7 +883,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
-  if (((L::TRANSPOSE && (use_tma_reduce & 1)) || (L::TMA_BF16 && (use_tma_reduce & 4))) && warp >= 2 && lane == 0) ptx::tma_store_wait<0>();  // reductions issued by this lane are complete
+  if (((L::TRANSPOSE && (use_tma_reduce & 1) && !(use_tma_reduce & 32)) || (L::TMA_BF16 && (use_tma_reduce & 4))) && warp >= 2 && lane == 0) ptx::tma_store_wait<0>();  // reductions issued by this lane are complete
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();
@@ -886,6 +926,8 @@ int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K,
   // L2 reduction units are not what holds the residual epilogue back; the reduce-add stays the default.
   static const bool resid_loadstore = [] { const char* v = getenv("LSVS_GEMM_RESID_LOADSTORE"); return v && atoi(v) != 0; }();
   if ((use_red & 1) && splits == 1 && resid_loadstore) use_red |= 16;
+  static const bool resid_red = [] { const char* v = getenv("LSVS_GEMM_RESID_RED"); return v && atoi(v) != 0; }();
+  if ((use_red & 1) && !(use_red & 16) && resid_red) use_red |= 32;
   use_red |= splits << 8;
   const int items = tiles * splits;
   const int pairs = items < max_pairs ? items : max_pairs;
