@@ -926,6 +926,9 @@ int launch2(const CUtensorMap* tmA, const CUtensorMap* tmB, int M, int N, int K,
   // L2 reduction units are not what holds the residual epilogue back; the reduce-add stays the default.
   static const bool resid_loadstore = [] { const char* v = getenv("LSVS_GEMM_RESID_LOADSTORE"); return v && atoi(v) != 0; }();
   if ((use_red & 1) && splits == 1 && resid_loadstore) use_red |= 16;
+  // LSVS_GEMM_RESID_RED=1 (A/B runs): register transpose + red.global.add.f32, no shared memory (epilogue_resid_red).  Measured slower
+  // too (projection 35.3 vs 33.6 us, step 56.9 vs 56.1 ms): the K = 1024 residual GEMM is HBM-bound by the 54 MB fp32 residual stream
+  // (135 MB per launch once the stream has left L2), not by its epilogue.
   static const bool resid_red = [] { const char* v = getenv("LSVS_GEMM_RESID_RED"); return v && atoi(v) != 0; }();
   if ((use_red & 1) && !(use_red & 16) && resid_red) use_red |= 32;
   use_red |= splits << 8;
