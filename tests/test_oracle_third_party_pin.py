@@ -97,3 +97,34 @@ def test_dpt_fusion_block_restatement_matches_transformers(with_residual):
         got = OF._fusion_block(p, pre, x0, x1 if with_residual else None, None, relu_inplace=False)
     assert got.shape == ref.shape
     assert float((got - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+def test_rotation_and_pose_encoding_helpers_match_scipy():
+    """UPSTREAM vggt.utils.rotation quat_to_mat / mat_to_quat (scalar-last x,y,z,w; canonical w >= 0), closed_form_inverse_se3 and
+    the absT_quaR_FoV pose encoding against scipy.spatial.transform.Rotation (scalar-last by default) and numpy.linalg."""
+    import numpy as np
+    from scipy.spatial.transform import Rotation
+    g = torch.Generator().manual_seed(21)
+    q = torch.randn(64, 4, generator=g, dtype=torch.float64)
+    ref_R = Rotation.from_quat(q.numpy()).as_matrix()                       # normalises, like the 2 / |q|^2 factor
+    assert np.abs(OF.quat_to_mat(q).numpy() - ref_R).max() < 1e-12
+    # matrices near every branch of matrix_to_quaternion (largest of w, x, y, z), incl. rotations by ~pi
+    axes = torch.tensor([[1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0], [1.0, 1.0, 1.0]], dtype=torch.float64)
+    rv = torch.cat([torch.randn(32, 3, generator=g, dtype=torch.float64), axes * (np.pi - 1e-3), axes * 1e-4], 0)
+    R = torch.from_numpy(Rotation.from_rotvec(rv.numpy()).as_matrix())
+    got = OF.mat_to_quat(R).numpy()
+    ref_q = Rotation.from_matrix(R.numpy()).as_quat()
+    ref_q = np.where(ref_q[:, 3:4] < 0, -ref_q, ref_q)
+    assert np.abs(got - ref_q).max() < 1e-9 and (got[:, 3] >= 0).all()
+    # SE(3) inverse and the pose-encoding round trip (T, quaternion, FoV from a pinhole intrinsic matrix)
+    se3 = torch.eye(4, dtype=torch.float64).repeat(len(R), 1, 1)
+    se3[:, :3, :3], se3[:, :3, 3] = R, torch.randn(len(R), 3, generator=g, dtype=torch.float64)
+    assert np.abs(OF.closed_form_inverse_se3(se3).numpy() - np.linalg.inv(se3.numpy())).max() < 1e-12
+    H, W = 154, 518
+    K = torch.zeros(1, len(R), 3, 3, dtype=torch.float64)
+    K[..., 0, 0], K[..., 1, 1], K[..., 0, 2], K[..., 1, 2], K[..., 2, 2] = 400.0, 380.0, W / 2, H / 2, 1.0
+    enc = OF.extri_intri_to_pose_encoding(se3[None, :, :3].float(), K.float(), (H, W))
+    assert enc.shape == (1, len(R), 9)
+    assert abs(float(enc[0, 0, 7]) - 2 * np.arctan(H / 2 / 380.0)) < 1e-6 and abs(float(enc[0, 0, 8]) - 2 * np.arctan(W / 2 / 400.0)) < 1e-6
+    ext, intr = OF.pose_encoding_to_extri_intri(enc, (H, W))
+    assert float((ext - se3[None, :, :3].float()).abs().max()) < 2e-6 and float((intr - K.float()).abs().max()) < 2e-3
