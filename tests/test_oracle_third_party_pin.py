@@ -128,3 +128,17 @@ def test_rotation_and_pose_encoding_helpers_match_scipy():
     assert abs(float(enc[0, 0, 7]) - 2 * np.arctan(H / 2 / 380.0)) < 1e-6 and abs(float(enc[0, 0, 8]) - 2 * np.arctan(W / 2 / 400.0)) < 1e-6
     ext, intr = OF.pose_encoding_to_extri_intri(enc, (H, W))
     assert float((ext - se3[None, :, :3].float()).abs().max()) < 2e-6 and float((intr - K.float()).abs().max()) < 2e-3
+
+
+def test_rope_2d_is_the_reference_pinned_1d_rope_on_each_half():
+    """UPSTREAM RotaryPositionEmbedding2D ("1-D sibling in-repo layers/rope.py has identical math"): the 2-D
+    restatement must equal the 1-D one — which tests/test_oracle_golden.py pins against the reference's own rope.py output — applied
+    to the first half of the head dimension with the y positions and to the second half with the x positions."""
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(2, 3, 5 + 11 * 37, 64, generator=g)
+    pos = OF.token_positions(2, 11, 37, 5, x.device)
+    got = OF.rope_apply_2d(x, pos, 100.0)
+    ref = torch.cat([OF.rope_apply_1d(x[..., :32], pos[..., 0], 100.0), OF.rope_apply_1d(x[..., 32:], pos[..., 1], 100.0)], dim=-1)
+    assert torch.equal(got, ref)
+    assert torch.equal(got[:, :, :5], x[:, :, :5])                      # special tokens sit at (0, 0): identity rotation
+    assert float((got.norm(dim=-1) - x.norm(dim=-1)).abs().max()) < 1e-4   # a rotation
